@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — UR5PlayAbsRPY1Obj-v0 env-steps/s on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference arm: CPU oracle port on the host cores
+
+A "step" is one env step of every environment of the shard: clip -> IK -> motor targets ->
+12 x 300 Hz substeps (collision, dynamics, 50-iteration PGS) -> observation dict -> reward.
+Envs are sharded by env index with no data-path collective (weak scaling: envs per GPU fixed);
+NCCL only gathers episode statistics and the max-over-ranks time.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENV_ID = 'UR5PlayAbsRPY1Obj-v0'
+BYTES_PER_ENV_STEP = {'UR5Reach-v0': 416, 'pandaPick-v0': 560, 'UR5PlayAbsRPY1Obj-v0': 1044}
+METRIC = 'UR5PlayAbsRPY1Obj-v0 env-steps/s'
+
+
+def synth_actions(rng, n, steps, env_id):
+    """Teleop-shaped synthetic actions: per env a piecewise-linear end-effector
+    trajectory between random workspace waypoints at <= 0.015 m / 0.1 rad per 25 Hz step, gripper
+    toggling at waypoints; 5% of the steps jump to a point of the full +-6 clip box."""
+    if env_id == 'UR5PlayAbsRPY1Obj-v0':
+        lo, hi = np.array([-0.30, -0.05, 0.0]), np.array([0.30, 0.50, 0.35])
+    else:
+        lo, hi = np.array([-0.18, -0.18, -0.05]), np.array([0.18, 0.18, 0.2])
+    pos = rng.uniform(lo, hi, (n, 3))
+    rpy = rng.uniform(-0.5, 0.5, (n, 3))
+    grip = rng.choice([-1.0, 1.0], (n, 1))
+    tgt_p, tgt_r = rng.uniform(lo, hi, (n, 3)), rng.uniform(-0.5, 0.5, (n, 3))
+    out = np.zeros((steps, n, 7), np.float32)
+    for s in range(steps):
+        dp = tgt_p - pos
+        dist = np.linalg.norm(dp, axis=1, keepdims=True)
+        pos = pos + dp * np.minimum(1.0, 0.015 / np.maximum(dist, 1e-9))
+        rpy = rpy + np.clip(tgt_r - rpy, -0.1, 0.1)
+        arrived = dist[:, 0] < 0.015
+        k = int(arrived.sum())
+        if k:
+            tgt_p[arrived] = rng.uniform(lo, hi, (k, 3))
+            tgt_r[arrived] = rng.uniform(-0.5, 0.5, (k, 3))
+            grip[arrived] = -grip[arrived]
+        a = np.concatenate([pos, rpy, grip], 1)
+        jump = rng.random(n) < 0.05
+        if jump.any():
+            a[jump, :6] = rng.uniform(-6, 6, (int(jump.sum()), 6))
+        out[s] = a
+    return out
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                    '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                p = [x.strip() for x in o.strip().split(',')]
+                if len(p) >= 6:
+                    self.samples.append(p)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
+                'samples': len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def _cpu_worker(args):
+    env_id, seed, wid, budget_s, warm = args
+    try:
+        os.sched_setaffinity(0, {wid % os.cpu_count()})
+    except Exception:
+        pass
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle
+    m = load_model(env_id)
+    o = Oracle(m, seed=seed + wid, env_id=wid)
+    o.reset()
+    acts = synth_actions(np.random.default_rng(seed + wid), 1, 4096, env_id)[:, 0, :]
+    for i in range(warm):
+        o.step(acts[i])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        o.step(acts[(warm + n) % len(acts)])
+        n += 1
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline(env_id, seed, budget_s=12.0, warm=20):
+    """Oracle (kind 'port') on every host core, one process per core, bounded to ~budget_s."""
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(env_id, seed, w, budget_s, warm) for w in range(cores)])
+    steps = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return {'value': steps / wall, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d procs x ~%.0fs of %s steps (reset + %d warm-up untimed), %d env-steps total; '
+                      'PyBullet itself is not installable here (DESIGN.md)' % (cores, budget_s, env_id, warm, steps)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    per = []
+    # each "step" = one bounded sample: ~ (budget / steps) seconds of oracle stepping on all cores
+    total_budget = min(150.0, max(10.0, 3.0 * (args.steps + args.warmup)))
+    b = cpu_baseline(args.env, args.seed, budget_s=total_budget, warm=20)
+    v = b['value']
+    line = {'impl': 'reference', 'metric': METRIC if args.env == ENV_ID else args.env + ' env-steps/s',
+            'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1000.0 / v if v > 0 else None, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': '%s, CPU oracle port (fp64 C restatement of the PyBullet path) on %d host cores'
+                       % (args.env, b['cores'])},
+            'cpu_baseline': dict(b, value=v),
+            'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0, 'wall_s': time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product has no CPU fallback (use --impl reference)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from roboticsplayroompybullet_b200.envs import make
+    N = args.envs_per_gpu
+    K, W = args.steps, args.warmup
+    env = make(args.env, num_envs=N, device=local, seed=args.seed, env_offset=rank * N)
+    acts_host = synth_actions(np.random.default_rng(args.seed + rank), N, K + W, args.env)
+    acts_dev = torch.as_tensor(acts_host).to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    env.reset_device()
+    torch.cuda.synchronize()
+    env.enable_kernel_timing(True)
+    for s in range(W):
+        env.step_device(acts_dev[s])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- device-resident timed region: exactly K steps, CUDA events on the launching stream,
+    #      L2 flushed between steps (outside the per-step event pairs)
+    l0 = env.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kern_ms, ik_ms = [], []
+    succ = torch.zeros((), device=dev)
+    rsum = torch.zeros((), device=dev)
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(K):
+        flush.fill_(float(s))
+        ev[s][0].record()
+        obs, r, _, info = env.step_device(acts_dev[W + s])
+        ev[s][1].record()
+        a, b = env.last_kernel_ms()
+        ik_ms.append(a)
+        kern_ms.append(b)
+        succ += info['is_success'].sum()
+        rsum += r.sum()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = env.launch_count() - l0
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    dev_s = sum(step_ms) / 1000.0
+    # ---- end-to-end through the public numpy API: pinned host actions -> H2D -> step -> D2H of the
+    #      whole observation block, every step
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        obs, r, done, info = env.step(acts_host[W + s])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    clocks = sampler.summary()
+    # ---- max over ranks, whole-job aggregate
+    t = torch.tensor([dev_s, e2e_s], device=dev, dtype=torch.float64)
+    stats = torch.stack([succ.double(), rsum.double(), torch.tensor(float(N * K), device=dev, dtype=torch.float64)])
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)       # the only collective: episode statistics
+    dev_s, e2e_s = float(t[0]), float(t[1])
+    total_env_steps = float(stats[2])
+    value = total_env_steps / dev_s
+    e2e = total_env_steps / e2e_s
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak_gbs = float(peaks.get('hbm_gbs', 6650.0))
+        which = 'measured' if 'hbm_gbs' in peaks else 'fallback'
+        kms = float(np.mean(kern_ms))
+        alg_bytes = BYTES_PER_ENV_STEP[args.env] * N
+        achieved = alg_bytes / (kms / 1000.0) / 1e9
+        info_k = env.kernel_info()
+        line = {'metric': METRIC if args.env == ENV_ID else args.env + ' env-steps/s', 'value': value,
+                'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+                'ms_per_step': 1000.0 * dev_s / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': '%s, %d envs per GPU (%d total), sharded by env index; teleop-shaped synthetic '
+                                       'actions; L2 flushed (256 MB fill) between timed steps' % (args.env, N, N * world),
+                           'envs_per_gpu': N, 'substeps_per_step': 12, 'solver_iterations': 50, 'seed': args.seed},
+                'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
+                             'frac': achieved / peak_gbs, 'traffic': None, 'kernel': 'prb_step_kernel',
+                             'kernel_ms': kms, 'ik_kernel_ms': float(np.mean(ik_ms)), 'peak_source': which,
+                             'algorithmic_bytes_per_env_step': BYTES_PER_ENV_STEP[args.env],
+                             'note': 'latency/FP32-issue bound by construction (SURVEY.md §8d); see profiles/',
+                             'smem_bytes_per_block': info_k['smem_bytes_per_block'],
+                             'regs_per_thread': info_k['regs_per_thread']},
+                'e2e': {'value': e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': env.h2d_bytes_per_step,
+                        'd2h_bytes_per_step': env.d2h_bytes_per_step},
+                'gpu_launches': int(launches), 'clocks': clocks,
+                'episode_stats': {'success_rate': float(stats[0]) / total_env_steps,
+                                  'mean_reward': float(stats[1]) / total_env_steps},
+                'wall_s_timed_region': t_wall}
+        if not args.no_cpu_baseline and world == 1:
+            line['cpu_baseline'] = cpu_baseline(args.env, args.seed, budget_s=args.cpu_seconds)
+        elif not args.no_cpu_baseline:
+            line['cpu_baseline'] = None
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--env', default=ENV_ID)
+    ap.add_argument('--envs-per-gpu', type=int, default=65536)
+    ap.add_argument('--seed', type=int, default=1234)
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

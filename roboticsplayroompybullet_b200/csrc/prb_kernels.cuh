@@ -1,0 +1,1326 @@
+// prb_kernels.cuh — the batched simulator's device code (sm_100a, fp32, CUDA cores).
+//
+// Execution model
+//   * prb_ik_kernel      one THREAD per env: action clip -> rpy->quat -> chained damped-least-
+//                        squares IK on the serial arm chain (registers only) -> joint-limit and
+//                        per-step clipping -> motor targets.  Reference path:
+//                        environments.py:206-208, 955-961, 984-1034, 1037-1073; inverseKinematics.py:44-50.
+//   * prb_step_kernel    one WARP per env, all 12 physics substeps of an env step fused in one
+//                        launch with the env's state, kinematics, mass matrix, contact manifold
+//                        and constraint rows resident in shared memory; lanes are links /
+//                        colliders / collider pairs / contacts in the set-up phases and velocity
+//                        DoF in the projected-Gauss-Seidel sweeps (J.dv by warp-shuffle
+//                        reduction).  Ends with the fused observation/reward write.  Reference
+//                        path: environments.py:209-214 (runSimulation, calc_state, reward).
+//   * prb_reset_kernel   one WARP per env, masked: environments.py:173-187, 492-603.
+//   * prb_reward_kernel  stateless batched compute_reward (relabelling): environments.py:278-304,
+//                        playRewardFunc.py:66-77.
+//
+// Dynamics formulation (differs from the oracle's articulated-body algorithm on purpose):
+// world-frame recursive Newton-Euler for the bias forces, composite-rigid-body mass matrix,
+// dense Cholesky -> M^-1 kept in shared memory; every constraint row stores J and M^-1 J^T.
+//
+// All warp-collective operations (__shfl*, __ballot, __syncwarp) are executed in warp-uniform
+// control flow with the full mask.
+#pragma once
+#include "prb_device.h"
+
+#define PRB_WPB 4              // warps (envs) per thread block
+#define PRB_MAXJROW 40         // limit + motor + gear rows
+#define PRB_MAXCONTACT 32      // contact points per env per substep (one per lane)
+#define PRB_MAXOVL 32          // overlapping collider pairs handed to the narrow phase (one per lane)
+#define PRB_POOL 2304          // floats of packed contact-row Jacobians (J and M^-1 J^T segments)
+#define FULL 0xffffffffu
+
+struct Contact {
+  float pbx, pby, pbz, nx, ny, nz, dist;
+  int cols;   // ca | cb << 8
+};
+
+struct WarpMem {
+  // ---- simulation state of this env (loaded once per launch, written back at the end)
+  float q[PRB_MAXD], qd[PRB_MAXD], mtarget[PRB_MAXD], mkp[PRB_MAXD], mmaximp[PRB_MAXD];
+  float fpos[PRB_MAXFREE][3], fquat[PRB_MAXFREE][4], fvel[PRB_MAXFREE][3], fang[PRB_MAXFREE][3];
+  float sq[PRB_MAXSLIDE], sqd[PRB_MAXSLIDE];
+  float goal[12], lastq[8], last_valid, reset_count;
+  // ---- kinematics / dynamics of the current substep
+  float lR[PRB_MAXD][9], lp[PRB_MAXD][3], la[PRB_MAXD][3], lc[PRB_MAXD][3], lIw[PRB_MAXD][6];
+  float lf[PRB_MAXD][3], ln[PRB_MAXD][3], lw[PRB_MAXD][3], lv[PRB_MAXD][3];
+  float fR[PRB_MAXFREE][9], fIinv[PRB_MAXFREE][6];
+  float sp[PRB_MAXSLIDE][3], sR[PRB_MAXSLIDE][9];
+  float Mm[PRB_MAXD][PRB_MAXD + 1], Minv[PRB_MAXD][PRB_MAXD + 1], Q[PRB_MAXD];
+  float vs[32];
+  // ---- collision
+  float aabb[PRB_MAXCOL][6];
+  unsigned short ovl[PRB_MAXOVL];
+  int n_ovl, n_contact, n_jrow, pool_used, overflow;
+  Contact ct[PRB_MAXCONTACT];
+  // ---- constraint rows
+  signed char jr_dof[PRB_MAXJROW], jr_dof2[PRB_MAXJROW];
+  float jr_sign[PRB_MAXJROW], jr_rhs[PRB_MAXJROW], jr_invD[PRB_MAXJROW], jr_lo[PRB_MAXJROW], jr_hi[PRB_MAXJROW], jr_lam[PRB_MAXJROW];
+  // per contact: rows 0 normal, 1 spin, 2 friction-1, 3 friction-2
+  float cr_rhs[PRB_MAXCONTACT][4], cr_invD[PRB_MAXCONTACT][4], cr_lam[PRB_MAXCONTACT][4];
+  float cr_cfm[PRB_MAXCONTACT], cr_mu[PRB_MAXCONTACT], cr_spin[PRB_MAXCONTACT];
+  signed char cr_bodyA[PRB_MAXCONTACT], cr_bodyB[PRB_MAXCONTACT];
+  unsigned short cr_offA[PRB_MAXCONTACT], cr_offB[PRB_MAXCONTACT];
+  // cand aliases pool: narrow-phase candidates are dead once compacted into ct[]
+  float pool[PRB_POOL];
+};
+
+PRB_D float warp_sum(float v) {
+  v += __shfl_xor_sync(FULL, v, 16);
+  v += __shfl_xor_sync(FULL, v, 8);
+  v += __shfl_xor_sync(FULL, v, 4);
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 1);
+  return v;
+}
+PRB_D int warp_excl_scan(int v, int lane, int* total) {
+  int s = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(FULL, s, o);
+    if (lane >= o) s += t;
+  }
+  *total = __shfl_sync(FULL, s, 31);
+  return s - v;
+}
+
+// body index of a velocity DoF and geometry helpers -------------------------------------------
+// bodies: 0 arm, 1..n_free free bodies, n_free+1.. slide bodies, -1 static
+PRB_D int dof_body(const DevModel& M, int d, int* li, int* n) {
+  if (d < M.nd) { *li = d; *n = M.nd; return 0; }
+  int r = d - M.nd;
+  if (r < 6 * M.n_free) { *li = r % 6; *n = 6; return 1 + r / 6; }
+  r -= 6 * M.n_free;
+  if (r < M.n_slide) { *li = 0; *n = 1; return 1 + M.n_free + r; }
+  *li = 0; *n = 0; return -2;
+}
+PRB_D int body_size(const DevModel& M, int body) { return body == 0 ? M.nd : (body <= M.n_free ? 6 : 1); }
+PRB_D int body_dof0(const DevModel& M, int body) {
+  return body == 0 ? 0 : (body <= M.n_free ? M.nd + 6 * (body - 1) : M.nd + 6 * M.n_free + (body - 1 - M.n_free));
+}
+
+// ============================================================================ IK (thread per env)
+// One calculateInverseKinematics call restated for a serial revolute chain of NJ joints whose
+// last link carries the end-effector site; base frame coordinates; q updated in place.
+template <int NJ>
+PRB_D void ik_call(const DevModel& M, float* q, v3 tp, const float* tq, int max_iters) {
+  const float lambda = M.params[P_IK_DAMPING], thresh = M.params[P_IK_THRESHOLD];
+  float diff = 1e30f;
+  for (int it = 0; it < max_iters && diff > thresh; it++) {
+    v3 a[NJ], pj[NJ];
+    m3 R = ident3();
+    v3 p = V3(0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      p = p + mul(R, ld3(M.jpos[j]));
+      m3 R0 = mul(R, ldm(M.jrot[j]));
+      v3 ax = ld3(M.axis[j]);
+      a[j] = mul(R0, ax);
+      pj[j] = p;
+      R = mul(R0, axis_angle(ax, q[j]));
+    }
+    v3 ep = p + mul(R, ld3(M.site_pos[0]));
+    m3 eR = mul(R, ldm(M.site_rot[0]));
+    float eq[4];
+    mat_to_quat(eR, eq);
+    v3 dp = tp - ep;
+    diff = norm(dp);
+    float e[6];
+    e[0] = dp.x; e[1] = dp.y; e[2] = dp.z;
+    {  // rotation error = angle * axis of (target * current^-1); atan2 form is fp32-safe near 0
+      float inv[4] = {-eq[0], -eq[1], -eq[2], eq[3]}, dq[4];
+      quat_mul(tq, inv, dq);
+      float s = sqrtf(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2]);
+      float angle = 2.0f * atan2f(s, dq[3]);
+      if (angle > PRB_PI_F) angle -= 2.0f * PRB_PI_F;
+      float k = s > 1e-12f ? angle / s : 0.f;
+      if (s <= 1e-12f) { e[3] = angle; e[4] = 0; e[5] = 0; }   // Bullet's getAxis() fallback (1,0,0)
+      else { e[3] = dq[0] * k; e[4] = dq[1] * k; e[5] = dq[2] * k; }
+    }
+    float J[6][NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      v3 jl = cross(a[j], ep - pj[j]);
+      J[0][j] = jl.x; J[1][j] = jl.y; J[2][j] = jl.z; J[3][j] = a[j].x; J[4][j] = a[j].y; J[5][j] = a[j].z;
+    }
+    // (J^T J + lambda I) x = J^T e, Cholesky in registers
+    float A[NJ][NJ], b[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; i++) {
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        float s = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s += J[k][i] * J[k][j];
+        A[i][j] = s + (i == j ? lambda : 0.f);
+      }
+      float s = 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) s += J[k][i] * e[k];
+      b[i] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < NJ; k++) {
+      float d = A[k][k];
+#pragma unroll
+      for (int m = 0; m < k; m++) d -= A[k][m] * A[k][m];
+      d = sqrtf(d);
+      A[k][k] = d;
+      float inv = 1.0f / d;
+#pragma unroll
+      for (int r = k + 1; r < NJ; r++) {
+        float s = A[r][k];
+#pragma unroll
+        for (int m = 0; m < k; m++) s -= A[r][m] * A[k][m];
+        A[r][k] = s * inv;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NJ; r++) {
+      float s = b[r];
+#pragma unroll
+      for (int m = 0; m < r; m++) s -= A[r][m] * b[m];
+      b[r] = s / A[r][r];
+    }
+#pragma unroll
+    for (int r = NJ - 1; r >= 0; r--) {
+      float s = b[r];
+#pragma unroll
+      for (int m = r + 1; m < NJ; m++) s -= A[m][r] * b[m];
+      b[r] = s / A[r][r];
+    }
+    float mx = 0;
+#pragma unroll
+    for (int i = 0; i < NJ; i++) mx = fmaxf(mx, fabsf(b[i]));
+    const float maxang = 45.0f * PRB_PI_F / 180.0f;
+    float sc = mx > maxang ? maxang / mx : 1.0f;
+#pragma unroll
+    for (int i = 0; i < NJ; i++) q[i] += b[i] * sc;
+  }
+}
+// world target -> base coordinates, then `calls` chained solves (inverseKinematics.py:44-50)
+template <int NJ>
+PRB_D void ik_world(const DevModel& M, float* q, const float* tpos_w, const float* tquat_w, int calls, int iters) {
+  m3 bR = ldm(M.base_rot);
+  v3 tp = tmul(bR, ld3(tpos_w) - ld3(M.base_pos));
+  float bqi[4] = {-M.base_quat[0], -M.base_quat[1], -M.base_quat[2], M.base_quat[3]}, tq[4];
+  quat_mul(bqi, tquat_w, tq);
+  for (int c = 0; c < calls; c++) ik_call<NJ>(M, q, tp, tq, iters);
+}
+
+template <int NJ>
+PRB_D void ik_action_env(const DevModel& M, float* st /* this env's state */, const float* act, float* target_out) {
+  const int nd = M.nd;
+  float a[7];
+#pragma unroll
+  for (int k = 0; k < 6; k++) a[k] = clampf(act[k], -M.params[P_ACTION_HIGH_XYZ], M.params[P_ACTION_HIGH_XYZ]);
+  a[6] = clampf(act[6], -M.params[P_ACTION_HIGH_GRIP], M.params[P_ACTION_HIGH_GRIP]);
+  float tq[4];
+  quat_from_euler(a + 3, tq);
+  float q[NJ], q0[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; i++) { q0[i] = st[i]; q[i] = q0[i]; }
+  ik_world<NJ>(M, q, a, tq, M.ik_calls, M.ik_iters);
+  const float dt = M.params[P_DT];
+#pragma unroll
+  for (int i = 0; i < NJ; i++) {
+    float t = clampf(q[i], M.ctrl_ll[i], M.ctrl_ul[i]);
+    t = clampf(t, q0[i] - M.ctrl_inc[i], q0[i] + M.ctrl_inc[i]);
+    st[2 * nd + i] = t;
+    st[3 * nd + i] = M.params[P_MOTOR_KP];
+    st[4 * nd + i] = M.params[P_ARM_FORCE] * dt;
+    target_out[i] = t;
+  }
+  for (int k = 0; k < M.n_grip; k++) {
+    int d = M.grip_dof[k];
+    float t = M.grip_mimic[k] >= 0 ? st[M.grip_mimic[k]] : M.grip_scale[k] * a[6] + M.grip_offset[k];
+    st[2 * nd + d] = t;
+    st[3 * nd + d] = M.params[P_MOTOR_KP];
+    st[4 * nd + d] = M.grip_force[k] * dt;
+  }
+}
+
+__global__ void __launch_bounds__(128) prb_ik_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
+                                                      const float* __restrict__ action, float* __restrict__ target_poses, int N) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  const DevModel& M = *Mp;
+  float* st = state + (size_t)e * M.state_stride;
+  if (M.n_ik == 6) ik_action_env<6>(M, st, action + (size_t)e * 7, target_poses + (size_t)e * 6);
+  else ik_action_env<7>(M, st, action + (size_t)e * 7, target_poses + (size_t)e * 7);
+}
+
+// ============================================================================ state <-> shared memory
+PRB_D void load_state(const DevModel& M, WarpMem& W, const float* st, int lane) {
+  const int nd = M.nd;
+  for (int i = lane; i < M.state_dim; i += 32) {
+    float v = st[i];
+    int k = i;
+    if (k < nd) { W.q[k] = v; continue; } k -= nd;
+    if (k < nd) { W.qd[k] = v; continue; } k -= nd;
+    if (k < nd) { W.mtarget[k] = v; continue; } k -= nd;
+    if (k < nd) { W.mkp[k] = v; continue; } k -= nd;
+    if (k < nd) { W.mmaximp[k] = v; continue; } k -= nd;
+    if (k < 13 * M.n_free) {
+      int b = k / 13, r = k % 13;
+      if (r < 3) W.fpos[b][r] = v; else if (r < 7) W.fquat[b][r - 3] = v; else if (r < 10) W.fvel[b][r - 7] = v; else W.fang[b][r - 10] = v;
+      continue;
+    }
+    k -= 13 * M.n_free;
+    if (k < 2 * M.n_slide) { if (k & 1) W.sqd[k >> 1] = v; else W.sq[k >> 1] = v; continue; }
+    k -= 2 * M.n_slide;
+    if (k < M.goal_dim) { W.goal[k] = v; continue; } k -= M.goal_dim;
+    if (k < 8) { W.lastq[k] = v; continue; } k -= 8;
+    if (k == 0) W.last_valid = v; else W.reset_count = v;
+  }
+  __syncwarp();
+}
+PRB_D void store_state(const DevModel& M, const WarpMem& W, float* st, int lane) {
+  const int nd = M.nd;
+  __syncwarp();
+  for (int i = lane; i < M.state_dim; i += 32) {
+    float v;
+    int k = i;
+    if (k < nd) v = W.q[k];
+    else if ((k -= nd) < nd) v = W.qd[k];
+    else if ((k -= nd) < nd) v = W.mtarget[k];
+    else if ((k -= nd) < nd) v = W.mkp[k];
+    else if ((k -= nd) < nd) v = W.mmaximp[k];
+    else if ((k -= nd) < 13 * M.n_free) {
+      int b = k / 13, r = k % 13;
+      v = r < 3 ? W.fpos[b][r] : (r < 7 ? W.fquat[b][r - 3] : (r < 10 ? W.fvel[b][r - 7] : W.fang[b][r - 10]));
+    } else if ((k -= 13 * M.n_free) < 2 * M.n_slide) v = (k & 1) ? W.sqd[k >> 1] : W.sq[k >> 1];
+    else if ((k -= 2 * M.n_slide) < M.goal_dim) v = W.goal[k];
+    else if ((k -= M.goal_dim) < 8) v = W.lastq[k];
+    else v = (k - 8 == 0) ? W.last_valid : W.reset_count;
+    st[i] = v;
+  }
+}
+
+// ============================================================================ kinematics + bias (lane = arm link)
+// Each lane walks its own root->link path, accumulating the frame, the velocity and the
+// velocity-product acceleration (recursive Newton-Euler forward pass with qdd = 0 and gravity
+// folded in as base acceleration); no inter-lane communication.
+PRB_D void phase_fk(const DevModel& M, WarpMem& W, int lane, bool dynamics) {
+  if (lane < M.nd) {
+    m3 R = ldm(M.base_rot);
+    v3 p = ld3(M.base_pos);
+    v3 w = V3(0, 0, 0), v = V3(0, 0, 0), al = V3(0, 0, 0), ac = V3(0, 0, -M.params[P_GRAVITY_Z]);
+    v3 aw = V3(0, 0, 0);
+    const int depth = M.depth[lane];
+    for (int k = 0; k < depth; k++) {
+      const int j = M.path[lane][k];
+      const float qj = W.q[j], qdj = W.qd[j];
+      v3 r = mul(R, ld3(M.jpos[j]));
+      v3 vo = v + cross(w, r);
+      v3 ao = ac + cross(al, r) + cross(w, cross(w, r));
+      p = p + r;
+      m3 R0 = mul(R, ldm(M.jrot[j]));
+      v3 ax = ld3(M.axis[j]);
+      aw = mul(R0, ax);
+      if (M.jtype[j] == 0) {
+        R = mul(R0, axis_angle(ax, qj));
+        v3 wj = aw * qdj;
+        al = al + cross(w, wj);
+        w = w + wj;
+        v = vo; ac = ao;
+      } else {
+        R = R0;
+        v3 d = aw * qj, dd = aw * qdj;
+        p = p + d;
+        v = vo + cross(w, d) + dd;
+        ac = ao + cross(al, d) + cross(w, cross(w, d)) + cross(w, dd) * 2.0f;
+      }
+    }
+    stm(W.lR[lane], R); st3(W.lp[lane], p); st3(W.la[lane], aw); st3(W.lw[lane], w); st3(W.lv[lane], v);
+    v3 rc = mul(R, ld3(M.com[lane]));
+    st3(W.lc[lane], p + rc);
+    if (dynamics) {
+      float Iw[6];
+      rot_sym(R, M.inertia[lane], Iw);
+      for (int k = 0; k < 6; k++) W.lIw[lane][k] = Iw[k];
+      v3 acom = ac + cross(al, rc) + cross(w, cross(w, rc));
+      st3(W.lf[lane], acom * M.mass[lane]);
+      st3(W.ln[lane], symmul(Iw, al) + cross(w, symmul(Iw, w)));
+    }
+  }
+  // free / slide body frames (lanes past the arm)
+  int b = lane - M.nd;
+  if (b >= 0 && b < M.n_free) {
+    m3 R; quat_to_mat(W.fquat[b], R); stm(W.fR[b], R);
+    if (dynamics) {
+      float Dg[6] = {1.0f / M.free_inertia[b][0], 0, 0, 1.0f / M.free_inertia[b][1], 0, 1.0f / M.free_inertia[b][2]}, o[6];
+      rot_sym(R, Dg, o);
+      for (int k = 0; k < 6; k++) W.fIinv[b][k] = o[k];
+    }
+  }
+  int s = lane - M.nd - M.n_free;
+  if (s >= 0 && s < M.n_slide) {
+    m3 R0 = ldm(M.slide_rot[s]);
+    v3 ax = ld3(M.slide_axis[s]), p0 = ld3(M.slide_pos[s]);
+    if (M.slide_jtype[s] == 0) { stm(W.sR[s], mul(R0, axis_angle(ax, W.sq[s]))); st3(W.sp[s], p0); }
+    else { stm(W.sR[s], R0); st3(W.sp[s], p0 + ld3(M.slide_axis_w[s]) * W.sq[s]); }
+  }
+  __syncwarp();
+}
+
+// bias forces tau_j and mass-matrix row j (lane = joint j), by direct sums over subtree(j)
+PRB_D void phase_crba(const DevModel& M, WarpMem& W, int lane) {
+  const int nd = M.nd;
+  if (lane < nd) {
+    const int j = lane;
+    const bool rev = M.jtype[j] == 0;
+    const v3 aj = ld3(W.la[j]), pj = ld3(W.lp[j]);
+    float tau = 0;
+    v3 P = V3(0, 0, 0), L = V3(0, 0, 0);
+    unsigned mask = M.sub_mask[j];
+    for (int i = j; i < nd; i++) {
+      if (!((mask >> i) & 1u)) continue;
+      v3 ci = ld3(W.lc[i]), fi = ld3(W.lf[i]), ni = ld3(W.ln[i]);
+      v3 rc = ci - pj;
+      tau += rev ? dot(aj, ni + cross(rc, fi)) : dot(aj, fi);
+      float mi = M.mass[i];
+      v3 ui = rev ? cross(aj, rc) : aj;
+      v3 pm = ui * mi;
+      P = P + pm;
+      L = L + cross(rc, pm);
+      if (rev) L = L + symmul(W.lIw[i], aj);
+    }
+    W.Q[j] = -tau - M.jdamp[j] * W.qd[j];
+    unsigned anc = M.anc_mask[j];
+    for (int k = 0; k <= j; k++) {
+      float val = 0.f;
+      if ((anc >> k) & 1u) {
+        v3 ak = ld3(W.la[k]);
+        val = M.jtype[k] == 0 ? dot(ak, L + cross(pj - ld3(W.lp[k]), P)) : dot(ak, P);
+      }
+      W.Mm[j][k] = val;
+      W.Mm[k][j] = val;
+    }
+  }
+  __syncwarp();
+}
+
+// Cholesky M = L L^T in place (lane = row), then lane c solves for column c of M^-1
+template <int ND>
+PRB_D void phase_minv(WarpMem& W, int lane) {
+  for (int k = 0; k < ND; k++) {
+    float d = sqrtf(W.Mm[k][k]);
+    __syncwarp();
+    if (lane == k) W.Mm[k][k] = d;
+    if (lane > k && lane < ND) W.Mm[lane][k] = W.Mm[lane][k] / d;
+    __syncwarp();
+    if (lane > k && lane < ND) {
+      float lrk = W.Mm[lane][k];
+      for (int c = k + 1; c <= lane; c++) W.Mm[lane][c] -= lrk * W.Mm[c][k];
+    }
+    __syncwarp();
+  }
+  if (lane < ND) {
+    float x[ND];
+#pragma unroll
+    for (int r = 0; r < ND; r++) {
+      float s = (r == lane) ? 1.0f : 0.0f;
+#pragma unroll
+      for (int m = 0; m < r; m++) s -= W.Mm[r][m] * x[m];
+      x[r] = s / W.Mm[r][r];
+    }
+#pragma unroll
+    for (int r = ND - 1; r >= 0; r--) {
+      float s = x[r];
+#pragma unroll
+      for (int m = r + 1; m < ND; m++) s -= W.Mm[m][r] * x[m];
+      x[r] = s / W.Mm[r][r];
+    }
+#pragma unroll
+    for (int r = 0; r < ND; r++) W.Minv[r][lane] = x[r];
+  }
+  __syncwarp();
+}
+
+// unconstrained velocity update v* = v + dt * a  (lane = velocity DoF); result in W.vs and returned
+PRB_D float phase_vstar(const DevModel& M, WarpMem& W, int lane) {
+  const float dt = M.params[P_DT], g = M.params[P_GRAVITY_Z], vmax = M.params[P_MAX_COORD_VEL];
+  const int nd = M.nd;
+  // free bodies: one lane per body does the coupled 3-vector algebra
+  int b = lane - nd;
+  if (b >= 0 && b < M.n_free) {
+    m3 R = ldm(W.fR[b]);
+    float kl = M.free_ld[b], ka = M.free_ad[b];
+    v3 vl = ld3(W.fvel[b]), w = ld3(W.fang[b]);
+    v3 acc = V3(0, 0, g) + vl * (-(kl + kl * norm(vl)));
+    v3 wb = tmul(R, w);
+    v3 Id = ld3(M.free_inertia[b]);
+    v3 gy = cross(wb, V3(Id.x * wb.x, Id.y * wb.y, Id.z * wb.z));
+    v3 wdb = V3(-gy.x / Id.x, -gy.y / Id.y, -gy.z / Id.z) + wb * (-(ka + ka * norm(wb)));
+    v3 wd = mul(R, wdb);
+    int o = nd + 6 * b;
+    W.vs[o] = clampf(vl.x + dt * acc.x, -vmax, vmax); W.vs[o + 1] = clampf(vl.y + dt * acc.y, -vmax, vmax);
+    W.vs[o + 2] = clampf(vl.z + dt * acc.z, -vmax, vmax); W.vs[o + 3] = clampf(w.x + dt * wd.x, -vmax, vmax);
+    W.vs[o + 4] = clampf(w.y + dt * wd.y, -vmax, vmax); W.vs[o + 5] = clampf(w.z + dt * wd.z, -vmax, vmax);
+  }
+  float v = 0.f;
+  if (lane < nd) {
+    float acc = 0;
+    for (int j = 0; j < nd; j++) acc += W.Minv[lane][j] * W.Q[j];
+    v = clampf(W.qd[lane] + dt * acc, -vmax, vmax);
+    W.vs[lane] = v;
+  }
+  int s = lane - nd - 6 * M.n_free;
+  if (s >= 0 && s < M.n_slide) {
+    float a;
+    if (M.slide_jtype[s] == 1) a = g * M.slide_axis_w[s][2];
+    else { float ka = M.slide_ad[s], w = W.sqd[s]; a = -w * (ka + ka * fabsf(w)); }
+    v = clampf(W.sqd[s] + dt * a, -vmax, vmax);
+    W.vs[lane] = v;
+  }
+  __syncwarp();
+  if (lane < M.nv) v = W.vs[lane];
+  return v;
+}
+
+// ============================================================================ collision
+PRB_D void body_frame(const DevModel& M, const WarpMem& W, int body, int link, m3& R, v3& p) {
+  if (body < 0) { R = ident3(); p = V3(0, 0, 0); }
+  else if (body == 0) {
+    if (link < 0) { R = ldm(M.base_rot); p = ld3(M.base_pos); }
+    else { R = ldm(W.lR[link]); p = ld3(W.lp[link]); }
+  } else if (body <= M.n_free) { R = ldm(W.fR[body - 1]); p = ld3(W.fpos[body - 1]); }
+  else { R = ldm(W.sR[body - 1 - M.n_free]); p = ld3(W.sp[body - 1 - M.n_free]); }
+}
+PRB_D void collider_frame(const DevModel& M, const WarpMem& W, int c, m3& R, v3& p) {
+  m3 Rb; v3 pb;
+  body_frame(M, W, M.col_body[c], M.col_link[c], Rb, pb);
+  R = mul(Rb, ldm(M.col_rot[c]));
+  p = pb + mul(Rb, ld3(M.col_pos[c]));
+}
+
+struct CPoint { v3 pos, n; float depth; };
+
+// clip the quad p (4 2-D points) against the rectangle +-h; returns the number of points in ret
+PRB_D int clip_quad(const float h[2], const float p_in[8], float ret[16]) {
+  int nq = 4, nr = 0;
+  float buffer[16];
+  const float* q = p_in;
+  float* r = ret;
+  for (int dir = 0; dir <= 1; dir++) {
+    for (int sign = -1; sign <= 1; sign += 2) {
+      const float* pq = q;
+      float* pr = r;
+      nr = 0;
+      bool full = false;
+      for (int i = nq; i > 0 && !full; i--) {
+        if (sign * pq[dir] < h[dir]) {
+          pr[0] = pq[0]; pr[1] = pq[1]; pr += 2; nr++;
+          if (nr & 8) { full = true; break; }
+        }
+        const float* nextq = (i > 1) ? pq + 2 : q;
+        if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
+          pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
+          pr[dir] = sign * h[dir];
+          pr += 2; nr++;
+          if (nr & 8) { full = true; break; }
+        }
+        pq += 2;
+      }
+      q = r;
+      if (full) goto done;
+      r = (q == ret) ? buffer : ret;
+      nq = nr;
+    }
+  }
+done:
+  if (q != ret) for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
+  return nr;
+}
+PRB_D void cull_points(int n, const float p[], int m, int i0, int iret[]) {
+  float a, cx, cy, q;
+  if (n == 1) { cx = p[0]; cy = p[1]; }
+  else if (n == 2) { cx = 0.5f * (p[0] + p[2]); cy = 0.5f * (p[1] + p[3]); }
+  else {
+    a = 0; cx = 0; cy = 0;
+    for (int i = 0; i < n - 1; i++) {
+      q = p[i * 2] * p[i * 2 + 3] - p[i * 2 + 2] * p[i * 2 + 1];
+      a += q; cx += q * (p[i * 2] + p[i * 2 + 2]); cy += q * (p[i * 2 + 1] + p[i * 2 + 3]);
+    }
+    q = p[n * 2 - 2] * p[1] - p[0] * p[n * 2 - 1];
+    if (fabsf(a + q) > 1.1920929e-7f) a = 1.0f / (3.0f * (a + q)); else a = 1e18f;
+    cx = a * (cx + q * (p[n * 2 - 2] + p[0])); cy = a * (cy + q * (p[n * 2 - 1] + p[1]));
+  }
+  float A[8]; int avail[8];
+  for (int i = 0; i < n; i++) { A[i] = atan2f(p[i * 2 + 1] - cy, p[i * 2] - cx); avail[i] = 1; }
+  avail[i0] = 0; iret[0] = i0; iret++;
+  for (int j = 1; j < m; j++) {
+    a = j * (2 * PRB_PI_F / m) + A[i0];
+    if (a > PRB_PI_F) a -= 2 * PRB_PI_F;
+    float maxdiff = 1e9f, diff; *iret = i0;
+    for (int i = 0; i < n; i++) if (avail[i]) {
+      diff = fabsf(A[i] - a); if (diff > PRB_PI_F) diff = 2 * PRB_PI_F - diff;
+      if (diff < maxdiff) { maxdiff = diff; *iret = i; }
+    }
+    avail[*iret] = 0; iret++;
+  }
+}
+// box-box: separating-axis search + face clipping / edge-edge closest points; normal from box 2
+// (B) to box 1 (A), points on B, depth >= 0; at most 4 points.
+PRB_D int box_box(v3 p1, const m3& R1, v3 h1, v3 p2, const m3& R2, v3 h2, CPoint* out) {
+  const float fudge = 1.05f, EPS = 1.1920929e-7f;
+  float A[3] = {h1.x, h1.y, h1.z}, B[3] = {h2.x, h2.y, h2.z};
+  v3 p = p2 - p1, ppv3 = tmul(R1, p);
+  float pp[3] = {ppv3.x, ppv3.y, ppv3.z};
+  float Rm[3][3], Q[3][3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { Rm[i][j] = dot(col(R1, i), col(R2, j)); Q[i][j] = fabsf(Rm[i][j]); }
+  float s = -1e30f, s2, l;
+  int invert = 0, code = 0, nrm_box = 0, nrm_col = 0;
+  v3 normalC = V3(0, 0, 0);
+#define PRB_TST(e1, e2, bx, cl, cc) { float E1 = (e1); s2 = fabsf(E1) - (e2); if (s2 > 0) return 0; \
+    if (s2 > s) { s = s2; nrm_box = bx; nrm_col = cl; invert = (E1 < 0); code = (cc); } }
+  PRB_TST(pp[0], (A[0] + B[0] * Q[0][0] + B[1] * Q[0][1] + B[2] * Q[0][2]), 1, 0, 1);
+  PRB_TST(pp[1], (A[1] + B[0] * Q[1][0] + B[1] * Q[1][1] + B[2] * Q[1][2]), 1, 1, 2);
+  PRB_TST(pp[2], (A[2] + B[0] * Q[2][0] + B[1] * Q[2][1] + B[2] * Q[2][2]), 1, 2, 3);
+  PRB_TST(dot(col(R2, 0), p), (A[0] * Q[0][0] + A[1] * Q[1][0] + A[2] * Q[2][0] + B[0]), 2, 0, 4);
+  PRB_TST(dot(col(R2, 1), p), (A[0] * Q[0][1] + A[1] * Q[1][1] + A[2] * Q[2][1] + B[1]), 2, 1, 5);
+  PRB_TST(dot(col(R2, 2), p), (A[0] * Q[0][2] + A[1] * Q[1][2] + A[2] * Q[2][2] + B[2]), 2, 2, 6);
+#undef PRB_TST
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Q[i][j] += 1.0e-5f;
+#define PRB_TST(e1, e2, n1, n2, n3, cc) { float E1 = (e1); s2 = fabsf(E1) - (e2); if (s2 > EPS) return 0; \
+    l = sqrtf((n1) * (n1) + (n2) * (n2) + (n3) * (n3)); \
+    if (l > EPS) { s2 /= l; if (s2 * fudge > s) { s = s2; nrm_box = 0; normalC = V3((n1) / l, (n2) / l, (n3) / l); invert = (E1 < 0); code = (cc); } } }
+  PRB_TST(pp[2] * Rm[1][0] - pp[1] * Rm[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + B[1] * Q[0][2] + B[2] * Q[0][1]), 0, -Rm[2][0], Rm[1][0], 7);
+  PRB_TST(pp[2] * Rm[1][1] - pp[1] * Rm[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + B[0] * Q[0][2] + B[2] * Q[0][0]), 0, -Rm[2][1], Rm[1][1], 8);
+  PRB_TST(pp[2] * Rm[1][2] - pp[1] * Rm[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + B[0] * Q[0][1] + B[1] * Q[0][0]), 0, -Rm[2][2], Rm[1][2], 9);
+  PRB_TST(pp[0] * Rm[2][0] - pp[2] * Rm[0][0], (A[0] * Q[2][0] + A[2] * Q[0][0] + B[1] * Q[1][2] + B[2] * Q[1][1]), Rm[2][0], 0, -Rm[0][0], 10);
+  PRB_TST(pp[0] * Rm[2][1] - pp[2] * Rm[0][1], (A[0] * Q[2][1] + A[2] * Q[0][1] + B[0] * Q[1][2] + B[2] * Q[1][0]), Rm[2][1], 0, -Rm[0][1], 11);
+  PRB_TST(pp[0] * Rm[2][2] - pp[2] * Rm[0][2], (A[0] * Q[2][2] + A[2] * Q[0][2] + B[0] * Q[1][1] + B[1] * Q[1][0]), Rm[2][2], 0, -Rm[0][2], 12);
+  PRB_TST(pp[1] * Rm[0][0] - pp[0] * Rm[1][0], (A[0] * Q[1][0] + A[1] * Q[0][0] + B[1] * Q[2][2] + B[2] * Q[2][1]), -Rm[1][0], Rm[0][0], 0, 13);
+  PRB_TST(pp[1] * Rm[0][1] - pp[0] * Rm[1][1], (A[0] * Q[1][1] + A[1] * Q[0][1] + B[0] * Q[2][2] + B[2] * Q[2][0]), -Rm[1][1], Rm[0][1], 0, 14);
+  PRB_TST(pp[1] * Rm[0][2] - pp[0] * Rm[1][2], (A[0] * Q[1][2] + A[1] * Q[0][2] + B[0] * Q[2][1] + B[1] * Q[2][0]), -Rm[1][2], Rm[0][2], 0, 15);
+#undef PRB_TST
+  if (!code) return 0;
+  v3 normal = nrm_box == 1 ? col(R1, nrm_col) : (nrm_box == 2 ? col(R2, nrm_col) : mul(R1, normalC));
+  if (invert) normal = normal * -1.0f;
+  float depth = -s;
+  if (code > 6) {
+    v3 pa = p1, pb = p2;
+    for (int j = 0; j < 3; j++) { float sg = dot(normal, col(R1, j)) > 0 ? 1.0f : -1.0f; pa = pa + col(R1, j) * (sg * A[j]); }
+    for (int j = 0; j < 3; j++) { float sg = dot(normal, col(R2, j)) > 0 ? -1.0f : 1.0f; pb = pb + col(R2, j) * (sg * B[j]); }
+    v3 ua = col(R1, (code - 7) / 3), ub = col(R2, (code - 7) % 3);
+    v3 dpp = pb - pa;
+    float uaub = dot(ua, ub), q1 = dot(ua, dpp), q2 = -dot(ub, dpp), d = 1 - uaub * uaub;
+    float beta = d <= 0.0001f ? 0.f : (uaub * q1 + q2) / d;
+    out[0].pos = pb + ub * beta; out[0].n = normal * -1.0f; out[0].depth = depth;
+    return 1;
+  }
+  const bool first = code <= 3;
+  const m3& Ra = first ? R1 : R2;
+  const m3& Rb = first ? R2 : R1;
+  v3 pa = first ? p1 : p2, pb = first ? p2 : p1;
+  const float* Sa = first ? A : B;
+  const float* Sb = first ? B : A;
+  v3 normal2 = first ? normal : normal * -1.0f;
+  v3 nr = tmul(Rb, normal2);
+  float anr[3] = {fabsf(nr.x), fabsf(nr.y), fabsf(nr.z)};
+  int lanr, a1, a2;
+  if (anr[1] > anr[0]) { if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; } }
+  else { if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; } }
+  v3 center = comp(nr, lanr) < 0 ? (pb - pa) + col(Rb, lanr) * Sb[lanr] : (pb - pa) - col(Rb, lanr) * Sb[lanr];
+  int codeN = first ? code - 1 : code - 4, code1, code2;
+  if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
+  float quad[8], c1 = dot(center, col(Ra, code1)), c2 = dot(center, col(Ra, code2));
+  float m11 = dot(col(Ra, code1), col(Rb, a1)), m12 = dot(col(Ra, code1), col(Rb, a2));
+  float m21 = dot(col(Ra, code2), col(Rb, a1)), m22 = dot(col(Ra, code2), col(Rb, a2));
+  {
+    float k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
+    quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4; quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
+    quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4; quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
+  }
+  float rect[2] = {Sa[code1], Sa[code2]}, ret[16];
+  int n = clip_quad(rect, quad, ret);
+  if (n < 1) return 0;
+  float point[24], dep[8], det1 = 1.0f / (m11 * m22 - m12 * m21);
+  m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
+  int cnum = 0;
+  for (int j = 0; j < n; j++) {
+    float k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
+    float k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
+    v3 pt = center + col(Rb, a1) * k1 + col(Rb, a2) * k2;
+    float d = Sa[codeN] - dot(normal2, pt);
+    if (d >= 0) {
+      point[cnum * 3] = pt.x; point[cnum * 3 + 1] = pt.y; point[cnum * 3 + 2] = pt.z;
+      dep[cnum] = d; ret[cnum * 2] = ret[j * 2]; ret[cnum * 2 + 1] = ret[j * 2 + 1]; cnum++;
+    }
+  }
+  if (cnum < 1) return 0;
+  int idx[8], m = cnum;
+  if (cnum > 4) {
+    int i1 = 0; float maxd = dep[0];
+    for (int i = 1; i < cnum; i++) if (dep[i] > maxd) { maxd = dep[i]; i1 = i; }
+    cull_points(cnum, ret, 4, i1, idx); m = 4;
+  } else for (int i = 0; i < cnum; i++) idx[i] = i;
+  for (int j = 0; j < m; j++) {
+    int i = idx[j];
+    v3 pw = V3(point[i * 3], point[i * 3 + 1], point[i * 3 + 2]) + pa;
+    if (code >= 4) pw = pw - normal * dep[i];
+    out[j].pos = pw; out[j].n = normal * -1.0f; out[j].depth = dep[i];
+  }
+  return m;
+}
+
+// collider AABBs -> broad phase over the static pair list -> narrow phase (lane = pair) ->
+// contacts compacted in pair order (deterministic: the PGS sweep order depends on it)
+PRB_D void phase_collide(const DevModel& M, WarpMem& W, int lane) {
+  for (int c = lane; c < M.n_col; c += 32) {
+    m3 R; v3 p;
+    collider_frame(M, W, c, R, p);
+    v3 h = ld3(M.col_half[c]);
+    v3 e = V3(fabsf(R.m[0]) * h.x + fabsf(R.m[1]) * h.y + fabsf(R.m[2]) * h.z,
+              fabsf(R.m[3]) * h.x + fabsf(R.m[4]) * h.y + fabsf(R.m[5]) * h.z,
+              fabsf(R.m[6]) * h.x + fabsf(R.m[7]) * h.y + fabsf(R.m[8]) * h.z);
+    st3(&W.aabb[c][0], p - e); st3(&W.aabb[c][3], p + e);
+  }
+  __syncwarp();
+  int n_ovl = 0;
+  for (int base = 0; base < M.n_pair; base += 32) {
+    int k = base + lane;
+    bool hit = false;
+    if (k < M.n_pair) {
+      const float* A = W.aabb[M.pair_a[k]];
+      const float* B = W.aabb[M.pair_b[k]];
+      hit = !(A[0] > B[3] || A[3] < B[0] || A[1] > B[4] || A[4] < B[1] || A[2] > B[5] || A[5] < B[2]);
+    }
+    unsigned bal = __ballot_sync(FULL, hit);
+    if (hit) {
+      int slot = n_ovl + __popc(bal & ((1u << lane) - 1u));
+      if (slot < PRB_MAXOVL) W.ovl[slot] = (unsigned short)k; else W.overflow = 1;
+    }
+    n_ovl += __popc(bal);
+  }
+  if (n_ovl > PRB_MAXOVL) n_ovl = PRB_MAXOVL;
+  __syncwarp();
+  // narrow phase: one overlapping pair per lane
+  CPoint cp[4];
+  int n = 0, ca = 0, cb = 0;
+  if (lane < n_ovl) {
+    int k = W.ovl[lane];
+    ca = M.pair_a[k]; cb = M.pair_b[k];
+    m3 Ra, Rb; v3 pa, pb;
+    collider_frame(M, W, ca, Ra, pa);
+    collider_frame(M, W, cb, Rb, pb);
+    n = box_box(pa, Ra, ld3(M.col_half[ca]), pb, Rb, ld3(M.col_half[cb]), cp);
+  }
+  int total;
+  int off = warp_excl_scan(n, lane, &total);
+  for (int i = 0; i < n; i++) {
+    int s = off + i;
+    if (s < PRB_MAXCONTACT) {
+      Contact& c = W.ct[s];
+      c.pbx = cp[i].pos.x; c.pby = cp[i].pos.y; c.pbz = cp[i].pos.z;
+      c.nx = cp[i].n.x; c.ny = cp[i].n.y; c.nz = cp[i].n.z; c.dist = -cp[i].depth; c.cols = ca | (cb << 8);
+    }
+  }
+  if (lane == 0) {
+    W.n_contact = total < PRB_MAXCONTACT ? total : PRB_MAXCONTACT;
+    if (total > PRB_MAXCONTACT) W.overflow = 1;
+  }
+  __syncwarp();
+}
+
+// ============================================================================ constraint rows
+// Jacobian of a unit force `dir` at world point pt (or unit torque when angular) on the body of
+// collider `col`, written as (J, B = M^-1 J^T) segment; returns J.B and accumulates J.v*
+PRB_D float fill_segment(const DevModel& M, const WarpMem& W, int col, v3 pt, v3 dir, float sign, bool angular,
+                         float* seg, float* rel) {
+  const int body = M.col_body[col];
+  float d = 0.f;
+  if (body == 0) {
+    const int link = M.col_link[col], nd = M.nd;
+    float* J = seg; float* B = seg + nd;
+    unsigned anc = M.anc_mask[link];
+    for (int j = 0; j < nd; j++) {
+      float g = 0.f;
+      if ((anc >> j) & 1u) {
+        v3 aj = ld3(W.la[j]);
+        if (M.jtype[j] == 0) g = angular ? dot(aj, dir) : dot(aj, cross(pt - ld3(W.lp[j]), dir));
+        else g = angular ? 0.f : dot(aj, dir);
+      }
+      J[j] = sign * g;
+    }
+    for (int i = 0; i < nd; i++) {
+      float s = 0.f;
+      for (int j = 0; j < nd; j++) s += W.Minv[i][j] * J[j];
+      B[i] = s;
+    }
+    for (int j = 0; j < nd; j++) { d += J[j] * B[j]; *rel += J[j] * W.vs[j]; }
+  } else if (body <= M.n_free) {
+    const int b = body - 1, o = M.nd + 6 * b;
+    float* J = seg; float* B = seg + 6;
+    v3 t = angular ? dir : cross(pt - ld3(W.fpos[b]), dir);
+    v3 jl = angular ? V3(0, 0, 0) : dir * sign, ja = t * sign;
+    float im = 1.0f / M.free_mass[b];
+    v3 bl = jl * im, ba = symmul(W.fIinv[b], ja);
+    J[0] = jl.x; J[1] = jl.y; J[2] = jl.z; J[3] = ja.x; J[4] = ja.y; J[5] = ja.z;
+    B[0] = bl.x; B[1] = bl.y; B[2] = bl.z; B[3] = ba.x; B[4] = ba.y; B[5] = ba.z;
+    for (int k = 0; k < 6; k++) { d += J[k] * B[k]; *rel += J[k] * W.vs[o + k]; }
+  } else {
+    const int s = body - 1 - M.n_free, o = M.nd + 6 * M.n_free + s;
+    v3 a = ld3(M.slide_axis_w[s]);
+    float g;
+    if (M.slide_jtype[s] == 0) g = angular ? dot(a, dir) : dot(a, cross(pt - ld3(W.sp[s]), dir));
+    else g = angular ? 0.f : dot(a, dir);
+    seg[0] = sign * g; seg[1] = sign * g * M.slide_minv[s];
+    d = seg[0] * seg[1]; *rel += seg[0] * W.vs[o];
+  }
+  return d;
+}
+PRB_D int col_dyn_body(const DevModel& M, int col) {  // -1 when the collider cannot move
+  int b = M.col_body[col];
+  if (b < 0 || (b == 0 && M.col_link[col] < 0)) return -1;
+  return b;
+}
+PRB_D void plane_space(v3 n, v3& p, v3& q) {
+  if (fabsf(n.z) > 0.70710678f) {
+    float a = n.y * n.y + n.z * n.z, k = 1.0f / sqrtf(a);
+    p = V3(0, -n.z * k, n.y * k);
+    q = V3(a * k, -n.x * p.z, n.x * p.y);
+  } else {
+    float a = n.x * n.x + n.y * n.y, k = 1.0f / sqrtf(a);
+    p = V3(-n.y * k, n.x * k, 0);
+    q = V3(-n.z * p.y, n.z * p.x, a * k);
+  }
+}
+
+PRB_D void phase_rows(const DevModel& M, WarpMem& W, int lane) {
+  const float dt = M.params[P_DT], erp = M.params[P_ERP_JOINT], erp2 = M.params[P_ERP_CONTACT];
+  const int nd = M.nd;
+  // ---- joint rows, built serially by lane 0 (<= 40 rows of a few flops each): limits, motors, gear
+  if (lane == 0) {
+    int nr = 0;
+    for (int i = 0; i < nd; i++) {
+      if (M.lo[i] > M.hi[i]) continue;
+      for (int side = 0; side < 2; side++) {
+        float pen = side == 0 ? W.q[i] - M.lo[i] : M.hi[i] - W.q[i];
+        if (pen > 0.f) continue;
+        float sg = side == 0 ? 1.0f : -1.0f;
+        float invD = 1.0f / W.Minv[i][i];
+        float rel = sg * W.vs[i];
+        float e = pen > -0.04f ? erp : erp2;
+        W.jr_dof[nr] = (signed char)i; W.jr_dof2[nr] = -1; W.jr_sign[nr] = sg;
+        W.jr_rhs[nr] = (-pen * e / dt - rel) * invD; W.jr_invD[nr] = invD;
+        W.jr_lo[nr] = 0.f; W.jr_hi[nr] = M.params[P_LIMIT_MAX_IMPULSE]; W.jr_lam[nr] = 0.f;
+        nr++;
+      }
+    }
+    for (int i = 0; i < nd; i++) {
+      if (W.mmaximp[i] <= 0.f) continue;
+      float invD = 1.0f / W.Minv[i][i];
+      float v = W.vs[i];
+      float target_v = W.mkp[i] * (W.mtarget[i] - W.q[i]) / dt + v + M.params[P_MOTOR_KD] * (0.f - v);
+      W.jr_dof[nr] = (signed char)i; W.jr_dof2[nr] = -1; W.jr_sign[nr] = 1.0f;
+      W.jr_rhs[nr] = (target_v - v) * invD; W.jr_invD[nr] = invD;
+      W.jr_lo[nr] = -W.mmaximp[i]; W.jr_hi[nr] = W.mmaximp[i]; W.jr_lam[nr] = 0.f;
+      nr++;
+    }
+    for (int s = 0; s < M.n_slide; s++) {
+      int o = nd + 6 * M.n_free + s;
+      float maximp = M.slide_motor[s][3] < 0 ? M.params[P_DEFAULT_MOTOR_IMPULSE] : M.slide_motor[s][3];
+      if (maximp <= 0.f) continue;
+      float invD = 1.0f / M.slide_minv[s];
+      float v = W.vs[o];
+      float target_v = M.slide_motor[s][1] * (M.slide_motor[s][0] - W.sq[s]) / dt + v + M.slide_motor[s][2] * (0.f - v);
+      W.jr_dof[nr] = (signed char)o; W.jr_dof2[nr] = -1; W.jr_sign[nr] = 1.0f;
+      W.jr_rhs[nr] = (target_v - v) * invD; W.jr_invD[nr] = invD;
+      W.jr_lo[nr] = -maximp; W.jr_hi[nr] = maximp; W.jr_lam[nr] = 0.f;
+      nr++;
+    }
+    if (M.gear_a >= 0) {
+      int a = M.gear_a, b = M.gear_b;
+      float r = M.params[P_GEAR_RATIO];
+      float D = W.Minv[a][a] + 2.f * r * W.Minv[a][b] + r * r * W.Minv[b][b];
+      float invD = 1.0f / D;
+      float rel = W.vs[a] + r * W.vs[b];
+      W.jr_dof[nr] = (signed char)a; W.jr_dof2[nr] = (signed char)b; W.jr_sign[nr] = 1.0f;
+      W.jr_rhs[nr] = (-rel * M.params[P_GEAR_ERP]) * invD; W.jr_invD[nr] = invD;
+      W.jr_lo[nr] = -M.params[P_GEAR_MAX_IMPULSE]; W.jr_hi[nr] = M.params[P_GEAR_MAX_IMPULSE]; W.jr_lam[nr] = 0.f;
+      nr++;
+    }
+    W.n_jrow = nr;
+  }
+  // ---- contact rows: lane = contact.  Pool space by exclusive scan of the segment sizes.
+  int nc = W.n_contact;
+  int bodyA = -1, bodyB = -1, need = 0, ca = 0, cb = 0;
+  if (lane < nc) {
+    int cols = W.ct[lane].cols;
+    ca = cols & 0xff; cb = (cols >> 8) & 0xff;
+    bodyA = col_dyn_body(M, ca); bodyB = col_dyn_body(M, cb);
+    int nA = bodyA >= 0 ? body_size(M, bodyA) : 0, nB = bodyB >= 0 ? body_size(M, bodyB) : 0;
+    need = 4 * 2 * (nA + nB);
+  }
+  int total;
+  int off = warp_excl_scan(need, lane, &total);
+  // contacts that do not fit in the pool are dropped (deepest-first ordering is not attempted)
+  bool fits = (lane < nc) && (off + need <= PRB_POOL);
+  unsigned fitmask = __ballot_sync(FULL, fits);
+  int nfit = __popc(fitmask & ((nc >= 32) ? FULL : ((1u << nc) - 1u)));
+  // since sizes are scanned in order, the fitting contacts are a prefix
+  if (lane == 0) { if (nfit < nc) W.overflow = 1; W.n_contact = nfit; }
+  nc = nfit;
+  if (lane < nc) {
+    const Contact c = W.ct[lane];
+    v3 n = V3(c.nx, c.ny, c.nz), pb = V3(c.pbx, c.pby, c.pbz), pa = pb + n * c.dist;
+    int nA = bodyA >= 0 ? body_size(M, bodyA) : 0, nB = bodyB >= 0 ? body_size(M, bodyB) : 0;
+    int offA = off, offB = off + 8 * nA;
+    W.cr_bodyA[lane] = (signed char)bodyA; W.cr_bodyB[lane] = (signed char)bodyB;
+    W.cr_offA[lane] = (unsigned short)offA; W.cr_offB[lane] = (unsigned short)offB;
+    // contact softness (URDF <contact> stiffness/damping on the gripper links)
+    float cfm = 0.f, e = erp2;
+    float sa = M.col_stiff[ca], sb = M.col_stiff[cb];
+    if (sa >= 0.f || sb >= 0.f) {
+      float ka = sa >= 0.f ? sa : 1e18f, kb = sb >= 0.f ? sb : 1e18f;
+      float da = sa >= 0.f ? M.col_damp[ca] : 0.1f, db = sb >= 0.f ? M.col_damp[cb] : 0.1f;
+      float kk = 1.0f / (1.0f / ka + 1.0f / kb), dd = da + db;
+      float denom = fmaxf(dt * kk + dd, 1.1920929e-7f);
+      cfm = 1.0f / denom; e = dt * kk / denom;
+    }
+    cfm /= dt;
+    float spin = M.col_spin[ca] * M.col_fric[ca] + M.col_spin[cb] * M.col_fric[cb];
+    float mu = clampf(M.col_fric[ca] * M.col_fric[cb], -10.f, 10.f);
+    v3 t1, t2;
+    plane_space(n, t1, t2);
+    for (int k = 0; k < 4; k++) {
+      v3 dir = k == 0 ? n : (k == 1 ? n : (k == 2 ? t1 : t2));
+      bool ang = (k == 1);
+      if (k == 1 && !(spin > 0.f)) { W.cr_invD[lane][1] = 0.f; W.cr_rhs[lane][1] = 0.f; W.cr_lam[lane][1] = 0.f; continue; }
+      float rel = 0.f, D = 0.f;
+      if (bodyA >= 0) D += fill_segment(M, W, ca, pa, dir, 1.0f, ang, &W.pool[offA + k * 2 * nA], &rel);
+      if (bodyB >= 0) D += fill_segment(M, W, cb, pb, dir, -1.0f, ang, &W.pool[offB + k * 2 * nB], &rel);
+      if (k == 0) D += cfm;
+      float invD = D > 1.1920929e-7f ? 1.0f / D : 0.f;
+      float rhs;
+      if (k == 0) {
+        float pen = c.dist + M.params[P_LINEAR_SLOP];
+        float poserr = 0.f, velerr = -rel;
+        if (pen > 0.f) velerr -= pen / dt; else poserr = -pen * e / dt;
+        rhs = (poserr + velerr) * invD;
+        W.cr_cfm[lane] = cfm * invD;
+      } else rhs = -rel * invD;
+      W.cr_rhs[lane][k] = rhs; W.cr_invD[lane][k] = invD; W.cr_lam[lane][k] = 0.f;
+    }
+    W.cr_mu[lane] = mu; W.cr_spin[lane] = spin > 0.f ? spin : 0.f;
+  }
+  __syncwarp();
+}
+
+// ============================================================================ PGS (lane = velocity DoF)
+// per-lane view of a contact row: which segment (if any) holds this lane's DoF
+struct LaneMap { int body, li, n; float self_minv; };
+
+PRB_D void contact_jb(const WarpMem& W, const LaneMap& lm, int c, int k, float& j, float& b) {
+  j = 0.f; b = 0.f;
+  int base = -1;
+  if (lm.body == W.cr_bodyA[c]) base = W.cr_offA[c];
+  else if (lm.body == W.cr_bodyB[c]) base = W.cr_offB[c];
+  if (base >= 0 && lm.body >= 0) {
+    const float* seg = &W.pool[base + k * 2 * lm.n];
+    j = seg[lm.li]; b = seg[lm.n + lm.li];
+  }
+}
+
+PRB_D float phase_pgs(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm) {
+  float dv = 0.f;
+  const int njr = W.n_jrow, nc = W.n_contact, nd = M.nd;
+  for (int it = 0; it < M.solver_iters; it++) {
+    // (1) non-contact rows, direction alternates per iteration
+    for (int jj = 0; jj < njr; jj++) {
+      const int r = (it & 1) ? jj : njr - 1 - jj;
+      const int d = W.jr_dof[r], d2 = W.jr_dof2[r];
+      const float sg = W.jr_sign[r];
+      float jdv = sg * __shfl_sync(FULL, dv, d);
+      if (d2 >= 0) jdv += M.params[P_GEAR_RATIO] * __shfl_sync(FULL, dv, d2);
+      float lam = W.jr_lam[r];
+      float delta = W.jr_rhs[r] - jdv * W.jr_invD[r];
+      float nl = clampf(lam + delta, W.jr_lo[r], W.jr_hi[r]);
+      delta = nl - lam;
+      float b = 0.f;
+      if (d < nd) { if (lane < nd) b = W.Minv[lane][d]; }
+      else if (lane == d) b = lm.self_minv;
+      b *= sg;
+      if (d2 >= 0 && lane < nd) b += M.params[P_GEAR_RATIO] * W.Minv[lane][d2];
+      dv += b * delta;
+      __syncwarp();
+      if (lane == 0) W.jr_lam[r] = nl;
+    }
+    // (2) contact normals
+    for (int c = 0; c < nc; c++) {
+      float j, b;
+      contact_jb(W, lm, c, 0, j, b);
+      float jdv = warp_sum(j * dv);
+      float lam = W.cr_lam[c][0];
+      float delta = W.cr_rhs[c][0] - lam * W.cr_cfm[c] - jdv * W.cr_invD[c][0];
+      float nl = fmaxf(lam + delta, 0.f);
+      delta = nl - lam;
+      dv += b * delta;
+      __syncwarp();
+      if (lane == 0) W.cr_lam[c][0] = nl;
+    }
+    __syncwarp();
+    // (3) spinning (torsional) friction rows
+    for (int c = 0; c < nc; c++) {
+      float sp = W.cr_spin[c];
+      float tot = W.cr_lam[c][0];
+      if (!(sp > 0.f) || !(tot > 0.f)) continue;     // warp-uniform
+      float j, b;
+      contact_jb(W, lm, c, 1, j, b);
+      float jdv = warp_sum(j * dv);
+      float lam = W.cr_lam[c][1];
+      float delta = W.cr_rhs[c][1] - jdv * W.cr_invD[c][1];
+      float nl = clampf(lam + delta, -sp * tot, sp * tot);
+      delta = nl - lam;
+      dv += b * delta;
+      __syncwarp();
+      if (lane == 0) W.cr_lam[c][1] = nl;
+    }
+    // (4) lateral friction, implicit cone over the pair of rows
+    for (int c = 0; c < nc; c++) {
+      float ja, ba, jb, bb;
+      contact_jb(W, lm, c, 2, ja, ba);
+      contact_jb(W, lm, c, 3, jb, bb);
+      float sa_ = ja * dv, sb_ = jb * dv;
+      for (int o = 16; o > 0; o >>= 1) { sa_ += __shfl_xor_sync(FULL, sa_, o); sb_ += __shfl_xor_sync(FULL, sb_, o); }
+      float lim = W.cr_mu[c] * W.cr_lam[c][0];
+      float la = W.cr_lam[c][2], lb = W.cr_lam[c][3];
+      float dA = W.cr_rhs[c][2] - sa_ * W.cr_invD[c][2], dB = W.cr_rhs[c][3] - sb_ * W.cr_invD[c][3];
+      float sumA = la + dA, sumB = lb + dB, na, nb;
+      if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
+        float ang = atan2f(sumA, sumB);
+        float sn, cs;
+        sincosf(ang, &sn, &cs);
+        float ca_ = fabsf(lim * sn), cb_ = fabsf(lim * cs);
+        na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
+      } else { na = sumA; nb = sumB; }
+      dv += ba * (na - la) + bb * (nb - lb);
+      __syncwarp();
+      if (lane == 0) { W.cr_lam[c][2] = na; W.cr_lam[c][3] = nb; }
+    }
+    __syncwarp();
+  }
+  return dv;
+}
+
+// ============================================================================ integrate (lane = DoF)
+PRB_D void phase_integrate(const DevModel& M, WarpMem& W, int lane, float vstar, float dv) {
+  const float dt = M.params[P_DT], vmax = M.params[P_MAX_COORD_VEL];
+  const int nd = M.nd;
+  float v = clampf(vstar + dv, -vmax, vmax);
+  if (lane < M.nv) W.vs[lane] = v;
+  __syncwarp();
+  if (lane < nd) { W.qd[lane] = v; W.q[lane] += dt * v; }
+  int b = lane - nd;
+  if (b >= 0 && b < M.n_free) {
+    int o = nd + 6 * b;
+    v3 vl = ld3(&W.vs[o]), w = ld3(&W.vs[o + 3]);
+    st3(W.fvel[b], vl); st3(W.fang[b], w);
+    st3(W.fpos[b], ld3(W.fpos[b]) + vl * dt);
+    float ang = norm(w);
+    if (ang * dt > 0.78539816f) ang = 0.5f * 1.57079633f / dt;
+    v3 ax;
+    if (ang < 0.001f) ax = w * (0.5f * dt - dt * dt * dt * 0.020833333333f * ang * ang);
+    else ax = w * (sinf(0.5f * ang * dt) / ang);
+    float dq[4] = {ax.x, ax.y, ax.z, cosf(ang * dt * 0.5f)}, nq[4];
+    quat_mul(dq, W.fquat[b], nq);
+    float inv = 1.0f / sqrtf(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+    for (int k = 0; k < 4; k++) W.fquat[b][k] = nq[k] * inv;
+  }
+  int s = lane - nd - 6 * M.n_free;
+  if (s >= 0 && s < M.n_slide) { W.sqd[s] = v; W.sq[s] += dt * v; }
+  __syncwarp();
+}
+
+// one stepSimulation()
+template <int ND>
+PRB_D void substep(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm) {
+  phase_fk(M, W, lane, true);
+  phase_collide(M, W, lane);
+  phase_crba(M, W, lane);
+  phase_minv<ND>(W, lane);
+  float vstar = phase_vstar(M, W, lane);
+  phase_rows(M, W, lane);
+  float dv = phase_pgs(M, W, lane, lm);
+  phase_integrate(M, W, lane, vstar, dv);
+}
+
+PRB_D LaneMap make_lanemap(const DevModel& M, int lane) {
+  LaneMap lm;
+  lm.body = dof_body(M, lane, &lm.li, &lm.n);
+  lm.self_minv = 0.f;
+  int s = lane - M.nd - 6 * M.n_free;
+  if (s >= 0 && s < M.n_slide) lm.self_minv = M.slide_minv[s];
+  return lm;
+}
+
+// ============================================================================ observation / reward
+PRB_D float py_mod2(float a) { float r = fmodf(a, 2.0f); if (r != 0.f && r < 0.f) r += 2.0f; return r; }
+PRB_D float reward_of(const DevModel& M, const float* ag, const float* dg) {
+  if (M.play) {  // playRewardFunc.py:66-77
+    for (int k = 0; k < 3; k++) if (fabsf(dg[k] - ag[k]) > 0.05f) return -1.f;
+    float eg[3], ea[3];
+    euler_from_quat(dg + 3, eg); euler_from_quat(ag + 3, ea);
+    for (int k = 0; k < 3; k++) if (fabsf(eg[k] - ea[k]) > PRB_PI_F / 4) return -1.f;
+    if (fabsf(dg[7] - ag[7]) > 0.025f) return -1.f;
+    if (fabsf(dg[8] - ag[8]) > 0.04f) return -1.f;
+    if (fabsf(dg[9] - ag[9]) > 0.01f) return -1.f;
+    if (fabsf(dg[10] - ag[10]) > 0.3f) return -1.f;
+    return 0.f;
+  }
+  float dx = ag[0] - dg[0], dy = ag[1] - dg[1], dz = ag[2] - dg[2];
+  float d = sqrtf(dx * dx + dy * dy + dz * dz);
+  return d > M.params[P_SPARSE_THRESH] ? -1.0f : -d;
+}
+PRB_D void site_pose(const DevModel& M, const WarpMem& W, int site, v3& pos, m3& R) {
+  int l = M.site_link[site];
+  m3 lR = ldm(W.lR[l]);
+  pos = ld3(W.lp[l]) + mul(lR, ld3(M.site_pos[site]));
+  R = mul(lR, ldm(M.site_rot[site]));
+}
+
+// calc_state (environments.py:799-864) fused with compute_reward; every lane assembles the small
+// vectors redundantly (a few hundred flops), the ray test is spread over lanes; returns reward.
+PRB_D float phase_observe(const DevModel& M, WarpMem& W, int lane, const DevOut& O, size_t e, bool write) {
+  phase_fk(M, W, lane, false);
+  v3 ep; m3 eR;
+  site_pose(M, W, 0, ep, eR);
+  float eq[4];
+  mat_to_quat(eR, eq);
+  const int el = M.site_link[0];
+  v3 w = ld3(W.lw[el]), vl = ld3(W.lv[el]) + cross(w, ep - ld3(W.lp[el]));
+  float grip = M.arm_kind == 0 ? W.q[M.grip_obs_dof] * 23.0f : W.q[M.grip_obs_dof];
+  // gripper_proprioception: ray from above the palm to between the pads, nearest box hit
+  float prop = -1.f;
+  if (M.arm_kind == 0) {
+    v3 g1, g2, wr; m3 t;
+    site_pose(M, W, 2, g1, t); site_pose(M, W, 3, g2, t); site_pose(M, W, 1, wr, t);
+    v3 avg = (g1 + g2) * 0.5f, ew = ep - wr;
+    v3 from = ep - ew * 0.5f, to = avg + ew * 0.2f, d = to - from;
+    float best = 1.0f; int hit = -1;
+    for (int c = lane; c < M.n_col; c += 32) {
+      m3 R; v3 p;
+      collider_frame(M, W, c, R, p);
+      v3 o = tmul(R, from - p), dl = tmul(R, d), h = ld3(M.col_half[c]);
+      float t0 = 0.f, t1 = 1.f; bool ok = true;
+      for (int k = 0; k < 3; k++) {
+        float ok_ = comp(o, k), dk = comp(dl, k), hk = comp(h, k);
+        if (fabsf(dk) < 1e-12f) { if (ok_ < -hk || ok_ > hk) ok = false; }
+        else {
+          float ta = (-hk - ok_) / dk, tb = (hk - ok_) / dk;
+          if (ta > tb) { float tt = ta; ta = tb; tb = tt; }
+          t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
+          if (t0 > t1) ok = false;
+        }
+      }
+      if (ok && t0 < best) { best = t0; hit = c; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(FULL, best, o); int oh = __shfl_xor_sync(FULL, hit, o);
+      if (ob < best || (ob == best && oh >= 0 && (hit < 0 || oh < hit))) { best = ob; hit = oh; }
+    }
+    int li = hit >= 0 ? M.col_urdf[hit] : -1;
+    prop = (hit < 0 || best == 1.0f || li == 18 || li == 20) ? 0.f : 1.f;
+  }
+  float st[24], ag[12];
+  int n = 0, na = 0;
+  st[n++] = ep.x; st[n++] = ep.y; st[n++] = ep.z;
+  if (M.return_velocity) { st[n++] = vl.x; st[n++] = vl.y; st[n++] = vl.z; }
+  if (M.use_orientation) for (int k = 0; k < 4; k++) st[n++] = eq[k];
+  st[n++] = grip;
+  if (M.n_free > 0) {
+    for (int k = 0; k < 3; k++) st[n++] = W.fpos[0][k];
+    if (M.use_orientation) for (int k = 0; k < 4; k++) st[n++] = W.fquat[0][k];
+    if (M.return_velocity) for (int k = 0; k < 3; k++) st[n++] = W.fvel[0][k];
+    for (int k = 0; k < 3; k++) ag[na++] = W.fpos[0][k];
+    if (M.use_orientation) for (int k = 0; k < 4; k++) ag[na++] = W.fquat[0][k];
+    if (M.play) {
+      float ex[4] = {W.fpos[1][1], W.sq[0], W.sq[1], (py_mod2(W.sq[2]) * PRB_PI_F) / (2.2f * PRB_PI_F)};
+      for (int k = 0; k < 4; k++) { st[n++] = ex[k]; ag[na++] = ex[k]; }
+    }
+  } else { ag[0] = ep.x; ag[1] = ep.y; ag[2] = ep.z; na = 3; }
+  if (M.play) {  // quaternion_safe_the_obs
+    if (W.last_valid > 0.5f) {
+      bool fe = true, fo = true;
+      for (int k = 0; k < 4; k++) {
+        float a = st[3 + k], l = W.lastq[k];
+        int sa = (a > 0.f) - (a < 0.f), sl = (l > 0.f) - (l < 0.f);
+        if (sa != -sl) fe = false;
+        a = st[11 + k]; l = W.lastq[4 + k]; sa = (a > 0.f) - (a < 0.f); sl = (l > 0.f) - (l < 0.f);
+        if (sa != -sl) fo = false;
+      }
+      if (fe) for (int k = 0; k < 4; k++) st[3 + k] = -st[3 + k];
+      if (fo) for (int k = 0; k < 4; k++) { st[11 + k] = -st[11 + k]; ag[3 + k] = -ag[3 + k]; }
+    }
+    __syncwarp();
+    if (lane < 4) W.lastq[lane] = st[3 + lane];
+    else if (lane < 8) W.lastq[lane] = st[11 + lane - 4];
+    if (lane == 8) W.last_valid = 1.0f;
+    __syncwarp();
+  }
+  float dg[12];
+  for (int k = 0; k < M.goal_dim; k++) dg[k] = W.goal[k];
+  float r = reward_of(M, ag, dg);
+  if (write) {
+    for (int k = lane; k < M.obs_dim; k += 32) O.obs_quat[e * M.obs_dim + k] = st[k];
+    if (lane < M.goal_dim) { O.achieved_goal[e * M.goal_dim + lane] = ag[lane]; O.desired_goal[e * M.goal_dim + lane] = dg[lane]; }
+    if (lane < 4) O.cag[e * 4 + lane] = lane < 3 ? comp(ep, lane) : grip;
+    {  // full_positional_state
+      float f[24]; int k = 0;
+      f[k++] = ep.x; f[k++] = ep.y; f[k++] = ep.z;
+      if (M.use_orientation) for (int j = 0; j < 4; j++) f[k++] = st[3 + j];
+      f[k++] = grip;
+      if (M.n_free > 0) for (int j = 0; j < na; j++) f[k++] = ag[j];
+      if (lane < M.fps_dim) O.fps[e * M.fps_dim + lane] = f[lane];
+    }
+    if (lane < 8) O.joints[e * 8 + lane] = M.joints_obs_dof[lane] >= 0 ? W.q[M.joints_obs_dof[lane]] : 0.f;
+    if (lane < 6) O.velocity[e * 6 + lane] = lane < 3 ? comp(vl, lane) : comp(w, lane - 3);
+    {  // 'observation' = state[0:3] + euler(state[3:7]) + state[7:]  (environments.py:859)
+      float eu[3], o[24]; int k = 0;
+      euler_from_quat(st + 3, eu);
+      o[k++] = st[0]; o[k++] = st[1]; o[k++] = st[2]; o[k++] = eu[0]; o[k++] = eu[1]; o[k++] = eu[2];
+      for (int j = 7; j < n; j++) o[k++] = st[j];
+      if (lane < M.observation_dim) O.observation[e * M.observation_dim + lane] = o[lane];
+    }
+    if (lane == 0) { O.proprio[e] = prop; O.reward[e] = r; O.success[e] = r < 0.f ? 0.f : 1.f; }
+  }
+  return r;
+}
+
+#ifdef PRB_EMU
+static char g_emu_smem[PRB_WPB * sizeof(WarpMem) + 256];
+#define PRB_SMEM_DECL WarpMem* wm = (WarpMem*)g_emu_smem
+#else
+#define PRB_SMEM_DECL extern __shared__ __align__(16) unsigned char prb_dyn_smem[]; WarpMem* wm = (WarpMem*)prb_dyn_smem
+#endif
+
+// ============================================================================ step kernel (warp per env)
+template <int ND>
+__global__ void __launch_bounds__(32 * PRB_WPB) prb_step_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
+                                                                 DevOut O, int N, int n_substeps, int observe) {
+  PRB_SMEM_DECL;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * PRB_WPB + wib;
+  if (e >= N) return;   // whole warp exits together
+  const DevModel& M = *Mp;
+  WarpMem& W = wm[wib];
+  float* st = state + (size_t)e * M.state_stride;
+  load_state(M, W, st, lane);
+  if (lane == 0) W.overflow = 0;
+  const LaneMap lm = make_lanemap(M, lane);
+  for (int s = 0; s < n_substeps; s++) substep<ND>(M, W, lane, lm);
+  if (observe) phase_observe(M, W, lane, O, (size_t)e, true);
+  store_state(M, W, st, lane);
+}
+
+// ============================================================================ reset kernel (warp per env, masked)
+template <int ND>
+__global__ void __launch_bounds__(32 * PRB_WPB) prb_reset_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
+                                                                  DevOut O, const unsigned char* __restrict__ mask, int N,
+                                                                  unsigned long long seed, unsigned env_offset) {
+  PRB_SMEM_DECL;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * PRB_WPB + wib;
+  if (e >= N) return;
+  if (mask != nullptr && mask[e] == 0) return;
+  const DevModel& M = *Mp;
+  WarpMem& W = wm[wib];
+  float* st = state + (size_t)e * M.state_stride;
+  load_state(M, W, st, lane);
+  if (lane == 0) W.overflow = 0;
+  const LaneMap lm = make_lanemap(M, lane);
+  const int nobj = M.n_free > 0 ? 1 : 0;
+  float r = 0.f;
+  for (int guard = 0; guard < 16 && r > -1.f; guard++) {
+    const uint32_t attempt = (uint32_t)W.reset_count;
+    __syncwarp();
+    if (lane == 0) W.reset_count += 1.0f;
+    float u[4];
+    // reset_object_pos (environments.py:519-556)
+    for (int t = 0; t < 4; t++) {
+      __syncwarp();
+      if (lane == 0) {
+        if (M.play) {
+          for (int k = 0; k < 3; k++) { W.fpos[1][k] = M.free_pos0[1][k]; W.fvel[1][k] = 0.f; W.fang[1][k] = 0.f; }
+          for (int k = 0; k < 4; k++) W.fquat[1][k] = M.free_quat0[1][k];
+          for (int s = 0; s < M.n_slide; s++) { W.sq[s] = 0.f; W.sqd[s] = 0.f; }
+        }
+        if (nobj) {
+          rng4(seed, env_offset + (uint32_t)e, attempt, (uint32_t)t, u);
+          for (int k = 0; k < 3; k++) { W.fpos[0][k] = M.obj_lo[k] + (M.obj_hi[k] - M.obj_lo[k]) * u[k]; W.fvel[0][k] = 0.f; W.fang[0][k] = 0.f; }
+          W.fpos[0][2] += M.params[P_OBJ_RESET_DZ];
+          W.fquat[0][0] = 0.f; W.fquat[0][1] = 0.f; W.fquat[0][2] = 0.7071f; W.fquat[0][3] = 0.7071f;
+        }
+      }
+      __syncwarp();
+      for (int i = 0; i < M.settle_steps; i++) substep<ND>(M, W, lane, lm);
+      bool oob = false;
+      if (nobj) for (int k = 0; k < 3; k++) if (W.fpos[0][k] > M.env_hi[k]) oob = true;
+      if (!oob) break;   // uniform: every lane reads the same shared values
+    }
+    // reset_arm (environments.py:575-596): rest pose -> one IK call on the live arm -> hard reset of joints [0:6]
+    __syncwarp();
+    if (lane == 0) {
+      rng4(seed, env_offset + (uint32_t)e, attempt, 4u, u);
+      float np_[3];
+      for (int k = 0; k < 3; k++) np_[k] = M.goal_lo[k] + (M.goal_hi[k] - M.goal_lo[k]) * u[k];
+      np_[2] += M.params[P_RESET_Z_OFFSET];
+      float qq[7];
+      for (int i = 0; i < M.n_ik; i++) { qq[i] = M.rest[i]; W.q[i] = M.rest[i]; W.qd[i] = 0.f; }
+      if (M.arm_kind == 1) { W.q[M.n_ik] = 0.f; W.qd[M.n_ik] = 0.f; }
+      if (M.n_ik == 6) ik_world<6>(M, qq, np_, M.default_orn, 1, M.ik_reset_iters);
+      else ik_world<7>(M, qq, np_, M.default_orn, 1, M.ik_reset_iters);
+      for (int i = 0; i < 6; i++) { W.q[i] = qq[i]; W.qd[i] = 0.f; }
+    }
+    __syncwarp();
+    // reset_goal_pos (environments.py:492-516)
+    rng4(seed, env_offset + (uint32_t)e, attempt, 5u, u);
+    if (!M.play) {
+      if (lane < 3) W.goal[lane] = M.goal_lo[lane] + (M.goal_hi[lane] - M.goal_lo[lane]) * u[lane];
+      __syncwarp();
+    } else {
+      phase_observe(M, W, lane, O, (size_t)e, true);   // writes achieved_goal for this env
+      __syncwarp();
+      int idx = (int)(u[0] * M.goal_dim);
+      if (idx >= M.goal_dim) idx = M.goal_dim - 1;
+      if (lane < M.goal_dim) {
+        float g = O.achieved_goal[(size_t)e * M.goal_dim + lane];
+        if (lane == idx) g = g + u[1];
+        W.goal[lane] = g;
+      }
+      __syncwarp();
+    }
+    r = phase_observe(M, W, lane, O, (size_t)e, true);
+  }
+  store_state(M, W, st, lane);
+}
+
+// ============================================================================ stateless reward (relabelling)
+__global__ void prb_reward_kernel(const DevModel* __restrict__ Mp, const float* __restrict__ ag, const float* __restrict__ dg,
+                                  long long B, float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const DevModel& M = *Mp;
+  float a[12], d[12];
+  for (int k = 0; k < M.goal_dim; k++) { a[k] = ag[i * M.goal_dim + k]; d[k] = dg[i * M.goal_dim + k]; }
+  out[i] = reward_of(M, a, d);
+}
+
+// initial state: arm at q = 0 with the default velocity motors, bodies at their load poses
+__global__ void prb_init_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state, int N) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  const DevModel& M = *Mp;
+  float* st = state + (size_t)e * M.state_stride;
+  const int nd = M.nd;
+  for (int i = 0; i < M.state_stride; i++) st[i] = 0.f;
+  for (int i = 0; i < nd; i++) st[4 * nd + i] = M.params[P_DEFAULT_MOTOR_IMPULSE];
+  for (int b = 0; b < M.n_free; b++) {
+    for (int k = 0; k < 3; k++) st[5 * nd + 13 * b + k] = M.free_pos0[b][k];
+    for (int k = 0; k < 4; k++) st[5 * nd + 13 * b + 3 + k] = M.free_quat0[b][k];
+  }
+}

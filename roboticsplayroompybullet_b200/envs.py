@@ -1,0 +1,260 @@
+"""Vectorised mirror of the reference's gym surface (roboticsPlayroomPybullet/envs/
+environments.py:58-314 `playEnv`, envList.py:18-22, 89-99) on top of the C-ABI.
+
+`VecPlayEnv` keeps the reference's method names, argument meaning, dict keys and per-key
+layouts, with a leading [num_envs] dimension:
+
+    reset(mask=None) -> obs dict          (playEnv.reset, :173-187)
+    step(action[N,7]) -> (obs, r[N], done[N], info)   (playEnv.step, :206-214)
+    reset_goal_pos(goal[N,G])             (:190-191)
+    compute_reward(ag, dg[, info])        (:274-304; sparse variant bound when sparse=True, :169-170)
+    _max_episode_steps, action_space / observation_space bounds as arrays
+
+Two calling styles: numpy in / numpy out (`step`), which goes through host buffers exactly like a
+reference user would (H2D of actions, D2H of the whole observation block every step), and
+`step_device` for learners that keep everything on the GPU (torch tensors, zero-copy views of the
+library's buffers).
+"""
+import ctypes
+
+import numpy as np
+
+from . import lib as _lib
+from .model import ENV_KINDS, load_model
+
+OUT_KEYS = ['obs_quat', 'achieved_goal', 'desired_goal', 'controllable_achieved_goal', 'full_positional_state',
+            'joints', 'velocity', 'observation', 'gripper_proprioception', 'reward', 'is_success', 'target_poses']
+OBS_KEYS = OUT_KEYS[:9]
+
+
+class _DevArray:
+    """Exposes a library-owned device buffer through __cuda_array_interface__ (zero-copy)."""
+
+    def __init__(self, ptr, shape, owner):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': '<f4', 'data': (int(ptr), False),
+                                         'version': 2, 'strides': None}
+        self._owner = owner
+
+
+class VecPlayEnv:
+    env_id = None
+
+    def __init__(self, env_id=None, num_envs=1, device=0, seed=1234, env_offset=0, sparse=True, model=None):
+        import torch  # device memory / streams only
+        self.torch = torch
+        env_id = env_id or self.env_id
+        if env_id not in ENV_KINDS:
+            raise NotImplementedError(env_id)           # environments.py:376,416,933
+        self.env_id = env_id
+        self.model = model if model is not None else load_model(env_id)
+        m = self.model
+        self.num_envs = int(num_envs)
+        self.device = torch.device('cuda', device)
+        self.L = _lib.load()
+        self._ms = m.as_struct()
+        cfg = _lib.PrbConfig(self.num_envs, int(env_offset), int(device), 0, int(seed))
+        self._h = ctypes.c_void_p()
+        rc = self.L.prb_create(ctypes.byref(self._ms), ctypes.byref(cfg), ctypes.byref(self._h))
+        if rc != 0:
+            raise _lib.PrbError('prb_create failed (%d): %s' % (rc, self.L.prb_last_error(self._h).decode()))
+        b = _lib.PrbBuffers()
+        _lib.check(self.L, self._h, self.L.prb_get_buffers(self._h, ctypes.byref(b)))
+        self.buffers = b
+        N = self.num_envs
+        self.dims = {'obs_quat': b.obs_dim, 'achieved_goal': b.goal_dim, 'desired_goal': b.goal_dim,
+                     'controllable_achieved_goal': 4, 'full_positional_state': b.fps_dim, 'joints': 8,
+                     'velocity': 6, 'observation': b.observation_dim, 'gripper_proprioception': 1, 'reward': 1,
+                     'is_success': 1, 'target_poses': b.n_ik}
+        self.out_floats = int(b.out_floats)
+        with torch.cuda.device(self.device):
+            self.dev = {k: torch.as_tensor(_DevArray(getattr(b, k), (N, self.dims[k]), self), device=self.device)
+                        for k in OUT_KEYS}
+            self.state_dev = torch.as_tensor(_DevArray(b.state, (N, b.state_stride), self), device=self.device)
+        # pinned host staging for the numpy path
+        self._h_action = torch.empty((N, 7), dtype=torch.float32).pin_memory()
+        self._h_out = torch.empty((self.out_floats,), dtype=torch.float32).pin_memory()
+        self._h_views = {}
+        off = 0
+        for k in OUT_KEYS:
+            n = N * self.dims[k]
+            self._h_views[k] = self._h_out[off:off + n].view(N, self.dims[k]).numpy()
+            off += n
+        # gym-like metadata (environments.py:84,108-117)
+        self._max_episode_steps = None if m['play'] else 250
+        high = np.array([6, 6, 6, 6, 6, 6, 1], np.float32)
+        self.action_low, self.action_high = -high, high
+        self.play = bool(m['play'])
+        self.sparse = sparse
+        self.h2d_bytes_per_step = N * 7 * 4
+        self.d2h_bytes_per_step = self.out_floats * 4
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _obs_dev(self):
+        return {k: self.dev[k] for k in OBS_KEYS}
+
+    def _obs_host(self):
+        d = {k: self._h_views[k].copy() for k in OBS_KEYS}
+        d['gripper_proprioception'] = d['gripper_proprioception'][:, 0].astype(np.int64)
+        d['img'] = None                                  # environments.py:844-845
+        return d
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            self.L.prb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ device-resident API
+    def reset_device(self, mask=None):
+        mp = None
+        if mask is not None:
+            self._mask = mask.to(self.device, self.torch.uint8).contiguous()
+            mp = ctypes.c_void_p(self._mask.data_ptr())
+        _lib.check(self.L, self._h, self.L.prb_reset(self._h, mp, self._stream()))
+        return self._obs_dev()
+
+    def step_device(self, action):
+        """action: float32 CUDA tensor [N,7].  Returns views of the library's output buffers."""
+        a = action.to(self.device, self.torch.float32).contiguous()
+        assert a.shape == (self.num_envs, 7), 'action must be [num_envs, 7]'   # environments.py:956
+        self._a_keep = a
+        _lib.check(self.L, self._h, self.L.prb_step(self._h, ctypes.c_void_p(a.data_ptr()), self._stream()))
+        info = {'is_success': self.dev['is_success'][:, 0], 'target_poses': self.dev['target_poses']}
+        return self._obs_dev(), self.dev['reward'][:, 0], None, info
+
+    def observe_device(self):
+        _lib.check(self.L, self._h, self.L.prb_observe(self._h, self._stream()))
+        return self._obs_dev()
+
+    # ------------------------------------------------------------------ reference-style (numpy) API
+    def reset(self, mask=None):
+        mt = None
+        if mask is not None:
+            mt = self.torch.as_tensor(np.asarray(mask, np.uint8))
+        self.reset_device(mt)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        self._pull()
+        return self._obs_host()
+
+    def _pull(self):
+        t = self.torch
+        with t.cuda.device(self.device):
+            src = t.as_tensor(_DevArray(self.buffers.out_base, (self.out_floats,), self), device=self.device)
+            self._h_out.copy_(src, non_blocking=True)
+            t.cuda.current_stream(self.device).synchronize()
+
+    def step(self, action):
+        a = np.asarray(action, np.float32)
+        assert a.shape == (self.num_envs, 7), 'action must be [num_envs, 7]'
+        self._h_action.numpy()[...] = a
+        _lib.check(self.L, self._h, self.L.prb_step_host(self._h, ctypes.c_void_p(self._h_action.data_ptr()),
+                                                        ctypes.c_void_p(self._h_out.data_ptr()), self._stream()))
+        r = self._h_views['reward'][:, 0].copy()
+        info = {'is_success': self._h_views['is_success'][:, 0].astype(np.int64),
+                'target_poses': self._h_views['target_poses'].copy()}
+        done = np.zeros(self.num_envs, dtype=bool)       # environments.py:212: always False
+        return self._obs_host(), r, done, info
+
+    def reset_goal_pos(self, goal):
+        t = self.torch
+        g = t.as_tensor(np.asarray(goal, np.float32)).reshape(self.num_envs, -1).to(self.device).contiguous()
+        self._g_keep = g
+        _lib.check(self.L, self._h, self.L.prb_set_goal(self._h, ctypes.c_void_p(g.data_ptr()), None, self._stream()))
+
+    def compute_reward(self, achieved_goal, desired_goal, info=None):
+        """Batched compute_reward_sparse (sparse=True) or dense -||ag-dg|| (environments.py:274-304)."""
+        t = self.torch
+        ag = np.asarray(achieved_goal, np.float32)
+        dg = np.asarray(desired_goal, np.float32)
+        single = ag.ndim == 1
+        G = self.dims['achieved_goal']
+        if not self.sparse:
+            d = -np.linalg.norm(ag.reshape(-1, G) - dg.reshape(-1, G), axis=1)
+            return d[0] if single else d
+        agd = t.as_tensor(ag.reshape(-1, G)).to(self.device).contiguous()
+        dgd = t.as_tensor(dg.reshape(-1, G)).to(self.device).contiguous()
+        out = t.empty(agd.shape[0], dtype=t.float32, device=self.device)
+        _lib.check(self.L, self._h, self.L.prb_compute_reward(self._h, ctypes.c_void_p(agd.data_ptr()),
+                                                             ctypes.c_void_p(dgd.data_ptr()), agd.shape[0],
+                                                             ctypes.c_void_p(out.data_ptr()), self._stream()))
+        r = out.cpu().numpy()
+        return r[0] if single else r
+
+    compute_reward_sparse = compute_reward
+
+    def compute_reward_device(self, ag, dg):
+        t = self.torch
+        G = self.dims['achieved_goal']
+        agd = ag.reshape(-1, G).to(self.device, t.float32).contiguous()
+        dgd = dg.reshape(-1, G).to(self.device, t.float32).contiguous()
+        out = t.empty(agd.shape[0], dtype=t.float32, device=self.device)
+        _lib.check(self.L, self._h, self.L.prb_compute_reward(self._h, ctypes.c_void_p(agd.data_ptr()),
+                                                             ctypes.c_void_p(dgd.data_ptr()), agd.shape[0],
+                                                             ctypes.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ raw state (tests, checkpoints)
+    def get_state(self):
+        out = np.zeros((self.num_envs, self.buffers.state_dim), np.float32)
+        _lib.check(self.L, self._h, self.L.prb_get_state(self._h, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def set_state(self, state):
+        s = np.ascontiguousarray(state, np.float32)
+        assert s.shape == (self.num_envs, self.buffers.state_dim)
+        _lib.check(self.L, self._h, self.L.prb_set_state(self._h, s.ctypes.data_as(ctypes.c_void_p)))
+
+    def substeps(self, n):
+        _lib.check(self.L, self._h, self.L.prb_substeps(self._h, int(n), self._stream()))
+
+    def observe(self):
+        self.observe_device()
+        self._pull()
+        return self._obs_host()
+
+    def enable_kernel_timing(self, on=True):
+        _lib.check(self.L, self._h, self.L.prb_enable_kernel_timing(self._h, 1 if on else 0))
+
+    def last_kernel_ms(self):
+        a, b = ctypes.c_float(), ctypes.c_float()
+        _lib.check(self.L, self._h, self.L.prb_last_kernel_ms(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def launch_count(self):
+        return int(self.L.prb_launch_count(self._h))
+
+    def kernel_info(self):
+        a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self.L.prb_kernel_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return {'smem_bytes_per_block': a.value, 'envs_per_block': b.value, 'regs_per_thread': c.value}
+
+
+# the three registered ids in scope (roboticsPlayroomPybullet/__init__.py:23-26,65-68,91-94)
+class UR5Reach(VecPlayEnv):
+    env_id = 'UR5Reach-v0'
+
+
+class pandaPick(VecPlayEnv):
+    env_id = 'pandaPick-v0'
+
+
+class UR5PlayAbsRPY1Obj(VecPlayEnv):
+    env_id = 'UR5PlayAbsRPY1Obj-v0'
+
+
+_REGISTRY = {c.env_id: c for c in (UR5Reach, pandaPick, UR5PlayAbsRPY1Obj)}
+
+
+def make(env_id, num_envs=1, **kw):
+    """gym.make analogue for the registered ids."""
+    if env_id not in _REGISTRY:
+        raise NotImplementedError('unknown env id %r (in scope: %s)' % (env_id, sorted(_REGISTRY)))
+    return _REGISTRY[env_id](num_envs=num_envs, **kw)

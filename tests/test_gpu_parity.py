@@ -1,0 +1,180 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the fp64 CPU oracle on the
+same seeded inputs, started from identical states."""
+import numpy as np
+import pytest
+
+from helpers import compare_step, random_actions, oracle_step_from, POS_TOL
+
+pytestmark = pytest.mark.gpu
+
+ENVS = ['UR5Reach-v0', 'UR5PlayAbsRPY1Obj-v0', 'pandaPick-v0']
+
+
+def _mk(env_id, n, seed=5):
+    from roboticsplayroompybullet_b200.envs import make
+    return make(env_id, num_envs=n, seed=seed)
+
+
+@pytest.mark.parametrize('env_id', ENVS)
+def test_layouts(env_id):
+    env = _mk(env_id, 4)
+    obs = env.reset()
+    dims = {'UR5Reach-v0': (7, 3, 4, 6), 'pandaPick-v0': (13, 3, 7, 12), 'UR5PlayAbsRPY1Obj-v0': (19, 11, 19, 18)}[env_id]
+    assert obs['obs_quat'].shape == (4, dims[0])
+    assert obs['achieved_goal'].shape == (4, dims[1]) and obs['desired_goal'].shape == (4, dims[1])
+    assert obs['full_positional_state'].shape == (4, dims[2])
+    assert obs['observation'].shape == (4, dims[3])
+    assert obs['controllable_achieved_goal'].shape == (4, 4)
+    assert obs['joints'].shape == (4, 8) and obs['velocity'].shape == (4, 6)
+    assert obs['img'] is None
+    o2, r, done, info = env.step(np.zeros((4, 7), np.float32))
+    assert r.shape == (4,) and not done.any()
+    assert set(info) == {'is_success', 'target_poses'}
+    assert np.isfinite(o2['obs_quat']).all()
+    env.close()
+
+
+@pytest.mark.parametrize('env_id', ENVS)
+def test_reset_matches_oracle(env_id):
+    """Same counter-based RNG stream => same sampled block / arm / goal; settle dynamics agree to
+    the pose tolerance."""
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle
+    n = 8
+    env = _mk(env_id, n, seed=21)
+    obs = env.reset()
+    m = load_model(env_id)
+    worst = 0.0
+    for i in range(n):
+        o = Oracle(m, seed=21, env_id=i)
+        d = o.reset()
+        for k in ['achieved_goal', 'desired_goal']:
+            worst = max(worst, float(np.abs(obs[k][i] - d[k]).max()))
+        worst = max(worst, float(np.abs(obs['obs_quat'][i][:3] - d['obs_quat'][:3]).max()))
+    assert worst < 2e-3, worst
+    env.close()
+
+
+@pytest.mark.parametrize('env_id', ENVS)
+def test_step_parity_identical_states(env_id):
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle
+    n = 48
+    env = _mk(env_id, n, seed=7)
+    env.reset()
+    m = load_model(env_id)
+    rng = np.random.default_rng(3)
+    total_bad, worst_all = 0, 0.0
+    for step in range(4):
+        st = env.get_state()
+        a = random_actions(rng, n, env_id)
+        obs, r, done, info = env.step(a)
+        outs = [oracle_step_from(m, st[i], a[i], Oracle)[0] for i in range(n)]
+        bad, worst = compare_step(obs, r, info, outs)
+        total_bad += bad
+        worst_all = max(worst_all, worst)
+        tp = np.array([o['target_poses'] for o in outs])
+        assert np.abs(info['target_poses'] - tp).max() < 2e-5      # IK + clipping (fp32 vs fp64)
+        rr = np.array([o['reward'][0] for o in outs])
+        agree = (r == rr) | (np.abs(r - rr) < 1e-4)
+        assert agree.mean() > 0.97
+    # contact onset can flip by one substep between fp32 and fp64: allow a few outlier envs
+    assert total_bad <= max(2, int(0.04 * 4 * n)), (total_bad, worst_all)
+    env.close()
+
+
+def test_ik_targets_parity():
+    """target_poses = clip(clip(IK(q, action)), q +- inc) against the oracle's calc_angles."""
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle, quat_from_euler, euler_from_quat
+    m = load_model('UR5Reach-v0')
+    n = 256
+    env = _mk('UR5Reach-v0', n)
+    rng = np.random.default_rng(11)
+    o = Oracle(m)
+    st = env.get_state()
+    q0 = (m['arm_rest'][:6] + rng.uniform(-0.3, 0.3, (n, 6))).astype(np.float32)
+    st[:, :6] = q0
+    env.set_state(st)
+    a = np.zeros((n, 7), np.float32)
+    for i in range(n):
+        q = np.zeros(12)
+        q[:6] = q0[i] + rng.uniform(-0.04, 0.04, 6)
+        s = o.fk_sites(q)[0]
+        a[i, :3] = s[:3]
+        a[i, 3:6] = euler_from_quat(s[3:7])
+    _, _, _, info = env.step(a)
+    ref = np.zeros((n, 6))
+    for i in range(n):
+        q = np.zeros(12)
+        q[:6] = q0[i]
+        r = o.calc_angles(q, a[i, :3], quat_from_euler(a[i, 3:6]))[:6]
+        r = np.clip(r, m['ctrl_ll'], m['ctrl_ul'])
+        ref[i] = np.clip(r, q[:6] - m['ctrl_inc'], q[:6] + m['ctrl_inc'])
+    err = np.abs(info['target_poses'] - ref)
+    assert err.max() < 1e-5 * max(1.0, np.abs(ref).max()), err.max()
+    env.close()
+
+
+def test_reward_batched_identical():
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle
+    for env_id in ['UR5Reach-v0', 'UR5PlayAbsRPY1Obj-v0']:
+        env = _mk(env_id, 2)
+        m = load_model(env_id)
+        G = m['goal_dim']
+        rng = np.random.default_rng(0)
+        B = 4096
+        ag = rng.normal(0, 0.1, (B, G)).astype(np.float32)
+        dg = (ag + rng.normal(0, 0.03, (B, G))).astype(np.float32)
+        if G == 11:
+            for x in (ag, dg):
+                x[:, 3:7] = rng.normal(0, 1, (B, 4))
+                x[:, 3:7] /= np.linalg.norm(x[:, 3:7], axis=1, keepdims=True)
+            dg[:, 3:7] = ag[:, 3:7] + rng.normal(0, 0.05, (B, 4)).astype(np.float32)
+        r = env.compute_reward(ag, dg)
+        ref = Oracle(m).compute_reward(ag, dg)
+        if G == 11:
+            assert (r == ref).mean() > 0.995       # identical away from thresholds
+        else:
+            assert np.abs(r - ref).max() < 1e-6
+        assert env.compute_reward(ag[0], dg[0]) == r[0]
+        env.close()
+
+
+def test_sharding_bit_identical():
+    """Env-index sharding: one handle with N envs == two handles with N/2 envs and env_offset."""
+    from roboticsplayroompybullet_b200.envs import make
+    n = 16
+    full = make('UR5PlayAbsRPY1Obj-v0', num_envs=n, seed=9)
+    a = make('UR5PlayAbsRPY1Obj-v0', num_envs=n // 2, seed=9, env_offset=0)
+    b = make('UR5PlayAbsRPY1Obj-v0', num_envs=n // 2, seed=9, env_offset=n // 2)
+    of = full.reset(); oa = a.reset(); ob = b.reset()
+    assert np.array_equal(of['obs_quat'], np.concatenate([oa['obs_quat'], ob['obs_quat']]))
+    act = random_actions(np.random.default_rng(1), n, 'UR5PlayAbsRPY1Obj-v0')
+    of, rf, _, _ = full.step(act)
+    oa, ra, _, _ = a.step(act[:n // 2]); ob, rb, _, _ = b.step(act[n // 2:])
+    assert np.array_equal(of['obs_quat'], np.concatenate([oa['obs_quat'], ob['obs_quat']]))
+    for e in (full, a, b):
+        e.close()
+
+
+def test_grasp_and_lift_statistics():
+    """Scripted pick: the block must end up lifted in most envs (contact + friction sanity at scale)."""
+    from roboticsplayroompybullet_b200.envs import make
+    n = 64
+    env = make('UR5PlayAbsRPY1Obj-v0', num_envs=n, seed=3)
+    obs = env.reset()
+    blk = obs['achieved_goal'][:, :3].copy()
+
+    def act(z, g):
+        a = np.zeros((n, 7), np.float32)
+        a[:, 0] = blk[:, 0]; a[:, 1] = blk[:, 1]; a[:, 2] = z; a[:, 6] = g
+        return a
+    for k in range(10): env.step(act(0.15, -1))
+    for k in range(15): env.step(act(-0.01, -1))
+    for k in range(12): env.step(act(-0.01, 1))
+    for k in range(15): obs, r, _, _ = env.step(act(0.2, 1))
+    lifted = obs['achieved_goal'][:, 2] > 0.1
+    assert lifted.mean() > 0.7, lifted.mean()
+    env.close()
