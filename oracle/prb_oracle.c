@@ -587,18 +587,54 @@ static void compute_poses(const prb_model* M, const State* S, Poses* P) {
 /* ---------------------------------------------------------------- contacts */
 typedef struct { int ca, cb; v3 pa, pb, n; real dist; } Contact;
 
+/* Persistent-manifold capacity: Bullet keeps at most 4 points per pair of collision objects
+ * (btPersistentManifold, MANIFOLD_CACHE_SIZE 4) and, when a 5th arrives, keeps the deepest and the
+ * three that span the largest area (sortCachedPoints).  Restated here as a batch reduction over
+ * the candidates of one object pair: deepest, farthest from it, largest triangle, largest gain. */
+static int reduce_manifold(const Contact* c, int n, int* keep) {
+  if (n <= 4) { for (int i = 0; i < n; i++) keep[i] = i; return n; }
+  int i0 = 0;
+  for (int i = 1; i < n; i++) if (c[i].dist < c[i0].dist) i0 = i;
+  int i1 = -1; real best = -1;
+  for (int i = 0; i < n; i++) if (i != i0) { v3 d = vsub(c[i].pb, c[i0].pb); real v = vdot(d, d); if (v > best) { best = v; i1 = i; } }
+  int i2 = -1; best = -1;
+  v3 e01 = vsub(c[i1].pb, c[i0].pb);
+  for (int i = 0; i < n; i++) if (i != i0 && i != i1) { v3 x = vcross(vsub(c[i].pb, c[i0].pb), e01); real v = vdot(x, x); if (v > best) { best = v; i2 = i; } }
+  int i3 = -1; best = -1;
+  for (int i = 0; i < n; i++) if (i != i0 && i != i1 && i != i2) {
+    v3 a = vsub(c[i].pb, c[i0].pb), b = vsub(c[i].pb, c[i1].pb), d = vsub(c[i].pb, c[i2].pb);
+    real v = vnorm(vcross(a, b)) + vnorm(vcross(b, d)) + vnorm(vcross(d, a));
+    if (v > best) { best = v; i3 = i; }
+  }
+  int sel[4] = {i0, i1, i2, i3}, m = 0;
+  for (int i = 0; i < n; i++) if (i == sel[0] || i == sel[1] || i == sel[2] || i == sel[3]) keep[m++] = i;
+  return m;
+}
 static int detect_contacts(const prb_model* M, const Poses* P, Contact* C, int maxc) {
-  int nc = 0;
-  for (int k = 0; k < M->n_pair; k++) {
+  static Contact cand[4 * MAXCONTACT];
+  int ncand = 0, nc = 0;
+  int run_start = 0, run_oa = -1, run_ob = -1;
+  for (int k = 0; k <= M->n_pair; k++) {
+    int oa = -2, ob = -2;
+    if (k < M->n_pair) { oa = M->col_obj[M->pair_a[k]]; ob = M->col_obj[M->pair_b[k]]; }
+    if (k == M->n_pair || oa != run_oa || ob != run_ob) {   /* close the run of the previous object pair */
+      int n = ncand - run_start, keep[4 * MAXCONTACT];
+      if (n > 0) {
+        int m = reduce_manifold(cand + run_start, n, keep);
+        for (int i = 0; i < m && nc < maxc; i++) C[nc++] = cand[run_start + keep[i]];
+      }
+      ncand = 0; run_start = 0; run_oa = oa; run_ob = ob;
+      if (k == M->n_pair) break;
+    }
     int a = M->pair_a[k], b = M->pair_b[k];
     if (P->lo[a].x > P->hi[b].x || P->hi[a].x < P->lo[b].x || P->lo[a].y > P->hi[b].y || P->hi[a].y < P->lo[b].y ||
         P->lo[a].z > P->hi[b].z || P->hi[a].z < P->lo[b].z) continue;
     CPoint cp[8];
     int n = orc_box_box_impl(P->cp[a], &P->cR[a], vload(M->col_half + 3 * a), P->cp[b], &P->cR[b], vload(M->col_half + 3 * b), cp);
-    for (int i = 0; i < n && nc < maxc; i++) {
-      C[nc].ca = a; C[nc].cb = b; C[nc].n = cp[i].n; C[nc].pb = cp[i].pos; C[nc].dist = -cp[i].depth;
-      C[nc].pa = vadd(cp[i].pos, vscale(cp[i].n, -cp[i].depth));
-      nc++;
+    for (int i = 0; i < n && ncand < 4 * MAXCONTACT; i++) {
+      cand[ncand].ca = a; cand[ncand].cb = b; cand[ncand].n = cp[i].n; cand[ncand].pb = cp[i].pos; cand[ncand].dist = -cp[i].depth;
+      cand[ncand].pa = vadd(cp[i].pos, vscale(cp[i].n, -cp[i].depth));
+      ncand++;
     }
   }
   return nc;
@@ -821,8 +857,10 @@ static void resolve_cone(Row* ra, Row* rb, real* dv, int nv) { /* btMultiBodyCon
   real dB = rb->rhs - rb->lambda * rb->cfm - jb * rb->invD, sumB = rb->lambda + dB;
   real dA = ra->rhs - ra->lambda * ra->cfm - ja * ra->invD, sumA = ra->lambda + dA;
   if (sumA < ra->lo || sumA > ra->hi || sumB < rb->lo || sumB > rb->hi) {
-    real angle = atan2(sumA, sumB);
-    real ca = fabs(ra->lo * sin(angle)), cb = fabs(rb->lo * cos(angle));
+    /* Bullet: angle = atan2(sumA, sumB); limits |lo*sin(angle)|, |lo*cos(angle)|; written without
+       the trigonometric round trip: sin = sumA/r, cos = sumB/r */
+    real rr = sqrt(sumA * sumA + sumB * sumB);
+    real ca = rr > 0 ? fabs(ra->lo * sumA / rr) : 0.0, cb = rr > 0 ? fabs(rb->lo * sumB / rr) : fabs(rb->lo);
     if (sumA < -ca) { dA = -ca - ra->lambda; ra->lambda = -ca; }
     else if (sumA > ca) { dA = ca - ra->lambda; ra->lambda = ca; }
     else ra->lambda = sumA;
@@ -835,6 +873,8 @@ static void resolve_cone(Row* ra, Row* rb, real* dv, int nv) { /* btMultiBodyCon
 
 /* diagnostics of the last substep (tests) */
 static int g_last_contacts = 0, g_last_rows = 0;
+static int g_last_pairs[MAXCONTACT][2];
+void orc_last_contact_pairs(int* out) { for (int i = 0; i < g_last_contacts; i++) { out[2 * i] = g_last_pairs[i][0]; out[2 * i + 1] = g_last_pairs[i][1]; } }
 int orc_last_contacts(void) { return g_last_contacts; }
 int orc_last_rows(void) { return g_last_rows; }
 
@@ -984,6 +1024,7 @@ static void substep(const prb_model* M, State* S) {
     }
   }
   g_last_contacts = nc; g_last_rows = nr;
+  for (int k = 0; k < nc; k++) { g_last_pairs[k][0] = C[k].ca; g_last_pairs[k][1] = C[k].cb; }
   /* ---- PGS, btMultiBodyConstraintSolver::solveSingleIteration order */
   real dv[MAXV]; for (int i = 0; i < nv; i++) dv[i] = 0;
   for (int it = 0; it < M->solver_iters; it++) {

@@ -27,10 +27,21 @@ class World:
         self.cols = []
         self.free = []
         self.slide = []
+        self.next_obj = 0
+
+    def new_obj(self):
+        self.next_obj += 1
+        return self.next_obj - 1
 
     def add_box(self, body, half, pos, R=None, link=-1, urdf_link=-1, friction=0.5, spin=0.0,
-                stiffness=-1.0, damping=-1.0):
-        self.cols.append(dict(body=body, link=link, urdf_link=urdf_link,
+                stiffness=-1.0, damping=-1.0, obj=None):
+        # obj: Bullet keeps one <=4-point manifold per pair of collision objects (per child-shape
+        # pair for compounds).  Boxes cut out of ONE concave trimesh share an object id; every
+        # other collider is its own object.
+        if obj is None:
+            obj = self.next_obj
+            self.next_obj += 1
+        self.cols.append(dict(body=body, link=link, urdf_link=urdf_link, obj=obj,
                               R=np.eye(3) if R is None else np.array(R, float),
                               p=np.array(pos, float), half=np.array(half, float),
                               friction=friction, spin=spin, stiffness=stiffness, damping=damping))
@@ -158,8 +169,9 @@ def complex_scene(world, ref_envs):
     world.add_box(STATIC, [0.03, 0.01, 0.045], [-0.0, -0.02, -0.08])
     boxes, _ = mesh_boxes.decompose(os.path.join(ref_envs, 'env_meshes', 'drawer2.obj'), 1.25)
     body = 1 + len(world.free)
+    drawer_obj = world.new_obj()
     for c, h in boxes:
-        world.add_box(body, h, c)
+        world.add_box(body, h, c, obj=drawer_obj)
     world.free.append(dict(mass=0.1, inertia=_free_inertia(0.1, boxes), lin_damp=0.04, ang_damp=0.04,
                            pos0=np.array([-0.10, -0.00, -0.04]),
                            quat0=rpy_to_quat([np.pi / 2, 0, 0])))
@@ -168,8 +180,9 @@ def complex_scene(world, ref_envs):
     Rl = rpy_to_mat([0, np.pi / 2, 0])
     boxes, _ = mesh_boxes.decompose(os.path.join(ref_envs, 'env_meshes', 'door.obj'), 0.0015)
     sb = slide_body0 + len(world.slide)
+    door_obj = world.new_obj()
     for c, h in boxes:
-        world.add_box(sb, h, c)
+        world.add_box(sb, h, c, obj=door_obj)
     world.slide.append(dict(jtype=1, pos=np.array([0, 0.4, -0.2]) + np.array([0, 0, 0.27]), R=Rl,
                             axis=[0, 0, 1], mass=0.1, inertia=0.0, ang_damp=0.04,
                             motor=[0.0, 0.0, 1.0, -1.0]))     # default velocity motor (target,kp,kd,maxImp<0 => default)
@@ -218,7 +231,9 @@ def make_pairs(world):
                 i2, j2 = i, j
             pa.append(i2)
             pb.append(j2)
-    return pa, pb
+    # pairs of the same object pair must be consecutive (manifold reduction works on runs)
+    order = sorted(range(len(pa)), key=lambda k: (world.cols[pa[k]]['obj'], world.cols[pb[k]]['obj'], pa[k], pb[k]))
+    return [pa[k] for k in order], [pb[k] for k in order]
 
 
 def compile_env(env_id, ref_envs):
@@ -273,6 +288,7 @@ def compile_env(env_id, ref_envs):
     d['col_body'] = [c['body'] for c in cols]
     d['col_link'] = [c['link'] for c in cols]
     d['col_urdf_link'] = [c['urdf_link'] for c in cols]
+    d['col_obj'] = [c['obj'] for c in cols]
     d['col_pos'] = np.array([c['p'] for c in cols])
     d['col_rot'] = np.array([c['R'] for c in cols])
     d['col_half'] = np.array([c['half'] for c in cols])

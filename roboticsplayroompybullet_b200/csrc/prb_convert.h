@@ -86,6 +86,8 @@ static inline std::string prb_convert_model(const prb_model* m, DevModel* D) {
   for (int j = 0; j < 8; j++) D->joints_obs_dof[j] = m->joints_obs_dof[j];
   for (int c = 0; c < m->n_col; c++) {
     D->col_body[c] = (signed char)m->col_body[c]; D->col_link[c] = (signed char)m->col_link[c]; D->col_urdf[c] = (signed char)m->col_urdf_link[c];
+    if (m->col_obj[c] < 0 || m->col_obj[c] > 255) return "collision object id out of range";
+    D->col_obj[c] = (unsigned char)m->col_obj[c];
     for (int k = 0; k < 3; k++) { D->col_pos[c][k] = (float)m->col_pos[3 * c + k]; D->col_half[c][k] = (float)m->col_half[3 * c + k]; }
     for (int k = 0; k < 9; k++) D->col_rot[c][k] = (float)m->col_rot[9 * c + k];
     D->col_fric[c] = (float)m->col_friction[c]; D->col_spin[c] = (float)m->col_spin[c];

@@ -52,6 +52,7 @@ struct DevModel {
   int joints_obs_dof[8];
   // ---- colliders (boxes)
   signed char col_body[PRB_MAXCOL], col_link[PRB_MAXCOL], col_urdf[PRB_MAXCOL];
+  unsigned char col_obj[PRB_MAXCOL];   // collision-object id (manifold reduction groups)
   float col_pos[PRB_MAXCOL][3], col_rot[PRB_MAXCOL][9], col_half[PRB_MAXCOL][3];
   float col_fric[PRB_MAXCOL], col_spin[PRB_MAXCOL], col_stiff[PRB_MAXCOL], col_damp[PRB_MAXCOL];
   unsigned char pair_a[PRB_MAXPAIR], pair_b[PRB_MAXPAIR];

@@ -25,11 +25,13 @@
 #pragma once
 #include "prb_device.h"
 
-#define PRB_WPB 4              // warps (envs) per thread block
+#define PRB_WPB 1              // warps (envs) per thread block
 #define PRB_MAXJROW 40         // limit + motor + gear rows
-#define PRB_MAXCONTACT 32      // contact points per env per substep (one per lane)
+#define PRB_MAXCONTACT 32      // contact points per env per substep after manifold reduction (one per lane)
 #define PRB_MAXOVL 32          // overlapping collider pairs handed to the narrow phase (one per lane)
-#define PRB_POOL 2304          // floats of packed contact-row Jacobians (J and M^-1 J^T segments)
+#define PRB_MAXCAND 128        // narrow-phase candidates (4 per overlapping pair) before reduction
+#define PRB_POOL 1664          // floats of packed contact-row Jacobians (J and M^-1 J^T segments)
+#define PRB_ACAP 4096          // floats of island-blocked, symmetric-packed Delassus matrix J M^-1 J^T
 #define FULL 0xffffffffu
 
 struct Contact {
@@ -51,19 +53,25 @@ struct WarpMem {
   float Mm[PRB_MAXD][PRB_MAXD + 1], Minv[PRB_MAXD][PRB_MAXD + 1], Q[PRB_MAXD];
   float vs[32];
   // ---- collision
-  float aabb[PRB_MAXCOL][6];
   unsigned short ovl[PRB_MAXOVL];
   int n_ovl, n_contact, n_jrow, pool_used, overflow;
   Contact ct[PRB_MAXCONTACT];
+  // collider AABBs and narrow-phase candidates are dead once the contacts are reduced into ct[],
+  // before the Delassus matrix is built
+  union {
+    struct { Contact cand[PRB_MAXCAND]; float aabb[PRB_MAXCOL][6]; };
+    float A[PRB_ACAP];
+  };
   // ---- constraint rows
   signed char jr_dof[PRB_MAXJROW], jr_dof2[PRB_MAXJROW];
   float jr_sign[PRB_MAXJROW], jr_rhs[PRB_MAXJROW], jr_invD[PRB_MAXJROW], jr_lo[PRB_MAXJROW], jr_hi[PRB_MAXJROW], jr_lam[PRB_MAXJROW];
+  unsigned jr_meta[PRB_MAXJROW];     // tsb (16 bits) | local row id (8) | island (8)
   // per contact: rows 0 normal, 1 spin, 2 friction-1, 3 friction-2
   float cr_rhs[PRB_MAXCONTACT][4], cr_invD[PRB_MAXCONTACT][4], cr_lam[PRB_MAXCONTACT][4];
   float cr_cfm[PRB_MAXCONTACT], cr_mu[PRB_MAXCONTACT], cr_spin[PRB_MAXCONTACT];
   signed char cr_bodyA[PRB_MAXCONTACT], cr_bodyB[PRB_MAXCONTACT];
   unsigned short cr_offA[PRB_MAXCONTACT], cr_offB[PRB_MAXCONTACT];
-  // cand aliases pool: narrow-phase candidates are dead once compacted into ct[]
+  unsigned ct_meta[PRB_MAXCONTACT];  // address base of the island block (16) | local id of the normal row (8) | island (8)
   float pool[PRB_POOL];
 };
 
@@ -83,6 +91,15 @@ PRB_D int warp_excl_scan(int v, int lane, int* total) {
   }
   *total = __shfl_sync(FULL, s, 31);
   return s - v;
+}
+
+PRB_D unsigned warp_or(unsigned v) {
+  v |= __shfl_xor_sync(FULL, v, 16);
+  v |= __shfl_xor_sync(FULL, v, 8);
+  v |= __shfl_xor_sync(FULL, v, 4);
+  v |= __shfl_xor_sync(FULL, v, 2);
+  v |= __shfl_xor_sync(FULL, v, 1);
+  return v;
 }
 
 // body index of a velocity DoF and geometry helpers -------------------------------------------
@@ -712,16 +729,52 @@ PRB_D void phase_collide(const DevModel& M, WarpMem& W, int lane) {
   int total;
   int off = warp_excl_scan(n, lane, &total);
   for (int i = 0; i < n; i++) {
-    int s = off + i;
-    if (s < PRB_MAXCONTACT) {
-      Contact& c = W.ct[s];
-      c.pbx = cp[i].pos.x; c.pby = cp[i].pos.y; c.pbz = cp[i].pos.z;
-      c.nx = cp[i].n.x; c.ny = cp[i].n.y; c.nz = cp[i].n.z; c.dist = -cp[i].depth; c.cols = ca | (cb << 8);
+    Contact& c = W.cand[off + i];     // off + i < 4 * PRB_MAXOVL = PRB_MAXCAND
+    c.pbx = cp[i].pos.x; c.pby = cp[i].pos.y; c.pbz = cp[i].pos.z;
+    c.nx = cp[i].n.x; c.ny = cp[i].n.y; c.nz = cp[i].n.z; c.dist = -cp[i].depth; c.cols = ca | (cb << 8);
+  }
+  // ---- manifold reduction: <= 4 points per pair of collision objects (runs of equal object pair;
+  //      the pair list is sorted by object pair, so runs are contiguous).  Lane = overlapping pair
+  //      marks run starts, lane = run reduces it, then an ordered compaction into ct[].
+  int key = lane < n_ovl ? ((int)M.col_obj[ca] << 8 | (int)M.col_obj[cb]) : -1;
+  int prev_key = __shfl_up_sync(FULL, key, 1);
+  bool run_start = (lane < n_ovl) && (lane == 0 || key != prev_key);
+  unsigned startmask = __ballot_sync(FULL, run_start);
+  int n_runs = __popc(startmask);
+  __syncwarp();
+  if (run_start) W.ovl[__popc(startmask & ((1u << lane) - 1u))] = (unsigned short)off;   // candidate index where the run begins
+  __syncwarp();
+  int keep[4], m = 0;
+  if (lane < n_runs) {
+    int b0 = W.ovl[lane], b1 = (lane + 1 < n_runs) ? (int)W.ovl[lane + 1] : total;
+    int nn = b1 - b0;
+    const Contact* c = &W.cand[b0];
+    if (nn <= 4) { m = nn; for (int i = 0; i < nn; i++) keep[i] = b0 + i; }
+    else {
+      int i0 = 0;
+      for (int i = 1; i < nn; i++) if (c[i].dist < c[i0].dist) i0 = i;
+      v3 p0 = V3(c[i0].pbx, c[i0].pby, c[i0].pbz);
+      int i1 = -1; float best = -1.f;
+      for (int i = 0; i < nn; i++) if (i != i0) { v3 d = V3(c[i].pbx, c[i].pby, c[i].pbz) - p0; float v = dot(d, d); if (v > best) { best = v; i1 = i; } }
+      v3 p1 = V3(c[i1].pbx, c[i1].pby, c[i1].pbz), e01 = p1 - p0;
+      int i2 = -1; best = -1.f;
+      for (int i = 0; i < nn; i++) if (i != i0 && i != i1) { v3 x = cross(V3(c[i].pbx, c[i].pby, c[i].pbz) - p0, e01); float v = dot(x, x); if (v > best) { best = v; i2 = i; } }
+      v3 p2 = V3(c[i2].pbx, c[i2].pby, c[i2].pbz);
+      int i3 = -1; best = -1.f;
+      for (int i = 0; i < nn; i++) if (i != i0 && i != i1 && i != i2) {
+        v3 pi = V3(c[i].pbx, c[i].pby, c[i].pbz), a = pi - p0, b = pi - p1, d = pi - p2;
+        float v = norm(cross(a, b)) + norm(cross(b, d)) + norm(cross(d, a));
+        if (v > best) { best = v; i3 = i; }
+      }
+      for (int i = 0; i < nn; i++) if (i == i0 || i == i1 || i == i2 || i == i3) keep[m++] = b0 + i;
     }
   }
+  int total2;
+  int off2 = warp_excl_scan(m, lane, &total2);
+  for (int i = 0; i < m; i++) if (off2 + i < PRB_MAXCONTACT) W.ct[off2 + i] = W.cand[keep[i]];
   if (lane == 0) {
-    W.n_contact = total < PRB_MAXCONTACT ? total : PRB_MAXCONTACT;
-    if (total > PRB_MAXCONTACT) W.overflow = 1;
+    W.n_contact = total2 < PRB_MAXCONTACT ? total2 : PRB_MAXCONTACT;
+    if (total2 > PRB_MAXCONTACT) W.overflow = 1;
   }
   __syncwarp();
 }
@@ -890,7 +943,12 @@ PRB_D void phase_rows(const DevModel& M, WarpMem& W, int lane) {
     for (int k = 0; k < 4; k++) {
       v3 dir = k == 0 ? n : (k == 1 ? n : (k == 2 ? t1 : t2));
       bool ang = (k == 1);
-      if (k == 1 && !(spin > 0.f)) { W.cr_invD[lane][1] = 0.f; W.cr_rhs[lane][1] = 0.f; W.cr_lam[lane][1] = 0.f; continue; }
+      if (k == 1 && !(spin > 0.f)) {   // no torsional row: keep its segment zeroed (it is still summed with lambda = 0)
+        for (int i = 0; i < 2 * nA; i++) W.pool[offA + 2 * nA + i] = 0.f;
+        for (int i = 0; i < 2 * nB; i++) W.pool[offB + 2 * nB + i] = 0.f;
+        W.cr_invD[lane][1] = 0.f; W.cr_rhs[lane][1] = 0.f; W.cr_lam[lane][1] = 0.f;
+        continue;
+      }
       float rel = 0.f, D = 0.f;
       if (bodyA >= 0) D += fill_segment(M, W, ca, pa, dir, 1.0f, ang, &W.pool[offA + k * 2 * nA], &rel);
       if (bodyB >= 0) D += fill_segment(M, W, cb, pb, dir, -1.0f, ang, &W.pool[offB + k * 2 * nB], &rel);
@@ -911,98 +969,355 @@ PRB_D void phase_rows(const DevModel& M, WarpMem& W, int lane) {
   __syncwarp();
 }
 
-// ============================================================================ PGS (lane = velocity DoF)
-// per-lane view of a contact row: which segment (if any) holds this lane's DoF
+// ============================================================================ islands + Delassus matrix
+// The PGS sweeps run in impulse space: u_r = (J M^-1 J^T lambda)_r is kept per row by the lane that
+// owns the row, and a row update only broadcasts its impulse change.  A = J M^-1 J^T is stored in
+// shared memory, symmetric-packed and blocked by simulation island (rows of different islands do
+// not couple), so memory is sum_i R_i (R_i + 1) / 2 instead of R^2.
+//
+// Row ownership: joint row j -> lane j & 31, slot j >> 5; contact c -> lane c (rows normal, spin,
+// friction 1, friction 2).  Local row ids inside an island: its joint rows first (in row order),
+// then its contacts in order, each contributing [normal, (spin), friction 1, friction 2].
 struct LaneMap { int body, li, n; float self_minv; };
 
-PRB_D void contact_jb(const WarpMem& W, const LaneMap& lm, int c, int k, float& j, float& b) {
-  j = 0.f; b = 0.f;
+// Constraint "units" in sweep order: joint rows, contact normals, spinning-friction rows, lateral
+// friction PAIRS (two rows solved together by the implicit cone).  Unit g is owned by lane g & 31
+// in slot g >> 5, so a lane holds at most PRB_MAXSLOT units and every sweep step has a uniform slot.
+#define PRB_MAXSLOT 4
+struct RowRegs {
+  float ua[PRB_MAXSLOT], ub[PRB_MAXSLOT];        // J M^-1 J^T lambda of the unit's row(s)
+  float la[PRB_MAXSLOT], lb[PRB_MAXSLOT];        // accumulated impulses
+  float rhsa[PRB_MAXSLOT], rhsb[PRB_MAXSLOT], ida[PRB_MAXSLOT], idb[PRB_MAXSLOT];
+  float p0[PRB_MAXSLOT], p1[PRB_MAXSLOT];        // joint: lo, hi | normal: cfm | spin: coefficient | pair: mu
+  int isl[PRB_MAXSLOT];                          // island (-1: empty slot)
+  int ra[PRB_MAXSLOT], tra[PRB_MAXSLOT];         // island-local row id of row a, and base + tri(ra); row b = ra + 1
+  int cidx[PRB_MAXSLOT];                         // contact index of the unit (contact units)
+  int nslots;
+};
+
+PRB_D int tri(int r) { return (r * (r + 1)) >> 1; }
+
+// B = M^-1 J^T of contact row (c,k) at velocity DoF `dof`
+PRB_D float contact_B_at(const DevModel& M, const WarpMem& W, int c, int k, int dof) {
+  int li, n;
+  int body = dof_body(M, dof, &li, &n);
   int base = -1;
-  if (lm.body == W.cr_bodyA[c]) base = W.cr_offA[c];
-  else if (lm.body == W.cr_bodyB[c]) base = W.cr_offB[c];
-  if (base >= 0 && lm.body >= 0) {
-    const float* seg = &W.pool[base + k * 2 * lm.n];
-    j = seg[lm.li]; b = seg[lm.n + lm.li];
+  if (body == W.cr_bodyA[c]) base = W.cr_offA[c];
+  else if (body == W.cr_bodyB[c]) base = W.cr_offB[c];
+  if (base < 0 || body < 0) return 0.f;
+  return W.pool[base + k * 2 * n + n + li];
+}
+// J_(c,k) . B_(c2,k2) over the bodies the two contacts share
+PRB_D float contact_dot(const DevModel& M, const WarpMem& W, int c, int k, int c2, int k2) {
+  float s = 0.f;
+  const int bA = W.cr_bodyA[c], bB = W.cr_bodyB[c], b2A = W.cr_bodyA[c2], b2B = W.cr_bodyB[c2];
+  for (int x = 0; x < 2; x++) {
+    const int bx = x == 0 ? bA : bB;
+    if (bx < 0) continue;
+    const int n = body_size(M, bx);
+    const float* J = &W.pool[(x == 0 ? W.cr_offA[c] : W.cr_offB[c]) + k * 2 * n];
+    for (int y = 0; y < 2; y++) {
+      const int by = y == 0 ? b2A : b2B;
+      if (by != bx) continue;
+      const float* B = &W.pool[(y == 0 ? W.cr_offA[c2] : W.cr_offB[c2]) + k2 * 2 * n + n];
+      for (int i = 0; i < n; i++) s += J[i] * B[i];
+    }
+  }
+  return s;
+}
+// inverse-mass coupling between two joint-row DoFs
+PRB_D float dof_minv(const DevModel& M, const WarpMem& W, int d, int d2) {
+  if (d < M.nd && d2 < M.nd) return W.Minv[d][d2];
+  if (d == d2) { int s = d - M.nd - 6 * M.n_free; return (s >= 0 && s < M.n_slide) ? M.slide_minv[s] : 0.f; }
+  return 0.f;
+}
+PRB_D float jrow_jrow(const DevModel& M, const WarpMem& W, int j, int j2) {
+  const float r = M.params[P_GEAR_RATIO];
+  int a = W.jr_dof[j], a2 = W.jr_dof2[j], b = W.jr_dof[j2], b2 = W.jr_dof2[j2];
+  float v = dof_minv(M, W, a, b);
+  if (a2 >= 0) v += r * dof_minv(M, W, a2, b);
+  if (b2 >= 0) { v += r * dof_minv(M, W, a, b2); if (a2 >= 0) v += r * r * dof_minv(M, W, a2, b2); }
+  return v * W.jr_sign[j] * W.jr_sign[j2];
+}
+PRB_D float jrow_contact(const DevModel& M, const WarpMem& W, int j, int c, int k) {
+  float v = contact_B_at(M, W, c, k, W.jr_dof[j]);
+  if (W.jr_dof2[j] >= 0) v += M.params[P_GEAR_RATIO] * contact_B_at(M, W, c, k, W.jr_dof2[j]);
+  return v * W.jr_sign[j];
+}
+
+// islands, local row ids, A; fills the per-lane row registers
+PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
+  const int nb = 1 + M.n_free + M.n_slide;
+  int nc = W.n_contact;
+  const int njr = W.n_jrow;
+  // ---- connected components over the (<= 6) dynamic bodies, from the contact list
+  int bA = -1, bB = -1;
+  if (lane < nc) { bA = W.cr_bodyA[lane]; bB = W.cr_bodyB[lane]; }
+  unsigned reach[8];
+  for (int x = 0; x < 8; x++) {
+    unsigned mine = 0;
+    if (x < nb && bA >= 0 && bB >= 0 && (bA == x || bB == x)) mine = (1u << bA) | (1u << bB);
+    reach[x] = warp_or(mine) | (1u << x);
+  }
+  for (int it = 0; it < 3; it++)
+    for (int x = 0; x < 8; x++) {
+      unsigned r = reach[x];
+      for (int y = 0; y < 8; y++) if ((r >> y) & 1u) r |= reach[y];
+      reach[x] = r;
+    }
+  // island label of a body = lowest body index it reaches
+  int my_islC = -1, my_islJ[2] = {-1, -1};
+  if (lane < nc) { int bb = bA >= 0 ? bA : bB; my_islC = __ffs((int)reach[bb & 7]) - 1; }
+  for (int sl = 0; sl < 2; sl++) {
+    int j = sl * 32 + lane;
+    if (j < njr) { int li, n; int body = dof_body(M, W.jr_dof[j], &li, &n); my_islJ[sl] = __ffs((int)reach[body & 7]) - 1; }
+  }
+  bool spin_on = lane < nc && W.cr_spin[lane] > 0.f;
+  // ---- local ids per island by one packed scan per island; block bases by running sum.
+  //      If the packed blocks do not fit, the last contact is dropped and the layout redone
+  //      (flagged in W.overflow; needs > ~89 coupled rows in one island).
+  int locJ[2] = {0, 0}, locC = 0, baseJ[2] = {0, 0}, baseC = 0;
+  for (;;) {
+    int used = 0;
+    const int my_rows = lane < nc ? (spin_on ? 4 : 3) : 0;
+    for (int L = 0; L < nb; L++) {
+      int cnt = (my_islJ[0] == L ? 1 : 0) | (my_islJ[1] == L ? 1 << 8 : 0) | ((lane < nc && my_islC == L) ? my_rows << 16 : 0);
+      int tot;
+      int pre = warp_excl_scan(cnt, lane, &tot);
+      int nJ0 = tot & 0xff, nJ1 = (tot >> 8) & 0xff, nC = tot >> 16;
+      int RL = nJ0 + nJ1 + nC;
+      if (RL == 0) continue;                        // uniform
+      if (my_islJ[0] == L) { locJ[0] = pre & 0xff; baseJ[0] = used; }
+      if (my_islJ[1] == L) { locJ[1] = nJ0 + ((pre >> 8) & 0xff); baseJ[1] = used; }
+      if (my_islC == L) { locC = nJ0 + nJ1 + (pre >> 16); baseC = used; }
+      used += tri(RL);
+    }
+    if (used <= PRB_ACAP || nc == 0) break;         // uniform
+    nc--;
+    if (lane == 0) { W.overflow = 1; W.n_contact = nc; }
+  }
+  if (lane >= nc) my_islC = -1;
+  spin_on = spin_on && lane < nc;
+  // ---- per-row uniform metadata for the sweeps
+  for (int sl = 0; sl < 2; sl++) {
+    int j = sl * 32 + lane;
+    if (j < njr) W.jr_meta[j] = (unsigned)(baseJ[sl] + tri(locJ[sl])) | ((unsigned)locJ[sl] << 16) | ((unsigned)my_islJ[sl] << 24);
+  }
+  if (lane < nc) W.ct_meta[lane] = (unsigned)baseC | ((unsigned)locC << 16) | ((unsigned)my_islC << 24);
+  __syncwarp();
+  // ---- fill A (lower triangle incl. diagonal of every island block): the lane owning the
+  //      receiving row computes its entries against every sender row with a smaller-or-equal id
+  for (int sl = 0; sl < 2; sl++) {
+    int j = sl * 32 + lane;
+    if (j >= njr) continue;
+    const int rowbase = baseJ[sl] + tri(locJ[sl]);
+    for (int j2 = 0; j2 <= j; j2++) {
+      unsigned m2 = W.jr_meta[j2];
+      if ((int)(m2 >> 24) != my_islJ[sl]) continue;
+      W.A[rowbase + (int)((m2 >> 16) & 0xff)] = jrow_jrow(M, W, j, j2);
+    }
+  }
+  if (lane < nc) {
+    const int c = lane;
+    int k_of[4] = {0, 1, 2, 3}, nk = 0;
+    k_of[nk++] = 0; if (spin_on) k_of[nk++] = 1; k_of[nk++] = 2; k_of[nk++] = 3;
+    for (int kk = 0; kk < nk; kk++) {
+      const int k = k_of[kk], r = locC + kk, rowbase = baseC + tri(r);
+      for (int j2 = 0; j2 < njr; j2++) {
+        unsigned m2 = W.jr_meta[j2];
+        if ((int)(m2 >> 24) != my_islC) continue;
+        W.A[rowbase + (int)((m2 >> 16) & 0xff)] = jrow_contact(M, W, j2, c, k);
+      }
+      for (int c2 = 0; c2 <= c; c2++) {
+        unsigned m2 = W.ct_meta[c2];
+        if ((int)(m2 >> 24) != my_islC) continue;
+        const int loc2 = (int)((m2 >> 16) & 0xff);
+        const bool sp2 = W.cr_spin[c2] > 0.f;
+        int kk2 = 0;
+        for (int k2 = 0; k2 < 4; k2++) {
+          if (k2 == 1 && !sp2) continue;
+          const int r2 = loc2 + kk2; kk2++;
+          if (r2 > r) break;
+          W.A[rowbase + r2] = contact_dot(M, W, c, k, c2, k2);
+        }
+      }
+    }
+  }
+  // ---- unit registers (sweep order: joint rows | normals | spin rows | friction pairs)
+  const unsigned spinmask = __ballot_sync(FULL, spin_on);
+  const int nspin = __popc(spinmask);
+  const int g_n = njr, g_s = njr + nc, g_f = njr + nc + nspin, g_end = g_f + nc;
+  R.nslots = (g_end + 31) >> 5;          // <= (40 + 96 + 31) / 32 = 5 in theory; capped below
+  if (R.nslots > PRB_MAXSLOT) { R.nslots = PRB_MAXSLOT; if (lane == 0) W.overflow = 1; }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < PRB_MAXSLOT; k++) {
+    const int g = 32 * k + lane;
+    R.ua[k] = 0.f; R.ub[k] = 0.f; R.la[k] = 0.f; R.lb[k] = 0.f;
+    R.rhsa[k] = 0.f; R.rhsb[k] = 0.f; R.ida[k] = 0.f; R.idb[k] = 0.f; R.p0[k] = 0.f; R.p1[k] = 0.f;
+    R.isl[k] = -1; R.ra[k] = 0; R.tra[k] = 0; R.cidx[k] = 0;
+    if (g < g_n) {
+      const unsigned m = W.jr_meta[g];
+      R.rhsa[k] = W.jr_rhs[g]; R.ida[k] = W.jr_invD[g]; R.p0[k] = W.jr_lo[g]; R.p1[k] = W.jr_hi[g];
+      R.isl[k] = (int)(m >> 24); R.ra[k] = (int)((m >> 16) & 0xff); R.tra[k] = (int)(m & 0xffff);
+    } else if (g < g_end) {
+      int c, row;
+      if (g < g_s) { c = g - g_n; row = 0; }
+      else if (g < g_f) {           // (g - g_s)-th contact with a spin row
+        unsigned mm = spinmask; for (int i = 0; i < g - g_s; i++) mm &= mm - 1;
+        c = __ffs((int)mm) - 1; row = 1;
+      } else { c = g - g_f; row = 2; }
+      const unsigned m = W.ct_meta[c];
+      const int base = (int)(m & 0xffff), loc = (int)((m >> 16) & 0xff);
+      const bool sp = (spinmask >> c) & 1u;
+      const int r = loc + (row == 0 ? 0 : (row == 1 ? 1 : (sp ? 2 : 1)));
+      R.isl[k] = (int)(m >> 24); R.ra[k] = r; R.tra[k] = base + tri(r); R.cidx[k] = c;
+      R.rhsa[k] = W.cr_rhs[c][row]; R.ida[k] = W.cr_invD[c][row];
+      if (row == 0) R.p0[k] = W.cr_cfm[c];
+      else if (row == 1) R.p0[k] = W.cr_spin[c];
+      else { R.p0[k] = W.cr_mu[c]; R.rhsb[k] = W.cr_rhs[c][3]; R.idb[k] = W.cr_invD[c][3]; }
+    }
+  }
+  __syncwarp();
+}
+
+// ============================================================================ PGS (lane = unit owner)
+// A[row s][row r] inside an island block, symmetric-packed: index = base + tri(max) + min.
+// `tsb` = base + tri(sloc) of the sending row (uniform); tra = base + tri(ra) of the receiving row.
+PRB_D int a_index(int sloc, int tsb, int r, int trr) { return sloc > r ? tsb + r : trr + sloc; }
+
+// Add the effect of impulse changes (d1 on row sloc, d2 on row sloc + 1; d2 = 0 for single rows)
+// to every unit this lane owns in the sender's island.  Branch-free: lanes outside the island
+// read A[0] and multiply by zero, so the loads do not depend on the broadcast values.
+template <bool PAIR>
+PRB_D void pgs_apply(const WarpMem& W, RowRegs& R, int isl, int sloc, int tsb, float d1, float d2) {
+  const int tsb2 = tsb + sloc + 1;          // base + tri(sloc + 1)
+#pragma unroll
+  for (int k = 0; k < PRB_MAXSLOT; k++) {
+    if (k < R.nslots) {                     // uniform
+      const bool on = R.isl[k] == isl;
+      const int ra = R.ra[k], rb = ra + 1, tra = R.tra[k], trb = tra + ra + 1;
+      const float m1 = on ? d1 : 0.f;
+      const int ia = on ? a_index(sloc, tsb, ra, tra) : 0, ib = on ? a_index(sloc, tsb, rb, trb) : 0;
+      R.ua[k] += W.A[ia] * m1;
+      R.ub[k] += W.A[ib] * m1;              // only meaningful for pair units; harmless otherwise
+      if (PAIR) {
+        const float m2 = on ? d2 : 0.f;
+        const int ja = on ? a_index(sloc + 1, tsb2, ra, tra) : 0, jb = on ? a_index(sloc + 1, tsb2, rb, trb) : 0;
+        R.ua[k] += W.A[ja] * m2;
+        R.ub[k] += W.A[jb] * m2;
+      }
+    }
   }
 }
 
-PRB_D float phase_pgs(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm) {
-  float dv = 0.f;
+enum { U_JOINT = 0, U_NORMAL = 1, U_SPIN = 2, U_PAIR = 3 };
+
+// one sweep step: the unit in slot K of lane `src` is solved, its impulse change broadcast
+template <int K, int TYPE>
+PRB_D void pgs_step(WarpMem& W, RowRegs& R, int lane, int src) {
+  float d1, d2 = 0.f;
+  if (TYPE == U_JOINT) {
+    const float delta = R.rhsa[K] - R.ua[K] * R.ida[K];
+    const float nl = clampf(R.la[K] + delta, R.p0[K], R.p1[K]);
+    d1 = nl - R.la[K];
+    if (lane == src) R.la[K] = nl;
+  } else if (TYPE == U_NORMAL) {
+    const float delta = R.rhsa[K] - R.la[K] * R.p0[K] - R.ua[K] * R.ida[K];
+    const float nl = fmaxf(R.la[K] + delta, 0.f);
+    d1 = nl - R.la[K];
+    if (lane == src) { R.la[K] = nl; W.cr_lam[R.cidx[K]][0] = nl; }     // read by the friction units of this contact
+  } else if (TYPE == U_SPIN) {
+    const float tot = W.cr_lam[R.cidx[K]][0];
+    const float lim = R.p0[K] * tot;
+    const float delta = R.rhsa[K] - R.ua[K] * R.ida[K];
+    const float nl = clampf(R.la[K] + delta, -lim, lim);
+    d1 = tot > 0.f ? nl - R.la[K] : 0.f;                              // Bullet skips the row while the normal impulse is 0
+    if (lane == src && tot > 0.f) R.la[K] = nl;
+  } else {
+    const float lim = R.p0[K] * W.cr_lam[R.cidx[K]][0];
+    const float sumA = R.la[K] + (R.rhsa[K] - R.ua[K] * R.ida[K]);
+    const float sumB = R.lb[K] + (R.rhsb[K] - R.ub[K] * R.idb[K]);
+    float na = sumA, nb = sumB;
+    if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
+      // |lim sin(atan2(A,B))| and |lim cos(atan2(A,B))| as |lim A| / r and |lim B| / r
+      const float ss = sumA * sumA + sumB * sumB;
+      const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+      const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
+      na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
+    }
+    d1 = na - R.la[K]; d2 = nb - R.lb[K];
+    if (lane == src) { R.la[K] = na; R.lb[K] = nb; }
+  }
+  // owner's row coordinates travel with the impulse change (3 more shuffles, off the critical path)
+  const int isl = __shfl_sync(FULL, R.isl[K], src);
+  const int sloc = __shfl_sync(FULL, R.ra[K], src);
+  const int tsb = __shfl_sync(FULL, R.tra[K], src);
+  d1 = __shfl_sync(FULL, d1, src);
+  if (TYPE == U_PAIR) { d2 = __shfl_sync(FULL, d2, src); pgs_apply<true>(W, R, isl, sloc, tsb, d1, d2); }
+  else pgs_apply<false>(W, R, isl, sloc, tsb, d1, 0.f);
+}
+template <int TYPE>
+PRB_D void pgs_unit(WarpMem& W, RowRegs& R, int lane, int g) {
+  const int src = g & 31;
+  switch (g >> 5) {                          // uniform
+    case 0: pgs_step<0, TYPE>(W, R, lane, src); break;
+    case 1: pgs_step<1, TYPE>(W, R, lane, src); break;
+    case 2: pgs_step<2, TYPE>(W, R, lane, src); break;
+    default: pgs_step<3, TYPE>(W, R, lane, src); break;
+  }
+}
+
+// 50 projected-Gauss-Seidel sweeps in btMultiBodyConstraintSolver::solveSingleIteration order:
+// non-contact rows (direction alternating per iteration), normals, spinning friction, lateral
+// friction as an implicit cone over the row pair.  Returns dv = M^-1 J^T lambda for this lane's DoF.
+PRB_D float phase_pgs(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm, RowRegs& R) {
   const int njr = W.n_jrow, nc = W.n_contact, nd = M.nd;
+  const unsigned spinmask = __ballot_sync(FULL, lane < nc && W.cr_spin[lane < nc ? lane : 0] > 0.f);
+  const int nspin = __popc(spinmask);
+  const int g_n = njr, g_s = njr + nc, g_f = g_s + nspin;
+  const int g_end = min(g_f + nc, 32 * PRB_MAXSLOT);
   for (int it = 0; it < M.solver_iters; it++) {
-    // (1) non-contact rows, direction alternates per iteration
-    for (int jj = 0; jj < njr; jj++) {
-      const int r = (it & 1) ? jj : njr - 1 - jj;
-      const int d = W.jr_dof[r], d2 = W.jr_dof2[r];
-      const float sg = W.jr_sign[r];
-      float jdv = sg * __shfl_sync(FULL, dv, d);
-      if (d2 >= 0) jdv += M.params[P_GEAR_RATIO] * __shfl_sync(FULL, dv, d2);
-      float lam = W.jr_lam[r];
-      float delta = W.jr_rhs[r] - jdv * W.jr_invD[r];
-      float nl = clampf(lam + delta, W.jr_lo[r], W.jr_hi[r]);
-      delta = nl - lam;
-      float b = 0.f;
-      if (d < nd) { if (lane < nd) b = W.Minv[lane][d]; }
-      else if (lane == d) b = lm.self_minv;
-      b *= sg;
-      if (d2 >= 0 && lane < nd) b += M.params[P_GEAR_RATIO] * W.Minv[lane][d2];
-      dv += b * delta;
-      __syncwarp();
-      if (lane == 0) W.jr_lam[r] = nl;
-    }
-    // (2) contact normals
-    for (int c = 0; c < nc; c++) {
-      float j, b;
-      contact_jb(W, lm, c, 0, j, b);
-      float jdv = warp_sum(j * dv);
-      float lam = W.cr_lam[c][0];
-      float delta = W.cr_rhs[c][0] - lam * W.cr_cfm[c] - jdv * W.cr_invD[c][0];
-      float nl = fmaxf(lam + delta, 0.f);
-      delta = nl - lam;
-      dv += b * delta;
-      __syncwarp();
-      if (lane == 0) W.cr_lam[c][0] = nl;
-    }
+    if (it & 1) { for (int g = 0; g < g_n; g++) pgs_unit<U_JOINT>(W, R, lane, g); }
+    else { for (int g = g_n - 1; g >= 0; g--) pgs_unit<U_JOINT>(W, R, lane, g); }
+    for (int g = g_n; g < min(g_s, g_end); g++) pgs_unit<U_NORMAL>(W, R, lane, g);
+    __syncwarp();                                      // normal impulses visible to the friction units
+    for (int g = g_s; g < min(g_f, g_end); g++) pgs_unit<U_SPIN>(W, R, lane, g);
+    for (int g = g_f; g < g_end; g++) pgs_unit<U_PAIR>(W, R, lane, g);
     __syncwarp();
-    // (3) spinning (torsional) friction rows
+  }
+  // ---- publish the impulses and rebuild dv = M^-1 J^T lambda with lane = velocity DoF
+  __syncwarp();
+  if (lane < nc) { W.cr_lam[lane][1] = 0.f; W.cr_lam[lane][2] = 0.f; W.cr_lam[lane][3] = 0.f; }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < PRB_MAXSLOT; k++) {
+    const int g = 32 * k + lane;
+    if (g < g_n) W.jr_lam[g] = R.la[k];
+    else if (g < g_s) W.cr_lam[R.cidx[k]][0] = R.la[k];
+    else if (g < g_f) W.cr_lam[R.cidx[k]][1] = R.la[k];
+    else if (g < g_end) { W.cr_lam[R.cidx[k]][2] = R.la[k]; W.cr_lam[R.cidx[k]][3] = R.lb[k]; }
+  }
+  __syncwarp();
+  float dv = 0.f;
+  const float ratio = M.params[P_GEAR_RATIO];
+  for (int j = 0; j < njr; j++) {
+    const int d = W.jr_dof[j], d2 = W.jr_dof2[j];
+    float b = 0.f;
+    if (d < nd) { if (lane < nd) b = W.Minv[lane][d]; }
+    else if (lane == d) b = lm.self_minv;
+    if (d2 >= 0 && lane < nd) b += ratio * W.Minv[lane][d2];
+    dv += b * W.jr_sign[j] * W.jr_lam[j];
+  }
+  if (lm.body >= 0) {
     for (int c = 0; c < nc; c++) {
-      float sp = W.cr_spin[c];
-      float tot = W.cr_lam[c][0];
-      if (!(sp > 0.f) || !(tot > 0.f)) continue;     // warp-uniform
-      float j, b;
-      contact_jb(W, lm, c, 1, j, b);
-      float jdv = warp_sum(j * dv);
-      float lam = W.cr_lam[c][1];
-      float delta = W.cr_rhs[c][1] - jdv * W.cr_invD[c][1];
-      float nl = clampf(lam + delta, -sp * tot, sp * tot);
-      delta = nl - lam;
-      dv += b * delta;
-      __syncwarp();
-      if (lane == 0) W.cr_lam[c][1] = nl;
+      int base = -1;
+      if (lm.body == W.cr_bodyA[c]) base = W.cr_offA[c];
+      else if (lm.body == W.cr_bodyB[c]) base = W.cr_offB[c];
+      if (base < 0) continue;
+      const float* seg = &W.pool[base + lm.n + lm.li];
+      dv += seg[0] * W.cr_lam[c][0] + seg[2 * lm.n] * W.cr_lam[c][1] + seg[4 * lm.n] * W.cr_lam[c][2] + seg[6 * lm.n] * W.cr_lam[c][3];
     }
-    // (4) lateral friction, implicit cone over the pair of rows
-    for (int c = 0; c < nc; c++) {
-      float ja, ba, jb, bb;
-      contact_jb(W, lm, c, 2, ja, ba);
-      contact_jb(W, lm, c, 3, jb, bb);
-      float sa_ = ja * dv, sb_ = jb * dv;
-      for (int o = 16; o > 0; o >>= 1) { sa_ += __shfl_xor_sync(FULL, sa_, o); sb_ += __shfl_xor_sync(FULL, sb_, o); }
-      float lim = W.cr_mu[c] * W.cr_lam[c][0];
-      float la = W.cr_lam[c][2], lb = W.cr_lam[c][3];
-      float dA = W.cr_rhs[c][2] - sa_ * W.cr_invD[c][2], dB = W.cr_rhs[c][3] - sb_ * W.cr_invD[c][3];
-      float sumA = la + dA, sumB = lb + dB, na, nb;
-      if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
-        float ang = atan2f(sumA, sumB);
-        float sn, cs;
-        sincosf(ang, &sn, &cs);
-        float ca_ = fabsf(lim * sn), cb_ = fabsf(lim * cs);
-        na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
-      } else { na = sumA; nb = sumB; }
-      dv += ba * (na - la) + bb * (nb - lb);
-      __syncwarp();
-      if (lane == 0) { W.cr_lam[c][2] = na; W.cr_lam[c][3] = nb; }
-    }
-    __syncwarp();
   }
   return dv;
 }
@@ -1045,7 +1360,9 @@ PRB_D void substep(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm) {
   phase_minv<ND>(W, lane);
   float vstar = phase_vstar(M, W, lane);
   phase_rows(M, W, lane);
-  float dv = phase_pgs(M, W, lane, lm);
+  RowRegs R;
+  phase_delassus(M, W, lane, R);
+  float dv = phase_pgs(M, W, lane, lm, R);
   phase_integrate(M, W, lane, vstar, dv);
 }
 

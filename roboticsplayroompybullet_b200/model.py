@@ -48,6 +48,7 @@ SCHEMA = [
     ('col_body', 'I'),          # -1 static, 0 arm, 1..n_free free bodies, then slide bodies
     ('col_link', 'I'),          # arm movable link (or -1: arm base, static)
     ('col_urdf_link', 'I'),     # PyBullet link index (ray-test classification)
+    ('col_obj', 'I'),           # collision-object id: contacts are reduced to <= 4 per object pair
     ('pair_a', 'I'), ('pair_b', 'I'),
     ('slide_jtype', 'I'),
     ('grip_dof', 'I'), ('grip_mimic', 'I'),

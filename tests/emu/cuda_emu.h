@@ -124,6 +124,9 @@ void launch(emu_dim3 grid, emu_dim3 block, F f) {
 #define blockDim (emu::g_blockDim)
 #define gridDim (emu::g_gridDim)
 
+using std::min;
+using std::max;
+
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)mask; emu::warp_barrier(); }
 static inline void __syncthreads() { emu::block_barrier(); }
 template <class T>
