@@ -259,6 +259,7 @@ def run_gpu(args):
                 'gpu_launches': int(launches), 'clocks': clocks,
                 'episode_stats': {'success_rate': float(stats[0]) / total_env_steps,
                                   'mean_reward': float(stats[1]) / total_env_steps},
+                'capacity_overflow_env_steps': env.overflow_count(),
                 'wall_s_timed_region': t_wall}
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(args.env, args.seed, budget_s=args.cpu_seconds)

@@ -115,6 +115,9 @@ int prb_last_kernel_ms(prb_handle* h, float* ik_ms, float* step_ms);
 
 /* Number of kernels launched by this handle since creation (bench.py reports it). */
 int64_t prb_launch_count(prb_handle* h);
+/* Env-steps (since creation) in which a contact had to be dropped because the per-env on-chip
+ * capacity (contacts, packed Jacobians or one island's Delassus block) was exceeded; synchronous. */
+int64_t prb_overflow_count(prb_handle* h);
 /* Static facts of the step kernel for reports: dynamic shared memory per block, warps per block. */
 int prb_kernel_info(prb_handle* h, int32_t* smem_bytes_per_block, int32_t* envs_per_block, int32_t* regs_per_thread);
 

@@ -127,6 +127,8 @@ def build_arm(world, ref_envs, arm_kind):
         d['ctrl_inc'] = [0.1, 0.1, 0.2, 0.2, 0.2, 0.2, 0.2]               # :1017
     d['n_grip'] = len(d['grip_dof'])
     d['names'] = arm['names']
+    # PyBullet joint index -> joint name for EVERY joint (fixed ones included), for the indexing fixture
+    d['urdf_joint_names'] = [L.jname for L in sorted(links, key=lambda L: L.index) if L.index >= 0]
     return d
 
 

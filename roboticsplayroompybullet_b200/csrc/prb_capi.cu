@@ -82,6 +82,8 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
   CK(h, cudaMalloc(&h->out, sizeof(float) * tot));
   CK(h, cudaMemset(h->out, 0, sizeof(float) * tot));
   CK(h, cudaMalloc(&h->action_stage, sizeof(float) * N * 7));
+  CK(h, cudaMalloc(&h->O.overflow, sizeof(unsigned long long)));
+  CK(h, cudaMemset(h->O.overflow, 0, sizeof(unsigned long long)));
   float** slots[12] = {&h->O.obs_quat, &h->O.achieved_goal, &h->O.desired_goal, &h->O.cag, &h->O.fps, &h->O.joints,
                        &h->O.velocity, &h->O.observation, &h->O.proprio, &h->O.reward, &h->O.success, &h->O.target_poses};
   int64_t off = 0;
@@ -108,7 +110,7 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
 int prb_destroy(prb_handle* h) {
   if (!h) return PRB_ERR_INVALID;
   cudaSetDevice(h->device);
-  cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage);
+  cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow);
   delete h;
   return PRB_OK;
 }
@@ -233,6 +235,13 @@ int prb_step_host(prb_handle* h, const float* action_host, float* out_host, void
 }
 
 int64_t prb_launch_count(prb_handle* h) { return h ? h->launches : 0; }
+
+int64_t prb_overflow_count(prb_handle* h) {
+  if (!h) return -1;
+  unsigned long long v = 0;
+  if (cudaMemcpy(&v, h->O.overflow, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
+}
 
 int prb_kernel_info(prb_handle* h, int32_t* smem_bytes_per_block, int32_t* envs_per_block, int32_t* regs_per_thread) {
   if (!h) return PRB_ERR_INVALID;

@@ -76,6 +76,7 @@ struct DevModel {
 struct DevOut {
   float *obs_quat, *achieved_goal, *desired_goal, *cag, *fps, *joints, *velocity, *observation;
   float *proprio, *reward, *success, *target_poses;
+  unsigned long long* overflow;   // [1] env-steps in which some contact had to be dropped (capacity)
 };
 
 // ------------------------------------------------------------------ vector algebra

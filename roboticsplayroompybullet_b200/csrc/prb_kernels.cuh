@@ -30,8 +30,9 @@
 #define PRB_MAXCONTACT 32      // contact points per env per substep after manifold reduction (one per lane)
 #define PRB_MAXOVL 32          // overlapping collider pairs handed to the narrow phase (one per lane)
 #define PRB_MAXCAND 128        // narrow-phase candidates (4 per overlapping pair) before reduction
-#define PRB_POOL 1664          // floats of packed contact-row Jacobians (J and M^-1 J^T segments)
-#define PRB_ACAP 4096          // floats of island-blocked, symmetric-packed Delassus matrix J M^-1 J^T
+#define PRB_POOL 1408          // floats of packed contact-row Jacobians (J and M^-1 J^T segments)
+#define PRB_ACAP 5888          // floats of island-blocked Delassus matrix J M^-1 J^T (full R_i x R_i blocks)
+#define PRB_APAD 160           // slack read (and multiplied by 0) by lanes outside the sender's island
 #define FULL 0xffffffffu
 
 struct Contact {
@@ -46,26 +47,32 @@ struct WarpMem {
   float sq[PRB_MAXSLIDE], sqd[PRB_MAXSLIDE];
   float goal[12], lastq[8], last_valid, reset_count;
   // ---- kinematics / dynamics of the current substep
-  float lR[PRB_MAXD][9], lp[PRB_MAXD][3], la[PRB_MAXD][3], lc[PRB_MAXD][3], lIw[PRB_MAXD][6];
-  float lf[PRB_MAXD][3], ln[PRB_MAXD][3], lw[PRB_MAXD][3], lv[PRB_MAXD][3];
+  float lp[PRB_MAXD][3], la[PRB_MAXD][3], lc[PRB_MAXD][3], lw[PRB_MAXD][3], lv[PRB_MAXD][3];
   float fR[PRB_MAXFREE][9], fIinv[PRB_MAXFREE][6];
   float sp[PRB_MAXSLIDE][3], sR[PRB_MAXSLIDE][9];
-  float Mm[PRB_MAXD][PRB_MAXD + 1], Minv[PRB_MAXD][PRB_MAXD + 1], Q[PRB_MAXD];
+  float Minv[PRB_MAXD][PRB_MAXD + 1], Q[PRB_MAXD];
   float vs[32];
   // ---- collision
   unsigned short ovl[PRB_MAXOVL];
   int n_ovl, n_contact, n_jrow, pool_used, overflow;
   Contact ct[PRB_MAXCONTACT];
-  // collider AABBs and narrow-phase candidates are dead once the contacts are reduced into ct[],
-  // before the Delassus matrix is built
+  // Everything in the first member is dead by the time the Delassus matrix is built (link
+  // rotations/inertias/bias wrenches, the Cholesky workspace, collider AABBs, narrow-phase
+  // candidates), so A overlays it.
   union {
-    struct { Contact cand[PRB_MAXCAND]; float aabb[PRB_MAXCOL][6]; };
-    float A[PRB_ACAP];
+    struct {
+      float lR[PRB_MAXD][9], lIw[PRB_MAXD][6], lf[PRB_MAXD][3], ln[PRB_MAXD][3];
+      float Mm[PRB_MAXD][PRB_MAXD + 1];
+      float aabb[PRB_MAXCOL][6];
+      Contact cand[PRB_MAXCAND];
+    };
+    float A[PRB_ACAP + PRB_APAD];
   };
   // ---- constraint rows
   signed char jr_dof[PRB_MAXJROW], jr_dof2[PRB_MAXJROW];
   float jr_sign[PRB_MAXJROW], jr_rhs[PRB_MAXJROW], jr_invD[PRB_MAXJROW], jr_lo[PRB_MAXJROW], jr_hi[PRB_MAXJROW], jr_lam[PRB_MAXJROW];
-  unsigned jr_meta[PRB_MAXJROW];     // tsb (16 bits) | local row id (8) | island (8)
+  unsigned jr_meta[PRB_MAXJROW];     // island block base (16 bits) | local row id (8) | island (8)
+  unsigned char jr_R[PRB_MAXJROW], ct_R[PRB_MAXCONTACT];   // rows in the unit's island block
   // per contact: rows 0 normal, 1 spin, 2 friction-1, 3 friction-2
   float cr_rhs[PRB_MAXCONTACT][4], cr_invD[PRB_MAXCONTACT][4], cr_lam[PRB_MAXCONTACT][4];
   float cr_cfm[PRB_MAXCONTACT], cr_mu[PRB_MAXCONTACT], cr_spin[PRB_MAXCONTACT];
@@ -989,8 +996,9 @@ struct RowRegs {
   float la[PRB_MAXSLOT], lb[PRB_MAXSLOT];        // accumulated impulses
   float rhsa[PRB_MAXSLOT], rhsb[PRB_MAXSLOT], ida[PRB_MAXSLOT], idb[PRB_MAXSLOT];
   float p0[PRB_MAXSLOT], p1[PRB_MAXSLOT];        // joint: lo, hi | normal: cfm | spin: coefficient | pair: mu
-  int isl[PRB_MAXSLOT];                          // island (-1: empty slot)
-  int ra[PRB_MAXSLOT], tra[PRB_MAXSLOT];         // island-local row id of row a, and base + tri(ra); row b = ra + 1
+  int meta[PRB_MAXSLOT];                         // island << 16 | island-local row id of row a (-1: empty slot)
+  int pa[PRB_MAXSLOT];                           // index in A of this unit's row a (row b follows at + R_island)
+  int pbo[PRB_MAXSLOT];                          // R_island for pair units (offset from row a to row b), else 0
   int cidx[PRB_MAXSLOT];                         // contact index of the unit (contact units)
   int nslots;
 };
@@ -1076,57 +1084,72 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
   // ---- local ids per island by one packed scan per island; block bases by running sum.
   //      If the packed blocks do not fit, the last contact is dropped and the layout redone
   //      (flagged in W.overflow; needs > ~89 coupled rows in one island).
-  int locJ[2] = {0, 0}, locC = 0, baseJ[2] = {0, 0}, baseC = 0;
+  int locJ[2] = {0, 0}, locC = 0, baseJ[2] = {0, 0}, baseC = 0, RJ[2] = {1, 1}, RC = 1;
+  int used = 0;
+  bool dead = false;      // contact dropped because its island block does not fit
   for (;;) {
-    int used = 0;
-    const int my_rows = lane < nc ? (spin_on ? 4 : 3) : 0;
+    used = 0;
+    int Lmax = -1, Rmax = 0;
+    const int my_rows = (lane < nc && !dead) ? (spin_on ? 4 : 3) : 0;
     for (int L = 0; L < nb; L++) {
-      int cnt = (my_islJ[0] == L ? 1 : 0) | (my_islJ[1] == L ? 1 << 8 : 0) | ((lane < nc && my_islC == L) ? my_rows << 16 : 0);
+      int cnt = (my_islJ[0] == L ? 1 : 0) | (my_islJ[1] == L ? 1 << 8 : 0) | ((my_rows && my_islC == L) ? my_rows << 16 : 0);
       int tot;
       int pre = warp_excl_scan(cnt, lane, &tot);
       int nJ0 = tot & 0xff, nJ1 = (tot >> 8) & 0xff, nC = tot >> 16;
       int RL = nJ0 + nJ1 + nC;
       if (RL == 0) continue;                        // uniform
-      if (my_islJ[0] == L) { locJ[0] = pre & 0xff; baseJ[0] = used; }
-      if (my_islJ[1] == L) { locJ[1] = nJ0 + ((pre >> 8) & 0xff); baseJ[1] = used; }
-      if (my_islC == L) { locC = nJ0 + nJ1 + (pre >> 16); baseC = used; }
-      used += tri(RL);
+      if (my_islJ[0] == L) { locJ[0] = pre & 0xff; baseJ[0] = used; RJ[0] = RL; }
+      if (my_islJ[1] == L) { locJ[1] = nJ0 + ((pre >> 8) & 0xff); baseJ[1] = used; RJ[1] = RL; }
+      if (my_islC == L) { locC = nJ0 + nJ1 + (pre >> 16); baseC = used; RC = RL; }
+      used += RL * RL;
+      if (RL > Rmax) { Rmax = RL; Lmax = L; }
     }
-    if (used <= PRB_ACAP || nc == 0) break;         // uniform
-    nc--;
-    if (lane == 0) { W.overflow = 1; W.n_contact = nc; }
+    if (used <= PRB_ACAP) break;                    // uniform
+    // drop the last contact of the largest island (flagged) and lay out again
+    unsigned mk = __ballot_sync(FULL, my_rows > 0 && my_islC == Lmax);
+    if (mk == 0u) break;
+    if (lane == 31 - __clz((int)mk)) dead = true;
+    if (lane == 0) W.overflow = 1;
   }
-  if (lane >= nc) my_islC = -1;
-  spin_on = spin_on && lane < nc;
-  // ---- per-row uniform metadata for the sweeps
+  if (lane >= nc || dead) my_islC = -1;
+  spin_on = spin_on && !dead;
+  if (dead) { for (int k = 0; k < 4; k++) { W.cr_rhs[lane][k] = 0.f; W.cr_invD[lane][k] = 0.f; } W.cr_spin[lane] = 0.f; }
+  __syncwarp();
+  // lanes outside a sender's island read up to 2 R + 1 floats past their own row: keep that finite
+  for (int i = used + lane; i < used + PRB_APAD && i < PRB_ACAP + PRB_APAD; i += 32) W.A[i] = 0.f;
+  // ---- per-row metadata: block base (16 bits) | island-local row id (8) | island (8); block size R
   for (int sl = 0; sl < 2; sl++) {
     int j = sl * 32 + lane;
-    if (j < njr) W.jr_meta[j] = (unsigned)(baseJ[sl] + tri(locJ[sl])) | ((unsigned)locJ[sl] << 16) | ((unsigned)my_islJ[sl] << 24);
+    if (j < njr) { W.jr_meta[j] = (unsigned)baseJ[sl] | ((unsigned)locJ[sl] << 16) | ((unsigned)my_islJ[sl] << 24); W.jr_R[j] = (unsigned char)RJ[sl]; }
   }
-  if (lane < nc) W.ct_meta[lane] = (unsigned)baseC | ((unsigned)locC << 16) | ((unsigned)my_islC << 24);
+  if (lane < nc) { W.ct_meta[lane] = (unsigned)baseC | ((unsigned)locC << 16) | ((unsigned)(my_islC & 0xff) << 24); W.ct_R[lane] = (unsigned char)RC; }
   __syncwarp();
-  // ---- fill A (lower triangle incl. diagonal of every island block): the lane owning the
-  //      receiving row computes its entries against every sender row with a smaller-or-equal id
+  // ---- fill A: full R x R block per island, A[base + r * R + s].  The lane owning receiving row r
+  //      computes the entries against every sender row s <= r and mirrors them.
   for (int sl = 0; sl < 2; sl++) {
     int j = sl * 32 + lane;
     if (j >= njr) continue;
-    const int rowbase = baseJ[sl] + tri(locJ[sl]);
+    const int r = locJ[sl], Rn = RJ[sl], base = baseJ[sl];
     for (int j2 = 0; j2 <= j; j2++) {
       unsigned m2 = W.jr_meta[j2];
       if ((int)(m2 >> 24) != my_islJ[sl]) continue;
-      W.A[rowbase + (int)((m2 >> 16) & 0xff)] = jrow_jrow(M, W, j, j2);
+      const int r2 = (int)((m2 >> 16) & 0xff);
+      const float v = jrow_jrow(M, W, j, j2);
+      W.A[base + r * Rn + r2] = v; W.A[base + r2 * Rn + r] = v;
     }
   }
-  if (lane < nc) {
-    const int c = lane;
-    int k_of[4] = {0, 1, 2, 3}, nk = 0;
+  if (lane < nc && !dead) {
+    const int c = lane, Rn = RC, base = baseC;
+    int k_of[4], nk = 0;
     k_of[nk++] = 0; if (spin_on) k_of[nk++] = 1; k_of[nk++] = 2; k_of[nk++] = 3;
     for (int kk = 0; kk < nk; kk++) {
-      const int k = k_of[kk], r = locC + kk, rowbase = baseC + tri(r);
+      const int k = k_of[kk], r = locC + kk;
       for (int j2 = 0; j2 < njr; j2++) {
         unsigned m2 = W.jr_meta[j2];
         if ((int)(m2 >> 24) != my_islC) continue;
-        W.A[rowbase + (int)((m2 >> 16) & 0xff)] = jrow_contact(M, W, j2, c, k);
+        const int r2 = (int)((m2 >> 16) & 0xff);
+        const float v = jrow_contact(M, W, j2, c, k);
+        W.A[base + r * Rn + r2] = v; W.A[base + r2 * Rn + r] = v;
       }
       for (int c2 = 0; c2 <= c; c2++) {
         unsigned m2 = W.ct_meta[c2];
@@ -1138,7 +1161,8 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
           if (k2 == 1 && !sp2) continue;
           const int r2 = loc2 + kk2; kk2++;
           if (r2 > r) break;
-          W.A[rowbase + r2] = contact_dot(M, W, c, k, c2, k2);
+          const float v = contact_dot(M, W, c, k, c2, k2);
+          W.A[base + r * Rn + r2] = v; W.A[base + r2 * Rn + r] = v;
         }
       }
     }
@@ -1155,11 +1179,12 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
     const int g = 32 * k + lane;
     R.ua[k] = 0.f; R.ub[k] = 0.f; R.la[k] = 0.f; R.lb[k] = 0.f;
     R.rhsa[k] = 0.f; R.rhsb[k] = 0.f; R.ida[k] = 0.f; R.idb[k] = 0.f; R.p0[k] = 0.f; R.p1[k] = 0.f;
-    R.isl[k] = -1; R.ra[k] = 0; R.tra[k] = 0; R.cidx[k] = 0;
+    R.meta[k] = 0x7fff0000; R.pa[k] = 0; R.pbo[k] = 0; R.cidx[k] = 0;      // empty slot: island no sender has
     if (g < g_n) {
       const unsigned m = W.jr_meta[g];
+      const int base = (int)(m & 0xffff), loc = (int)((m >> 16) & 0xff), isl = (int)(m >> 24);
       R.rhsa[k] = W.jr_rhs[g]; R.ida[k] = W.jr_invD[g]; R.p0[k] = W.jr_lo[g]; R.p1[k] = W.jr_hi[g];
-      R.isl[k] = (int)(m >> 24); R.ra[k] = (int)((m >> 16) & 0xff); R.tra[k] = (int)(m & 0xffff);
+      R.meta[k] = (isl << 16) | loc; R.pa[k] = base + loc * (int)W.jr_R[g];
     } else if (g < g_end) {
       int c, row;
       if (g < g_s) { c = g - g_n; row = 0; }
@@ -1168,45 +1193,40 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
         c = __ffs((int)mm) - 1; row = 1;
       } else { c = g - g_f; row = 2; }
       const unsigned m = W.ct_meta[c];
-      const int base = (int)(m & 0xffff), loc = (int)((m >> 16) & 0xff);
+      const int base = (int)(m & 0xffff), loc = (int)((m >> 16) & 0xff), isl = (int)(m >> 24), Rn = (int)W.ct_R[c];
       const bool sp = (spinmask >> c) & 1u;
       const int r = loc + (row == 0 ? 0 : (row == 1 ? 1 : (sp ? 2 : 1)));
-      R.isl[k] = (int)(m >> 24); R.ra[k] = r; R.tra[k] = base + tri(r); R.cidx[k] = c;
-      R.rhsa[k] = W.cr_rhs[c][row]; R.ida[k] = W.cr_invD[c][row];
-      if (row == 0) R.p0[k] = W.cr_cfm[c];
-      else if (row == 1) R.p0[k] = W.cr_spin[c];
-      else { R.p0[k] = W.cr_mu[c]; R.rhsb[k] = W.cr_rhs[c][3]; R.idb[k] = W.cr_invD[c][3]; }
+      R.cidx[k] = c;
+      if (isl != 255) {          // 255: contact dropped on overflow -> inert unit (rhs = invD = 0, couples with nothing)
+        R.meta[k] = (isl << 16) | r; R.pa[k] = base + r * Rn;
+        R.rhsa[k] = W.cr_rhs[c][row]; R.ida[k] = W.cr_invD[c][row];
+        if (row == 0) R.p0[k] = W.cr_cfm[c];
+        else if (row == 1) R.p0[k] = W.cr_spin[c];
+        else { R.p0[k] = W.cr_mu[c]; R.rhsb[k] = W.cr_rhs[c][3]; R.idb[k] = W.cr_invD[c][3]; R.pbo[k] = Rn; }
+      }
     }
   }
   __syncwarp();
 }
 
 // ============================================================================ PGS (lane = unit owner)
-// A[row s][row r] inside an island block, symmetric-packed: index = base + tri(max) + min.
-// `tsb` = base + tri(sloc) of the sending row (uniform); tra = base + tri(ra) of the receiving row.
-PRB_D int a_index(int sloc, int tsb, int r, int trr) { return sloc > r ? tsb + r : trr + sloc; }
-
-// Add the effect of impulse changes (d1 on row sloc, d2 on row sloc + 1; d2 = 0 for single rows)
-// to every unit this lane owns in the sender's island.  Branch-free: lanes outside the island
-// read A[0] and multiply by zero, so the loads do not depend on the broadcast values.
-template <bool PAIR>
-PRB_D void pgs_apply(const WarpMem& W, RowRegs& R, int isl, int sloc, int tsb, float d1, float d2) {
-  const int tsb2 = tsb + sloc + 1;          // base + tri(sloc + 1)
+// Each unit keeps the index of its own row(s) of the island block, so the coupling to sender row s
+// is A[pa + s] (A is symmetric).  Lanes whose unit is in another island read a finite in-range
+// value and multiply it by zero; nothing in the loads depends on the broadcast impulse change.
+template <int NS, bool PAIR>
+PRB_D void pgs_apply(const WarpMem& W, RowRegs& R, int smeta, float d1, float d2) {
+  const int sloc = smeta & 0xffff, sisl = smeta >> 16;
 #pragma unroll
-  for (int k = 0; k < PRB_MAXSLOT; k++) {
-    if (k < R.nslots) {                     // uniform
-      const bool on = R.isl[k] == isl;
-      const int ra = R.ra[k], rb = ra + 1, tra = R.tra[k], trb = tra + ra + 1;
-      const float m1 = on ? d1 : 0.f;
-      const int ia = on ? a_index(sloc, tsb, ra, tra) : 0, ib = on ? a_index(sloc, tsb, rb, trb) : 0;
-      R.ua[k] += W.A[ia] * m1;
-      R.ub[k] += W.A[ib] * m1;              // only meaningful for pair units; harmless otherwise
-      if (PAIR) {
-        const float m2 = on ? d2 : 0.f;
-        const int ja = on ? a_index(sloc + 1, tsb2, ra, tra) : 0, jb = on ? a_index(sloc + 1, tsb2, rb, trb) : 0;
-        R.ua[k] += W.A[ja] * m2;
-        R.ub[k] += W.A[jb] * m2;
-      }
+  for (int k = 0; k < NS; k++) {
+    const bool on = (R.meta[k] >> 16) == sisl;
+    const float m1 = on ? d1 : 0.f;
+    const float* row = &W.A[R.pa[k] + sloc];
+    R.ua[k] += row[0] * m1;
+    R.ub[k] += row[R.pbo[k]] * m1;           // pair units: second row; single units: pbo = 0, ub unused
+    if (PAIR) {
+      const float m2 = on ? d2 : 0.f;
+      R.ua[k] += row[1] * m2;
+      R.ub[k] += row[R.pbo[k] + 1] * m2;
     }
   }
 }
@@ -1214,7 +1234,7 @@ PRB_D void pgs_apply(const WarpMem& W, RowRegs& R, int isl, int sloc, int tsb, f
 enum { U_JOINT = 0, U_NORMAL = 1, U_SPIN = 2, U_PAIR = 3 };
 
 // one sweep step: the unit in slot K of lane `src` is solved, its impulse change broadcast
-template <int K, int TYPE>
+template <int NS, int K, int TYPE>
 PRB_D void pgs_step(WarpMem& W, RowRegs& R, int lane, int src) {
   float d1, d2 = 0.f;
   if (TYPE == U_JOINT) {
@@ -1249,22 +1269,35 @@ PRB_D void pgs_step(WarpMem& W, RowRegs& R, int lane, int src) {
     d1 = na - R.la[K]; d2 = nb - R.lb[K];
     if (lane == src) { R.la[K] = na; R.lb[K] = nb; }
   }
-  // owner's row coordinates travel with the impulse change (3 more shuffles, off the critical path)
-  const int isl = __shfl_sync(FULL, R.isl[K], src);
-  const int sloc = __shfl_sync(FULL, R.ra[K], src);
-  const int tsb = __shfl_sync(FULL, R.tra[K], src);
+  const int smeta = __shfl_sync(FULL, R.meta[K], src);       // sender's island and row id
   d1 = __shfl_sync(FULL, d1, src);
-  if (TYPE == U_PAIR) { d2 = __shfl_sync(FULL, d2, src); pgs_apply<true>(W, R, isl, sloc, tsb, d1, d2); }
-  else pgs_apply<false>(W, R, isl, sloc, tsb, d1, 0.f);
+  if (TYPE == U_PAIR) { d2 = __shfl_sync(FULL, d2, src); pgs_apply<NS, true>(W, R, smeta, d1, d2); }
+  else pgs_apply<NS, false>(W, R, smeta, d1, 0.f);
 }
-template <int TYPE>
+template <int NS, int TYPE>
 PRB_D void pgs_unit(WarpMem& W, RowRegs& R, int lane, int g) {
   const int src = g & 31;
-  switch (g >> 5) {                          // uniform
-    case 0: pgs_step<0, TYPE>(W, R, lane, src); break;
-    case 1: pgs_step<1, TYPE>(W, R, lane, src); break;
-    case 2: pgs_step<2, TYPE>(W, R, lane, src); break;
-    default: pgs_step<3, TYPE>(W, R, lane, src); break;
+  if (NS <= 2) {
+    if ((g >> 5) == 0) pgs_step<NS, 0, TYPE>(W, R, lane, src); else pgs_step<NS, 1, TYPE>(W, R, lane, src);
+  } else {
+    switch (g >> 5) {                          // uniform
+      case 0: pgs_step<NS, 0, TYPE>(W, R, lane, src); break;
+      case 1: pgs_step<NS, 1, TYPE>(W, R, lane, src); break;
+      case 2: pgs_step<NS, 2, TYPE>(W, R, lane, src); break;
+      default: pgs_step<NS, 3, TYPE>(W, R, lane, src); break;
+    }
+  }
+}
+template <int NS>
+PRB_D void pgs_sweeps(const DevModel& M, WarpMem& W, RowRegs& R, int lane, int g_n, int g_s, int g_f, int g_end) {
+  for (int it = 0; it < M.solver_iters; it++) {
+    if (it & 1) { for (int g = 0; g < g_n; g++) pgs_unit<NS, U_JOINT>(W, R, lane, g); }
+    else { for (int g = g_n - 1; g >= 0; g--) pgs_unit<NS, U_JOINT>(W, R, lane, g); }
+    for (int g = g_n; g < min(g_s, g_end); g++) pgs_unit<NS, U_NORMAL>(W, R, lane, g);
+    __syncwarp();                                      // normal impulses visible to the friction units
+    for (int g = g_s; g < min(g_f, g_end); g++) pgs_unit<NS, U_SPIN>(W, R, lane, g);
+    for (int g = g_f; g < g_end; g++) pgs_unit<NS, U_PAIR>(W, R, lane, g);
+    __syncwarp();
   }
 }
 
@@ -1277,15 +1310,8 @@ PRB_D float phase_pgs(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm
   const int nspin = __popc(spinmask);
   const int g_n = njr, g_s = njr + nc, g_f = g_s + nspin;
   const int g_end = min(g_f + nc, 32 * PRB_MAXSLOT);
-  for (int it = 0; it < M.solver_iters; it++) {
-    if (it & 1) { for (int g = 0; g < g_n; g++) pgs_unit<U_JOINT>(W, R, lane, g); }
-    else { for (int g = g_n - 1; g >= 0; g--) pgs_unit<U_JOINT>(W, R, lane, g); }
-    for (int g = g_n; g < min(g_s, g_end); g++) pgs_unit<U_NORMAL>(W, R, lane, g);
-    __syncwarp();                                      // normal impulses visible to the friction units
-    for (int g = g_s; g < min(g_f, g_end); g++) pgs_unit<U_SPIN>(W, R, lane, g);
-    for (int g = g_f; g < g_end; g++) pgs_unit<U_PAIR>(W, R, lane, g);
-    __syncwarp();
-  }
+  if (R.nslots <= 2) pgs_sweeps<2>(M, W, R, lane, g_n, g_s, g_f, g_end);
+  else pgs_sweeps<PRB_MAXSLOT>(M, W, R, lane, g_n, g_s, g_f, g_end);
   // ---- publish the impulses and rebuild dv = M^-1 J^T lambda with lane = velocity DoF
   __syncwarp();
   if (lane < nc) { W.cr_lam[lane][1] = 0.f; W.cr_lam[lane][2] = 0.f; W.cr_lam[lane][3] = 0.f; }
@@ -1531,6 +1557,8 @@ __global__ void __launch_bounds__(32 * PRB_WPB) prb_step_kernel(const DevModel* 
   const LaneMap lm = make_lanemap(M, lane);
   for (int s = 0; s < n_substeps; s++) substep<ND>(M, W, lane, lm);
   if (observe) phase_observe(M, W, lane, O, (size_t)e, true);
+  __syncwarp();
+  if (lane == 0 && W.overflow && O.overflow) atomicAdd(O.overflow, 1ull);
   store_state(M, W, st, lane);
 }
 

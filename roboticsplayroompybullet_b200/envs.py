@@ -231,6 +231,9 @@ class VecPlayEnv:
     def launch_count(self):
         return int(self.L.prb_launch_count(self._h))
 
+    def overflow_count(self):
+        return int(self.L.prb_overflow_count(self._h))
+
     def kernel_info(self):
         a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         self.L.prb_kernel_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))

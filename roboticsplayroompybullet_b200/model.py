@@ -109,11 +109,20 @@ class CompiledModel:
 
     def save(self, path):
         np.savez(path, **{k: np.asarray(v) for k, v in self.d.items()})
+        import json
+        meta = {k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in self.meta.items()
+                if isinstance(v, (list, tuple, str, int, float))}
+        json.dump(meta, open(os.path.splitext(path)[0] + '.meta.json', 'w'), indent=1)
 
     @staticmethod
     def load(path):
         z = np.load(path)
-        return CompiledModel({k: z[k] for k in z.files})
+        d = {k: z[k] for k in z.files}
+        mp = os.path.splitext(path)[0] + '.meta.json'
+        if os.path.exists(mp):
+            import json
+            d.update(json.load(open(mp)))
+        return CompiledModel(d)
 
     def as_struct(self):
         """ctypes view; keeps references to the arrays alive on the returned object."""

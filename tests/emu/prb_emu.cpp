@@ -27,15 +27,19 @@ static void run_step(float* state, DevOut O, int N, int nsub, int observe) {
   if (g_M.nd == 12) emu::launch(g, b, [&]() { prb_step_kernel<12>(&g_M, state, O, N, nsub, observe); });
   else emu::launch(g, b, [&]() { prb_step_kernel<9>(&g_M, state, O, N, nsub, observe); });
 }
-void emu_substeps(float* state, int N, int nsub) { DevOut O; memset(&O, 0, sizeof(O)); run_step(state, O, N, nsub, 0); }
+static unsigned long long g_overflow = 0;
+unsigned long long emu_overflow() { return g_overflow; }
+void emu_substeps(float* state, int N, int nsub) { DevOut O; memset(&O, 0, sizeof(O)); O.overflow = &g_overflow; run_step(state, O, N, nsub, 0); }
 void emu_step(float* state, const float* action, DevOut* O, int N) {
+  O->overflow = &g_overflow;
   emu_ik(state, action, O->target_poses, N);
   run_step(state, *O, N, g_M.n_substeps, 1);
 }
-void emu_observe(float* state, DevOut* O, int N) { run_step(state, *O, N, 0, 1); }
+void emu_observe(float* state, DevOut* O, int N) { O->overflow = &g_overflow; run_step(state, *O, N, 0, 1); }
 void emu_reset(float* state, DevOut* O, const unsigned char* mask, int N, unsigned long long seed, unsigned env_offset) {
   emu_dim3 g, b; b.x = 32 * PRB_WPB; g.x = (N + PRB_WPB - 1) / PRB_WPB;
   DevOut o = *O;
+  o.overflow = &g_overflow;
   if (g_M.nd == 12) emu::launch(g, b, [&]() { prb_reset_kernel<12>(&g_M, state, o, mask, N, seed, env_offset); });
   else emu::launch(g, b, [&]() { prb_reset_kernel<9>(&g_M, state, o, mask, N, seed, env_offset); });
 }

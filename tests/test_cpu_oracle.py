@@ -1,0 +1,236 @@
+"""CPU tests of the oracle: pinned against the reference's only recorded PyBullet outputs (the
+notebook fixture), frozen by regression fixtures, and cross-checked by independent numpy physics."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from roboticsplayroompybullet_b200.model import CompiledModel, load_model
+from oracle.oracle import Oracle, box_box, quat_from_euler, euler_from_quat, rng4
+import np_dynamics
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+ENVS = ['UR5Reach-v0', 'pandaPick-v0', 'UR5PlayAbsRPY1Obj-v0']
+
+
+def test_notebook_joint_table():
+    """PyBullet's own getNumJoints / getJointInfo output (notebook cells 1-2) == our DFS indexing."""
+    g = json.load(open(os.path.join(GOLD, 'notebook_ur5.json')))
+    m = load_model('UR5Reach-v0')
+    names = m.meta['urdf_joint_names']
+    assert len(names) == g['n_joints'] == 22
+    assert names == g['joint_names']
+    movable = [int(i) for i in m['arm_urdf_index']]
+    assert movable == [0, 1, 2, 3, 4, 5, 10, 12, 13, 15, 18, 20]
+    # indices hard-coded in the reference (environments.py:368, 722-725, 1053-1073)
+    assert names[7] == 'grasptarget_hand' and names[18].endswith('left_driver_joint') and names[20].endswith('right_driver_joint')
+
+
+def test_notebook_fk_readout():
+    """FK at the notebook's default_joints for link 6 with the base at the origin: PyBullet printed
+    euler (0, pi/2, pi/2) and pos (-0.00506, 0.23994, 0.50000).  The notebook ran an OLDER URDF
+    (preserved in ur5e.urdf.ipynb): shoulder height 0.163 there vs 0.083 in the shipped ur5e2.urdf and
+    different wrist offsets, so only the orientation and z - 0.08 carry over."""
+    g = json.load(open(os.path.join(GOLD, 'notebook_ur5.json')))
+    m = load_model('UR5Reach-v0')
+    d = dict(m.d)
+    d.update(m.meta)
+    d['arm_base_pos'] = np.zeros(3)
+    d['arm_base_rot'] = np.eye(3).reshape(-1)
+    o = Oracle(CompiledModel(d))
+    q = np.zeros(12)
+    q[:6] = g['default_joints']
+    site = o.fk_sites(q)[1]                       # site 1 = link 6 (ee_link)
+    rec = np.array(g['ee_pos_recorded'])
+    assert abs(site[2] - (rec[2] - g['ee_pos_stale_dz'])) < 2e-6
+    # orientation as a rotation (euler angles are degenerate at pitch = pi/2)
+    R1 = _quat_to_mat(site[3:7])
+    R2 = _quat_to_mat(quat_from_euler(g['ee_euler']))
+    assert np.abs(R1 - R2).max() < 1e-4      # PyBullet printed the gimbal-lock branch of getEulerFromQuaternion
+
+
+def _quat_to_mat(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+@pytest.mark.parametrize('env_id', ENVS)
+def test_oracle_regression_fixture(env_id):
+    z = np.load(os.path.join(GOLD, 'oracle_regression.npz'))
+    tag = env_id.replace('-', '_')
+    o = Oracle(load_model(env_id), seed=77, env_id=3)
+    d = o.reset()
+    assert np.allclose(o.state, z[tag + '__reset_state'], atol=1e-9)
+    assert np.allclose(d['desired_goal'], z[tag + '__reset_goal'], atol=1e-9)
+    for a in z[tag + '__actions']:
+        d = o.step(a)
+    assert np.allclose(o.state, z[tag + '__final_state'], atol=1e-7)
+    assert np.allclose(d['obs_quat'], z[tag + '__final_obs_quat'], atol=1e-7)
+    assert np.allclose(d['target_poses'], z[tag + '__final_target_poses'], atol=1e-9)
+
+
+def test_euler_quaternion_conventions():
+    """Bullet Euler = intrinsic ZYX [roll, pitch, yaw]; cross-check with scipy."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        rpy = rng.uniform(-1.4, 1.4, 3)
+        q = quat_from_euler(rpy)
+        qs = Rotation.from_euler('xyz', rpy).as_quat()        # extrinsic xyz == intrinsic ZYX
+        assert np.abs(q - qs).max() < 1e-12 or np.abs(q + qs).max() < 1e-12
+        assert np.abs(euler_from_quat(q) - rpy).max() < 1e-9
+
+
+@pytest.mark.parametrize('env_id', ['UR5Reach-v0', 'pandaPick-v0'])
+def test_aba_against_crba_rnea(env_id):
+    """Oracle forward dynamics (articulated-body algorithm) == independent numpy CRBA + RNEA."""
+    m = load_model(env_id)
+    o = Oracle(m)
+    nd = m['nd']
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        q = m['arm_rest'] + rng.uniform(-0.4, 0.4, nd)
+        lo, hi = m['arm_lo'], m['arm_hi']
+        q = np.where(hi - lo < 1.0, rng.uniform(np.maximum(lo, 0), np.maximum(hi, 0.001), nd), q)
+        qd = rng.uniform(-1, 1, nd)
+        M = np_dynamics.mass_matrix(m, q)
+        assert np.abs(M @ o.minv(q) - np.eye(nd)).max() < 1e-9
+        b = np_dynamics.bias(m, q, qd)
+        assert np.abs(M @ o.qdd(q, qd) + b).max() < 1e-8
+        assert np.linalg.eigvalsh(M).min() > 0
+
+
+def test_fk_jacobian_finite_difference():
+    m = load_model('UR5Reach-v0')
+    o = Oracle(m)
+    q = np.zeros(12)
+    q[:6] = m['arm_rest'][:6]
+    p0 = o.fk_sites(q)[0][:3]
+    eps = 1e-6
+    R, P, A, C = np_dynamics.fk(m, q)
+    for j in range(6):
+        dq = q.copy(); dq[j] += eps
+        num = (o.fk_sites(dq)[0][:3] - p0) / eps
+        ana = np.cross(A[j], p0 - P[j])
+        assert np.abs(num - ana).max() < 1e-5
+
+
+def test_ik_reaches_target_and_is_damped():
+    """The chained 4x20 DLS iterations converge to ~1e-4 m; one 20-iteration call does not (which
+    is why the reference chains them, inverseKinematics.py:10-13,47-50)."""
+    m = load_model('UR5Reach-v0')
+    o = Oracle(m)
+    q0 = np.zeros(12); q0[:6] = m['arm_rest'][:6]
+    tq = quat_from_euler([0, 0, 0])
+    tgt = np.array([0.1, 0.1, 0.2])
+    q4 = o.calc_angles(q0, tgt, tq)
+    q1 = o.ik(q0, tgt, tq, 20)
+    e4 = np.linalg.norm(o.fk_sites(q4)[0][:3] - tgt)
+    e1 = np.linalg.norm(o.fk_sites(q1)[0][:3] - tgt)
+    assert e4 < 3e-4 and e1 > e4
+    assert np.all(q4[6:] == 0)
+
+
+def test_box_box_known_answers():
+    I = np.eye(3).reshape(-1)
+    # unit cube resting 1 mm into a big slab: 4 corner points, normal +z (from slab B to cube A)
+    c = box_box([0, 0, 0.499], I, [0.5, 0.5, 0.5], [0, 0, -0.5], I, [5, 5, 0.5])
+    assert len(c) == 4
+    assert np.allclose(c[:, 3:6], [[0, 0, 1]] * 4) and np.allclose(c[:, 6], 0.001, atol=1e-12)
+    assert np.allclose(sorted(map(tuple, np.round(np.abs(c[:, :2]), 9))), [(0.5, 0.5)] * 4)
+    # separated
+    assert len(box_box([0, 0, 1.01], I, [0.5, 0.5, 0.5], [0, 0, -0.5], I, [5, 5, 0.5])) == 0
+    # edge-edge: cube rotated 45 deg about x and y axes crossing another rotated cube -> one point
+    a = np.pi / 4
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    c = box_box([0, 0, 1.40], Rx.reshape(-1), [0.5, 0.5, 0.5], [0, 0, 0], Ry.reshape(-1), [0.5, 0.5, 0.5])
+    assert len(c) == 1 and abs(c[0, 5]) > 0.99 and 0 < c[0, 6] < 0.02
+
+
+def test_free_fall_and_rest():
+    """Block released above the table: free-fall matches g t^2/2 (with Bullet's linear damping),
+    then it comes to rest on the table top within a millimetre."""
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    o = Oracle(m)
+    nd = 12
+    s = o.state
+    s[5 * nd:5 * nd + 3] = [0.1, 0.2, 0.3]
+    s[5 * nd + 3:5 * nd + 7] = [0, 0, 0, 1]
+    z0 = 0.3
+    o.substeps(30)
+    t = 30 / 300
+    assert abs(s[5 * nd + 2] - (z0 - 0.5 * 9.8 * t * t)) < 2e-3
+    o.substeps(400)
+    assert abs(s[5 * nd + 2] - 0.0) < 1.5e-3                      # table top z=-0.025 + half height 0.025
+    assert np.abs(s[5 * nd + 7:5 * nd + 13]).max() < 1e-2
+
+
+def test_button_hovers_on_its_motor():
+    """scenes.py:238: the 0.1 kg button is held at 0.03 by a 1 N position motor (weight 0.98 N)."""
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    o = Oracle(m)
+    o.substeps(900)
+    off = 5 * 12 + 26
+    assert abs(o.state[off + 2] - 0.03) < 2e-3
+
+
+def test_reward_truth_table():
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    o = Oracle(m)
+    base = np.array([0.1, 0.2, 0.0, 0, 0, 0, 1, 0.05, 0.1, 0.03, 0.2])
+    assert o.compute_reward(base, base)[0] == 0
+    for idx, tol in [(0, 0.05), (1, 0.05), (2, 0.05), (7, 0.025), (8, 0.04), (9, 0.01), (10, 0.3)]:
+        g = base.copy(); g[idx] += tol * 0.98
+        assert o.compute_reward(base, g)[0] == 0, idx
+        g = base.copy(); g[idx] += tol * 1.02
+        assert o.compute_reward(base, g)[0] == -1, idx
+    # orientation clause: 44 deg yaw ok, 46 deg not (playRewardFunc.py:24-31)
+    for deg, want in [(44, 0), (46, -1)]:
+        g = base.copy(); g[3:7] = quat_from_euler([0, 0, np.radians(deg)])
+        assert o.compute_reward(base, g)[0] == want
+    # non-play piecewise reward (environments.py:294-299)
+    o2 = Oracle(load_model('UR5Reach-v0'))
+    assert o2.compute_reward([0, 0, 0], [0.06, 0, 0])[0] == -1
+    assert abs(o2.compute_reward([0, 0, 0], [0.03, 0, 0])[0] + 0.03) < 1e-12
+
+
+@pytest.mark.parametrize('env_id,dims', [('UR5Reach-v0', (7, 3, 4, 6)), ('pandaPick-v0', (13, 3, 7, 12)),
+                                         ('UR5PlayAbsRPY1Obj-v0', (19, 11, 19, 18))])
+def test_layouts(env_id, dims):
+    o = Oracle(load_model(env_id), seed=1)
+    d = o.reset()
+    assert (len(d['obs_quat']), len(d['achieved_goal']), len(d['full_positional_state']), len(d['observation'])) == dims
+    assert len(d['desired_goal']) == dims[1] and len(d['joints']) == 8 and len(d['velocity']) == 6
+    assert d['reward'][0] == -1          # reset loops until the sampled state is NOT already successful
+    assert d['joints'][6] == 0 and d['joints'][7] == 0 if env_id != 'pandaPick-v0' else d['joints'][7] == 0
+
+
+def test_dial_precedence_quirk():
+    """dial_to_0_1_range parses as ((q % 2) * pi) / (2.2 pi)  (scenes.py:342-343)."""
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    o = Oracle(m)
+    o.state[5 * 12 + 26 + 4] = 2.5
+    d = o.calc_state()
+    assert abs(d['achieved_goal'][10] - (2.5 % 2) / 2.2) < 1e-6
+
+
+def test_rng_is_counter_based():
+    a = rng4(1234, 5, 0, 0)
+    assert np.array_equal(a, rng4(1234, 5, 0, 0)) and not np.array_equal(a, rng4(1234, 6, 0, 0))
+    assert (a >= 0).all() and (a < 1).all()
+    assert np.array_equal(a, a.astype(np.float32).astype(np.float64))      # 24-bit: exact in fp32
+
+
+def test_grasp_and_lift_oracle():
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    o = Oracle(m, seed=3)
+    o.reset()
+    blk = o.state[60:63].copy()
+    for z, g, n in [(0.15, -1, 10), (-0.01, -1, 15), (-0.01, 1, 12), (0.2, 1, 15)]:
+        for _ in range(n):
+            d = o.step([blk[0], blk[1], z, 0, 0, 0, g])
+    assert o.state[62] > 0.15 and 0.3 < d['obs_quat'][7] < 0.6
