@@ -112,12 +112,17 @@ int prb_step_host(prb_handle* h, const float* action_host, float* out_host, void
  * durations of the most recent step's IK kernel and fused substep kernel. */
 int prb_enable_kernel_timing(prb_handle* h, int32_t enable);
 int prb_last_kernel_ms(prb_handle* h, float* ik_ms, float* step_ms);
+/* split of step_ms into the small-capacity tier (all envs) and the large tier (envs it handed over) */
+int prb_last_tier_ms(prb_handle* h, float* small_ms, float* large_ms);
 
 /* Number of kernels launched by this handle since creation (bench.py reports it). */
 int64_t prb_launch_count(prb_handle* h);
 /* Env-steps (since creation) in which a contact had to be dropped because the per-env on-chip
  * capacity (contacts, packed Jacobians or one island's Delassus block) was exceeded; synchronous. */
 int64_t prb_overflow_count(prb_handle* h);
+/* Per-env maxima over the last env step of the on-chip resources used: [N,4] int32 =
+ * {Delassus floats, contacts, packed-Jacobian floats, sweep units}; synchronous; for sizing reports. */
+int prb_debug_usage(prb_handle* h, int32_t* host_out);
 /* Static facts of the step kernel for reports: dynamic shared memory per block, warps per block. */
 int prb_kernel_info(prb_handle* h, int32_t* smem_bytes_per_block, int32_t* envs_per_block, int32_t* regs_per_thread);
 

@@ -21,9 +21,13 @@ struct prb_handle {
   int64_t out_floats = 0;
   DevOut O;
   int64_t launches = 0;
-  int smem = 0, regs = 0;
+  int smem = 0, regs = 0;          // small tier (reported)
+  int smem_large = 0, regs_large = 0, smem_reset = 0;
+  int* redo_list = nullptr;        // [2][N] envs handed from the small to the medium / medium to the large tier
+  int* redo_count = nullptr;       // [2]
+  int smem_medium = 0;
   int timing = 0;
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
 };
 
@@ -38,16 +42,48 @@ static std::string g_err;  // errors before a handle exists
     }                                                                            \
   } while (0)
 
+// One env step (or n raw substeps) = small tier over every env, then the large tier over the envs
+// the small tier marked.  Two launches, no host synchronisation in between.
 template <int ND>
 static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
-  dim3 grid((h->N + PRB_WPB - 1) / PRB_WPB), block(32 * PRB_WPB);
-  prb_step_kernel<ND><<<grid, block, h->smem, s>>>(h->dm, h->state, h->O, h->N, nsub, observe);
+  CK(h, cudaMemsetAsync(h->redo_count, 0, 2 * sizeof(int), s));
+  int* l1 = h->redo_list; int* l2 = h->redo_list + h->N;
+  int* c1 = h->redo_count; int* c2 = h->redo_count + 1;
+  dim3 gs((h->N + CfgS::WPB - 1) / CfgS::WPB), bs(32 * CfgS::WPB);
+  prb_step_kernel<ND, CfgS><<<gs, bs, h->smem, s>>>(h->dm, h->state, h->O, nullptr, nullptr, l1, c1, h->N, nsub, observe);
   h->launches++;
   CK(h, cudaGetLastError());
+  if (h->timing) CK(h, cudaEventRecord(h->ev[3], s));
+  if (nsub > 0) {
+    dim3 gm((h->N + CfgM::WPB - 1) / CfgM::WPB), bm(32 * CfgM::WPB);
+    prb_step_kernel<ND, CfgM><<<gm, bm, h->smem_medium, s>>>(h->dm, h->state, h->O, l1, c1, l2, c2, h->N, nsub, observe);
+    dim3 gl((h->N + CfgL::WPB - 1) / CfgL::WPB), bl(32 * CfgL::WPB);
+    prb_step_kernel<ND, CfgL><<<gl, bl, h->smem_large, s>>>(h->dm, h->state, h->O, l2, c2, nullptr, nullptr, h->N, nsub, observe);
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+  }
   return PRB_OK;
 }
 static int run_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
   return h->hm.nd == 12 ? launch_step<12>(h, nsub, observe, s) : launch_step<9>(h, nsub, observe, s);
+}
+
+template <int ND>
+static int setup_kernels(prb_handle* h) {
+  h->smem = CfgS::WPB * (int)sizeof(WarpMemT<CfgS>);
+  h->smem_large = CfgL::WPB * (int)sizeof(WarpMemT<CfgL>);
+  h->smem_reset = (int)sizeof(WarpMemT<CfgL>);
+  h->smem_medium = CfgM::WPB * (int)sizeof(WarpMemT<CfgM>);
+  CK(h, cudaFuncSetAttribute(prb_step_kernel<ND, CfgM>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_medium));
+  CK(h, cudaFuncSetAttribute(prb_step_kernel<ND, CfgS>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+  CK(h, cudaFuncSetAttribute(prb_step_kernel<ND, CfgL>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_large));
+  CK(h, cudaFuncSetAttribute(prb_reset_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_reset));
+  cudaFuncAttributes fa;
+  CK(h, cudaFuncGetAttributes(&fa, prb_step_kernel<ND, CfgS>));
+  h->regs = fa.numRegs;
+  CK(h, cudaFuncGetAttributes(&fa, prb_step_kernel<ND, CfgL>));
+  h->regs_large = fa.numRegs;
+  return PRB_OK;
 }
 
 extern "C" {
@@ -84,22 +120,19 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
   CK(h, cudaMalloc(&h->action_stage, sizeof(float) * N * 7));
   CK(h, cudaMalloc(&h->O.overflow, sizeof(unsigned long long)));
   CK(h, cudaMemset(h->O.overflow, 0, sizeof(unsigned long long)));
+  CK(h, cudaMalloc(&h->O.dbg, sizeof(int) * 4 * N));
+  CK(h, cudaMemset(h->O.dbg, 0, sizeof(int) * 4 * N));
   float** slots[12] = {&h->O.obs_quat, &h->O.achieved_goal, &h->O.desired_goal, &h->O.cag, &h->O.fps, &h->O.joints,
                        &h->O.velocity, &h->O.observation, &h->O.proprio, &h->O.reward, &h->O.success, &h->O.target_poses};
   int64_t off = 0;
   for (int i = 0; i < 12; i++) { *slots[i] = h->out + off; off += N * dims[i]; }
-  h->smem = PRB_WPB * (int)sizeof(WarpMem);
-  cudaFuncAttributes fa;
-  if (M.nd == 12) {
-    CK(h, cudaFuncSetAttribute(prb_step_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
-    CK(h, cudaFuncSetAttribute(prb_reset_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
-    CK(h, cudaFuncGetAttributes(&fa, prb_step_kernel<12>));
-  } else {
-    CK(h, cudaFuncSetAttribute(prb_step_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
-    CK(h, cudaFuncSetAttribute(prb_reset_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
-    CK(h, cudaFuncGetAttributes(&fa, prb_step_kernel<9>));
+  CK(h, cudaMalloc(&h->redo_list, sizeof(int) * 2 * N));
+  CK(h, cudaMalloc(&h->redo_count, 2 * sizeof(int)));
+  CK(h, cudaMemset(h->redo_count, 0, 2 * sizeof(int)));
+  {
+    int rc = M.nd == 12 ? setup_kernels<12>(h) : setup_kernels<9>(h);
+    if (rc != PRB_OK) return rc;
   }
-  h->regs = fa.numRegs;
   prb_init_kernel<<<(h->N + 127) / 128, 128>>>(h->dm, h->state, h->N);
   h->launches++;
   CK(h, cudaGetLastError());
@@ -110,7 +143,7 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
 int prb_destroy(prb_handle* h) {
   if (!h) return PRB_ERR_INVALID;
   cudaSetDevice(h->device);
-  cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow);
+  cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->redo_list); cudaFree(h->redo_count);
   delete h;
   return PRB_OK;
 }
@@ -143,7 +176,7 @@ int prb_step(prb_handle* h, const float* action_dev, void* stream) {
 
 int prb_enable_kernel_timing(prb_handle* h, int32_t enable) {
   if (!h) return PRB_ERR_INVALID;
-  if (enable && !h->ev[0]) for (int i = 0; i < 3; i++) CK(h, cudaEventCreate(&h->ev[i]));
+  if (enable && !h->ev[0]) for (int i = 0; i < 4; i++) CK(h, cudaEventCreate(&h->ev[i]));
   h->timing = enable ? 1 : 0;
   return PRB_OK;
 }
@@ -153,6 +186,14 @@ int prb_last_kernel_ms(prb_handle* h, float* ik_ms, float* step_ms) {
   CK(h, cudaEventSynchronize(h->ev[2]));
   if (ik_ms) CK(h, cudaEventElapsedTime(ik_ms, h->ev[0], h->ev[1]));
   if (step_ms) CK(h, cudaEventElapsedTime(step_ms, h->ev[1], h->ev[2]));
+  return PRB_OK;
+}
+
+int prb_last_tier_ms(prb_handle* h, float* small_ms, float* large_ms) {
+  if (!h || !h->ev[0]) return PRB_ERR_INVALID;
+  CK(h, cudaEventSynchronize(h->ev[2]));
+  if (small_ms) CK(h, cudaEventElapsedTime(small_ms, h->ev[1], h->ev[3]));
+  if (large_ms) CK(h, cudaEventElapsedTime(large_ms, h->ev[3], h->ev[2]));
   return PRB_OK;
 }
 
@@ -169,9 +210,9 @@ int prb_substeps(prb_handle* h, int32_t n, void* stream) {
 int prb_reset(prb_handle* h, const uint8_t* mask_dev, void* stream) {
   if (!h) return PRB_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid((h->N + PRB_WPB - 1) / PRB_WPB), block(32 * PRB_WPB);
-  if (h->hm.nd == 12) prb_reset_kernel<12><<<grid, block, h->smem, s>>>(h->dm, h->state, h->O, mask_dev, h->N, h->seed, h->env_offset);
-  else prb_reset_kernel<9><<<grid, block, h->smem, s>>>(h->dm, h->state, h->O, mask_dev, h->N, h->seed, h->env_offset);
+  dim3 grid(h->N), block(32);
+  if (h->hm.nd == 12) prb_reset_kernel<12><<<grid, block, h->smem_reset, s>>>(h->dm, h->state, h->O, mask_dev, h->N, h->seed, h->env_offset);
+  else prb_reset_kernel<9><<<grid, block, h->smem_reset, s>>>(h->dm, h->state, h->O, mask_dev, h->N, h->seed, h->env_offset);
   h->launches++;
   CK(h, cudaGetLastError());
   return PRB_OK;
@@ -236,6 +277,13 @@ int prb_step_host(prb_handle* h, const float* action_host, float* out_host, void
 
 int64_t prb_launch_count(prb_handle* h) { return h ? h->launches : 0; }
 
+int prb_debug_usage(prb_handle* h, int32_t* host_out /* [N,4] */) {
+  if (!h || !host_out) return PRB_ERR_INVALID;
+  CK(h, cudaDeviceSynchronize());
+  CK(h, cudaMemcpy(host_out, h->O.dbg, sizeof(int) * 4 * h->N, cudaMemcpyDeviceToHost));
+  return PRB_OK;
+}
+
 int64_t prb_overflow_count(prb_handle* h) {
   if (!h) return -1;
   unsigned long long v = 0;
@@ -246,7 +294,7 @@ int64_t prb_overflow_count(prb_handle* h) {
 int prb_kernel_info(prb_handle* h, int32_t* smem_bytes_per_block, int32_t* envs_per_block, int32_t* regs_per_thread) {
   if (!h) return PRB_ERR_INVALID;
   if (smem_bytes_per_block) *smem_bytes_per_block = h->smem;
-  if (envs_per_block) *envs_per_block = PRB_WPB;
+  if (envs_per_block) *envs_per_block = CfgS::WPB;
   if (regs_per_thread) *regs_per_thread = h->regs;
   return PRB_OK;
 }

@@ -7,9 +7,11 @@
 #include <cuda_runtime.h>
 #define PRB_HD __host__ __device__ __forceinline__
 #define PRB_D __device__ __forceinline__
+#define PRB_DN __device__ __noinline__
 #else
 #define PRB_HD inline
 #define PRB_D inline
+#define PRB_DN inline
 #endif
 
 #define PRB_MAXD 12
@@ -76,7 +78,8 @@ struct DevModel {
 struct DevOut {
   float *obs_quat, *achieved_goal, *desired_goal, *cag, *fps, *joints, *velocity, *observation;
   float *proprio, *reward, *success, *target_poses;
-  unsigned long long* overflow;   // [1] env-steps in which some contact had to be dropped (capacity)
+  unsigned long long* overflow;
+  int* dbg;                       // optional [N,4] per-env-step maxima: A floats, contacts, pool floats, units   // [1] env-steps in which some contact had to be dropped (capacity)
 };
 
 // ------------------------------------------------------------------ vector algebra

@@ -25,22 +25,64 @@
 #pragma once
 #include "prb_device.h"
 
-#define PRB_WPB 1              // warps (envs) per thread block
-#define PRB_MAXJROW 40         // limit + motor + gear rows
-#define PRB_MAXCONTACT 32      // contact points per env per substep after manifold reduction (one per lane)
-#define PRB_MAXOVL 32          // overlapping collider pairs handed to the narrow phase (one per lane)
-#define PRB_MAXCAND 128        // narrow-phase candidates (4 per overlapping pair) before reduction
-#define PRB_POOL 1408          // floats of packed contact-row Jacobians (J and M^-1 J^T segments)
-#define PRB_ACAP 5888          // floats of island-blocked Delassus matrix J M^-1 J^T (full R_i x R_i blocks)
-#define PRB_APAD 160           // slack read (and multiplied by 0) by lanes outside the sender's island
 #define FULL 0xffffffffu
+
+// Per-env on-chip capacities.  Two tiers of the same kernels:
+//   CfgS  "small": sized for the common case (arm free or lightly touching, block and drawer at
+//         rest): ~13 KB of shared memory per env -> 16 resident warps per SM.  If an env needs
+//         more in any substep, the env step is ABANDONED (nothing written back) and the env is
+//         marked for the large tier.
+//   CfgM  "medium": ~27 KB per env (8 resident warps per SM), takes what the small tier hands over.
+//   CfgL  "large": worst-case capacities (~44 KB per env), runs only what the medium tier hands
+//         over; if even these overflow, contacts are dropped (counted in DevOut::overflow).
+struct CfgL {
+  static constexpr int MAXJROW = 40;       // limit + motor + gear rows
+  static constexpr int MAXCONTACT = 32;    // contact points per substep after manifold reduction (one per lane)
+  static constexpr int MAXOVL = 32;        // overlapping collider pairs handed to the narrow phase (one per lane)
+  static constexpr int MAXCAND = 128;      // narrow-phase candidates (4 per overlapping pair) before reduction
+  static constexpr int POOL = 3072;        // floats of packed contact-row Jacobians (J and M^-1 J^T segments)
+  static constexpr int ACAP = 5888;        // floats of island-blocked Delassus matrix J M^-1 J^T (full R_i x R_i blocks)
+  static constexpr int APAD = 160;         // slack read (and multiplied by 0) by lanes outside the sender's island
+  static constexpr int MAXSLOT = 4;        // sweep units per lane
+  static constexpr bool ABORT = false;
+  static constexpr int WPB = 5;            // warps (envs) per thread block; the block's warps are re-aligned every substep
+  static constexpr int MINBLOCKS = 1;      // resident blocks per SM the register allocation targets
+};
+struct CfgM {
+  static constexpr int MAXJROW = 40;
+  static constexpr int MAXCONTACT = 24;
+  static constexpr int MAXOVL = 32;
+  static constexpr int MAXCAND = 96;
+  static constexpr int POOL = 1792;
+  static constexpr int ACAP = 3072;
+  static constexpr int APAD = 160;
+  static constexpr int MAXSLOT = 3;
+  static constexpr bool ABORT = true;
+  static constexpr int WPB = 4;
+  static constexpr int MINBLOCKS = 2;
+};
+struct CfgS {
+  static constexpr int MAXJROW = 32;
+  static constexpr int MAXCONTACT = 16;
+  static constexpr int MAXOVL = 32;
+  static constexpr int MAXCAND = 64;
+  static constexpr int POOL = 768;
+  static constexpr int ACAP = 1536;
+  static constexpr int APAD = 160;
+  static constexpr int MAXSLOT = 2;
+  static constexpr bool ABORT = true;
+  static constexpr int WPB = 7;
+  static constexpr int MINBLOCKS = 2;
+};
 
 struct Contact {
   float pbx, pby, pbz, nx, ny, nz, dist;
   int cols;   // ca | cb << 8
 };
 
-struct WarpMem {
+template <class CFG>
+struct WarpMemT {
+  typedef CFG Cfg;
   // ---- simulation state of this env (loaded once per launch, written back at the end)
   float q[PRB_MAXD], qd[PRB_MAXD], mtarget[PRB_MAXD], mkp[PRB_MAXD], mmaximp[PRB_MAXD];
   float fpos[PRB_MAXFREE][3], fquat[PRB_MAXFREE][4], fvel[PRB_MAXFREE][3], fang[PRB_MAXFREE][3];
@@ -53,9 +95,10 @@ struct WarpMem {
   float Minv[PRB_MAXD][PRB_MAXD + 1], Q[PRB_MAXD];
   float vs[32];
   // ---- collision
-  unsigned short ovl[PRB_MAXOVL];
+  unsigned short ovl[CFG::MAXOVL];
   int n_ovl, n_contact, n_jrow, pool_used, overflow;
-  Contact ct[PRB_MAXCONTACT];
+  int dbg_a, dbg_c, dbg_p, dbg_u;
+  Contact ct[CFG::MAXCONTACT];
   // Everything in the first member is dead by the time the Delassus matrix is built (link
   // rotations/inertias/bias wrenches, the Cholesky workspace, collider AABBs, narrow-phase
   // candidates), so A overlays it.
@@ -64,22 +107,23 @@ struct WarpMem {
       float lR[PRB_MAXD][9], lIw[PRB_MAXD][6], lf[PRB_MAXD][3], ln[PRB_MAXD][3];
       float Mm[PRB_MAXD][PRB_MAXD + 1];
       float aabb[PRB_MAXCOL][6];
-      Contact cand[PRB_MAXCAND];
+      Contact cand[CFG::MAXCAND];
     };
-    float A[PRB_ACAP + PRB_APAD];
+    float A[CFG::ACAP + CFG::APAD];
   };
   // ---- constraint rows
-  signed char jr_dof[PRB_MAXJROW], jr_dof2[PRB_MAXJROW];
-  float jr_sign[PRB_MAXJROW], jr_rhs[PRB_MAXJROW], jr_invD[PRB_MAXJROW], jr_lo[PRB_MAXJROW], jr_hi[PRB_MAXJROW], jr_lam[PRB_MAXJROW];
-  unsigned jr_meta[PRB_MAXJROW];     // island block base (16 bits) | local row id (8) | island (8)
-  unsigned char jr_R[PRB_MAXJROW], ct_R[PRB_MAXCONTACT];   // rows in the unit's island block
+  signed char jr_dof[CFG::MAXJROW], jr_dof2[CFG::MAXJROW];
+  float jr_sign[CFG::MAXJROW], jr_rhs[CFG::MAXJROW], jr_invD[CFG::MAXJROW], jr_lo[CFG::MAXJROW], jr_hi[CFG::MAXJROW], jr_lam[CFG::MAXJROW];
+  unsigned jr_meta[CFG::MAXJROW];     // island block base (16 bits) | local row id (8) | island (8)
+  unsigned char jr_R[CFG::MAXJROW], ct_R[CFG::MAXCONTACT];   // rows in the unit's island block
+  int unit_meta[32 * CFG::MAXSLOT + 2];         // per sweep unit g (at index g + 1): island << 16 | island-local row id
   // per contact: rows 0 normal, 1 spin, 2 friction-1, 3 friction-2
-  float cr_rhs[PRB_MAXCONTACT][4], cr_invD[PRB_MAXCONTACT][4], cr_lam[PRB_MAXCONTACT][4];
-  float cr_cfm[PRB_MAXCONTACT], cr_mu[PRB_MAXCONTACT], cr_spin[PRB_MAXCONTACT];
-  signed char cr_bodyA[PRB_MAXCONTACT], cr_bodyB[PRB_MAXCONTACT];
-  unsigned short cr_offA[PRB_MAXCONTACT], cr_offB[PRB_MAXCONTACT];
-  unsigned ct_meta[PRB_MAXCONTACT];  // address base of the island block (16) | local id of the normal row (8) | island (8)
-  float pool[PRB_POOL];
+  float cr_rhs[CFG::MAXCONTACT][4], cr_invD[CFG::MAXCONTACT][4], cr_lam[CFG::MAXCONTACT][4];
+  float cr_cfm[CFG::MAXCONTACT], cr_mu[CFG::MAXCONTACT], cr_spin[CFG::MAXCONTACT];
+  signed char cr_bodyA[CFG::MAXCONTACT], cr_bodyB[CFG::MAXCONTACT];
+  unsigned short cr_offA[CFG::MAXCONTACT], cr_offB[CFG::MAXCONTACT];
+  unsigned ct_meta[CFG::MAXCONTACT];  // address base of the island block (16) | local id of the normal row (8) | island (8)
+  float pool[CFG::POOL];
 };
 
 PRB_D float warp_sum(float v) {
@@ -276,7 +320,8 @@ __global__ void __launch_bounds__(128) prb_ik_kernel(const DevModel* __restrict_
 }
 
 // ============================================================================ state <-> shared memory
-PRB_D void load_state(const DevModel& M, WarpMem& W, const float* st, int lane) {
+template <class WM>
+PRB_D void load_state(const DevModel& M, WM& W, const float* st, int lane) {
   const int nd = M.nd;
   for (int i = lane; i < M.state_dim; i += 32) {
     float v = st[i];
@@ -300,7 +345,8 @@ PRB_D void load_state(const DevModel& M, WarpMem& W, const float* st, int lane) 
   }
   __syncwarp();
 }
-PRB_D void store_state(const DevModel& M, const WarpMem& W, float* st, int lane) {
+template <class WM>
+PRB_D void store_state(const DevModel& M, const WM& W, float* st, int lane) {
   const int nd = M.nd;
   __syncwarp();
   for (int i = lane; i < M.state_dim; i += 32) {
@@ -326,13 +372,15 @@ PRB_D void store_state(const DevModel& M, const WarpMem& W, float* st, int lane)
 // Each lane walks its own root->link path, accumulating the frame, the velocity and the
 // velocity-product acceleration (recursive Newton-Euler forward pass with qdd = 0 and gravity
 // folded in as base acceleration); no inter-lane communication.
-PRB_D void phase_fk(const DevModel& M, WarpMem& W, int lane, bool dynamics) {
+template <class WM>
+PRB_D void phase_fk(const DevModel& M, WM& W, int lane, bool dynamics) {
   if (lane < M.nd) {
     m3 R = ldm(M.base_rot);
     v3 p = ld3(M.base_pos);
     v3 w = V3(0, 0, 0), v = V3(0, 0, 0), al = V3(0, 0, 0), ac = V3(0, 0, -M.params[P_GRAVITY_Z]);
     v3 aw = V3(0, 0, 0);
     const int depth = M.depth[lane];
+#pragma unroll 1
     for (int k = 0; k < depth; k++) {
       const int j = M.path[lane][k];
       const float qj = W.q[j], qdj = W.qd[j];
@@ -390,7 +438,8 @@ PRB_D void phase_fk(const DevModel& M, WarpMem& W, int lane, bool dynamics) {
 }
 
 // bias forces tau_j and mass-matrix row j (lane = joint j), by direct sums over subtree(j)
-PRB_D void phase_crba(const DevModel& M, WarpMem& W, int lane) {
+template <class WM>
+PRB_D void phase_crba(const DevModel& M, WM& W, int lane) {
   const int nd = M.nd;
   if (lane < nd) {
     const int j = lane;
@@ -399,6 +448,7 @@ PRB_D void phase_crba(const DevModel& M, WarpMem& W, int lane) {
     float tau = 0;
     v3 P = V3(0, 0, 0), L = V3(0, 0, 0);
     unsigned mask = M.sub_mask[j];
+#pragma unroll 1
     for (int i = j; i < nd; i++) {
       if (!((mask >> i) & 1u)) continue;
       v3 ci = ld3(W.lc[i]), fi = ld3(W.lf[i]), ni = ld3(W.ln[i]);
@@ -413,6 +463,7 @@ PRB_D void phase_crba(const DevModel& M, WarpMem& W, int lane) {
     }
     W.Q[j] = -tau - M.jdamp[j] * W.qd[j];
     unsigned anc = M.anc_mask[j];
+#pragma unroll 1
     for (int k = 0; k <= j; k++) {
       float val = 0.f;
       if ((anc >> k) & 1u) {
@@ -427,8 +478,8 @@ PRB_D void phase_crba(const DevModel& M, WarpMem& W, int lane) {
 }
 
 // Cholesky M = L L^T in place (lane = row), then lane c solves for column c of M^-1
-template <int ND>
-PRB_D void phase_minv(WarpMem& W, int lane) {
+template <int ND, class WM>
+PRB_D void phase_minv(WM& W, int lane) {
   for (int k = 0; k < ND; k++) {
     float d = sqrtf(W.Mm[k][k]);
     __syncwarp();
@@ -464,7 +515,8 @@ PRB_D void phase_minv(WarpMem& W, int lane) {
 }
 
 // unconstrained velocity update v* = v + dt * a  (lane = velocity DoF); result in W.vs and returned
-PRB_D float phase_vstar(const DevModel& M, WarpMem& W, int lane) {
+template <class WM>
+PRB_D float phase_vstar(const DevModel& M, WM& W, int lane) {
   const float dt = M.params[P_DT], g = M.params[P_GRAVITY_Z], vmax = M.params[P_MAX_COORD_VEL];
   const int nd = M.nd;
   // free bodies: one lane per body does the coupled 3-vector algebra
@@ -505,7 +557,8 @@ PRB_D float phase_vstar(const DevModel& M, WarpMem& W, int lane) {
 }
 
 // ============================================================================ collision
-PRB_D void body_frame(const DevModel& M, const WarpMem& W, int body, int link, m3& R, v3& p) {
+template <class WM>
+PRB_D void body_frame(const DevModel& M, const WM& W, int body, int link, m3& R, v3& p) {
   if (body < 0) { R = ident3(); p = V3(0, 0, 0); }
   else if (body == 0) {
     if (link < 0) { R = ldm(M.base_rot); p = ld3(M.base_pos); }
@@ -513,7 +566,8 @@ PRB_D void body_frame(const DevModel& M, const WarpMem& W, int body, int link, m
   } else if (body <= M.n_free) { R = ldm(W.fR[body - 1]); p = ld3(W.fpos[body - 1]); }
   else { R = ldm(W.sR[body - 1 - M.n_free]); p = ld3(W.sp[body - 1 - M.n_free]); }
 }
-PRB_D void collider_frame(const DevModel& M, const WarpMem& W, int c, m3& R, v3& p) {
+template <class WM>
+PRB_D void collider_frame(const DevModel& M, const WM& W, int c, m3& R, v3& p) {
   m3 Rb; v3 pb;
   body_frame(M, W, M.col_body[c], M.col_link[c], Rb, pb);
   R = mul(Rb, ldm(M.col_rot[c]));
@@ -523,7 +577,7 @@ PRB_D void collider_frame(const DevModel& M, const WarpMem& W, int c, m3& R, v3&
 struct CPoint { v3 pos, n; float depth; };
 
 // clip the quad p (4 2-D points) against the rectangle +-h; returns the number of points in ret
-PRB_D int clip_quad(const float h[2], const float p_in[8], float ret[16]) {
+PRB_DN int clip_quad(const float h[2], const float p_in[8], float ret[16]) {
   int nq = 4, nr = 0;
   float buffer[16];
   const float* q = p_in;
@@ -558,7 +612,7 @@ done:
   if (q != ret) for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
   return nr;
 }
-PRB_D void cull_points(int n, const float p[], int m, int i0, int iret[]) {
+PRB_DN void cull_points(int n, const float p[], int m, int i0, int iret[]) {
   float a, cx, cy, q;
   if (n == 1) { cx = p[0]; cy = p[1]; }
   else if (n == 2) { cx = 0.5f * (p[0] + p[2]); cy = 0.5f * (p[1] + p[3]); }
@@ -588,7 +642,7 @@ PRB_D void cull_points(int n, const float p[], int m, int i0, int iret[]) {
 }
 // box-box: separating-axis search + face clipping / edge-edge closest points; normal from box 2
 // (B) to box 1 (A), points on B, depth >= 0; at most 4 points.
-PRB_D int box_box(v3 p1, const m3& R1, v3 h1, v3 p2, const m3& R2, v3 h2, CPoint* out) {
+PRB_DN int box_box(v3 p1, const m3& R1, v3 h1, v3 p2, const m3& R2, v3 h2, CPoint* out) {
   const float fudge = 1.05f, EPS = 1.1920929e-7f;
   float A[3] = {h1.x, h1.y, h1.z}, B[3] = {h2.x, h2.y, h2.z};
   v3 p = p2 - p1, ppv3 = tmul(R1, p);
@@ -693,7 +747,9 @@ PRB_D int box_box(v3 p1, const m3& R1, v3 h1, v3 p2, const m3& R2, v3 h2, CPoint
 
 // collider AABBs -> broad phase over the static pair list -> narrow phase (lane = pair) ->
 // contacts compacted in pair order (deterministic: the PGS sweep order depends on it)
-PRB_D void phase_collide(const DevModel& M, WarpMem& W, int lane) {
+template <class WM>
+PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
+#pragma unroll 1
   for (int c = lane; c < M.n_col; c += 32) {
     m3 R; v3 p;
     collider_frame(M, W, c, R, p);
@@ -705,6 +761,7 @@ PRB_D void phase_collide(const DevModel& M, WarpMem& W, int lane) {
   }
   __syncwarp();
   int n_ovl = 0;
+#pragma unroll 1
   for (int base = 0; base < M.n_pair; base += 32) {
     int k = base + lane;
     bool hit = false;
@@ -716,11 +773,11 @@ PRB_D void phase_collide(const DevModel& M, WarpMem& W, int lane) {
     unsigned bal = __ballot_sync(FULL, hit);
     if (hit) {
       int slot = n_ovl + __popc(bal & ((1u << lane) - 1u));
-      if (slot < PRB_MAXOVL) W.ovl[slot] = (unsigned short)k; else W.overflow = 1;
+      if (slot < WM::Cfg::MAXOVL) W.ovl[slot] = (unsigned short)k; else W.overflow = 1;
     }
     n_ovl += __popc(bal);
   }
-  if (n_ovl > PRB_MAXOVL) n_ovl = PRB_MAXOVL;
+  if (n_ovl > WM::Cfg::MAXOVL) n_ovl = WM::Cfg::MAXOVL;
   __syncwarp();
   // narrow phase: one overlapping pair per lane
   CPoint cp[4];
@@ -736,7 +793,7 @@ PRB_D void phase_collide(const DevModel& M, WarpMem& W, int lane) {
   int total;
   int off = warp_excl_scan(n, lane, &total);
   for (int i = 0; i < n; i++) {
-    Contact& c = W.cand[off + i];     // off + i < 4 * PRB_MAXOVL = PRB_MAXCAND
+    Contact& c = W.cand[off + i];     // off + i < 4 * WM::Cfg::MAXOVL = WM::Cfg::MAXCAND
     c.pbx = cp[i].pos.x; c.pby = cp[i].pos.y; c.pbz = cp[i].pos.z;
     c.nx = cp[i].n.x; c.ny = cp[i].n.y; c.nz = cp[i].n.z; c.dist = -cp[i].depth; c.cols = ca | (cb << 8);
   }
@@ -778,10 +835,10 @@ PRB_D void phase_collide(const DevModel& M, WarpMem& W, int lane) {
   }
   int total2;
   int off2 = warp_excl_scan(m, lane, &total2);
-  for (int i = 0; i < m; i++) if (off2 + i < PRB_MAXCONTACT) W.ct[off2 + i] = W.cand[keep[i]];
+  for (int i = 0; i < m; i++) if (off2 + i < WM::Cfg::MAXCONTACT) W.ct[off2 + i] = W.cand[keep[i]];
   if (lane == 0) {
-    W.n_contact = total2 < PRB_MAXCONTACT ? total2 : PRB_MAXCONTACT;
-    if (total2 > PRB_MAXCONTACT) W.overflow = 1;
+    W.n_contact = total2 < WM::Cfg::MAXCONTACT ? total2 : WM::Cfg::MAXCONTACT;
+    if (total2 > WM::Cfg::MAXCONTACT) W.overflow = 1;
   }
   __syncwarp();
 }
@@ -789,7 +846,8 @@ PRB_D void phase_collide(const DevModel& M, WarpMem& W, int lane) {
 // ============================================================================ constraint rows
 // Jacobian of a unit force `dir` at world point pt (or unit torque when angular) on the body of
 // collider `col`, written as (J, B = M^-1 J^T) segment; returns J.B and accumulates J.v*
-PRB_D float fill_segment(const DevModel& M, const WarpMem& W, int col, v3 pt, v3 dir, float sign, bool angular,
+template <class WM>
+PRB_DN float fill_segment(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, float sign, bool angular,
                          float* seg, float* rel) {
   const int body = M.col_body[col];
   float d = 0.f;
@@ -850,7 +908,8 @@ PRB_D void plane_space(v3 n, v3& p, v3& q) {
   }
 }
 
-PRB_D void phase_rows(const DevModel& M, WarpMem& W, int lane) {
+template <class WM>
+PRB_D void phase_rows(const DevModel& M, WM& W, int lane) {
   const float dt = M.params[P_DT], erp = M.params[P_ERP_JOINT], erp2 = M.params[P_ERP_CONTACT];
   const int nd = M.nd;
   // ---- joint rows, built serially by lane 0 (<= 40 rows of a few flops each): limits, motors, gear
@@ -865,6 +924,7 @@ PRB_D void phase_rows(const DevModel& M, WarpMem& W, int lane) {
         float invD = 1.0f / W.Minv[i][i];
         float rel = sg * W.vs[i];
         float e = pen > -0.04f ? erp : erp2;
+        if (nr >= WM::Cfg::MAXJROW) { W.overflow = 1; break; }
         W.jr_dof[nr] = (signed char)i; W.jr_dof2[nr] = -1; W.jr_sign[nr] = sg;
         W.jr_rhs[nr] = (-pen * e / dt - rel) * invD; W.jr_invD[nr] = invD;
         W.jr_lo[nr] = 0.f; W.jr_hi[nr] = M.params[P_LIMIT_MAX_IMPULSE]; W.jr_lam[nr] = 0.f;
@@ -876,6 +936,7 @@ PRB_D void phase_rows(const DevModel& M, WarpMem& W, int lane) {
       float invD = 1.0f / W.Minv[i][i];
       float v = W.vs[i];
       float target_v = W.mkp[i] * (W.mtarget[i] - W.q[i]) / dt + v + M.params[P_MOTOR_KD] * (0.f - v);
+      if (nr >= WM::Cfg::MAXJROW) { W.overflow = 1; break; }
       W.jr_dof[nr] = (signed char)i; W.jr_dof2[nr] = -1; W.jr_sign[nr] = 1.0f;
       W.jr_rhs[nr] = (target_v - v) * invD; W.jr_invD[nr] = invD;
       W.jr_lo[nr] = -W.mmaximp[i]; W.jr_hi[nr] = W.mmaximp[i]; W.jr_lam[nr] = 0.f;
@@ -888,12 +949,13 @@ PRB_D void phase_rows(const DevModel& M, WarpMem& W, int lane) {
       float invD = 1.0f / M.slide_minv[s];
       float v = W.vs[o];
       float target_v = M.slide_motor[s][1] * (M.slide_motor[s][0] - W.sq[s]) / dt + v + M.slide_motor[s][2] * (0.f - v);
+      if (nr >= WM::Cfg::MAXJROW) { W.overflow = 1; break; }
       W.jr_dof[nr] = (signed char)o; W.jr_dof2[nr] = -1; W.jr_sign[nr] = 1.0f;
       W.jr_rhs[nr] = (target_v - v) * invD; W.jr_invD[nr] = invD;
       W.jr_lo[nr] = -maximp; W.jr_hi[nr] = maximp; W.jr_lam[nr] = 0.f;
       nr++;
     }
-    if (M.gear_a >= 0) {
+    if (M.gear_a >= 0 && nr < WM::Cfg::MAXJROW) {
       int a = M.gear_a, b = M.gear_b;
       float r = M.params[P_GEAR_RATIO];
       float D = W.Minv[a][a] + 2.f * r * W.Minv[a][b] + r * r * W.Minv[b][b];
@@ -919,7 +981,8 @@ PRB_D void phase_rows(const DevModel& M, WarpMem& W, int lane) {
   int total;
   int off = warp_excl_scan(need, lane, &total);
   // contacts that do not fit in the pool are dropped (deepest-first ordering is not attempted)
-  bool fits = (lane < nc) && (off + need <= PRB_POOL);
+  if (lane == 0 && total > W.dbg_p) W.dbg_p = total;
+  bool fits = (lane < nc) && (off + need <= WM::Cfg::POOL);
   unsigned fitmask = __ballot_sync(FULL, fits);
   int nfit = __popc(fitmask & ((nc >= 32) ? FULL : ((1u << nc) - 1u)));
   // since sizes are scanned in order, the fitting contacts are a prefix
@@ -947,6 +1010,7 @@ PRB_D void phase_rows(const DevModel& M, WarpMem& W, int lane) {
     float mu = clampf(M.col_fric[ca] * M.col_fric[cb], -10.f, 10.f);
     v3 t1, t2;
     plane_space(n, t1, t2);
+#pragma unroll 1
     for (int k = 0; k < 4; k++) {
       v3 dir = k == 0 ? n : (k == 1 ? n : (k == 2 ? t1 : t2));
       bool ang = (k == 1);
@@ -989,24 +1053,26 @@ struct LaneMap { int body, li, n; float self_minv; };
 
 // Constraint "units" in sweep order: joint rows, contact normals, spinning-friction rows, lateral
 // friction PAIRS (two rows solved together by the implicit cone).  Unit g is owned by lane g & 31
-// in slot g >> 5, so a lane holds at most PRB_MAXSLOT units and every sweep step has a uniform slot.
-#define PRB_MAXSLOT 4
-struct RowRegs {
-  float ua[PRB_MAXSLOT], ub[PRB_MAXSLOT];        // J M^-1 J^T lambda of the unit's row(s)
-  float la[PRB_MAXSLOT], lb[PRB_MAXSLOT];        // accumulated impulses
-  float rhsa[PRB_MAXSLOT], rhsb[PRB_MAXSLOT], ida[PRB_MAXSLOT], idb[PRB_MAXSLOT];
-  float p0[PRB_MAXSLOT], p1[PRB_MAXSLOT];        // joint: lo, hi | normal: cfm | spin: coefficient | pair: mu
-  int meta[PRB_MAXSLOT];                         // island << 16 | island-local row id of row a (-1: empty slot)
-  int pa[PRB_MAXSLOT];                           // index in A of this unit's row a (row b follows at + R_island)
-  int pbo[PRB_MAXSLOT];                          // R_island for pair units (offset from row a to row b), else 0
-  int cidx[PRB_MAXSLOT];                         // contact index of the unit (contact units)
+// in slot g >> 5, so a lane holds at most RR::MS units and every sweep step has a uniform slot.
+template <int MAXSLOT_>
+struct RowRegsT {
+  static constexpr int MS = MAXSLOT_;
+  float ua[MAXSLOT_], ub[MAXSLOT_];        // J M^-1 J^T lambda of the unit's row(s)
+  float la[MAXSLOT_], lb[MAXSLOT_];        // accumulated impulses
+  float rhsa[MAXSLOT_], rhsb[MAXSLOT_], ida[MAXSLOT_], idb[MAXSLOT_];
+  float p0[MAXSLOT_], p1[MAXSLOT_];        // joint: lo, hi | normal: cfm | spin: coefficient | pair: mu
+  int meta[MAXSLOT_];                         // island << 16 | island-local row id of row a (-1: empty slot)
+  int pa[MAXSLOT_];                           // index in A of this unit's row a (row b follows at + R_island)
+  int pbo[MAXSLOT_];                          // R_island for pair units (offset from row a to row b), else 0
+  int cidx[MAXSLOT_];                         // contact index of the unit (contact units)
   int nslots;
 };
 
 PRB_D int tri(int r) { return (r * (r + 1)) >> 1; }
 
 // B = M^-1 J^T of contact row (c,k) at velocity DoF `dof`
-PRB_D float contact_B_at(const DevModel& M, const WarpMem& W, int c, int k, int dof) {
+template <class WM>
+PRB_DN float contact_B_at(const DevModel& M, const WM& W, int c, int k, int dof) {
   int li, n;
   int body = dof_body(M, dof, &li, &n);
   int base = -1;
@@ -1016,14 +1082,17 @@ PRB_D float contact_B_at(const DevModel& M, const WarpMem& W, int c, int k, int 
   return W.pool[base + k * 2 * n + n + li];
 }
 // J_(c,k) . B_(c2,k2) over the bodies the two contacts share
-PRB_D float contact_dot(const DevModel& M, const WarpMem& W, int c, int k, int c2, int k2) {
+template <class WM>
+PRB_DN float contact_dot(const DevModel& M, const WM& W, int c, int k, int c2, int k2) {
   float s = 0.f;
   const int bA = W.cr_bodyA[c], bB = W.cr_bodyB[c], b2A = W.cr_bodyA[c2], b2B = W.cr_bodyB[c2];
+#pragma unroll 1
   for (int x = 0; x < 2; x++) {
     const int bx = x == 0 ? bA : bB;
     if (bx < 0) continue;
     const int n = body_size(M, bx);
     const float* J = &W.pool[(x == 0 ? W.cr_offA[c] : W.cr_offB[c]) + k * 2 * n];
+#pragma unroll 1
     for (int y = 0; y < 2; y++) {
       const int by = y == 0 ? b2A : b2B;
       if (by != bx) continue;
@@ -1034,12 +1103,14 @@ PRB_D float contact_dot(const DevModel& M, const WarpMem& W, int c, int k, int c
   return s;
 }
 // inverse-mass coupling between two joint-row DoFs
-PRB_D float dof_minv(const DevModel& M, const WarpMem& W, int d, int d2) {
+template <class WM>
+PRB_D float dof_minv(const DevModel& M, const WM& W, int d, int d2) {
   if (d < M.nd && d2 < M.nd) return W.Minv[d][d2];
   if (d == d2) { int s = d - M.nd - 6 * M.n_free; return (s >= 0 && s < M.n_slide) ? M.slide_minv[s] : 0.f; }
   return 0.f;
 }
-PRB_D float jrow_jrow(const DevModel& M, const WarpMem& W, int j, int j2) {
+template <class WM>
+PRB_D float jrow_jrow(const DevModel& M, const WM& W, int j, int j2) {
   const float r = M.params[P_GEAR_RATIO];
   int a = W.jr_dof[j], a2 = W.jr_dof2[j], b = W.jr_dof[j2], b2 = W.jr_dof2[j2];
   float v = dof_minv(M, W, a, b);
@@ -1047,14 +1118,16 @@ PRB_D float jrow_jrow(const DevModel& M, const WarpMem& W, int j, int j2) {
   if (b2 >= 0) { v += r * dof_minv(M, W, a, b2); if (a2 >= 0) v += r * r * dof_minv(M, W, a2, b2); }
   return v * W.jr_sign[j] * W.jr_sign[j2];
 }
-PRB_D float jrow_contact(const DevModel& M, const WarpMem& W, int j, int c, int k) {
+template <class WM>
+PRB_D float jrow_contact(const DevModel& M, const WM& W, int j, int c, int k) {
   float v = contact_B_at(M, W, c, k, W.jr_dof[j]);
   if (W.jr_dof2[j] >= 0) v += M.params[P_GEAR_RATIO] * contact_B_at(M, W, c, k, W.jr_dof2[j]);
   return v * W.jr_sign[j];
 }
 
 // islands, local row ids, A; fills the per-lane row registers
-PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
+template <class WM, class RR>
+PRB_D void phase_delassus(const DevModel& M, WM& W, int lane, RR& R) {
   const int nb = 1 + M.n_free + M.n_slide;
   int nc = W.n_contact;
   const int njr = W.n_jrow;
@@ -1091,6 +1164,7 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
     used = 0;
     int Lmax = -1, Rmax = 0;
     const int my_rows = (lane < nc && !dead) ? (spin_on ? 4 : 3) : 0;
+#pragma unroll 1
     for (int L = 0; L < nb; L++) {
       int cnt = (my_islJ[0] == L ? 1 : 0) | (my_islJ[1] == L ? 1 << 8 : 0) | ((my_rows && my_islC == L) ? my_rows << 16 : 0);
       int tot;
@@ -1104,7 +1178,7 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
       used += RL * RL;
       if (RL > Rmax) { Rmax = RL; Lmax = L; }
     }
-    if (used <= PRB_ACAP) break;                    // uniform
+    if (used <= WM::Cfg::ACAP) break;                    // uniform
     // drop the last contact of the largest island (flagged) and lay out again
     unsigned mk = __ballot_sync(FULL, my_rows > 0 && my_islC == Lmax);
     if (mk == 0u) break;
@@ -1115,8 +1189,9 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
   spin_on = spin_on && !dead;
   if (dead) { for (int k = 0; k < 4; k++) { W.cr_rhs[lane][k] = 0.f; W.cr_invD[lane][k] = 0.f; } W.cr_spin[lane] = 0.f; }
   __syncwarp();
+  if (lane == 0) { if (used > W.dbg_a) W.dbg_a = used; if (nc > W.dbg_c) W.dbg_c = nc; }
   // lanes outside a sender's island read up to 2 R + 1 floats past their own row: keep that finite
-  for (int i = used + lane; i < used + PRB_APAD && i < PRB_ACAP + PRB_APAD; i += 32) W.A[i] = 0.f;
+  for (int i = used + lane; i < used + WM::Cfg::APAD && i < WM::Cfg::ACAP + WM::Cfg::APAD; i += 32) W.A[i] = 0.f;
   // ---- per-row metadata: block base (16 bits) | island-local row id (8) | island (8); block size R
   for (int sl = 0; sl < 2; sl++) {
     int j = sl * 32 + lane;
@@ -1130,6 +1205,7 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
     int j = sl * 32 + lane;
     if (j >= njr) continue;
     const int r = locJ[sl], Rn = RJ[sl], base = baseJ[sl];
+#pragma unroll 1
     for (int j2 = 0; j2 <= j; j2++) {
       unsigned m2 = W.jr_meta[j2];
       if ((int)(m2 >> 24) != my_islJ[sl]) continue;
@@ -1142,8 +1218,10 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
     const int c = lane, Rn = RC, base = baseC;
     int k_of[4], nk = 0;
     k_of[nk++] = 0; if (spin_on) k_of[nk++] = 1; k_of[nk++] = 2; k_of[nk++] = 3;
+#pragma unroll 1
     for (int kk = 0; kk < nk; kk++) {
       const int k = k_of[kk], r = locC + kk;
+#pragma unroll 1
       for (int j2 = 0; j2 < njr; j2++) {
         unsigned m2 = W.jr_meta[j2];
         if ((int)(m2 >> 24) != my_islC) continue;
@@ -1151,12 +1229,14 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
         const float v = jrow_contact(M, W, j2, c, k);
         W.A[base + r * Rn + r2] = v; W.A[base + r2 * Rn + r] = v;
       }
+#pragma unroll 1
       for (int c2 = 0; c2 <= c; c2++) {
         unsigned m2 = W.ct_meta[c2];
         if ((int)(m2 >> 24) != my_islC) continue;
         const int loc2 = (int)((m2 >> 16) & 0xff);
         const bool sp2 = W.cr_spin[c2] > 0.f;
         int kk2 = 0;
+#pragma unroll 1
         for (int k2 = 0; k2 < 4; k2++) {
           if (k2 == 1 && !sp2) continue;
           const int r2 = loc2 + kk2; kk2++;
@@ -1171,11 +1251,12 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
   const unsigned spinmask = __ballot_sync(FULL, spin_on);
   const int nspin = __popc(spinmask);
   const int g_n = njr, g_s = njr + nc, g_f = njr + nc + nspin, g_end = g_f + nc;
+  if (lane == 0 && g_end > W.dbg_u) W.dbg_u = g_end;
   R.nslots = (g_end + 31) >> 5;          // <= (40 + 96 + 31) / 32 = 5 in theory; capped below
-  if (R.nslots > PRB_MAXSLOT) { R.nslots = PRB_MAXSLOT; if (lane == 0) W.overflow = 1; }
+  if (R.nslots > RR::MS) { R.nslots = RR::MS; if (lane == 0) W.overflow = 1; }
   __syncwarp();
 #pragma unroll
-  for (int k = 0; k < PRB_MAXSLOT; k++) {
+  for (int k = 0; k < RR::MS; k++) {
     const int g = 32 * k + lane;
     R.ua[k] = 0.f; R.ub[k] = 0.f; R.la[k] = 0.f; R.lb[k] = 0.f;
     R.rhsa[k] = 0.f; R.rhsb[k] = 0.f; R.ida[k] = 0.f; R.idb[k] = 0.f; R.p0[k] = 0.f; R.p1[k] = 0.f;
@@ -1205,38 +1286,55 @@ PRB_D void phase_delassus(const DevModel& M, WarpMem& W, int lane, RowRegs& R) {
         else { R.p0[k] = W.cr_mu[c]; R.rhsb[k] = W.cr_rhs[c][3]; R.idb[k] = W.cr_invD[c][3]; R.pbo[k] = Rn; }
       }
     }
+    W.unit_meta[1 + g] = R.meta[k];
   }
+  if (lane == 0) { W.unit_meta[0] = 0x7fff0000; W.unit_meta[1 + 32 * RR::MS] = 0x7fff0000; }
   __syncwarp();
 }
 
 // ============================================================================ PGS (lane = unit owner)
 // Each unit keeps the index of its own row(s) of the island block, so the coupling to sender row s
 // is A[pa + s] (A is symmetric).  Lanes whose unit is in another island read a finite in-range
-// value and multiply it by zero; nothing in the loads depends on the broadcast impulse change.
+// value and multiply it by zero.  The sender's row id comes from a per-unit table (it is known
+// before the sweep starts), so the A loads of the NEXT step are issued before the current step's
+// impulse change is broadcast: the dependent chain per step is candidate -> shuffle -> FMA.
+enum { U_JOINT = 0, U_NORMAL = 1, U_SPIN = 2, U_PAIR = 3 };
+
 template <int NS, bool PAIR>
-PRB_D void pgs_apply(const WarpMem& W, RowRegs& R, int smeta, float d1, float d2) {
-  const int sloc = smeta & 0xffff, sisl = smeta >> 16;
+struct ACoef { float a[NS], b[NS], a2[PAIR ? NS : 1], b2[PAIR ? NS : 1]; };
+
+template <int NS, bool PAIR, class WM, class RR>
+PRB_D void pgs_load(const WM& W, const RR& R, int smeta, ACoef<NS, PAIR>& C) {
+  const int sloc = smeta & 0xffff;
+#pragma unroll
+  for (int k = 0; k < NS; k++) {
+    const float* row = &W.A[R.pa[k] + sloc];
+    C.a[k] = row[0];
+    C.b[k] = row[R.pbo[k]];                  // pair units: second row; single units: pbo = 0, ub unused
+    if (PAIR) { C.a2[k] = row[1]; C.b2[k] = row[R.pbo[k] + 1]; }
+  }
+}
+template <int NS, bool PAIR, class RR>
+PRB_D void pgs_apply(RR& R, int smeta, const ACoef<NS, PAIR>& C, float d1, float d2) {
+  const int sisl = smeta >> 16;
 #pragma unroll
   for (int k = 0; k < NS; k++) {
     const bool on = (R.meta[k] >> 16) == sisl;
     const float m1 = on ? d1 : 0.f;
-    const float* row = &W.A[R.pa[k] + sloc];
-    R.ua[k] += row[0] * m1;
-    R.ub[k] += row[R.pbo[k]] * m1;           // pair units: second row; single units: pbo = 0, ub unused
+    R.ua[k] = fmaf(C.a[k], m1, R.ua[k]);
+    R.ub[k] = fmaf(C.b[k], m1, R.ub[k]);
     if (PAIR) {
       const float m2 = on ? d2 : 0.f;
-      R.ua[k] += row[1] * m2;
-      R.ub[k] += row[R.pbo[k] + 1] * m2;
+      R.ua[k] = fmaf(C.a2[k], m2, R.ua[k]);
+      R.ub[k] = fmaf(C.b2[k], m2, R.ub[k]);
     }
   }
 }
 
-enum { U_JOINT = 0, U_NORMAL = 1, U_SPIN = 2, U_PAIR = 3 };
-
-// one sweep step: the unit in slot K of lane `src` is solved, its impulse change broadcast
-template <int NS, int K, int TYPE>
-PRB_D void pgs_step(WarpMem& W, RowRegs& R, int lane, int src) {
-  float d1, d2 = 0.f;
+// solve the unit in slot K of lane src; returns the impulse change(s) as seen by the owner
+template <int K, int TYPE, class WM, class RR>
+PRB_D void pgs_candidate(WM& W, RR& R, int lane, int src, float& d1, float& d2) {
+  d2 = 0.f;
   if (TYPE == U_JOINT) {
     const float delta = R.rhsa[K] - R.ua[K] * R.ida[K];
     const float nl = clampf(R.la[K] + delta, R.p0[K], R.p1[K]);
@@ -1269,34 +1367,56 @@ PRB_D void pgs_step(WarpMem& W, RowRegs& R, int lane, int src) {
     d1 = na - R.la[K]; d2 = nb - R.lb[K];
     if (lane == src) { R.la[K] = na; R.lb[K] = nb; }
   }
-  const int smeta = __shfl_sync(FULL, R.meta[K], src);       // sender's island and row id
-  d1 = __shfl_sync(FULL, d1, src);
-  if (TYPE == U_PAIR) { d2 = __shfl_sync(FULL, d2, src); pgs_apply<NS, true>(W, R, smeta, d1, d2); }
-  else pgs_apply<NS, false>(W, R, smeta, d1, 0.f);
 }
-template <int NS, int TYPE>
-PRB_D void pgs_unit(WarpMem& W, RowRegs& R, int lane, int g) {
-  const int src = g & 31;
-  if (NS <= 2) {
-    if ((g >> 5) == 0) pgs_step<NS, 0, TYPE>(W, R, lane, src); else pgs_step<NS, 1, TYPE>(W, R, lane, src);
-  } else {
-    switch (g >> 5) {                          // uniform
-      case 0: pgs_step<NS, 0, TYPE>(W, R, lane, src); break;
-      case 1: pgs_step<NS, 1, TYPE>(W, R, lane, src); break;
-      case 2: pgs_step<NS, 2, TYPE>(W, R, lane, src); break;
-      default: pgs_step<NS, 3, TYPE>(W, R, lane, src); break;
-    }
+
+// units g in [ga, gb), all living in slot K, swept upwards (dir = +1) or downwards (dir = -1)
+template <int NS, int K, int TYPE, class WM, class RR>
+PRB_D void pgs_range(WM& W, RR& R, int lane, int ga, int gb, int dir) {
+  constexpr bool PAIR = (TYPE == U_PAIR);
+  const int n = gb - ga;
+  if (n <= 0) return;
+  int g = dir > 0 ? ga : gb - 1;
+  int smeta = W.unit_meta[1 + g];
+  ACoef<NS, PAIR> C;
+  pgs_load<NS, PAIR>(W, R, smeta, C);
+#pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    const int smeta_n = W.unit_meta[1 + g + dir];          // table is padded on both ends
+    ACoef<NS, PAIR> Cn;
+    pgs_load<NS, PAIR>(W, R, smeta_n, Cn);                 // next step's coefficients, independent of this step
+    float d1, d2;
+    const int src = g & 31;
+    pgs_candidate<K, TYPE>(W, R, lane, src, d1, d2);
+    d1 = __shfl_sync(FULL, d1, src);
+    if (PAIR) d2 = __shfl_sync(FULL, d2, src);
+    pgs_apply<NS, PAIR>(R, smeta, C, d1, d2);
+    C = Cn; smeta = smeta_n; g += dir;
   }
 }
-template <int NS>
-PRB_D void pgs_sweeps(const DevModel& M, WarpMem& W, RowRegs& R, int lane, int g_n, int g_s, int g_f, int g_end) {
+// a phase's units [g0, g1) split by the slot they live in
+template <int NS, int TYPE, class WM, class RR>
+PRB_D void pgs_phase(WM& W, RR& R, int lane, int g0, int g1, int dir) {
+  if (dir > 0) {
+    pgs_range<NS, 0, TYPE>(W, R, lane, max(g0, 0), min(g1, 32), 1);
+    if (NS > 1) pgs_range<NS, (NS > 1 ? 1 : 0), TYPE>(W, R, lane, max(g0, 32), min(g1, 64), 1);
+    if (NS > 2) pgs_range<NS, (NS > 2 ? 2 : 0), TYPE>(W, R, lane, max(g0, 64), min(g1, 96), 1);
+    if (NS > 3) pgs_range<NS, (NS > 3 ? 3 : 0), TYPE>(W, R, lane, max(g0, 96), min(g1, 128), 1);
+  } else {
+    if (NS > 3) pgs_range<NS, (NS > 3 ? 3 : 0), TYPE>(W, R, lane, max(g0, 96), min(g1, 128), -1);
+    if (NS > 2) pgs_range<NS, (NS > 2 ? 2 : 0), TYPE>(W, R, lane, max(g0, 64), min(g1, 96), -1);
+    if (NS > 1) pgs_range<NS, (NS > 1 ? 1 : 0), TYPE>(W, R, lane, max(g0, 32), min(g1, 64), -1);
+    pgs_range<NS, 0, TYPE>(W, R, lane, max(g0, 0), min(g1, 32), -1);
+  }
+}
+template <int NS, class WM, class RR>
+PRB_D void pgs_sweeps(const DevModel& M, WM& W, RR& R, int lane, int g_n, int g_s, int g_f, int g_end) {
+#pragma unroll 1
   for (int it = 0; it < M.solver_iters; it++) {
-    if (it & 1) { for (int g = 0; g < g_n; g++) pgs_unit<NS, U_JOINT>(W, R, lane, g); }
-    else { for (int g = g_n - 1; g >= 0; g--) pgs_unit<NS, U_JOINT>(W, R, lane, g); }
-    for (int g = g_n; g < min(g_s, g_end); g++) pgs_unit<NS, U_NORMAL>(W, R, lane, g);
+    pgs_phase<NS, U_JOINT>(W, R, lane, 0, g_n, (it & 1) ? 1 : -1);
+    pgs_phase<NS, U_NORMAL>(W, R, lane, g_n, min(g_s, g_end), 1);
     __syncwarp();                                      // normal impulses visible to the friction units
-    for (int g = g_s; g < min(g_f, g_end); g++) pgs_unit<NS, U_SPIN>(W, R, lane, g);
-    for (int g = g_f; g < g_end; g++) pgs_unit<NS, U_PAIR>(W, R, lane, g);
+    pgs_phase<NS, U_SPIN>(W, R, lane, g_s, min(g_f, g_end), 1);
+    pgs_phase<NS, U_PAIR>(W, R, lane, g_f, g_end, 1);
     __syncwarp();
   }
 }
@@ -1304,20 +1424,21 @@ PRB_D void pgs_sweeps(const DevModel& M, WarpMem& W, RowRegs& R, int lane, int g
 // 50 projected-Gauss-Seidel sweeps in btMultiBodyConstraintSolver::solveSingleIteration order:
 // non-contact rows (direction alternating per iteration), normals, spinning friction, lateral
 // friction as an implicit cone over the row pair.  Returns dv = M^-1 J^T lambda for this lane's DoF.
-PRB_D float phase_pgs(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm, RowRegs& R) {
+template <class WM, class RR>
+PRB_D float phase_pgs(const DevModel& M, WM& W, int lane, const LaneMap& lm, RR& R) {
   const int njr = W.n_jrow, nc = W.n_contact, nd = M.nd;
   const unsigned spinmask = __ballot_sync(FULL, lane < nc && W.cr_spin[lane < nc ? lane : 0] > 0.f);
   const int nspin = __popc(spinmask);
   const int g_n = njr, g_s = njr + nc, g_f = g_s + nspin;
-  const int g_end = min(g_f + nc, 32 * PRB_MAXSLOT);
-  if (R.nslots <= 2) pgs_sweeps<2>(M, W, R, lane, g_n, g_s, g_f, g_end);
-  else pgs_sweeps<PRB_MAXSLOT>(M, W, R, lane, g_n, g_s, g_f, g_end);
+  const int g_end = min(g_f + nc, 32 * RR::MS);
+  if (RR::MS <= 2 || R.nslots <= 2) pgs_sweeps<2>(M, W, R, lane, g_n, g_s, g_f, g_end);
+  else pgs_sweeps<RR::MS>(M, W, R, lane, g_n, g_s, g_f, g_end);
   // ---- publish the impulses and rebuild dv = M^-1 J^T lambda with lane = velocity DoF
   __syncwarp();
   if (lane < nc) { W.cr_lam[lane][1] = 0.f; W.cr_lam[lane][2] = 0.f; W.cr_lam[lane][3] = 0.f; }
   __syncwarp();
 #pragma unroll
-  for (int k = 0; k < PRB_MAXSLOT; k++) {
+  for (int k = 0; k < RR::MS; k++) {
     const int g = 32 * k + lane;
     if (g < g_n) W.jr_lam[g] = R.la[k];
     else if (g < g_s) W.cr_lam[R.cidx[k]][0] = R.la[k];
@@ -1327,6 +1448,7 @@ PRB_D float phase_pgs(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm
   __syncwarp();
   float dv = 0.f;
   const float ratio = M.params[P_GEAR_RATIO];
+#pragma unroll 1
   for (int j = 0; j < njr; j++) {
     const int d = W.jr_dof[j], d2 = W.jr_dof2[j];
     float b = 0.f;
@@ -1336,6 +1458,7 @@ PRB_D float phase_pgs(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm
     dv += b * W.jr_sign[j] * W.jr_lam[j];
   }
   if (lm.body >= 0) {
+#pragma unroll 1
     for (int c = 0; c < nc; c++) {
       int base = -1;
       if (lm.body == W.cr_bodyA[c]) base = W.cr_offA[c];
@@ -1349,7 +1472,8 @@ PRB_D float phase_pgs(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm
 }
 
 // ============================================================================ integrate (lane = DoF)
-PRB_D void phase_integrate(const DevModel& M, WarpMem& W, int lane, float vstar, float dv) {
+template <class WM>
+PRB_D void phase_integrate(const DevModel& M, WM& W, int lane, float vstar, float dv) {
   const float dt = M.params[P_DT], vmax = M.params[P_MAX_COORD_VEL];
   const int nd = M.nd;
   float v = clampf(vstar + dv, -vmax, vmax);
@@ -1378,15 +1502,15 @@ PRB_D void phase_integrate(const DevModel& M, WarpMem& W, int lane, float vstar,
 }
 
 // one stepSimulation()
-template <int ND>
-PRB_D void substep(const DevModel& M, WarpMem& W, int lane, const LaneMap& lm) {
+template <int ND, class WM>
+PRB_D void substep(const DevModel& M, WM& W, int lane, const LaneMap& lm) {
   phase_fk(M, W, lane, true);
   phase_collide(M, W, lane);
   phase_crba(M, W, lane);
   phase_minv<ND>(W, lane);
   float vstar = phase_vstar(M, W, lane);
   phase_rows(M, W, lane);
-  RowRegs R;
+  RowRegsT<WM::Cfg::MAXSLOT> R;
   phase_delassus(M, W, lane, R);
   float dv = phase_pgs(M, W, lane, lm, R);
   phase_integrate(M, W, lane, vstar, dv);
@@ -1419,7 +1543,8 @@ PRB_D float reward_of(const DevModel& M, const float* ag, const float* dg) {
   float d = sqrtf(dx * dx + dy * dy + dz * dz);
   return d > M.params[P_SPARSE_THRESH] ? -1.0f : -d;
 }
-PRB_D void site_pose(const DevModel& M, const WarpMem& W, int site, v3& pos, m3& R) {
+template <class WM>
+PRB_D void site_pose(const DevModel& M, const WM& W, int site, v3& pos, m3& R) {
   int l = M.site_link[site];
   m3 lR = ldm(W.lR[l]);
   pos = ld3(W.lp[l]) + mul(lR, ld3(M.site_pos[site]));
@@ -1428,7 +1553,8 @@ PRB_D void site_pose(const DevModel& M, const WarpMem& W, int site, v3& pos, m3&
 
 // calc_state (environments.py:799-864) fused with compute_reward; every lane assembles the small
 // vectors redundantly (a few hundred flops), the ray test is spread over lanes; returns reward.
-PRB_D float phase_observe(const DevModel& M, WarpMem& W, int lane, const DevOut& O, size_t e, bool write) {
+template <class WM>
+PRB_D float phase_observe(const DevModel& M, WM& W, int lane, const DevOut& O, size_t e, bool write) {
   phase_fk(M, W, lane, false);
   v3 ep; m3 eR;
   site_pose(M, W, 0, ep, eR);
@@ -1535,27 +1661,58 @@ PRB_D float phase_observe(const DevModel& M, WarpMem& W, int lane, const DevOut&
 }
 
 #ifdef PRB_EMU
-static char g_emu_smem[PRB_WPB * sizeof(WarpMem) + 256];
-#define PRB_SMEM_DECL WarpMem* wm = (WarpMem*)g_emu_smem
+static char g_emu_smem[8 * sizeof(WarpMemT<CfgL>) + 256];
+#define PRB_SMEM_DECL WM* wm = (WM*)g_emu_smem
 #else
-#define PRB_SMEM_DECL extern __shared__ __align__(16) unsigned char prb_dyn_smem[]; WarpMem* wm = (WarpMem*)prb_dyn_smem
+#define PRB_SMEM_DECL extern __shared__ __align__(16) unsigned char prb_dyn_smem[]; WM* wm = (WM*)prb_dyn_smem
 #endif
 
 // ============================================================================ step kernel (warp per env)
-template <int ND>
-__global__ void __launch_bounds__(32 * PRB_WPB) prb_step_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
-                                                                 DevOut O, int N, int n_substeps, int observe) {
+// Small tier (CfgS): warp w of the grid steps env w.  An env that outgrows the small capacities is
+// appended to `redo_list` and left untouched.  Large tier (CfgL): warp w steps env redo_list[w].
+// The warps of a block are re-aligned with a block barrier at every substep: the substep's set-up
+// code is far larger than the instruction cache, so warps drifting apart would each stream it
+// from L2 separately (measured: 3 stall cycles per issue on instruction fetch without this).
+template <int ND, class CFG>
+__global__ void __launch_bounds__(32 * CFG::WPB, CFG::MINBLOCKS) prb_step_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
+                                                                              DevOut O, const int* __restrict__ in_list, const int* __restrict__ in_count,
+                                                                              int* __restrict__ redo_list, int* __restrict__ redo_count,
+                                                                              int N, int n_substeps, int observe) {
+  typedef WarpMemT<CFG> WM;
   PRB_SMEM_DECL;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int e = blockIdx.x * PRB_WPB + wib;
-  if (e >= N) return;   // whole warp exits together
+  const int slot = blockIdx.x * CFG::WPB + wib;
+  int e = slot;
+  bool active = slot < N;
+  if (in_list != nullptr) {                        // this tier only runs what the previous one handed over
+    const int cnt = *in_count;
+    if (blockIdx.x * CFG::WPB >= cnt) return;      // whole block idle
+    active = slot < cnt;
+    e = active ? in_list[slot] : 0;
+  }
   const DevModel& M = *Mp;
-  WarpMem& W = wm[wib];
+  WM& W = wm[wib];
   float* st = state + (size_t)e * M.state_stride;
-  load_state(M, W, st, lane);
-  if (lane == 0) W.overflow = 0;
+  if (active) {
+    load_state(M, W, st, lane);
+    if (lane == 0) { W.overflow = 0; W.dbg_a = 0; W.dbg_c = 0; W.dbg_p = 0; W.dbg_u = 0; }
+    __syncwarp();
+  }
   const LaneMap lm = make_lanemap(M, lane);
-  for (int s = 0; s < n_substeps; s++) substep<ND>(M, W, lane, lm);
+#pragma unroll 1
+  for (int s = 0; s < n_substeps; s++) {
+    __syncthreads();
+    if (active) {
+      substep<ND>(M, W, lane, lm);
+      if (CFG::ABORT && W.overflow) {            // uniform per warp: shared flag read after the substep's final __syncwarp
+        if (lane == 0) redo_list[atomicAdd(redo_count, 1)] = e;
+        active = false;
+      }
+    }
+  }
+  if (!active) return;
+  __syncwarp();
+  if (lane == 0 && O.dbg) { O.dbg[4 * e] = W.dbg_a; O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.dbg_u; }
   if (observe) phase_observe(M, W, lane, O, (size_t)e, true);
   __syncwarp();
   if (lane == 0 && W.overflow && O.overflow) atomicAdd(O.overflow, 1ull);
@@ -1564,16 +1721,17 @@ __global__ void __launch_bounds__(32 * PRB_WPB) prb_step_kernel(const DevModel* 
 
 // ============================================================================ reset kernel (warp per env, masked)
 template <int ND>
-__global__ void __launch_bounds__(32 * PRB_WPB) prb_reset_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
+__global__ void __launch_bounds__(32) prb_reset_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
                                                                   DevOut O, const unsigned char* __restrict__ mask, int N,
                                                                   unsigned long long seed, unsigned env_offset) {
+  typedef WarpMemT<CfgL> WM;
   PRB_SMEM_DECL;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int e = blockIdx.x * PRB_WPB + wib;
+  const int e = blockIdx.x + wib;
   if (e >= N) return;
   if (mask != nullptr && mask[e] == 0) return;
   const DevModel& M = *Mp;
-  WarpMem& W = wm[wib];
+  WM& W = wm[wib];
   float* st = state + (size_t)e * M.state_stride;
   load_state(M, W, st, lane);
   if (lane == 0) W.overflow = 0;

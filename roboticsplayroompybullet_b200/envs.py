@@ -228,8 +228,18 @@ class VecPlayEnv:
         _lib.check(self.L, self._h, self.L.prb_last_kernel_ms(self._h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def last_tier_ms(self):
+        a, b = ctypes.c_float(), ctypes.c_float()
+        _lib.check(self.L, self._h, self.L.prb_last_tier_ms(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def launch_count(self):
         return int(self.L.prb_launch_count(self._h))
+
+    def debug_usage(self):
+        out = np.zeros((self.num_envs, 4), np.int32)
+        _lib.check(self.L, self._h, self.L.prb_debug_usage(self._h, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
 
     def overflow_count(self):
         return int(self.L.prb_overflow_count(self._h))

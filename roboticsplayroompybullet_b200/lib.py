@@ -30,7 +30,7 @@ class PrbBuffers(ctypes.Structure):
 # every symbol include/prb.h declares (a CPU test checks the built library exports them all)
 SYMBOLS = ['prb_create', 'prb_destroy', 'prb_reset', 'prb_set_goal', 'prb_step', 'prb_observe', 'prb_substeps',
            'prb_get_buffers', 'prb_compute_reward', 'prb_get_state', 'prb_set_state', 'prb_step_host',
-           'prb_enable_kernel_timing', 'prb_last_kernel_ms', 'prb_launch_count', 'prb_overflow_count', 'prb_kernel_info', 'prb_last_error', 'prb_version']
+           'prb_enable_kernel_timing', 'prb_last_kernel_ms', 'prb_last_tier_ms', 'prb_launch_count', 'prb_overflow_count', 'prb_debug_usage', 'prb_kernel_info', 'prb_last_error', 'prb_version']
 
 
 class PrbError(RuntimeError):
@@ -60,9 +60,11 @@ def load():
     L.prb_step_host.argtypes = [vp, vp, vp, vp]
     L.prb_enable_kernel_timing.argtypes = [vp, i32]
     L.prb_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    L.prb_last_tier_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     L.prb_launch_count.argtypes = [vp]
     L.prb_launch_count.restype = i64
     L.prb_overflow_count.argtypes = [vp]
+    L.prb_debug_usage.argtypes = [vp, vp]
     L.prb_overflow_count.restype = i64
     L.prb_kernel_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.prb_last_error.argtypes = [vp]

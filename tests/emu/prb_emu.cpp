@@ -6,12 +6,37 @@
 static DevModel g_M;
 static std::string g_err;
 
+static std::vector<int> g_redo;
+static int g_redo_count = 0;
+template <int ND, class CFG>
+static void run_tier(float* state, DevOut O, const int* in_list, const int* in_count, int* out_list, int* out_count, int N, int nsub, int observe) {
+  emu_dim3 g, b; b.x = 32 * CFG::WPB; g.x = (N + CFG::WPB - 1) / CFG::WPB;
+  emu::launch(g, b, [&]() { prb_step_kernel<ND, CFG>(&g_M, state, O, in_list, in_count, out_list, out_count, N, nsub, observe); });
+}
+template <int ND>
+static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
+  g_redo.assign(2 * N + 2, 0);
+  int* l1 = g_redo.data(); int* l2 = l1 + N;
+  int c1 = 0, c2 = 0;
+  run_tier<ND, CfgS>(state, O, nullptr, nullptr, l1, &c1, N, nsub, observe);
+  g_redo_count += c1;
+  if (nsub > 0) {
+    run_tier<ND, CfgM>(state, O, l1, &c1, l2, &c2, N, nsub, observe);
+    g_redo_count += 1000 * c2;
+    run_tier<ND, CfgL>(state, O, l2, &c2, nullptr, nullptr, N, nsub, observe);
+  }
+}
+static void run_step(float* state, DevOut O, int N, int nsub, int observe) {
+  if (g_M.nd == 12) run_step_nd<12>(state, O, N, nsub, observe); else run_step_nd<9>(state, O, N, nsub, observe);
+}
+
 extern "C" {
 int emu_set_model(const prb_model* m) { g_err = prb_convert_model(m, &g_M); return g_err.empty() ? 0 : -1; }
 const char* emu_error() { return g_err.c_str(); }
 int emu_state_stride() { return g_M.state_stride; }
 int emu_state_dim() { return g_M.state_dim; }
-int emu_warpmem_bytes() { return (int)sizeof(WarpMem); }
+int emu_warpmem_bytes() { return (int)sizeof(WarpMemT<CfgS>); }
+int emu_warpmem_large_bytes() { return (int)sizeof(WarpMemT<CfgL>); }
 int emu_devmodel_bytes() { return (int)sizeof(DevModel); }
 
 void emu_init(float* state, int N) {
@@ -22,24 +47,20 @@ void emu_ik(float* state, const float* action, float* target, int N) {
   emu_dim3 g, b; b.x = 128; g.x = (N + 127) / 128;
   emu::launch(g, b, [&]() { prb_ik_kernel(&g_M, state, action, target, N); });
 }
-static void run_step(float* state, DevOut O, int N, int nsub, int observe) {
-  emu_dim3 g, b; b.x = 32 * PRB_WPB; g.x = (N + PRB_WPB - 1) / PRB_WPB;
-  if (g_M.nd == 12) emu::launch(g, b, [&]() { prb_step_kernel<12>(&g_M, state, O, N, nsub, observe); });
-  else emu::launch(g, b, [&]() { prb_step_kernel<9>(&g_M, state, O, N, nsub, observe); });
-}
+int emu_redo_count() { return g_redo_count; }
 static unsigned long long g_overflow = 0;
 unsigned long long emu_overflow() { return g_overflow; }
-void emu_substeps(float* state, int N, int nsub) { DevOut O; memset(&O, 0, sizeof(O)); O.overflow = &g_overflow; run_step(state, O, N, nsub, 0); }
+void emu_substeps(float* state, int N, int nsub) { DevOut O; memset(&O, 0, sizeof(O)); O.overflow = &g_overflow; O.dbg = nullptr; run_step(state, O, N, nsub, 0); }
 void emu_step(float* state, const float* action, DevOut* O, int N) {
-  O->overflow = &g_overflow;
+  O->overflow = &g_overflow; O->dbg = nullptr;
   emu_ik(state, action, O->target_poses, N);
   run_step(state, *O, N, g_M.n_substeps, 1);
 }
-void emu_observe(float* state, DevOut* O, int N) { O->overflow = &g_overflow; run_step(state, *O, N, 0, 1); }
+void emu_observe(float* state, DevOut* O, int N) { O->overflow = &g_overflow; O->dbg = nullptr; run_step(state, *O, N, 0, 1); }
 void emu_reset(float* state, DevOut* O, const unsigned char* mask, int N, unsigned long long seed, unsigned env_offset) {
-  emu_dim3 g, b; b.x = 32 * PRB_WPB; g.x = (N + PRB_WPB - 1) / PRB_WPB;
+  emu_dim3 g, b; b.x = 32; g.x = N;
   DevOut o = *O;
-  o.overflow = &g_overflow;
+  o.overflow = &g_overflow; o.dbg = nullptr;
   if (g_M.nd == 12) emu::launch(g, b, [&]() { prb_reset_kernel<12>(&g_M, state, o, mask, N, seed, env_offset); });
   else emu::launch(g, b, [&]() { prb_reset_kernel<9>(&g_M, state, o, mask, N, seed, env_offset); });
 }

@@ -15,7 +15,7 @@ OUT_KEYS = ['obs_quat', 'achieved_goal', 'desired_goal', 'controllable_achieved_
 
 
 class DevOut(ctypes.Structure):
-    _fields_ = [(k, ctypes.c_void_p) for k in OUT_KEYS] + [('overflow', ctypes.c_void_p)]
+    _fields_ = [(k, ctypes.c_void_p) for k in OUT_KEYS] + [('overflow', ctypes.c_void_p), ('dbg', ctypes.c_void_p)]
 
 
 def out_dims(m):
@@ -52,7 +52,7 @@ class EmuSim:
         self.state = np.zeros((N, self.stride), np.float32)
         self.seed, self.env_offset = seed, env_offset
         self.out = {k: np.zeros((N, d), np.float32) for k, d in out_dims(model).items()}
-        self.O = DevOut(*([self.out[k].ctypes.data for k in OUT_KEYS] + [None]))
+        self.O = DevOut(*([self.out[k].ctypes.data for k in OUT_KEYS] + [None, None]))
         self.L.emu_init(self.state.ctypes.data_as(ctypes.c_void_p), N)
 
     def _sel(self):
