@@ -1,0 +1,17 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, the bench line, the reference arm, the ncu launch list and a
+# full capture of the step kernels.  Usage: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh TAG'
+TAG=${1:-r1}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 500 > gpurun_out/clocks_$TAG.csv &
+SMI=$!
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_$TAG.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/smoke_$TAG.log
+python bench.py --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_$TAG.json
+python bench.py --impl reference --steps 3 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_ref_$TAG.json
+kill $SMI
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
+    python bench.py --steps 3 --warmup 3 --envs-per-gpu 8192 --no-cpu-baseline > gpurun_out/b_launch_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:prb_step_kernel -s 9 -c 3 -f -o gpurun_out/prof_$TAG \
+    python bench.py --steps 3 --warmup 3 --envs-per-gpu 8192 --no-cpu-baseline > gpurun_out/b_ncu_$TAG.log 2>&1
+tail -c 600 gpurun_out/b_ncu_$TAG.log
