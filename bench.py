@@ -188,7 +188,7 @@ def run_gpu(args):
     #      L2 flushed between steps (outside the per-step event pairs)
     l0 = env.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kern_ms, ik_ms = [], []
+    kern_ms, ik_ms, tier_ms = [], [], []
     succ = torch.zeros((), device=dev)
     rsum = torch.zeros((), device=dev)
     barrier()
@@ -201,6 +201,7 @@ def run_gpu(args):
         a, b = env.last_kernel_ms()
         ik_ms.append(a)
         kern_ms.append(b)
+        tier_ms.append(env.last_tier_ms())
         succ += info['is_success'].sum()
         rsum += r.sum()
     barrier()
@@ -248,7 +249,10 @@ def run_gpu(args):
                                        'actions; L2 flushed (256 MB fill) between timed steps' % (args.env, N, N * world),
                            'envs_per_gpu': N, 'substeps_per_step': 12, 'solver_iterations': 50, 'seed': args.seed},
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
-                             'frac': achieved / peak_gbs, 'traffic': None, 'kernel': 'prb_step_kernel',
+                             'frac': achieved / peak_gbs, 'traffic': None,
+                             'kernel': 'step pipeline: 13 x prb_setup_kernel + 12 x prb_pgs_kernel per env step',
+                             'setup_kernels_ms': float(np.mean([t[0] for t in tier_ms])),
+                             'pgs_kernels_ms': float(np.mean([t[1] for t in tier_ms])),
                              'kernel_ms': kms, 'ik_kernel_ms': float(np.mean(ik_ms)), 'peak_source': which,
                              'algorithmic_bytes_per_env_step': BYTES_PER_ENV_STEP[args.env],
                              'note': 'latency/FP32-issue bound by construction (SURVEY.md §8d); see profiles/',

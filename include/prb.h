@@ -112,8 +112,9 @@ int prb_step_host(prb_handle* h, const float* action_host, float* out_host, void
  * durations of the most recent step's IK kernel and fused substep kernel. */
 int prb_enable_kernel_timing(prb_handle* h, int32_t enable);
 int prb_last_kernel_ms(prb_handle* h, float* ik_ms, float* step_ms);
-/* split of step_ms into the small-capacity tier (all envs) and the large tier (envs it handed over) */
-int prb_last_tier_ms(prb_handle* h, float* small_ms, float* large_ms);
+/* split of step_ms into the summed durations of the warp-per-env setup launches and the
+ * thread-per-env solver launches of the most recent step */
+int prb_last_tier_ms(prb_handle* h, float* setup_ms, float* pgs_ms);
 
 /* Number of kernels launched by this handle since creation (bench.py reports it). */
 int64_t prb_launch_count(prb_handle* h);

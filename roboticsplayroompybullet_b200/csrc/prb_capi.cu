@@ -7,7 +7,9 @@
 
 #include "../../include/prb.h"
 #include "prb_convert.h"
-#include "prb_kernels.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include "prb_stream.cuh"
 
 struct prb_handle {
   DevModel hm;
@@ -21,13 +23,15 @@ struct prb_handle {
   int64_t out_floats = 0;
   DevOut O;
   int64_t launches = 0;
-  int smem = 0, regs = 0;          // small tier (reported)
-  int smem_large = 0, regs_large = 0, smem_reset = 0;
-  int* redo_list = nullptr;        // [2][N] envs handed from the small to the medium / medium to the large tier
-  int* redo_count = nullptr;       // [2]
-  int smem_medium = 0;
+  int fused = 0;                   // PRB_PIPELINE=fused: A/B reference path (warp-per-env kernel, 12 substeps in one launch)
+  float* sbuf = nullptr;           // [N][SB_STRIDE] constraint-row record stream of the split pipeline
+  int smem = 0, regs = 0;          // setup kernel (reported)
+  int regs_pgs = 0;
+  int smem_fused = 0, smem_reset = 0;
   int timing = 0;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t evk[64];             // per-launch events of the most recent step (timing mode)
+  int n_evk = 0;
   std::string err;
 };
 
@@ -42,26 +46,35 @@ static std::string g_err;  // errors before a handle exists
     }                                                                            \
   } while (0)
 
-// One env step (or n raw substeps) = small tier over every env, then the large tier over the envs
-// the small tier marked.  Two launches, no host synchronisation in between.
+// One env step (or n raw substeps).  Split pipeline: per substep one warp-per-env setup launch
+// (integrate previous solution + build rows) and one thread-per-env solver launch; a final setup
+// launch integrates the last solution and writes the observation.  No host synchronisation.
 template <int ND>
 static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
-  CK(h, cudaMemsetAsync(h->redo_count, 0, 2 * sizeof(int), s));
-  int* l1 = h->redo_list; int* l2 = h->redo_list + h->N;
-  int* c1 = h->redo_count; int* c2 = h->redo_count + 1;
-  dim3 gs((h->N + CfgS::WPB - 1) / CfgS::WPB), bs(32 * CfgS::WPB);
-  prb_step_kernel<ND, CfgS><<<gs, bs, h->smem, s>>>(h->dm, h->state, h->O, nullptr, nullptr, l1, c1, h->N, nsub, observe);
-  h->launches++;
-  CK(h, cudaGetLastError());
-  if (h->timing) CK(h, cudaEventRecord(h->ev[3], s));
-  if (nsub > 0) {
-    dim3 gm((h->N + CfgM::WPB - 1) / CfgM::WPB), bm(32 * CfgM::WPB);
-    prb_step_kernel<ND, CfgM><<<gm, bm, h->smem_medium, s>>>(h->dm, h->state, h->O, l1, c1, l2, c2, h->N, nsub, observe);
+  if (h->fused) {
     dim3 gl((h->N + CfgL::WPB - 1) / CfgL::WPB), bl(32 * CfgL::WPB);
-    prb_step_kernel<ND, CfgL><<<gl, bl, h->smem_large, s>>>(h->dm, h->state, h->O, l2, c2, nullptr, nullptr, h->N, nsub, observe);
-    h->launches += 2;
+    prb_step_kernel<ND, CfgL><<<gl, bl, h->smem_fused, s>>>(h->dm, h->state, h->O, nullptr, nullptr, nullptr, nullptr, h->N, nsub, observe);
+    h->launches++;
     CK(h, cudaGetLastError());
+    return PRB_OK;
   }
+  dim3 gs((h->N + SetupCfg::WPB - 1) / SetupCfg::WPB), bs(32 * SetupCfg::WPB);
+  dim3 gp((h->N + PGS_BLOCK - 1) / PGS_BLOCK), bp(PGS_BLOCK);
+  h->n_evk = 0;
+  for (int i = 0; i <= nsub; i++) {
+    int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
+    if (flags == 0) break;
+    if (h->timing && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
+    prb_setup_kernel<ND><<<gs, bs, h->smem, s>>>(h->dm, h->state, h->sbuf, h->O, h->N, flags);
+    h->launches++;
+    if (i < nsub) {
+      if (h->timing && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
+      prb_pgs_kernel<ND><<<gp, bp, 0, s>>>(h->dm, h->sbuf, h->N);
+      h->launches++;
+    }
+  }
+  if (h->timing && h->n_evk < 64) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
+  CK(h, cudaGetLastError());
   return PRB_OK;
 }
 static int run_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
@@ -70,19 +83,17 @@ static int run_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
 
 template <int ND>
 static int setup_kernels(prb_handle* h) {
-  h->smem = CfgS::WPB * (int)sizeof(WarpMemT<CfgS>);
-  h->smem_large = CfgL::WPB * (int)sizeof(WarpMemT<CfgL>);
+  h->smem = SetupCfg::WPB * (int)sizeof(SetupMemT<SetupCfg>);
+  h->smem_fused = CfgL::WPB * (int)sizeof(WarpMemT<CfgL>);
   h->smem_reset = (int)sizeof(WarpMemT<CfgL>);
-  h->smem_medium = CfgM::WPB * (int)sizeof(WarpMemT<CfgM>);
-  CK(h, cudaFuncSetAttribute(prb_step_kernel<ND, CfgM>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_medium));
-  CK(h, cudaFuncSetAttribute(prb_step_kernel<ND, CfgS>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
-  CK(h, cudaFuncSetAttribute(prb_step_kernel<ND, CfgL>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_large));
+  CK(h, cudaFuncSetAttribute(prb_setup_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+  CK(h, cudaFuncSetAttribute(prb_step_kernel<ND, CfgL>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_fused));
   CK(h, cudaFuncSetAttribute(prb_reset_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_reset));
   cudaFuncAttributes fa;
-  CK(h, cudaFuncGetAttributes(&fa, prb_step_kernel<ND, CfgS>));
+  CK(h, cudaFuncGetAttributes(&fa, prb_setup_kernel<ND>));
   h->regs = fa.numRegs;
-  CK(h, cudaFuncGetAttributes(&fa, prb_step_kernel<ND, CfgL>));
-  h->regs_large = fa.numRegs;
+  CK(h, cudaFuncGetAttributes(&fa, prb_pgs_kernel<ND>));
+  h->regs_pgs = fa.numRegs;
   return PRB_OK;
 }
 
@@ -126,9 +137,15 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
                        &h->O.velocity, &h->O.observation, &h->O.proprio, &h->O.reward, &h->O.success, &h->O.target_poses};
   int64_t off = 0;
   for (int i = 0; i < 12; i++) { *slots[i] = h->out + off; off += N * dims[i]; }
-  CK(h, cudaMalloc(&h->redo_list, sizeof(int) * 2 * N));
-  CK(h, cudaMalloc(&h->redo_count, 2 * sizeof(int)));
-  CK(h, cudaMemset(h->redo_count, 0, 2 * sizeof(int)));
+  {
+    const char* p = getenv("PRB_PIPELINE");
+    h->fused = (p && strcmp(p, "fused") == 0) ? 1 : 0;
+  }
+  if (!h->fused) {
+    const size_t sb_bytes = (size_t)((N + 31) / 32) * 32 * SB_Q * sizeof(float4);   // whole 32-env groups
+    CK(h, cudaMalloc(&h->sbuf, sb_bytes));
+    CK(h, cudaMemset(h->sbuf, 0, sb_bytes));
+  }
   {
     int rc = M.nd == 12 ? setup_kernels<12>(h) : setup_kernels<9>(h);
     if (rc != PRB_OK) return rc;
@@ -143,7 +160,7 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
 int prb_destroy(prb_handle* h) {
   if (!h) return PRB_ERR_INVALID;
   cudaSetDevice(h->device);
-  cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->redo_list); cudaFree(h->redo_count);
+  cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->sbuf);
   delete h;
   return PRB_OK;
 }
@@ -176,7 +193,10 @@ int prb_step(prb_handle* h, const float* action_dev, void* stream) {
 
 int prb_enable_kernel_timing(prb_handle* h, int32_t enable) {
   if (!h) return PRB_ERR_INVALID;
-  if (enable && !h->ev[0]) for (int i = 0; i < 4; i++) CK(h, cudaEventCreate(&h->ev[i]));
+  if (enable && !h->ev[0]) {
+    for (int i = 0; i < 3; i++) CK(h, cudaEventCreate(&h->ev[i]));
+    for (int i = 0; i < 64; i++) CK(h, cudaEventCreate(&h->evk[i]));
+  }
   h->timing = enable ? 1 : 0;
   return PRB_OK;
 }
@@ -189,11 +209,18 @@ int prb_last_kernel_ms(prb_handle* h, float* ik_ms, float* step_ms) {
   return PRB_OK;
 }
 
-int prb_last_tier_ms(prb_handle* h, float* small_ms, float* large_ms) {
+int prb_last_tier_ms(prb_handle* h, float* setup_ms, float* pgs_ms) {
   if (!h || !h->ev[0]) return PRB_ERR_INVALID;
   CK(h, cudaEventSynchronize(h->ev[2]));
-  if (small_ms) CK(h, cudaEventElapsedTime(small_ms, h->ev[1], h->ev[3]));
-  if (large_ms) CK(h, cudaEventElapsedTime(large_ms, h->ev[3], h->ev[2]));
+  float a = 0.f, b = 0.f;
+  // per-launch events alternate setup, solver, setup, solver, ..., setup, end
+  for (int i = 0; i + 1 < h->n_evk; i++) {
+    float ms = 0.f;
+    CK(h, cudaEventElapsedTime(&ms, h->evk[i], h->evk[i + 1]));
+    if (i & 1) b += ms; else a += ms;
+  }
+  if (setup_ms) *setup_ms = a;
+  if (pgs_ms) *pgs_ms = b;
   return PRB_OK;
 }
 
@@ -294,7 +321,7 @@ int64_t prb_overflow_count(prb_handle* h) {
 int prb_kernel_info(prb_handle* h, int32_t* smem_bytes_per_block, int32_t* envs_per_block, int32_t* regs_per_thread) {
   if (!h) return PRB_ERR_INVALID;
   if (smem_bytes_per_block) *smem_bytes_per_block = h->smem;
-  if (envs_per_block) *envs_per_block = CfgS::WPB;
+  if (envs_per_block) *envs_per_block = SetupCfg::WPB;
   if (regs_per_thread) *regs_per_thread = h->regs;
   return PRB_OK;
 }

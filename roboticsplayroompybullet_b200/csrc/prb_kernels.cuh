@@ -5,7 +5,9 @@
 //                        squares IK on the serial arm chain (registers only) -> joint-limit and
 //                        per-step clipping -> motor targets.  Reference path:
 //                        environments.py:206-208, 955-961, 984-1034, 1037-1073; inverseKinematics.py:44-50.
-//   * prb_step_kernel    one WARP per env, all 12 physics substeps of an env step fused in one
+//   * prb_step_kernel    (fused variant; the default step path is the split pipeline of
+//                        prb_stream.cuh, which reuses every phase below except the solver)
+//                        one WARP per env, all 12 physics substeps of an env step fused in one
 //                        launch with the env's state, kinematics, mass matrix, contact manifold
 //                        and constraint rows resident in shared memory; lanes are links /
 //                        colliders / collider pairs / contacts in the set-up phases and velocity
@@ -27,14 +29,11 @@
 
 #define FULL 0xffffffffu
 
-// Per-env on-chip capacities.  Two tiers of the same kernels:
-//   CfgS  "small": sized for the common case (arm free or lightly touching, block and drawer at
-//         rest): ~13 KB of shared memory per env -> 16 resident warps per SM.  If an env needs
-//         more in any substep, the env step is ABANDONED (nothing written back) and the env is
-//         marked for the large tier.
-//   CfgM  "medium": ~27 KB per env (8 resident warps per SM), takes what the small tier hands over.
-//   CfgL  "large": worst-case capacities (~44 KB per env), runs only what the medium tier hands
-//         over; if even these overflow, contacts are dropped (counted in DevOut::overflow).
+// Per-env on-chip capacities of the FUSED kernel (prb_step_kernel / prb_reset_kernel): worst-case
+// sizes, ~44 KB of shared memory per env.  If even these overflow, contacts are dropped (counted in
+// DevOut::overflow).  The step path proper uses the split pipeline of prb_stream.cuh, whose
+// constraint rows live in HBM and cannot overflow; the fused kernel remains for reset (100 settle
+// substeps inside one launch) and as an A/B reference (PRB_PIPELINE=fused).
 struct CfgL {
   static constexpr int MAXJROW = 40;       // limit + motor + gear rows
   static constexpr int MAXCONTACT = 32;    // contact points per substep after manifold reduction (one per lane)
@@ -47,32 +46,6 @@ struct CfgL {
   static constexpr bool ABORT = false;
   static constexpr int WPB = 5;            // warps (envs) per thread block; the block's warps are re-aligned every substep
   static constexpr int MINBLOCKS = 1;      // resident blocks per SM the register allocation targets
-};
-struct CfgM {
-  static constexpr int MAXJROW = 40;
-  static constexpr int MAXCONTACT = 24;
-  static constexpr int MAXOVL = 32;
-  static constexpr int MAXCAND = 96;
-  static constexpr int POOL = 1792;
-  static constexpr int ACAP = 3072;
-  static constexpr int APAD = 160;
-  static constexpr int MAXSLOT = 3;
-  static constexpr bool ABORT = true;
-  static constexpr int WPB = 4;
-  static constexpr int MINBLOCKS = 2;
-};
-struct CfgS {
-  static constexpr int MAXJROW = 32;
-  static constexpr int MAXCONTACT = 16;
-  static constexpr int MAXOVL = 32;
-  static constexpr int MAXCAND = 64;
-  static constexpr int POOL = 768;
-  static constexpr int ACAP = 1536;
-  static constexpr int APAD = 160;
-  static constexpr int MAXSLOT = 2;
-  static constexpr bool ABORT = true;
-  static constexpr int WPB = 7;
-  static constexpr int MINBLOCKS = 2;
 };
 
 struct Contact {

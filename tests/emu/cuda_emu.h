@@ -34,8 +34,10 @@
 #define __constant__ static
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+struct float2 { float x, y; };
 struct float3 { float x, y, z; };
 struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { float2 r = {x, y}; return r; }
 static inline float3 make_float3(float x, float y, float z) { float3 r = {x, y, z}; return r; }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 

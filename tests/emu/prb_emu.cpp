@@ -1,29 +1,29 @@
 // prb_emu.cpp — runs the product's kernel source under the CPU SIMT emulator (tests only).
 #include "cuda_emu.h"
-#include "../../roboticsplayroompybullet_b200/csrc/prb_kernels.cuh"
+#include "../../roboticsplayroompybullet_b200/csrc/prb_stream.cuh"
 #include "../../roboticsplayroompybullet_b200/csrc/prb_convert.h"
 
 static DevModel g_M;
 static std::string g_err;
 
-static std::vector<int> g_redo;
-static int g_redo_count = 0;
-template <int ND, class CFG>
-static void run_tier(float* state, DevOut O, const int* in_list, const int* in_count, int* out_list, int* out_count, int N, int nsub, int observe) {
-  emu_dim3 g, b; b.x = 32 * CFG::WPB; g.x = (N + CFG::WPB - 1) / CFG::WPB;
-  emu::launch(g, b, [&]() { prb_step_kernel<ND, CFG>(&g_M, state, O, in_list, in_count, out_list, out_count, N, nsub, observe); });
-}
+static std::vector<float> g_sbuf;
+static int g_fused = 0;     // 1: run the fused warp-per-env kernel instead of the split pipeline
 template <int ND>
 static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
-  g_redo.assign(2 * N + 2, 0);
-  int* l1 = g_redo.data(); int* l2 = l1 + N;
-  int c1 = 0, c2 = 0;
-  run_tier<ND, CfgS>(state, O, nullptr, nullptr, l1, &c1, N, nsub, observe);
-  g_redo_count += c1;
-  if (nsub > 0) {
-    run_tier<ND, CfgM>(state, O, l1, &c1, l2, &c2, N, nsub, observe);
-    g_redo_count += 1000 * c2;
-    run_tier<ND, CfgL>(state, O, l2, &c2, nullptr, nullptr, N, nsub, observe);
+  if (g_fused) {
+    emu_dim3 g, b; b.x = 32 * CfgL::WPB; g.x = (N + CfgL::WPB - 1) / CfgL::WPB;
+    emu::launch(g, b, [&]() { prb_step_kernel<ND, CfgL>(&g_M, state, O, nullptr, nullptr, nullptr, nullptr, N, nsub, observe); });
+    return;
+  }
+  g_sbuf.assign((size_t)((N + 31) / 32) * 32 * SB_Q * 4, 0.f);
+  emu_dim3 gs, bs, gp, bp;
+  bs.x = 32 * SetupCfg::WPB; gs.x = (N + SetupCfg::WPB - 1) / SetupCfg::WPB;
+  bp.x = PGS_BLOCK; gp.x = (N + PGS_BLOCK - 1) / PGS_BLOCK;
+  for (int i = 0; i <= nsub; i++) {
+    int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
+    if (flags == 0) break;
+    emu::launch(gs, bs, [&]() { prb_setup_kernel<ND>(&g_M, state, g_sbuf.data(), O, N, flags); });
+    if (i < nsub) emu::launch(gp, bp, [&]() { prb_pgs_kernel<ND>(&g_M, g_sbuf.data(), N); });
   }
 }
 static void run_step(float* state, DevOut O, int N, int nsub, int observe) {
@@ -35,7 +35,7 @@ int emu_set_model(const prb_model* m) { g_err = prb_convert_model(m, &g_M); retu
 const char* emu_error() { return g_err.c_str(); }
 int emu_state_stride() { return g_M.state_stride; }
 int emu_state_dim() { return g_M.state_dim; }
-int emu_warpmem_bytes() { return (int)sizeof(WarpMemT<CfgS>); }
+int emu_warpmem_bytes() { return (int)sizeof(SetupMemT<SetupCfg>); }
 int emu_warpmem_large_bytes() { return (int)sizeof(WarpMemT<CfgL>); }
 int emu_devmodel_bytes() { return (int)sizeof(DevModel); }
 
@@ -47,7 +47,7 @@ void emu_ik(float* state, const float* action, float* target, int N) {
   emu_dim3 g, b; b.x = 128; g.x = (N + 127) / 128;
   emu::launch(g, b, [&]() { prb_ik_kernel(&g_M, state, action, target, N); });
 }
-int emu_redo_count() { return g_redo_count; }
+void emu_set_fused(int f) { g_fused = f; }
 static unsigned long long g_overflow = 0;
 unsigned long long emu_overflow() { return g_overflow; }
 void emu_substeps(float* state, int N, int nsub) { DevOut O; memset(&O, 0, sizeof(O)); O.overflow = &g_overflow; O.dbg = nullptr; run_step(state, O, N, nsub, 0); }

@@ -30,7 +30,7 @@ def lib():
     if _LIB is None:
         so = os.path.join(_HERE, 'libprb_emu.so')
         deps = [os.path.join(_HERE, f) for f in ('prb_emu.cpp', 'cuda_emu.h')] + \
-               [os.path.join(_SRC, f) for f in ('prb_kernels.cuh', 'prb_device.h', 'prb_convert.h')]
+               [os.path.join(_SRC, f) for f in ('prb_kernels.cuh', 'prb_stream.cuh', 'prb_device.h', 'prb_convert.h')]
         if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
             subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-U_FORTIFY_SOURCE',
                                    '-Wno-unknown-pragmas', '-o', so, os.path.join(_HERE, 'prb_emu.cpp')])

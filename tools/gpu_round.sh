@@ -10,8 +10,8 @@ python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_o
 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_$TAG.json
 python bench.py --impl reference --steps 3 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_ref_$TAG.json
 kill $SMI
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --envs-per-gpu 8192 --no-cpu-baseline > gpurun_out/b_launch_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:prb_step_kernel -s 9 -c 3 -f -o gpurun_out/prof_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:"prb_setup_kernel|prb_pgs_kernel" -s 85 -c 4 -f -o gpurun_out/prof_$TAG \
     python bench.py --steps 3 --warmup 3 --envs-per-gpu 8192 --no-cpu-baseline > gpurun_out/b_ncu_$TAG.log 2>&1
 tail -c 600 gpurun_out/b_ncu_$TAG.log
