@@ -69,8 +69,7 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
     h->launches++;
     if (i < nsub) {
       if (h->timing && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
-      if (h->hm.gear_a >= 0) prb_pgs_kernel<ND, true><<<gp, bp, 0, s>>>(h->dm, h->sbuf, h->N);
-      else prb_pgs_kernel<ND, false><<<gp, bp, 0, s>>>(h->dm, h->sbuf, h->N);
+      prb_pgs_kernel<ND><<<gp, bp, 0, s>>>(h->dm, h->sbuf, h->N);
       h->launches++;
     }
   }
@@ -93,7 +92,7 @@ static int setup_kernels(prb_handle* h) {
   cudaFuncAttributes fa;
   CK(h, cudaFuncGetAttributes(&fa, prb_setup_kernel<ND>));
   h->regs = fa.numRegs;
-  CK(h, cudaFuncGetAttributes(&fa, prb_pgs_kernel<ND, false>));
+  CK(h, cudaFuncGetAttributes(&fa, prb_pgs_kernel<ND>));
   h->regs_pgs = fa.numRegs;
   return PRB_OK;
 }

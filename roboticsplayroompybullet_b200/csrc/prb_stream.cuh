@@ -30,22 +30,18 @@
 #define Q_HDR 0          // {n_jrow, n_contact, n_spin, overflow flag} as ints
 #define Q_VSTAR 2        // 8 q: unconstrained velocities v* of the substep (word i = DoF i)
 #define Q_DV 10          // 8 q: solver output M^-1 J^T lambda
-#define Q_JROW 18        // SB_MAXJROW x 8 q: {d | d2 << 8, sign, rhs, invD} {lo, hi, 1/m of a slide DoF, LAMBDA}
-                         //   {row d of the arm's M^-1: 3 q} {row d2 (gear rows only): 3 q}
+#define Q_MINV 18        // 12 rows x 3 q: arm inverse mass matrix (row d at Q_MINV + 3 d, zero padded)
+#define Q_JROW 54        // SB_MAXJROW x 2 q: {d | d2 << 8, sign, rhs, invD} {lo, hi, -, -}
 #define SB_MAXJROW 40
-#define Q_CN 338         // SB_MAXCONTACT x 2 q, normal pass:   {packed, cfm * invD, rhs0, invD0} {LAMBDA normal, LAMBDA spin, -, -}
+#define Q_CN 134         // SB_MAXCONTACT x 1 q, normal pass:   {packed, cfm * invD, rhs0, invD0}
 #define SB_MAXCONTACT 32
-#define Q_CF 402         // SB_MAXCONTACT x 2 q, friction pass: {packed, mu, rhs2, rhs3} {invD2, invD3, LAMBDA 2, LAMBDA 3}
-#define Q_CS 466         // SB_MAXCONTACT x 1 q, spin pass (compact list of the contacts that have a
+#define Q_CF 166         // SB_MAXCONTACT x 2 q, friction pass: {packed, mu, rhs2, rhs3} {invD2, invD3, -, -}
+#define Q_CS 230         // SB_MAXCONTACT x 1 q, spin pass (compact list of the contacts that have a
                          // torsional row): {packed, spin coefficient, rhs1, invD1}
-#define Q_POOL 498       // SB_MAXCONTACT x 48 q: contact c, row k (normal, spin, friction 1, 2), body x (A, B)
-                         // at Q_POOL + 48 c + 6 (2 k + x): J in float4 0..2, B = M^-1 J^T in float4 3..5, zero
-                         // padded (n = 12 | 9 arm, 1 slide body); a free body (n = 6) stores J only: the
-                         // solver rebuilds B from Q_BODY
-#define Q_BODY 2034      // PRB_MAXFREE x 2 q: free body b: {1/m, Iinv xx, xy, xz} {Iinv yy, yz, zz, -} (world frame)
-#define SB_Q 2038        // float4 per env (even)
-// The accumulated impulses (LAMBDA words) live in the rows' own records: the setup kernel zeroes them,
-// the solver reads them with the row (same sector as the row header) and writes them back.
+#define Q_POOL 262       // SB_MAXCONTACT x 48 q: contact c, row k (normal, spin, friction 1, 2), body x (A, B)
+                         // at Q_POOL + 48 c + 6 (2 k + x): J in the first nq float4, B = M^-1 J^T in the
+                         // next nq, nq = ceil(n / 4), zero padded (n = 12 | 9 arm, 6 free body, 1 slide body)
+#define SB_Q 1798        // float4 per env (even)
 // packed contact word: offA | nA << 5 | offB << 9 | nB << 14 | c << 18  (offX: first dv index of body X's
 // segment, nX: its length, 0 when the body is static; c: contact index)
 
@@ -86,8 +82,6 @@ struct SetupMemT {
   int n_ovl, n_contact, n_jrow, pool_used, overflow;
   int dbg_a, dbg_c, dbg_p, dbg_u;
   Contact ct[CFG::MAXCONTACT];
-  int jr_pk[CFG::MAXJROW];
-  float jr_sign[CFG::MAXJROW], jr_rhs[CFG::MAXJROW], jr_invD[CFG::MAXJROW], jr_lo[CFG::MAXJROW], jr_hi[CFG::MAXJROW];
   float lR[PRB_MAXD][9], lIw[PRB_MAXD][6], lf[PRB_MAXD][3], ln[PRB_MAXD][3];
   float Mm[PRB_MAXD][PRB_MAXD + 1];
   float aabb[PRB_MAXCOL][6];
@@ -146,6 +140,7 @@ PRB_D float stream_segment(const DevModel& M, const WM& W, int col, v3 pt, v3 di
 #pragma unroll
     for (int k = 0; k < 6; k++) { d = fmaf(J[k], B[k], d); r = fmaf(J[k], W.vs[o + k], r); }
     S.q(q0) = make_float4(J[0], J[1], J[2], J[3]); S.q(q0 + 1) = make_float4(J[4], J[5], 0.f, 0.f);
+    S.q(q0 + 2) = make_float4(B[0], B[1], B[2], B[3]); S.q(q0 + 3) = make_float4(B[4], B[5], 0.f, 0.f);
     *rel += r;
   } else {
     const int s = body - 1 - M.n_free, o = M.nd + 6 * M.n_free + s;
@@ -154,7 +149,7 @@ PRB_D float stream_segment(const DevModel& M, const WM& W, int col, v3 pt, v3 di
     if (M.slide_jtype[s] == 0) g = angular ? dot(a, dir) : dot(a, cross(pt - ld3(W.sp[s]), dir));
     else g = angular ? 0.f : dot(a, dir);
     const float j = sign * g, bb = j * M.slide_minv[s];
-    S.q(q0) = make_float4(j, 0.f, 0.f, 0.f); S.q(q0 + 3) = make_float4(bb, 0.f, 0.f, 0.f);
+    S.q(q0) = make_float4(j, 0.f, 0.f, 0.f); S.q(q0 + 1) = make_float4(bb, 0.f, 0.f, 0.f);
     d = j * bb; *rel += j * W.vs[o];
   }
   return d;
@@ -165,18 +160,17 @@ template <int ND, class WM>
 PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
   const float dt = M.params[P_DT], erp = M.params[P_ERP_JOINT], erp2 = M.params[P_ERP_CONTACT];
   const int nd = M.nd;
-  // ---- joint rows: lane 0 lists them (serial: <= 40 rows of a few flops each): limits, motors, gear;
-  //      then lane = row writes the 8-float4 record, including the M^-1 row(s) the row's update needs
+  // ---- joint rows (lane 0, serial: <= 40 rows of a few flops each): limits, motors, gear
   if (lane == 0) {
     int nr = 0;
-#define PRB_PUT_JROW(d_, d2_, sg_, rhs_, invD_, lo_, hi_)                                   \
-    do {                                                                                   \
-      if (nr >= SB_MAXJROW) { W.overflow = 1; }                                             \
-      else {                                                                               \
-        W.jr_pk[nr] = (int)(d_) | (((int)(d2_) & 0xff) << 8); W.jr_sign[nr] = sg_;          \
-        W.jr_rhs[nr] = rhs_; W.jr_invD[nr] = invD_; W.jr_lo[nr] = lo_; W.jr_hi[nr] = hi_;   \
-        nr++;                                                                              \
-      }                                                                                    \
+#define PRB_PUT_JROW(d_, d2_, sg_, rhs_, invD_, lo_, hi_)                                                  \
+    do {                                                                                                  \
+      if (nr >= SB_MAXJROW) { W.overflow = 1; }                                                            \
+      else {                                                                                              \
+        S.q(Q_JROW + 2 * nr) = make_float4(__int_as_float((int)(d_) | (((int)(d2_) & 0xff) << 8)), sg_, rhs_, invD_); \
+        S.q(Q_JROW + 2 * nr + 1) = make_float4(lo_, hi_, 0.f, 0.f);                                         \
+        nr++;                                                                                             \
+      }                                                                                                   \
     } while (0)
     for (int i = 0; i < nd; i++) {
       if (M.lo[i] > M.hi[i]) continue;
@@ -217,34 +211,13 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
 #undef PRB_PUT_JROW
     W.n_jrow = nr;
   }
-  __syncwarp();
-  for (int j = lane; j < W.n_jrow; j += 32) {
-    const int pk = W.jr_pk[j], d = pk & 0xff, d2 = (pk >> 8) & 0xff;
-    const int qj = Q_JROW + 8 * j;
-    float sminv = 0.f;
-    if (d >= nd) sminv = M.slide_minv[d - nd - 6 * M.n_free];
-    S.q(qj) = make_float4(__int_as_float(pk), W.jr_sign[j], W.jr_rhs[j], W.jr_invD[j]);
-    S.q(qj + 1) = make_float4(W.jr_lo[j], W.jr_hi[j], sminv, 0.f);
-    if (d < nd) {
-      float r[12];
+  // ---- arm inverse mass matrix (lane = row), zero padded to 12 columns
+  if (lane < ND) {
+    float r[12];
 #pragma unroll
-      for (int k = 0; k < 12; k++) r[k] = k < ND ? W.Minv[d][k] : 0.f;       // M^-1 is symmetric: column d = row d
+    for (int j = 0; j < 12; j++) r[j] = j < ND ? W.Minv[lane][j] : 0.f;
 #pragma unroll
-      for (int k = 0; k < 3; k++) S.q(qj + 2 + k) = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
-    }
-    if (d2 != 0xff) {
-      float r[12];
-#pragma unroll
-      for (int k = 0; k < 12; k++) r[k] = k < ND ? W.Minv[d2][k] : 0.f;
-#pragma unroll
-      for (int k = 0; k < 3; k++) S.q(qj + 5 + k) = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
-    }
-  }
-  // ---- free-body inverse inertia (the solver rebuilds B = M^-1 J^T of free-body segments from it)
-  if (lane < M.n_free) {
-    const float* I = W.fIinv[lane];
-    S.q(Q_BODY + 2 * lane) = make_float4(1.0f / M.free_mass[lane], I[0], I[1], I[2]);
-    S.q(Q_BODY + 2 * lane + 1) = make_float4(I[3], I[4], I[5], 0.f);
+    for (int k = 0; k < 3; k++) S.q(Q_MINV + 3 * lane + k) = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
   }
   // ---- contact rows: lane = contact, fixed 48-float4 slot per contact
   const int nc = W.n_contact;
@@ -295,8 +268,7 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
     }
     const int offA = bodyA >= 0 ? body_dof0(M, bodyA) : 0, offB = bodyB >= 0 ? body_dof0(M, bodyB) : 0;
     packed = pack_contact(offA, nA, offB, nB, lane);
-    S.q(Q_CN + 2 * lane) = make_float4(__int_as_float(packed), cfms, rhs[0], invDs[0]);
-    S.q(Q_CN + 2 * lane + 1) = make_float4(0.f, 0.f, 0.f, 0.f);
+    S.q(Q_CN + lane) = make_float4(__int_as_float(packed), cfms, rhs[0], invDs[0]);
     S.q(Q_CF + 2 * lane) = make_float4(__int_as_float(packed), mu, rhs[2], rhs[3]);
     S.q(Q_CF + 2 * lane + 1) = make_float4(invDs[2], invDs[3], 0.f, 0.f);
   }
@@ -357,18 +329,57 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
 }
 
 // ============================================================================ PGS kernel (thread per env)
-// The solver thread walks its env's rows in sweep order: per iteration the joint rows (direction
-// alternating), the contact normals, [the rare torsional rows,] the friction pairs.  Every row's
-// record is self-contained and at an address known without reading anything else, so all loads of a
-// row are issued together, and the NEXT row's record (joint rows) or header + first-body Jacobian
-// (contacts; the common free-body-vs-static case needs nothing more) is loaded into registers
-// while the current row is being solved: global-memory latency is off the dependent chain.
-#define PGS_BLOCK 128
+#ifndef PGS_BLOCK
+#define PGS_BLOCK 64
+#endif
+#define PGS_MAXLAM (SB_MAXJROW + 4 * SB_MAXCONTACT)
 
-// float4 `off` of the stream region that starts at the EVEN float4 index the pointer was built from
-PRB_D const float4* region_ptr(const SV& S, int q_even) { return S.b + ((q_even >> 1) << 6); }
-PRB_D const float4& at(const float4* p, int off) { return p[((off >> 1) << 6) + (off & 1)]; }
-
+// One body segment of a constraint row: up to 3 float4 of J and of B, zero padded, so the arithmetic
+// runs on whole float4 (dv rows past the segment are multiplied by 0).  All loads of a row are issued
+// before the first use: one memory round trip per row.
+struct Seg { float4 j[3], b[3]; };
+template <bool WITH_B>
+PRB_D void seg_load(const SV& S, int q0, int n, Seg& g) {
+  const int nq = nq_of(n);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    g.j[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (WITH_B) g.b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < nq) { g.j[k] = S.q(q0 + k); if (WITH_B) g.b[k] = S.q(q0 + nq + k); }
+  }
+}
+PRB_D void seg_load_b(const SV& S, int q0, int n, Seg& g) {
+  const int nq = nq_of(n);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    g.b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < nq) g.b[k] = S.q(q0 + nq + k);
+  }
+}
+PRB_D float seg_dot(const Seg& g, const float* dv, int n) {
+  const int nq = nq_of(n);
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    if (k < nq) {
+      s0 = fmaf(g.j[k].x, dv[(4 * k) * PGS_BLOCK], s0);
+      s1 = fmaf(g.j[k].y, dv[(4 * k + 1) * PGS_BLOCK], s1);
+      s0 = fmaf(g.j[k].z, dv[(4 * k + 2) * PGS_BLOCK], s0);
+      s1 = fmaf(g.j[k].w, dv[(4 * k + 3) * PGS_BLOCK], s1);
+    }
+  return s0 + s1;
+}
+PRB_D void seg_axpy(const Seg& g, float* dv, int n, float dl) {
+  const int nq = nq_of(n);
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    if (k < nq) {
+      dv[(4 * k) * PGS_BLOCK] = fmaf(g.b[k].x, dl, dv[(4 * k) * PGS_BLOCK]);
+      dv[(4 * k + 1) * PGS_BLOCK] = fmaf(g.b[k].y, dl, dv[(4 * k + 1) * PGS_BLOCK]);
+      dv[(4 * k + 2) * PGS_BLOCK] = fmaf(g.b[k].z, dl, dv[(4 * k + 2) * PGS_BLOCK]);
+      dv[(4 * k + 3) * PGS_BLOCK] = fmaf(g.b[k].w, dl, dv[(4 * k + 3) * PGS_BLOCK]);
+    }
+}
 struct CPk { int offA, nA, offB, nB, c; };
 PRB_D CPk unpack_contact(float f) {
   const int pk = __float_as_int(f);
@@ -377,227 +388,146 @@ PRB_D CPk unpack_contact(float f) {
   return r;
 }
 
-PRB_D float dot4(float4 j, const float* dv, float s) {
-  s = fmaf(j.x, dv[0], s); s = fmaf(j.y, dv[PGS_BLOCK], s);
-  s = fmaf(j.z, dv[2 * PGS_BLOCK], s); return fmaf(j.w, dv[3 * PGS_BLOCK], s);
-}
-PRB_D void axpy4(float4 b, float* dv, float dl) {
-  dv[0] = fmaf(b.x, dl, dv[0]); dv[PGS_BLOCK] = fmaf(b.y, dl, dv[PGS_BLOCK]);
-  dv[2 * PGS_BLOCK] = fmaf(b.z, dl, dv[2 * PGS_BLOCK]); dv[3 * PGS_BLOCK] = fmaf(b.w, dl, dv[3 * PGS_BLOCK]);
-}
-// J . dv of one body segment whose first two float4 (j0, j1) are already in registers; a third (arm
-// segments) is read from the segment's stream region
-PRB_D float seg_dot(float4 j0, float4 j1, const float4* reg, const float* dv, int n) {
-  if (n == 0) return 0.f;
-  float s = dot4(j0, dv, 0.f);
-  if (n > 4) s = dot4(j1, dv + 4 * PGS_BLOCK, s);
-  if (n > 8) s = dot4(at(reg, 2), dv + 8 * PGS_BLOCK, s);
-  return s;
-}
-// dv += B dl.  Free bodies (n == 6): B = (J_lin / m, I^-1 J_ang) rebuilt from J; otherwise B is float4
-// 3..5 of the segment's stream region (touched only when the impulse changes).
-PRB_D void seg_axpy(float4 j0, float4 j1, const float4* reg, int n, bool first, const float* fi, float* dv, float dl) {
-  if (n == 6) {
-    const float* f = fi + (first ? 0 : 7 * PGS_BLOCK);
-    const float im = f[0] * dl;
-    const float xx = f[PGS_BLOCK], xy = f[2 * PGS_BLOCK], xz = f[3 * PGS_BLOCK];
-    const float yy = f[4 * PGS_BLOCK], yz = f[5 * PGS_BLOCK], zz = f[6 * PGS_BLOCK];
-    const float ax = j0.w * dl, ay = j1.x * dl, az = j1.y * dl;
-    dv[0] = fmaf(j0.x, im, dv[0]);
-    dv[PGS_BLOCK] = fmaf(j0.y, im, dv[PGS_BLOCK]);
-    dv[2 * PGS_BLOCK] = fmaf(j0.z, im, dv[2 * PGS_BLOCK]);
-    dv[3 * PGS_BLOCK] += xx * ax + xy * ay + xz * az;
-    dv[4 * PGS_BLOCK] += xy * ax + yy * ay + yz * az;
-    dv[5 * PGS_BLOCK] += xz * ax + yz * ay + zz * az;
-  } else if (n > 0) {
-    const float4 b0 = at(reg, 3);
-    float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b1;
-    if (n > 4) b1 = at(reg, 4);
-    if (n > 8) b2 = at(reg, 5);
-    axpy4(b0, dv, dl);
-    if (n > 4) axpy4(b1, dv + 4 * PGS_BLOCK, dl);
-    if (n > 8) axpy4(b2, dv + 8 * PGS_BLOCK, dl);
-  }
-}
-// second-body segment of a row (absent in the common case): nothing prefetched
-PRB_D float seg_dot_g(const float4* reg, const float* dv, int n) {
-  if (n == 0) return 0.f;
-  return seg_dot(at(reg, 0), n > 4 ? at(reg, 1) : make_float4(0.f, 0.f, 0.f, 0.f), reg, dv, n);
-}
-PRB_D void seg_axpy_g(const float4* reg, int n, bool first, const float* fi, float* dv, float dl) {
-  if (n == 0) return;
-  seg_axpy(at(reg, 0), n > 4 ? at(reg, 1) : make_float4(0.f, 0.f, 0.f, 0.f), reg, n, first, fi, dv, dl);
-}
-
-// friction cone of Bullet's implicit pair solve (see pgs_candidate<U_PAIR> of the fused kernel)
-PRB_D void cone_clamp(float lim, float sumA, float sumB, float& na, float& nb) {
-  na = sumA; nb = sumB;
-  if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
-    const float ss = sumA * sumA + sumB * sumB;
-    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
-    const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
-    na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
-  }
-}
-
-struct JRow { float4 r0, r1, m0, m1, m2; };
-PRB_D JRow load_jrow(const SV& S, int j) {
-  const float4* p = region_ptr(S, Q_JROW + 8 * j);
-  JRow r;
-  r.r0 = at(p, 0); r.r1 = at(p, 1); r.m0 = at(p, 2); r.m1 = at(p, 3); r.m2 = at(p, 4);
-  return r;
-}
-
-// address of word w (0..3) of a float4 of the stream (impulse write-back)
-PRB_D float* word_of(const float4* p, int off, int w) { return const_cast<float*>(reinterpret_cast<const float*>(&at(p, off))) + w; }
-
-template <int ND, bool GEAR>
-__global__ void __launch_bounds__(PGS_BLOCK, 4) prb_pgs_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N) {
-  __shared__ float dvs[32 * PGS_BLOCK];       // velocity change, lane-interleaved (rows >= nv stay 0: padding of the last segment)
-  __shared__ float fis[14 * PGS_BLOCK];       // free-body inverse mass / inertia: 7 floats per body
+template <int ND>
+__global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N) {
+  // 36 rows: 27 velocity DoF + slack for the zero-padded tail of the last segment
+  __shared__ float dvs[36 * PGS_BLOCK];
   const int e = blockIdx.x * PGS_BLOCK + threadIdx.x;
   if (e >= N) return;
   const DevModel& M = *Mp;
   const SV S = sv_of(sbuf, e);
   float* dv = dvs + threadIdx.x;
-  float* fi = fis + threadIdx.x;
   const int nv = M.nv, nd = M.nd;
   const float4 hdr = S.q(Q_HDR);
   const int njr = __float_as_int(hdr.x), nc = __float_as_int(hdr.y), ns = __float_as_int(hdr.z);
   const float ratio = M.params[P_GEAR_RATIO];
-  {
-    const float4 a0 = S.q(Q_BODY), a1 = S.q(Q_BODY + 1), b0 = S.q(Q_BODY + 2), b1 = S.q(Q_BODY + 3);
-    fi[0] = a0.x; fi[PGS_BLOCK] = a0.y; fi[2 * PGS_BLOCK] = a0.z; fi[3 * PGS_BLOCK] = a0.w;
-    fi[4 * PGS_BLOCK] = a1.x; fi[5 * PGS_BLOCK] = a1.y; fi[6 * PGS_BLOCK] = a1.z;
-    fi[7 * PGS_BLOCK] = b0.x; fi[8 * PGS_BLOCK] = b0.y; fi[9 * PGS_BLOCK] = b0.z; fi[10 * PGS_BLOCK] = b0.w;
-    fi[11 * PGS_BLOCK] = b1.x; fi[12 * PGS_BLOCK] = b1.y; fi[13 * PGS_BLOCK] = b1.z;
-  }
+  float lam[PGS_MAXLAM];       // thread-local (lane-interleaved by the hardware): joint rows, then 4 per contact
 #pragma unroll 1
-  for (int i = 0; i < 32; i++) dv[i * PGS_BLOCK] = 0.f;
+  for (int i = 0; i < 36; i++) dv[i * PGS_BLOCK] = 0.f;
+#pragma unroll 1
+  for (int i = 0; i < njr + 4 * nc; i++) lam[i] = 0.f;
   const int iters = M.solver_iters;
-  const float4* pool = region_ptr(S, Q_POOL);
-  const float4* cn = region_ptr(S, Q_CN);
-  const float4* cf = region_ptr(S, Q_CF);
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
-    // ---- non-contact rows (limit, motor, gear), sweep direction alternating per iteration
-    if (njr > 0) {
-      const int dir = (it & 1) ? 1 : -1;
-      int j = (it & 1) ? 0 : njr - 1;
-      JRow cur = load_jrow(S, j);
+    // ---- non-contact rows, sweep direction alternating per iteration
 #pragma unroll 1
-      for (int i = 0; i < njr; i++) {
-        const int jn = (i + 1 < njr) ? j + dir : j;
-        const JRow nxt = load_jrow(S, jn);                 // next row's record: in flight while this row is solved
-        const float l0 = cur.r1.w;
-        const int w = __float_as_int(cur.r0.x);
-        const int d = w & 0xff, d2 = (w >> 8) & 0xff;
-        float u = dv[d * PGS_BLOCK];
-        if (GEAR && d2 != 0xff) u = fmaf(ratio, dv[d2 * PGS_BLOCK], u);
-        u *= cur.r0.y;
-        const float nl = clampf(l0 + (cur.r0.z - u * cur.r0.w), cur.r1.x, cur.r1.y);
-        const float dl = (nl - l0) * cur.r0.y;
-        if (dl != 0.f) {
-          const float4* p = region_ptr(S, Q_JROW + 8 * j);
-          *word_of(p, 1, 3) = nl;
-          if (d < nd) {
-            axpy4(cur.m0, dv, dl); axpy4(cur.m1, dv + 4 * PGS_BLOCK, dl);
-            if (ND > 8) axpy4(cur.m2, dv + 8 * PGS_BLOCK, dl);
-            if (GEAR && d2 != 0xff) {
-              const float dl2 = dl * ratio;
-              axpy4(at(p, 5), dv, dl2); axpy4(at(p, 6), dv + 4 * PGS_BLOCK, dl2);
-              if (ND > 8) axpy4(at(p, 7), dv + 8 * PGS_BLOCK, dl2);
+    for (int i = 0; i < njr; i++) {
+      const int j = (it & 1) ? i : njr - 1 - i;
+      const float4 r0 = S.q(Q_JROW + 2 * j), r1 = S.q(Q_JROW + 2 * j + 1);
+      const int pk = __float_as_int(r0.x);
+      const int d = pk & 0xff, d2 = (pk >> 8) & 0xff;
+      const bool arm = d < nd;
+      // the M^-1 row is needed only if the impulse changes; issue its loads now anyway (same round trip)
+      float4 m0[3], m1[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        m0[k] = make_float4(0.f, 0.f, 0.f, 0.f); m1[k] = m0[k];
+        if (arm) m0[k] = S.q(Q_MINV + 3 * d + k);
+        if (d2 != 0xff) m1[k] = S.q(Q_MINV + 3 * d2 + k);
+      }
+      float u = dv[d * PGS_BLOCK];
+      if (d2 != 0xff) u = fmaf(ratio, dv[d2 * PGS_BLOCK], u);
+      u *= r0.y;
+      const float l0 = lam[j];
+      const float nl = clampf(l0 + (r0.z - u * r0.w), r1.x, r1.y);
+      const float dl = (nl - l0) * r0.y;
+      lam[j] = nl;
+      if (dl != 0.f) {
+        if (arm) {
+          const float dl2 = dl * ratio;
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            if (4 * k < ND) {
+              dv[(4 * k) * PGS_BLOCK] = fmaf(m1[k].x, dl2, fmaf(m0[k].x, dl, dv[(4 * k) * PGS_BLOCK]));
+              dv[(4 * k + 1) * PGS_BLOCK] = fmaf(m1[k].y, dl2, fmaf(m0[k].y, dl, dv[(4 * k + 1) * PGS_BLOCK]));
+              dv[(4 * k + 2) * PGS_BLOCK] = fmaf(m1[k].z, dl2, fmaf(m0[k].z, dl, dv[(4 * k + 2) * PGS_BLOCK]));
+              dv[(4 * k + 3) * PGS_BLOCK] = fmaf(m1[k].w, dl2, fmaf(m0[k].w, dl, dv[(4 * k + 3) * PGS_BLOCK]));
             }
-          } else {
-            dv[d * PGS_BLOCK] = fmaf(cur.r1.z, dl, dv[d * PGS_BLOCK]);
           }
+        } else {
+          dv[d * PGS_BLOCK] = fmaf(M.slide_minv[d - nd - 6 * M.n_free], dl, dv[d * PGS_BLOCK]);
         }
-        cur = nxt; j = jn;
       }
     }
     // ---- contact normals
-    if (nc > 0) {
-      float4 h = at(cn, 0), hl = at(cn, 1), j0 = at(pool, 0), j1 = at(pool, 1);
+    {
+      float4 h = S.q(Q_CN);
 #pragma unroll 1
       for (int c = 0; c < nc; c++) {
-        const float4* reg = pool + 24 * 64 * c;                      // region_ptr(S, Q_POOL + 48 c)
-        const int cnx = min(c + 1, SB_MAXCONTACT - 1);
-        const float4* nreg = pool + 24 * 64 * cnx;
-        const float4 hn = at(cn, 2 * cnx), hln = at(cn, 2 * cnx + 1), jn0 = at(nreg, 0), jn1 = at(nreg, 1);   // next contact
-        const float l0 = hl.x;
+        const float4 hn = S.q(Q_CN + c + 1);          // next header (slot SB_MAXCONTACT is readable padding)
         const CPk p = unpack_contact(h.x);
-        float* dvA = dv + p.offA * PGS_BLOCK;
-        float* dvB = dv + p.offB * PGS_BLOCK;
-        const float u = seg_dot(j0, j1, reg, dvA, p.nA) + seg_dot_g(reg + 3 * 64, dvB, p.nB);
+        Seg A, B;
+        seg_load<true>(S, Q_POOL + 48 * c, p.nA, A);
+        seg_load<true>(S, Q_POOL + 48 * c + 6, p.nB, B);
+        const float u = seg_dot(A, dv + p.offA * PGS_BLOCK, p.nA) + seg_dot(B, dv + p.offB * PGS_BLOCK, p.nB);
+        const float l0 = lam[njr + 4 * c];
         const float nl = fmaxf(l0 + (h.z - l0 * h.y - u * h.w), 0.f);
         const float dl = nl - l0;
+        lam[njr + 4 * c] = nl;
         if (dl != 0.f) {
-          *word_of(cn, 2 * c + 1, 0) = nl;
-          seg_axpy(j0, j1, reg, p.nA, p.offA == nd, fi, dvA, dl);
-          seg_axpy_g(reg + 3 * 64, p.nB, p.offB == nd, fi, dvB, dl);
+          seg_axpy(A, dv + p.offA * PGS_BLOCK, p.nA, dl);
+          seg_axpy(B, dv + p.offB * PGS_BLOCK, p.nB, dl);
         }
-        h = hn; hl = hln; j0 = jn0; j1 = jn1;
+        h = hn;
       }
     }
-    // ---- torsional friction rows (rare: not prefetched); Bullet skips the row while its normal impulse is 0
+    // ---- spinning friction (Bullet skips the row while the normal impulse is 0)
 #pragma unroll 1
     for (int i = 0; i < ns; i++) {
       const float4 h = S.q(Q_CS + i);
       const CPk p = unpack_contact(h.x);
-      const float4 hl = at(cn, 2 * p.c + 1);
-      const float tot = hl.x;
+      const float tot = lam[njr + 4 * p.c];
       if (!(tot > 0.f)) continue;
-      const float4* rA = pool + 24 * 64 * p.c + 6 * 64;              // row 1, body A: float4 12 of the contact's slot
-      const float4* rB = rA + 3 * 64;
-      float* dvA = dv + p.offA * PGS_BLOCK;
-      float* dvB = dv + p.offB * PGS_BLOCK;
-      const float l0 = hl.y;
-      const float u = seg_dot_g(rA, dvA, p.nA) + seg_dot_g(rB, dvB, p.nB);
+      Seg A, B;
+      seg_load<true>(S, Q_POOL + 48 * p.c + 12, p.nA, A);
+      seg_load<true>(S, Q_POOL + 48 * p.c + 18, p.nB, B);
+      const float u = seg_dot(A, dv + p.offA * PGS_BLOCK, p.nA) + seg_dot(B, dv + p.offB * PGS_BLOCK, p.nB);
       const float lim = h.y * tot;
+      const float l0 = lam[njr + 4 * p.c + 1];
       const float nl = clampf(l0 + (h.z - u * h.w), -lim, lim);
       const float dl = nl - l0;
+      lam[njr + 4 * p.c + 1] = nl;
       if (dl != 0.f) {
-        *word_of(cn, 2 * p.c + 1, 1) = nl;
-        seg_axpy_g(rA, p.nA, p.offA == nd, fi, dvA, dl);
-        seg_axpy_g(rB, p.nB, p.offB == nd, fi, dvB, dl);
+        seg_axpy(A, dv + p.offA * PGS_BLOCK, p.nA, dl);
+        seg_axpy(B, dv + p.offB * PGS_BLOCK, p.nB, dl);
       }
     }
     // ---- lateral friction: the two rows of a contact are solved together (implicit cone)
-    if (nc > 0) {
-      float4 h0 = at(cf, 0), h1 = at(cf, 1);
-      float4 a0 = at(pool, 24), a1 = at(pool, 25), b0 = at(pool, 36), b1 = at(pool, 37);
-      float ln = at(cn, 1).x;
+    {
+      float4 h0 = S.q(Q_CF), h1 = S.q(Q_CF + 1);
 #pragma unroll 1
       for (int c = 0; c < nc; c++) {
-        const float4* reg = pool + 24 * 64 * c;
-        const int cnx = min(c + 1, SB_MAXCONTACT - 1);
-        const float4* nreg = pool + 24 * 64 * cnx;
-        const float4 hn0 = at(cf, 2 * cnx), hn1 = at(cf, 2 * cnx + 1);
-        const float4 an0 = at(nreg, 24), an1 = at(nreg, 25), bn0 = at(nreg, 36), bn1 = at(nreg, 37);
-        const float lnn = at(cn, 2 * cnx + 1).x;
-        const float la = h1.z, lb = h1.w;
+        const float4 hn0 = S.q(Q_CF + 2 * c + 2), hn1 = S.q(Q_CF + 2 * c + 3);
         const CPk p = unpack_contact(h0.x);
-        float* dvA = dv + p.offA * PGS_BLOCK;
-        float* dvB = dv + p.offB * PGS_BLOCK;
-        const float4* rA1 = reg + 12 * 64;       // row 2 body A (float4 24), body B (30); row 3 body A (36), body B (42)
-        const float4* rB1 = reg + 15 * 64;
-        const float4* rA2 = reg + 18 * 64;
-        const float4* rB2 = reg + 21 * 64;
-        const float ua = seg_dot(a0, a1, rA1, dvA, p.nA) + seg_dot_g(rB1, dvB, p.nB);
-        const float ub = seg_dot(b0, b1, rA2, dvA, p.nA) + seg_dot_g(rB2, dvB, p.nB);
-        float na, nb;
-        cone_clamp(h0.y * ln, la + (h0.z - ua * h1.x), lb + (h0.w - ub * h1.y), na, nb);
+        Seg A1, B1, A2, B2;
+        seg_load<true>(S, Q_POOL + 48 * c + 24, p.nA, A1);
+        seg_load<true>(S, Q_POOL + 48 * c + 30, p.nB, B1);
+        seg_load<true>(S, Q_POOL + 48 * c + 36, p.nA, A2);
+        seg_load<true>(S, Q_POOL + 48 * c + 42, p.nB, B2);
+        const float ua = seg_dot(A1, dv + p.offA * PGS_BLOCK, p.nA) + seg_dot(B1, dv + p.offB * PGS_BLOCK, p.nB);
+        const float ub = seg_dot(A2, dv + p.offA * PGS_BLOCK, p.nA) + seg_dot(B2, dv + p.offB * PGS_BLOCK, p.nB);
+        const float lim = h0.y * lam[njr + 4 * c];
+        const float la = lam[njr + 4 * c + 2], lb = lam[njr + 4 * c + 3];
+        const float sumA = la + (h0.z - ua * h1.x);
+        const float sumB = lb + (h0.w - ub * h1.y);
+        float na = sumA, nb = sumB;
+        if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
+          const float ss = sumA * sumA + sumB * sumB;
+          const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+          const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
+          na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
+        }
         const float d1 = na - la, d2 = nb - lb;
-        if (d1 != 0.f || d2 != 0.f) *reinterpret_cast<float2*>(word_of(cf, 2 * c + 1, 2)) = make_float2(na, nb);
+        lam[njr + 4 * c + 2] = na; lam[njr + 4 * c + 3] = nb;
         if (d1 != 0.f) {
-          seg_axpy(a0, a1, rA1, p.nA, p.offA == nd, fi, dvA, d1);
-          seg_axpy_g(rB1, p.nB, p.offB == nd, fi, dvB, d1);
+          seg_axpy(A1, dv + p.offA * PGS_BLOCK, p.nA, d1);
+          seg_axpy(B1, dv + p.offB * PGS_BLOCK, p.nB, d1);
         }
         if (d2 != 0.f) {
-          seg_axpy(b0, b1, rA2, p.nA, p.offA == nd, fi, dvA, d2);
-          seg_axpy_g(rB2, p.nB, p.offB == nd, fi, dvB, d2);
+          seg_axpy(A2, dv + p.offA * PGS_BLOCK, p.nA, d2);
+          seg_axpy(B2, dv + p.offB * PGS_BLOCK, p.nB, d2);
         }
-        h0 = hn0; h1 = hn1; a0 = an0; a1 = an1; b0 = bn0; b1 = bn1; ln = lnn;
+        h0 = hn0; h1 = hn1;
       }
     }
   }

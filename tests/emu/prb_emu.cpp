@@ -23,10 +23,7 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
     int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
     if (flags == 0) break;
     emu::launch(gs, bs, [&]() { prb_setup_kernel<ND>(&g_M, state, g_sbuf.data(), O, N, flags); });
-    if (i < nsub) {
-      if (g_M.gear_a >= 0) emu::launch(gp, bp, [&]() { prb_pgs_kernel<ND, true>(&g_M, g_sbuf.data(), N); });
-      else emu::launch(gp, bp, [&]() { prb_pgs_kernel<ND, false>(&g_M, g_sbuf.data(), N); });
-    }
+    if (i < nsub) emu::launch(gp, bp, [&]() { prb_pgs_kernel<ND>(&g_M, g_sbuf.data(), N); });
   }
 }
 static void run_step(float* state, DevOut O, int N, int nsub, int observe) {
@@ -51,8 +48,6 @@ void emu_ik(float* state, const float* action, float* target, int N) {
   emu::launch(g, b, [&]() { prb_ik_kernel(&g_M, state, action, target, N); });
 }
 void emu_set_fused(int f) { g_fused = f; }
-float* emu_sbuf() { return g_sbuf.data(); }
-int emu_sb_q() { return SB_Q; }
 static unsigned long long g_overflow = 0;
 unsigned long long emu_overflow() { return g_overflow; }
 void emu_substeps(float* state, int N, int nsub) { DevOut O; memset(&O, 0, sizeof(O)); O.overflow = &g_overflow; O.dbg = nullptr; run_step(state, O, N, nsub, 0); }
