@@ -48,6 +48,8 @@ void emu_ik(float* state, const float* action, float* target, int N) {
   emu::launch(g, b, [&]() { prb_ik_kernel(&g_M, state, action, target, N); });
 }
 void emu_set_fused(int f) { g_fused = f; }
+float* emu_sbuf() { return g_sbuf.data(); }
+int emu_sbuf_q() { return SB_Q; }
 static unsigned long long g_overflow = 0;
 unsigned long long emu_overflow() { return g_overflow; }
 void emu_substeps(float* state, int N, int nsub) { DevOut O; memset(&O, 0, sizeof(O)); O.overflow = &g_overflow; O.dbg = nullptr; run_step(state, O, N, nsub, 0); }

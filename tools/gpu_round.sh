@@ -15,3 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"prb_setup_kernel|prb_pgs_kernel" -s 85 -c 4 -f -o gpurun_out/prof_$TAG \
     python bench.py --steps 3 --warmup 3 --envs-per-gpu 8192 --no-cpu-baseline > gpurun_out/b_ncu_$TAG.log 2>&1
 tail -c 600 gpurun_out/b_ncu_$TAG.log
+# the same two kernels at the bench size (65536 envs: the record stream no longer fits L2)
+ncu --set full --clock-control none --import-source on -k regex:"prb_setup_kernel|prb_pgs_kernel" -s 85 -c 2 -f -o gpurun_out/prof64k_$TAG \
+    python bench.py --steps 3 --warmup 3 --envs-per-gpu 65536 --no-cpu-baseline > gpurun_out/b_ncu64k_$TAG.log 2>&1
+tail -c 300 gpurun_out/b_ncu64k_$TAG.log
