@@ -24,7 +24,11 @@ struct prb_handle {
   DevOut O;
   int64_t launches = 0;
   int fused = 0;                   // PRB_PIPELINE=fused: A/B reference path (warp-per-env kernel, 12 substeps in one launch)
-  float* sbuf = nullptr;           // [N][SB_STRIDE] constraint-row record stream of the split pipeline
+  float* sbuf = nullptr;           // constraint-row record stream of the split pipeline (prb_stream.cuh)
+  int* heavy_list = nullptr;       // env ids whose arm island has contacts this substep (general solver kernel)
+  int* heavy_cnt = nullptr;
+  cudaStream_t side = nullptr;     // high-priority side stream: the arm-island solver overlaps the joint / free-body solvers
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int smem = 0, regs = 0;          // setup kernel (reported)
   int regs_pgs = 0;
   int smem_fused = 0, smem_reset = 0;
@@ -59,18 +63,34 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
     return PRB_OK;
   }
   dim3 gs((h->N + SetupCfg::WPB - 1) / SetupCfg::WPB), bs(32 * SetupCfg::WPB);
-  dim3 gp((h->N + PGS_BLOCK - 1) / PGS_BLOCK), bp(PGS_BLOCK);
+  const int ng = (h->N + PGS_BLOCK - 1) / PGS_BLOCK;
+  dim3 gp(ng), gf(ng, h->hm.n_free), bp(PGS_BLOCK);
   h->n_evk = 0;
   for (int i = 0; i <= nsub; i++) {
     int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
     if (flags == 0) break;
     if (h->timing && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
-    prb_setup_kernel<ND><<<gs, bs, h->smem, s>>>(h->dm, h->state, h->sbuf, h->O, h->N, flags);
+    if (i < nsub) CK(h, cudaMemsetAsync(h->heavy_cnt, 0, 2 * sizeof(int), s));
+    prb_setup_kernel<ND><<<gs, bs, h->smem, s>>>(h->dm, h->state, h->sbuf, h->O, h->N, flags, h->heavy_list, h->heavy_cnt);
     h->launches++;
     if (i < nsub) {
       if (h->timing && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
-      prb_pgs_kernel<ND><<<gp, bp, 0, s>>>(h->dm, h->sbuf, h->N);
-      h->launches++;
+      // the islands of a substep are independent: three solver kernels, any order
+      // the islands of a substep are independent: the arm-island solver (few envs, long dependent
+      // chains) goes first on the high-priority side stream, the two throughput kernels fill the
+      // machine behind it; the streams join before the next setup launch
+      CK(h, cudaEventRecord(h->ev_fork, s));
+      CK(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      {
+        dim3 gh((h->N + PGS_G_EPW - 1) / PGS_G_EPW);     // blocks past the list's length exit at once
+        prb_pgs_kernel<ND><<<gh, bp, PGS_SMEM_G(PGS_ROWS_GB), h->side>>>(h->dm, h->sbuf, h->heavy_list + h->N, h->heavy_cnt + 1, PGS_ROWS_GB);
+        prb_pgs_kernel<ND><<<gh, bp, PGS_SMEM_G(PGS_ROWS_GA), h->side>>>(h->dm, h->sbuf, h->heavy_list, h->heavy_cnt, PGS_ROWS_GA);
+      }
+      CK(h, cudaEventRecord(h->ev_join, h->side));
+      prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, s>>>(h->dm, h->sbuf, h->N);
+      if (h->hm.n_free > 0) prb_pgs_free_kernel<<<gf, bp, PGS_SMEM_F, s>>>(h->dm, h->sbuf, h->N);
+      CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+      h->launches += h->hm.n_free > 0 ? 4 : 3;
     }
   }
   if (h->timing && h->n_evk < 64) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
@@ -92,6 +112,12 @@ static int setup_kernels(prb_handle* h) {
   cudaFuncAttributes fa;
   CK(h, cudaFuncGetAttributes(&fa, prb_setup_kernel<ND>));
   h->regs = fa.numRegs;
+  CK(h, cudaFuncSetAttribute(prb_pgs_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_G(PGS_ROWS_GB)));
+  CK(h, cudaFuncSetAttribute(prb_pgs_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_J));
+  CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(h, cudaFuncSetAttribute(prb_pgs_free_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_F));
+  CK(h, cudaFuncSetAttribute(prb_pgs_free_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(h, cudaFuncGetAttributes(&fa, prb_pgs_kernel<ND>));
   h->regs_pgs = fa.numRegs;
   return PRB_OK;
@@ -142,9 +168,16 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
     h->fused = (p && strcmp(p, "fused") == 0) ? 1 : 0;
   }
   if (!h->fused) {
-    const size_t sb_bytes = (size_t)((N + 31) / 32) * 32 * SB_Q * sizeof(float4);   // whole 32-env groups
+    const size_t sb_bytes = sbuf_bytes(N);   // whole 32-env groups + prefetch slack
     CK(h, cudaMalloc(&h->sbuf, sb_bytes));
     CK(h, cudaMemset(h->sbuf, 0, sb_bytes));
+    CK(h, cudaMalloc(&h->heavy_list, sizeof(int) * 2 * N));
+    CK(h, cudaMalloc(&h->heavy_cnt, 2 * sizeof(int)));
+    int lo_pri = 0, hi_pri = 0;
+    CK(h, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    CK(h, cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi_pri));
+    CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   }
   {
     int rc = M.nd == 12 ? setup_kernels<12>(h) : setup_kernels<9>(h);
@@ -160,7 +193,10 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
 int prb_destroy(prb_handle* h) {
   if (!h) return PRB_ERR_INVALID;
   cudaSetDevice(h->device);
-  cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->sbuf);
+  cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->sbuf); cudaFree(h->heavy_list); cudaFree(h->heavy_cnt);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return PRB_OK;
 }

@@ -86,11 +86,11 @@ static inline void block_barrier() {
 static const size_t STACK = 256 * 1024;
 
 template <class F>
-void launch(emu_dim3 grid, emu_dim3 block, F f) {
+void launch_y(emu_dim3 grid, emu_dim3 block, unsigned by, F f) {
   g_gridDim = grid; g_blockDim = block;
   nthreads = block.x;
   for (unsigned b = 0; b < grid.x; b++) {
-    g_blockIdx.x = b;
+    g_blockIdx.x = b; g_blockIdx.y = by;
     fibers.assign(nthreads, Fiber());
     warps.assign((nthreads + 31) / 32, Warp());
     block_gen = block_arrived = 0;
@@ -119,6 +119,8 @@ void launch(emu_dim3 grid, emu_dim3 block, F f) {
     for (int t = 0; t < nthreads; t++) free(fibers[t].stack);
   }
 }
+template <class F>
+void launch(emu_dim3 grid, emu_dim3 block, F f) { launch_y(grid, block, 0, f); }
 }  // namespace emu
 
 #define threadIdx (emu::fibers[emu::cur].tid)
