@@ -14,7 +14,7 @@
 struct prb_handle {
   DevModel hm;
   DevModel* dm = nullptr;
-  int N = 0, device = 0;
+  int N = 0, device = 0, sms = 148;
   unsigned env_offset = 0;
   unsigned long long seed = 0;
   float* state = nullptr;
@@ -28,7 +28,8 @@ struct prb_handle {
   int* heavy_list = nullptr;       // env ids whose arm island has contacts this substep (general solver kernel)
   int* heavy_cnt = nullptr;
   cudaStream_t side = nullptr;     // high-priority side stream: the arm-island solver overlaps the joint / free-body solvers
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side2 = nullptr;    // second side stream: the two size classes of the arm-island solver overlap too
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   int smem = 0, regs = 0;          // setup kernel (reported)
   int regs_pgs = 0;
   int smem_fused = 0, smem_reset = 0;
@@ -63,8 +64,10 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
     return PRB_OK;
   }
   dim3 gs((h->N + SetupCfg::WPB - 1) / SetupCfg::WPB), bs(32 * SetupCfg::WPB);
-  const int ng = (h->N + PGS_BLOCK - 1) / PGS_BLOCK;
-  dim3 gp(ng), gf(ng, h->hm.n_free), bp(PGS_BLOCK);
+  // persistent solver blocks: resident blocks per SM (shared-memory limited) x SMs, grid-stride inside
+  const int ng = (h->N + PGS_BLOCK - 1) / PGS_BLOCK, nq = (h->N + PGS_G_EPW - 1) / PGS_G_EPW;
+  dim3 gp(ng < 6 * h->sms ? ng : 6 * h->sms), gf(ng < 3 * h->sms ? ng : 3 * h->sms, h->hm.n_free), bp(PGS_BLOCK);
+  dim3 gha(nq < 4 * h->sms ? nq : 4 * h->sms), ghb(nq < 2 * h->sms ? nq : 2 * h->sms);
   h->n_evk = 0;
   for (int i = 0; i <= nsub; i++) {
     int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
@@ -81,15 +84,15 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
       // machine behind it; the streams join before the next setup launch
       CK(h, cudaEventRecord(h->ev_fork, s));
       CK(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-      {
-        dim3 gh((h->N + PGS_G_EPW - 1) / PGS_G_EPW);     // blocks past the list's length exit at once
-        prb_pgs_kernel<ND><<<gh, bp, PGS_SMEM_G(PGS_ROWS_GB), h->side>>>(h->dm, h->sbuf, h->heavy_list + h->N, h->heavy_cnt + 1, PGS_ROWS_GB);
-        prb_pgs_kernel<ND><<<gh, bp, PGS_SMEM_G(PGS_ROWS_GA), h->side>>>(h->dm, h->sbuf, h->heavy_list, h->heavy_cnt, PGS_ROWS_GA);
-      }
+      CK(h, cudaStreamWaitEvent(h->side2, h->ev_fork, 0));
+      prb_pgs_arm_kernel<ND><<<ghb, bp, PGS_SMEM_G(PGS_ROWS_GB), h->side2>>>(h->dm, h->sbuf, h->heavy_list + h->N, h->heavy_cnt + 1, PGS_ROWS_GB);
+      prb_pgs_arm_kernel<ND><<<gha, bp, PGS_SMEM_G(PGS_ROWS_GA), h->side>>>(h->dm, h->sbuf, h->heavy_list, h->heavy_cnt, PGS_ROWS_GA);
       CK(h, cudaEventRecord(h->ev_join, h->side));
+      CK(h, cudaEventRecord(h->ev_join2, h->side2));
       prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, s>>>(h->dm, h->sbuf, h->N);
       if (h->hm.n_free > 0) prb_pgs_free_kernel<<<gf, bp, PGS_SMEM_F, s>>>(h->dm, h->sbuf, h->N);
       CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+      CK(h, cudaStreamWaitEvent(s, h->ev_join2, 0));
       h->launches += h->hm.n_free > 0 ? 4 : 3;
     }
   }
@@ -112,13 +115,13 @@ static int setup_kernels(prb_handle* h) {
   cudaFuncAttributes fa;
   CK(h, cudaFuncGetAttributes(&fa, prb_setup_kernel<ND>));
   h->regs = fa.numRegs;
-  CK(h, cudaFuncSetAttribute(prb_pgs_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_G(PGS_ROWS_GB)));
-  CK(h, cudaFuncSetAttribute(prb_pgs_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_G(PGS_ROWS_GB)));
+  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_J));
   CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(h, cudaFuncSetAttribute(prb_pgs_free_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_F));
   CK(h, cudaFuncSetAttribute(prb_pgs_free_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(h, cudaFuncGetAttributes(&fa, prb_pgs_kernel<ND>));
+  CK(h, cudaFuncGetAttributes(&fa, prb_pgs_arm_kernel<ND>));
   h->regs_pgs = fa.numRegs;
   return PRB_OK;
 }
@@ -143,6 +146,7 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
   h->N = cfg->num_envs; h->device = cfg->device; h->env_offset = (unsigned)cfg->env_offset; h->seed = cfg->seed;
   *out = h;
   CK(h, cudaSetDevice(h->device));
+  CK(h, cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device));
   CK(h, cudaMalloc(&h->dm, sizeof(DevModel)));
   CK(h, cudaMemcpy(h->dm, &h->hm, sizeof(DevModel), cudaMemcpyHostToDevice));
   const DevModel& M = h->hm;
@@ -176,6 +180,8 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
     int lo_pri = 0, hi_pri = 0;
     CK(h, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
     CK(h, cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi_pri));
+    CK(h, cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, hi_pri));
+    CK(h, cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
     CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   }
@@ -195,6 +201,8 @@ int prb_destroy(prb_handle* h) {
   cudaSetDevice(h->device);
   cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->sbuf); cudaFree(h->heavy_list); cudaFree(h->heavy_cnt);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->side2) cudaStreamDestroy(h->side2);
+  if (h->ev_join2) cudaEventDestroy(h->ev_join2);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;

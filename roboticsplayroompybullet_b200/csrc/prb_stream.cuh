@@ -1,34 +1,31 @@
 // prb_stream.cuh — the split ("stream") step pipeline.
 //
-// One stepSimulation() substep = two launches:
+// One stepSimulation() substep = one setup launch + the constraint solve:
 //   prb_setup_kernel   one WARP per env: integrate the previous substep's solution, then kinematics,
 //                      collision detection, mass matrix and its inverse, unconstrained velocities and
-//                      the constraint rows of this substep.  The rows are written as COMPACT records
-//                      to a per-env record stream in HBM (~2.3 kB per env-substep).  The last launch
-//                      of an env step also runs the fused observation / reward write.
-//   prb_pgs_kernel     one THREAD per env, one warp per block: the block stages its 32 envs' records
-//                      into shared memory ONCE (coalesced 512-byte rows), then runs the 50
-//                      projected-Gauss-Seidel sweeps, in velocity space, in
-//                      btMultiBodyConstraintSolver::solveSingleIteration order, entirely out of
-//                      shared memory: records, accumulated impulses and the velocity change dv are
-//                      lane-interleaved float4 columns (conflict-free).  Records past the per-env
-//                      stage capacity are read from the stream in place (L2), so capacity only costs
-//                      speed, never contacts.
+//                      the constraint rows of this substep, written as records to a per-env record
+//                      stream in HBM (~2-3 kB per env-substep).  The last launch of an env step also
+//                      runs the fused observation / reward write.
+//   solver kernels     the 50 projected-Gauss-Seidel sweeps, in velocity space, in
+//                      btMultiBodyConstraintSolver::solveSingleIteration order.  Every kernel stages its
+//                      envs' records ONCE into shared memory (one warp per block, lane-interleaved
+//                      float4 columns, conflict-free) and sweeps them there; the constraint islands of
+//                      an env are solved by different kernels concurrently (see "Constraint islands").
 //
-// Why: the first thread-per-env solver re-streamed 4.5 kB of explicit Jacobian rows per env per
-// iteration from HBM (14.7 GB of DRAM reads per launch at 65536 envs, profiles/r1_v9_ncu.md) and was
+// Why (profiles/r1_v9_ncu.md): the first thread-per-env solver re-streamed 4.5 kB of explicit Jacobian
+// rows per env per iteration from HBM (14.7 GB of DRAM reads per launch at 65536 envs) and was
 // latency-bound on dependent global loads.  95 % of the contacts in the playroom are a free body
-// (block, drawer) against static geometry: their three rows are fully described by the contact
-// frame (n, t1), the lever arm r and the body's inverse inertia, so the record is 6 float4 instead
-// of 15 and the Jacobians are rebuilt in registers.  Arm-side rows keep explicit J and M^-1 J^T.
+// (block, drawer) against static geometry: their three rows are fully described by the contact frame
+// (n, t1), the lever arm r and the body's inverse inertia, so the record is 6 float4 instead of 15 and
+// the Jacobians are rebuilt in registers.  Rows that involve the arm keep explicit J and M^-1 J^T and are
+// solved by four lanes per env.
 //
 // Reference path: environments.py:485-490 (12 x stepSimulation), Bullet btMultiBodyDynamicsWorld.
 #pragma once
 #include "prb_kernels.cuh"
 
-// ---- record stream.  Envs are grouped by 32 (one group = the 32 envs a solver warp serves); float4
-// number q of env (g, l) lives at float4 index  g * 32 * SB_Q + q * 32 + l.  All offsets are in
-// float4 units ("q").
+// ---- record stream.  Envs are grouped by 32; float4 number q of env (g, l) lives at float4 index
+// g * 32 * SB_Q + q * 32 + l.  All offsets are in float4 units ("q").
 //
 // Constraint islands.  Rows that share no dynamic body never exchange data in Gauss-Seidel, so the
 // sweep order BETWEEN islands is immaterial (bit-identical results) and islands can be solved
@@ -38,54 +35,57 @@
 //   slot 1, 2: contacts of a free body (block, drawer) that touches only static geometry (or the
 //              other free body) — the common case; these records need no arm data at all.
 // Within a slot the contacts keep Bullet's order.
-#define Q_HDR 0          // ints {n_jrow, n_contact[0], n_spin[0], t_spin[0]}
+#define Q_HDR 0          // ints {n_jrow | n_contact[0] << 8 | n_spin[0] << 16, t of slot 0's spin rows, t of its friction rows, t end of region 0}
                          //      {n_contact[1] | n_spin[1] << 8 | slot of free body 0 << 16 | slot of free body 1 << 18, start[1], t_spin[1], -}
                          //      {n_contact[2] | n_spin[2] << 8, start[2], t_spin[2], -}
 #define Q_VSTAR 3        // 8 q: unconstrained velocities v* of the substep (word i = DoF i)
 #define Q_DV 11          // 8 q: solver output M^-1 J^T lambda (word i = DoF i)
 #define Q_ST 19          // start of the slot regions; region 0 starts here, region s at Q_ST + start[s];
                          // "t" offsets are relative to the start of the slot's region
-#define T_BODY 0         // (region 0) 2 q per free body: world inverse inertia {xx xy xz yy} {yz zz 1/m -}
-#define T_MINV 4         // (region 0) 12 rows x 3 q: arm inverse mass matrix (row d at T_MINV + 3 d, zero padded)
-#define T_JROW 40        // (region 0) n_jrow x 1 q: {packed, rhs, invD, hi}
+// ---- region 0
+#define T_BODY 0         // 2 q per free body: world inverse inertia {xx xy xz yy} {yz zz 1/m -}
+#define T_MINV 4         // 12 rows x 3 q: arm inverse mass matrix (row d at T_MINV + 3 d, zero padded)
+#define T_JROW 40        // n_jrow x 1 q: {packed, rhs, invD, hi}
                          //   packed: pd | pd2 << 8 | a << 16 | a2 << 20 | neg << 24 | sym << 25
-                         //   pd/pd2: solver dv word of the DoF (pd2 = 0xff: none); a/a2: arm row (15: not arm)
-                         //   neg: J = -e_d; sym: lo = -hi (else lo = 0)
-                         // then ceil(n_jrow / 4) q of accumulated impulses, then the slot's contacts and spin list
+                         //   pd/pd2: dv word of the DoF (arm: d, slide s: DVW_SLIDE(s); pd2 = 0xff: none);
+                         //   a/a2: arm row (15: not arm); neg: J = -e_d; sym: lo = -hi (else lo = 0)
+                         // then ceil(n_jrow / 4) q of accumulated impulses, then (4-q aligned) slot 0's contact rows
 #define SB_MAXJROW 40
 #define SB_MAXCONTACT 32
-// contact record (>= 6 q), P = primary side, S = secondary side (see kind_rank):
+// slot 0 contact rows are EXPLICIT.  The island's velocity change is two 16-float vectors:
+//   A: arm DoF 0..11 (words 12..15 unused)      F: free body b at words 6 b .. 6 b + 5, slide body s at word 12 + s
+// A row is 8 q: {JA[0..3], JA[4..7], JA[8..11], H1} {BA[0..3], BA[4..7], BA[8..11], H2}, followed, when
+// bit 0 of the flags is set, by 8 q {JF[0..15]} {BF[0..15]}.   J: Jacobian, B = M^-1 J^T.
+//   H1 = {flags, rhs, invD, lambda}      H2 = normal: {cfm * invD, -, -, -}; spin: {coefficient, t of the normal row, -, -};
+//                                             friction 1: {mu, t of the normal row, -, -}; friction 2: unused
+// Rows are grouped by pass: all normal rows (contact order), all spin rows, all friction pairs (rows of a
+// pair adjacent).  The solver kernel gives an env four lanes: lane c holds words 4c..4c+3 of A and F in
+// registers and column c of the rows.
+#define XROW_Q 8
+// ---- slots 1, 2: compact contact record (6 q, +1 q when the second side is the other free body):
 //   +0 {packed, cfm * invD0, rhs0, invD0}     +1 {n.xyz, lambda0}        +2 {rP.xyz, mu}
 //   +3 {t1.xyz, lambda1 (spin)}               +4 {rhs2, rhs3, invD2, invD3}   +5 {lambda2, lambda3, -, -}
-//   then the geometry of P (free: none, its lever arm is rP; slide: 1 q {j0 j1 j2 j3}; arm: 4 rows x
-//   {3 q J, 3 q B = M^-1 J^T}, rows = normal, spin, friction 1, friction 2) and of S (free: 1 q {r.xyz, -};
-//   slide, arm as for P).
-//   packed: kP | kS << 2 | iP << 4 | iS << 7 | neg << 10 | spin << 11 | stride << 12
-//   (kX: 0 static, 1 free, 2 slide, 3 arm; iX: free / slide index; neg: sign of P is -1; stride: q to the
-//   slot's next record — a record never straddles the slot's stage boundary)
+//   +6 {rS.xyz, -} when side S is a free body
+//   packed: kS << 2 | iP << 4 | iS << 7 | neg << 10 | spin << 11 | stride << 12
+//   (kS: 0 static, 1 free; iX: free body index; neg: sign of P is -1; stride: q to the slot's next
+//   record — a record never straddles the stage boundary PGS_STAGE_F)
 // spin list entry (1 q): {t of the contact record, spin coefficient, rhs1, invD1}
 #define CT_BASE_Q 6
-#define CT_ARM_Q 24
-#define SB_Q (Q_ST + T_JROW + SB_MAXJROW + SB_MAXJROW / 4 + SB_MAXCONTACT * (CT_BASE_Q + 2 * CT_ARM_Q) + SB_MAXCONTACT + 3 * 64)   // + stage-boundary gaps
+#define SB_Q (Q_ST + 96 + SB_MAXCONTACT * 4 * 2 * XROW_Q + SB_MAXCONTACT + 64 + 8)
 #define SB_PAD_Q 48      // readable slack after the last group (the solvers prefetch one record ahead)
-// stage capacities (q of shared memory per env) of the three solver kernels
+// stage capacities (q of shared memory per env) of the solver kernels
 #ifndef PGS_STAGE_J
 #define PGS_STAGE_J 68   // joint-row kernel: region 0 up to the impulses of <= 22 joint rows; 6 blocks per SM
 #endif
 #ifndef PGS_STAGE_F
 #define PGS_STAGE_F 64   // free-body kernel: 10 contact records; 6 blocks per SM
 #endif
-#ifndef PGS_STAGE_G
-#define PGS_STAGE_G 200  // general kernel (islands that contain the arm): 2 blocks per SM
-#endif
-#define PGS_G_LW 2       // general kernel: an env owns 4 shared-memory columns (8 envs per warp)
+#define PGS_G_LW 2       // arm-island kernel: an env owns 4 shared-memory columns (8 envs per warp)
 #define PGS_ROWS_GA 104  // class A: 416 q per env, 4 blocks per SM
 #define PGS_ROWS_GB 216  // class B: 864 q per env, 2 blocks per SM
 #define PGS_CLASS_A_MAXQ (PGS_ROWS_GA << PGS_G_LW)
 #define PGS_MAXJROW_J ((PGS_STAGE_J - T_JROW) * 4 / 5)     // njr + ceil(njr / 4) <= PGS_STAGE_J - T_JROW
-#define PGS_DVQ 8        // general solver dv: arm q 0..2, free body b q 3+2b..4+2b (6 words used), slides q 7
-#define DVW_FREE(b) (12 + 8 * (b))
-#define DVW_SLIDE(s) (12 + 8 * PRB_MAXFREE + (s))
+#define DVW_SLIDE(s) (28 + (s))
 enum { K_STATIC = 0, K_FREE = 1, K_SLIDE = 2, K_ARM = 3 };
 
 struct SV {              // one env's column of its group
@@ -133,20 +133,19 @@ struct SetupMemT {
 
 PRB_D int body_kind(const DevModel& M, int body) { return body < 0 ? K_STATIC : (body == 0 ? K_ARM : (body <= M.n_free ? K_FREE : K_SLIDE)); }
 PRB_D int kind_rank(int k) { return k == K_ARM ? 3 : (k == K_SLIDE ? 2 : (k == K_FREE ? 1 : 0)); }
-PRB_D int geom_q(int kind, bool primary) { return kind == K_ARM ? CT_ARM_Q : (kind == K_SLIDE ? 1 : ((kind == K_FREE && !primary) ? 1 : 0)); }
 
 // One side of one constraint row: J = unit force `dir` at world point pt (or unit torque when angular)
-// on the body of collider col, times sign; B = M^-1 J^T.  Returns J.B and accumulates J.v*.  Arm sides
-// store J and B (3 q each, stride 32) at garm; slide sides return the scalar J in *jslide; free-body
-// sides store nothing (the solver rebuilds them from the contact frame and the lever arm).
+// on the body of collider col, times sign; B = M^-1 J^T.  Returns J.B and accumulates J.v*.  When JA is
+// given the explicit row is accumulated: arm sides into JA / BA (12 floats), free and slide sides into
+// JF / BF (16 floats, layout F above).
 template <int ND, class WM>
 PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, float sign, bool angular,
-                     float4* garm, float* jslide, float* rel) {
+                     float* JA, float* BA, float* JF, float* BF, float* rel) {
   const int body = M.col_body[col];
   float d = 0.f;
   if (body == 0) {
     const int link = M.col_link[col];
-    float J[12], B[12];
+    float J[12];
     const unsigned anc = M.anc_mask[link];
 #pragma unroll
     for (int j = 0; j < 12; j++) {
@@ -167,12 +166,7 @@ PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, flo
         for (int j = 0; j < ND; j++) s = fmaf(W.Minv[i][j], J[j], s);
         d = fmaf(J[i], s, d); r = fmaf(J[i], W.vs[i], r);
       }
-      B[i] = s;
-    }
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      garm[k * 32] = make_float4(J[4 * k], J[4 * k + 1], J[4 * k + 2], J[4 * k + 3]);
-      garm[(3 + k) * 32] = make_float4(B[4 * k], B[4 * k + 1], B[4 * k + 2], B[4 * k + 3]);
+      if (JA) { JA[i] += J[i]; BA[i] += s; }
     }
     *rel += r;
   } else if (body <= M.n_free) {
@@ -184,7 +178,10 @@ PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, flo
     float J[6] = {jl.x, jl.y, jl.z, ja.x, ja.y, ja.z}, B[6] = {bl.x, bl.y, bl.z, ba.x, ba.y, ba.z};
     float r = 0.f;
 #pragma unroll
-    for (int k = 0; k < 6; k++) { d = fmaf(J[k], B[k], d); r = fmaf(J[k], W.vs[o + k], r); }
+    for (int k = 0; k < 6; k++) {
+      d = fmaf(J[k], B[k], d); r = fmaf(J[k], W.vs[o + k], r);
+      if (JF) { JF[6 * b + k] += J[k]; BF[6 * b + k] += B[k]; }
+    }
     *rel += r;
   } else {
     const int s = body - 1 - M.n_free, o = M.nd + 6 * M.n_free + s;
@@ -193,17 +190,15 @@ PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, flo
     if (M.slide_jtype[s] == 0) g = angular ? dot(a, dir) : dot(a, cross(pt - ld3(W.sp[s]), dir));
     else g = angular ? 0.f : dot(a, dir);
     const float j = sign * g, bb = j * M.slide_minv[s];
-    *jslide = j;
+    if (JF) { JF[12 + s] += j; BF[12 + s] += bb; }
     d = j * bb; *rel += j * W.vs[o];
   }
   return d;
 }
 
-PRB_D int dvw_of(const DevModel& M, int d) {     // velocity DoF -> solver dv word
+PRB_D int dvw_of(const DevModel& M, int d) {     // velocity DoF -> dv word of a joint row
   if (d < M.nd) return d;
-  int r = d - M.nd;
-  if (r < 6 * M.n_free) return DVW_FREE(r / 6) + r % 6;
-  return DVW_SLIDE(r - 6 * M.n_free);
+  return DVW_SLIDE(d - M.nd - 6 * M.n_free);
 }
 
 // constraint rows of the substep -> record stream
@@ -278,10 +273,11 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
     S.q(Q_ST + T_BODY + 2 * b + 1) = make_float4(W.fIinv[b][4], W.fIinv[b][5], 1.0f / M.free_mass[b], 0.f);
   }
   __syncwarp();
-  // ---- contact records: lane = contact
+  // ---- contacts: lane = contact
   const int nc = W.n_contact, njr = W.n_jrow;
-  int colP = 0, colS = 0, kP = K_STATIC, kS = K_STATIC, size = 0, grpP = 0, grpS = -1;
-  bool swapped = false;
+  int colP = 0, colS = 0, kP = K_STATIC, kS = K_STATIC, grpP = 0, grpS = -1;
+  bool swapped = false, has_spin = false;
+  float spin = 0.f;
   Contact c;
   if (lane < nc) {
     c = W.ct[lane];
@@ -290,9 +286,10 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
     swapped = kind_rank(kB) > kind_rank(kA);
     colP = swapped ? cb : ca; colS = swapped ? ca : cb;
     kP = swapped ? kB : kA; kS = swapped ? kA : kB;
-    size = CT_BASE_Q + geom_q(kP, true) + geom_q(kS, false);
     grpP = kP == K_FREE ? M.col_body[colP] : 0;                 // 0: arm + slide bodies, 1 + b: free body b
     grpS = kS == K_STATIC ? -1 : (kS == K_FREE ? M.col_body[colS] : 0);
+    spin = M.col_spin[ca] * M.col_fric[ca] + M.col_spin[cb] * M.col_fric[cb];
+    has_spin = spin > 0.f;
   }
   // islands over the three groups -> slot of each free body and of each contact
   int slotf[PRB_MAXFREE];
@@ -307,41 +304,43 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
     slotf[1] = c02 ? 0 : (c12 ? 1 : 2);
   }
   const int slot = lane < nc ? (grpP == 0 ? 0 : slotf[grpP - 1]) : -1;
-  // per-slot placement: region 0 = fixed part + slot-0 contacts + spin list, then regions 1 and 2
-  const int t_ct0 = T_JROW + njr + ((njr + 3) >> 2);
-  bool has_spin = false;
-  float spin = 0.f;
-  if (lane < nc) {
-    const int ca = c.cols & 0xff, cb = (c.cols >> 8) & 0xff;
-    spin = M.col_spin[ca] * M.col_fric[ca] + M.col_spin[cb] * M.col_fric[cb];
-    has_spin = spin > 0.f;
-  }
+  // ---- placement.  Slot 0: explicit rows grouped by pass
+  const bool s0 = slot == 0;
+  const bool hasF = s0 && (kP != K_ARM || kS != K_STATIC);
+  const int su = s0 ? (hasF ? 2 * XROW_Q : XROW_Q) : 0;
+  int totN, totS;
+  const int offN = warp_excl_scan(su, lane, &totN);
+  const int offS = warp_excl_scan((s0 && has_spin) ? su : 0, lane, &totS);
+  const int tN0 = (T_JROW + njr + ((njr + 3) >> 2) + 3) & ~3;
+  const int tS0 = tN0 + totN, tT0 = tS0 + totS, tEnd0 = tT0 + 2 * totN;
+  const int nc0 = __popc(__ballot_sync(FULL, s0)), ns0 = __popc(__ballot_sync(FULL, s0 && has_spin));
+  // slots 1, 2: compact records + spin list per region
+  const int size = (lane < nc && !s0) ? CT_BASE_Q + (kS == K_FREE ? 1 : 0) : 0;
   int t = 0, stride = size, t_spin_mine = 0, spin_rank = 0, region_mine = 0;
-  int ncs[3], nss[3], tsp[3], start[3];
+  int ncs[3] = {nc0, 0, 0}, nss[3] = {ns0, 0, 0}, tsp[3] = {tS0, 0, 0}, start[3] = {0, 0, 0};
   {
-    int region = 0;                                   // start of the slot's region relative to Q_ST
+    int region = tEnd0;                               // start of the slot's region relative to Q_ST
 #pragma unroll
-    for (int sidx = 0; sidx < 3; sidx++) {
-      const int stage = sidx == 0 ? PGS_STAGE_G : PGS_STAGE_F;
+    for (int sidx = 1; sidx < 3; sidx++) {
       const bool mine = slot == sidx;
       const unsigned mask = __ballot_sync(FULL, mine);
       const unsigned smask = __ballot_sync(FULL, mine && has_spin);
       int total;
-      int ts = (sidx == 0 ? t_ct0 : 0) + warp_excl_scan(mine ? size : 0, lane, &total);
-      const bool straddle = mine && ts < stage && ts + size > stage;
+      int ts = warp_excl_scan(mine ? size : 0, lane, &total);
+      const bool straddle = mine && ts < PGS_STAGE_F && ts + size > PGS_STAGE_F;
       const unsigned sm = __ballot_sync(FULL, straddle);
       int shift = 0;
       if (sm) {
         const int sl_ = __ffs((int)sm) - 1;
-        shift = stage - __shfl_sync(FULL, ts, sl_);
+        shift = PGS_STAGE_F - __shfl_sync(FULL, ts, sl_);
         if (lane >= sl_) ts += shift;
       }
       const unsigned later = mask & ~((2u << lane) - 1u);          // lanes of this slot after me (lane 31: none)
       const int nl = later ? __ffs((int)later) - 1 : lane;
       const int tnext = __shfl_sync(FULL, ts, nl);
-      const int tend = (sidx == 0 ? t_ct0 : 0) + total + shift;
+      const int tend = total + shift;
       if (mine) {
-        t = ts; stride = (lane < 31 && later) ? tnext - ts : size;
+        t = ts; stride = later ? tnext - ts : size;
         t_spin_mine = tend; spin_rank = __popc(smask & ((1u << lane) - 1u)); region_mine = region;
       }
       ncs[sidx] = __popc(mask); nss[sidx] = __popc(smask); tsp[sidx] = tend; start[sidx] = region;
@@ -349,7 +348,6 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
     }
     if (lane == 0) W.dbg_p = region;
   }
-  float rhs[4] = {0.f, 0.f, 0.f, 0.f}, invDs[4] = {0.f, 0.f, 0.f, 0.f};
   if (lane < nc) {
     const int ca = c.cols & 0xff, cb = (c.cols >> 8) & 0xff;
     v3 n = V3(c.nx, c.ny, c.nz), pb = V3(c.pbx, c.pby, c.pbz), pa = pb + n * c.dist;
@@ -369,18 +367,23 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
     v3 t1, t2;
     plane_space(n, t1, t2);
     float cfms = 0.f;
-    float4* rec = &S.q(Q_ST + region_mine + t);
-    float4* gP = rec + CT_BASE_Q * 32;
-    float4* gS = gP + geom_q(kP, true) * 32;
-    float jP[4] = {0.f, 0.f, 0.f, 0.f}, jS[4] = {0.f, 0.f, 0.f, 0.f};
+    float rhs[4] = {0.f, 0.f, 0.f, 0.f}, invDs[4] = {0.f, 0.f, 0.f, 0.f};
+    const int tN = tN0 + offN;
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
       v3 dir = k == 0 ? n : (k == 1 ? n : (k == 2 ? t1 : t2));
       const bool ang = (k == 1);
       if (k == 1 && !has_spin) continue;      // no torsional row: never visited by the solver
+      float JA[12], BA[12], JF[16], BF[16];
+      if (s0) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) { JA[i] = 0.f; BA[i] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < 16; i++) { JF[i] = 0.f; BF[i] = 0.f; }
+      }
       float rel = 0.f, D = 0.f;
-      D += side_row<ND>(M, W, colP, pP, dir, sP, ang, gP + 6 * k * 32, &jP[k], &rel);
-      if (kS != K_STATIC) D += side_row<ND>(M, W, colS, pS, dir, -sP, ang, gS + 6 * k * 32, &jS[k], &rel);
+      D += side_row<ND>(M, W, colP, pP, dir, sP, ang, s0 ? JA : nullptr, BA, s0 ? JF : nullptr, BF, &rel);
+      if (kS != K_STATIC) D += side_row<ND>(M, W, colS, pS, dir, -sP, ang, s0 ? JA : nullptr, BA, s0 ? JF : nullptr, BF, &rel);
       if (k == 0) D += cfm;
       const float invD = D > 1.1920929e-7f ? 1.0f / D : 0.f;
       if (k == 0) {
@@ -391,33 +394,49 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
         cfms = cfm * invD;
       } else rhs[k] = -rel * invD;
       invDs[k] = invD;
+      if (s0) {                                // explicit row
+        const int tr = k == 0 ? tN : (k == 1 ? tS0 + offS : tT0 + 2 * offN + (k == 3 ? su : 0));
+        float4* row = &S.q(Q_ST + tr);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          row[j * 32] = make_float4(JA[4 * j], JA[4 * j + 1], JA[4 * j + 2], JA[4 * j + 3]);
+          row[(4 + j) * 32] = make_float4(BA[4 * j], BA[4 * j + 1], BA[4 * j + 2], BA[4 * j + 3]);
+        }
+        row[3 * 32] = make_float4(__int_as_float(hasF ? 1 : 0), rhs[k], invD, 0.f);
+        row[7 * 32] = make_float4(k == 0 ? cfms : (k == 1 ? spin : (k == 2 ? mu : 0.f)), __int_as_float(tN), 0.f, 0.f);
+        if (hasF) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            row[(8 + j) * 32] = make_float4(JF[4 * j], JF[4 * j + 1], JF[4 * j + 2], JF[4 * j + 3]);
+            row[(12 + j) * 32] = make_float4(BF[4 * j], BF[4 * j + 1], BF[4 * j + 2], BF[4 * j + 3]);
+          }
+        }
+      }
     }
-    const int bP = M.col_body[colP], bS = M.col_body[colS];
-    const int iP = kP == K_FREE ? bP - 1 : (kP == K_SLIDE ? bP - 1 - M.n_free : 0);
-    const int iS = kS == K_FREE ? bS - 1 : (kS == K_SLIDE ? bS - 1 - M.n_free : 0);
-    v3 rP = V3(0, 0, 0);
-    if (kP == K_FREE) rP = pP - ld3(W.fpos[iP]);
-    if (kP == K_SLIDE) gP[0] = make_float4(jP[0], jP[1], jP[2], jP[3]);
-    if (kS == K_FREE) { v3 rS = pS - ld3(W.fpos[iS]); gS[0] = make_float4(rS.x, rS.y, rS.z, 0.f); }
-    if (kS == K_SLIDE) gS[0] = make_float4(jS[0], jS[1], jS[2], jS[3]);
-    const int packed = kP | (kS << 2) | (iP << 4) | (iS << 7) | ((swapped ? 1 : 0) << 10) | ((has_spin ? 1 : 0) << 11) | (stride << 12);
-    rec[0] = make_float4(__int_as_float(packed), cfms, rhs[0], invDs[0]);
-    rec[32] = make_float4(n.x, n.y, n.z, 0.f);
-    rec[64] = make_float4(rP.x, rP.y, rP.z, mu);
-    rec[96] = make_float4(t1.x, t1.y, t1.z, 0.f);
-    rec[128] = make_float4(rhs[2], rhs[3], invDs[2], invDs[3]);
-    rec[160] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_spin) S.q(Q_ST + region_mine + t_spin_mine + spin_rank) = make_float4(__int_as_float(t), spin, rhs[1], invDs[1]);
+    if (!s0) {                                 // compact record (both sides are free bodies or static)
+      const int iP = M.col_body[colP] - 1, iS = kS == K_FREE ? M.col_body[colS] - 1 : 0;
+      const v3 rP = pP - ld3(W.fpos[iP]);
+      float4* rec = &S.q(Q_ST + region_mine + t);
+      const int packed = (kS << 2) | (iP << 4) | (iS << 7) | ((swapped ? 1 : 0) << 10) | ((has_spin ? 1 : 0) << 11) | (stride << 12);
+      rec[0] = make_float4(__int_as_float(packed), cfms, rhs[0], invDs[0]);
+      rec[32] = make_float4(n.x, n.y, n.z, 0.f);
+      rec[64] = make_float4(rP.x, rP.y, rP.z, mu);
+      rec[96] = make_float4(t1.x, t1.y, t1.z, 0.f);
+      rec[128] = make_float4(rhs[2], rhs[3], invDs[2], invDs[3]);
+      rec[160] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kS == K_FREE) { const v3 rS = pS - ld3(W.fpos[iS]); rec[192] = make_float4(rS.x, rS.y, rS.z, 0.f); }
+      if (has_spin) S.q(Q_ST + region_mine + t_spin_mine + spin_rank) = make_float4(__int_as_float(t), spin, rhs[1], invDs[1]);
+    }
   }
   __syncwarp();
   if (lane == 0) {
-    S.q(Q_HDR) = make_float4(__int_as_float(njr), __int_as_float(ncs[0]), __int_as_float(nss[0]), __int_as_float(tsp[0]));
+    S.q(Q_HDR) = make_float4(__int_as_float(njr | (nc0 << 8) | (ns0 << 16)), __int_as_float(tS0), __int_as_float(tT0), __int_as_float(tEnd0));
     S.q(Q_HDR + 1) = make_float4(__int_as_float(ncs[1] | (nss[1] << 8) | (slotf[0] << 16) | (slotf[1] << 18)), __int_as_float(start[1]),
                                  __int_as_float(tsp[1]), 0.f);
     S.q(Q_HDR + 2) = make_float4(__int_as_float(ncs[2] | (nss[2] << 8)), __int_as_float(start[2]), __int_as_float(tsp[2]), 0.f);
     if (nc > W.dbg_c) W.dbg_c = nc;
-    // island of the arm needs the general solver: size class by the q count of region 0
-    W.dbg_u = (ncs[0] > 0 || njr > PGS_MAXJROW_J) ? ((tsp[0] + nss[0] <= PGS_CLASS_A_MAXQ) ? 1 : 2) : 0;
+    // island of the arm needs the arm-island solver: size class by the q count of region 0
+    W.dbg_u = (nc0 > 0 || njr > PGS_MAXJROW_J) ? ((tEnd0 <= PGS_CLASS_A_MAXQ) ? 1 : 2) : 0;
   }
   if (lane < M.nv) S.w(4 * Q_VSTAR + lane) = W.vs[lane];
 }
@@ -473,21 +492,19 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
   if (flags & (SETUP_INTEGRATE | SETUP_OBSERVE)) store_state(M, W, st, lane);
 }
 
-// ============================================================================ PGS kernels (thread per env-island)
-// Three kernels, all one warp per block, records staged once into shared memory and swept 50 times there:
+// ============================================================================ solver kernels
 //   prb_pgs_joint_kernel   slot 0 of the envs whose arm island has no contacts: joint rows only (32 envs / warp)
-//   prb_pgs_free_kernel    slots 1 and 2 (blockIdx.y): free-body islands, compact records only (32 envs / warp)
-//   prb_pgs_kernel         slot 0 of the envs on a "heavy" list: joint rows + every record kind.  The arm
-//                          island's records are large (explicit 12-wide J and M^-1 J^T per row), so an
-//                          env owns FOUR adjacent shared-memory columns here (8 envs / warp): q number t
-//                          sits in row t >> 2, column t & 3.  Two size classes, two launches.
+//   prb_pgs_free_kernel    slots 1 and 2 (blockIdx.y): free-body islands, compact records (32 envs / warp)
+//   prb_pgs_arm_kernel     slot 0 of the envs on a "heavy" list (arm island with contacts): joint rows +
+//                          explicit rows; FOUR lanes per env (8 envs / warp), velocities in registers,
+//                          one 2-step quad shuffle reduction per row.  Two size classes, two launches.
 #define PGS_BLOCK 32
 #define PGS_J_DVQ 4      // arm q 0..2, slides q 3
 #define PGS_F_TAILQ 8    // free-body kernel: dv 4 q (body b at 2b, 2b+1) + body table 4 q
-#define PGS_G_EPW (32 >> PGS_G_LW)                      // envs per warp
+#define PGS_G_EPW (32 >> PGS_G_LW)                      // envs per warp of the arm-island kernel
 #define PGS_SMEM_J ((PGS_STAGE_J + PGS_J_DVQ) * 32 * 16)
 #define PGS_SMEM_F ((PGS_STAGE_F + PGS_F_TAILQ) * 32 * 16)
-#define PGS_SMEM_G(rows) (((rows) + (PGS_DVQ >> PGS_G_LW)) * 32 * 16)
+#define PGS_SMEM_G(rows) ((rows) * 32 * 16)
 
 #ifdef PRB_EMU
 static float4 g_emu_pgs_smem[(PGS_ROWS_GB + 2) * 32 + (PGS_STAGE_J + PGS_STAGE_F + 16) * 32];
@@ -497,315 +514,135 @@ static float4 g_emu_pgs_smem[(PGS_ROWS_GB + 2) * 32 + (PGS_STAGE_J + PGS_STAGE_F
 #endif
 
 PRB_D float f4comp(const float4& a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : (k == 2 ? a.z : a.w)); }
+PRB_D void f4add(float4& a, int k, float v) { a.x += k == 0 ? v : 0.f; a.y += k == 1 ? v : 0.f; a.z += k == 2 ? v : 0.f; a.w += k == 3 ? v : 0.f; }
 PRB_D float dot4(const float4& a, const float4& b, float s) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s)))); }
 PRB_D void axpy4(float4& y, const float4& b, float a) { y.x = fmaf(b.x, a, y.x); y.y = fmaf(b.y, a, y.y); y.z = fmaf(b.z, a, y.z); y.w = fmaf(b.w, a, y.w); }
-
-// Where an env-island's q number t lives: LW = 0: one column (row t); LW = 2: four columns.  q numbers
-// at or past `cap` were not staged and are read from the stream in place.
-template <int LW>
-struct PgsMem {
-  float4* sl;              // first column of this env in shared memory
-  float4* Gr;              // this env's column of the slot's region in the stream
-  int cap;
-  PRB_D float4& s(int t) const { return sl[(t >> LW) * 32 + (t & ((1 << LW) - 1))]; }       // always staged
-  PRB_D float4& g(int t) const { return *(t < cap ? &s(t) : Gr + t * 32); }
-  PRB_D float& sw(int t0, int w) const { return reinterpret_cast<float*>(&s(t0 + (w >> 2)))[w & 3]; }   // word w of the q array at t0
-};
-
-// one side of a contact inside the solver
-struct PSide { int kind, idx, gt; float sgn; v3 r; };       // gt: t of the side's geometry
-// the dv of that side's body, loaded once per row visit
-struct PVel { v3 v, w, pv; float4 a0, a1, a2; float sl; };
-
-// The contact sweeps.  LIGHT: only free-body sides exist (slots 1, 2); dv q array at t = dvt: general
-// layout arm 0..2, free body b at 3 + 2 b, slides 7; LIGHT layout free body b at 2 b.
-template <bool LIGHT, int LW>
-struct PgsSweep {
-  static constexpr int FQ0 = LIGHT ? 0 : 3;
-  static constexpr int SLQ = 3 + 2 * PRB_MAXFREE;
-  PgsMem<LW> m;
-  int dvt;                 // t of the dv array (past the records, always staged)
-  int bodyt;               // t of the free-body table (always staged)
-  const DevModel* M;
-
-  PRB_D void load(const PSide& s, PVel& V) const {
-    if (LIGHT || s.kind == K_FREE) {
-      const float4 x = m.s(dvt + FQ0 + 2 * s.idx), y = m.s(dvt + FQ0 + 1 + 2 * s.idx);
-      V.v = V3(x.x, x.y, x.z); V.w = V3(x.w, y.x, y.y);
-      V.pv = V.v + cross(V.w, s.r);
-    } else if (s.kind == K_ARM) {
-      V.a0 = m.s(dvt); V.a1 = m.s(dvt + 1); V.a2 = m.s(dvt + 2);
-    } else if (s.kind == K_SLIDE) {
-      V.sl = m.sw(dvt + SLQ, s.idx);
-    }
-  }
-  // J_k . dv of one side (row k: 0 normal, 1 spin, 2 / 3 friction; d: the row's direction)
-  PRB_D float jdot(const PSide& s, const PVel& V, v3 d, int k, bool ang) const {
-    if (LIGHT || s.kind == K_FREE) return s.sgn * (ang ? dot(d, V.w) : dot(d, V.pv));
-    if (s.kind == K_ARM) {
-      const float4 j0 = m.g(s.gt + 6 * k), j1 = m.g(s.gt + 6 * k + 1), j2 = m.g(s.gt + 6 * k + 2);
-      return dot4(j0, V.a0, 0.f) + dot4(j1, V.a1, dot4(j2, V.a2, 0.f));
-    }
-    if (s.kind == K_SLIDE) return f4comp(m.g(s.gt), k) * V.sl;
-    return 0.f;
-  }
-  // dv += B_k dl (+ B_k2 dl2): P = sum of direction * impulse (linear rows) or the angular impulse (spin)
-  template <bool PAIR>
-  PRB_D void apply(const PSide& s, PVel& V, v3 P, bool ang, int k, float dl, int k2, float dl2) const {
-    if (LIGHT || s.kind == K_FREE) {
-      const float4 i0 = m.s(bodyt + 2 * s.idx), i1 = m.s(bodyt + 2 * s.idx + 1);
-      const float I[6] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y};
-      const v3 Ps = P * s.sgn;
-      v3 v = V.v, w = V.w;
-      if (ang) w = w + symmul(I, Ps);
-      else { v = v + Ps * i1.z; w = w + symmul(I, cross(s.r, Ps)); }
-      m.s(dvt + FQ0 + 2 * s.idx) = make_float4(v.x, v.y, v.z, w.x);
-      m.s(dvt + FQ0 + 1 + 2 * s.idx) = make_float4(w.y, w.z, 0.f, 0.f);
-    } else if (s.kind == K_ARM) {
-      float4 a0 = V.a0, a1 = V.a1, a2 = V.a2;
-      axpy4(a0, m.g(s.gt + 6 * k + 3), dl); axpy4(a1, m.g(s.gt + 6 * k + 4), dl); axpy4(a2, m.g(s.gt + 6 * k + 5), dl);
-      if (PAIR) { axpy4(a0, m.g(s.gt + 6 * k2 + 3), dl2); axpy4(a1, m.g(s.gt + 6 * k2 + 4), dl2); axpy4(a2, m.g(s.gt + 6 * k2 + 5), dl2); }
-      m.s(dvt) = a0; m.s(dvt + 1) = a1; m.s(dvt + 2) = a2;
-    } else if (s.kind == K_SLIDE) {
-      const float4 j = m.g(s.gt);
-      float tt = f4comp(j, k) * dl;
-      if (PAIR) tt = fmaf(f4comp(j, k2), dl2, tt);
-      m.sw(dvt + SLQ, s.idx) = fmaf(tt, M->slide_minv[s.idx], V.sl);
-    }
-  }
-  PRB_D void sides_of(int pk, int t, const float4& q2, PSide& P, PSide& Sd) const {
-    P.kind = pk & 3; Sd.kind = (pk >> 2) & 3;
-    P.idx = (pk >> 4) & 7; Sd.idx = (pk >> 7) & 7;
-    P.sgn = ((pk >> 10) & 1) ? -1.0f : 1.0f; Sd.sgn = -P.sgn;
-    P.r = V3(q2.x, q2.y, q2.z);
-    P.gt = t + CT_BASE_Q;
-    Sd.gt = LIGHT ? P.gt : P.gt + geom_q(P.kind, true);
-    Sd.r = V3(0, 0, 0);
-    if (Sd.kind == K_FREE) { const float4 g = m.g(Sd.gt); Sd.r = V3(g.x, g.y, g.z); }
-  }
-  PRB_D bool same_body(const PSide& P, const PSide& Sd) const { return !LIGHT && Sd.kind == K_ARM && P.kind == K_ARM; }
-
-  // ---- contact normals
-  PRB_D void normals(int t_ct, int nc) const {
-    int t = t_ct;
-    float4 q0 = m.g(t), q1 = m.g(t + 1), q2 = m.g(t + 2);
-#pragma unroll 1
-    for (int c = 0; c < nc; c++) {
-      const int pk = __float_as_int(q0.x);
-      const int tn = t + ((pk >> 12) & 255);
-      const float4 n0 = m.g(tn), n1 = m.g(tn + 1), n2 = m.g(tn + 2);     // next record (readable slack after the last)
-      PSide P, Sd;
-      sides_of(pk, t, q2, P, Sd);
-      const v3 n = V3(q1.x, q1.y, q1.z);
-      PVel VP, VS;
-      load(P, VP);
-      float u = jdot(P, VP, n, 0, false);
-      if (Sd.kind != K_STATIC) { load(Sd, VS); u += jdot(Sd, VS, n, 0, false); }
-      const float l0 = q1.w;
-      const float nl = fmaxf(l0 + (q0.z - l0 * q0.y - u * q0.w), 0.f);
-      const float dl = nl - l0;
-      if (dl != 0.f) {
-        m.g(t + 1).w = nl;
-        apply<false>(P, VP, n * dl, false, 0, dl, 0, 0.f);
-        if (Sd.kind != K_STATIC) {
-          if (same_body(P, Sd)) load(Sd, VS);       // same body: see P's update
-          apply<false>(Sd, VS, n * dl, false, 0, dl, 0, 0.f);
-        }
-      }
-      t = tn; q0 = n0; q1 = n1; q2 = n2;
-    }
-  }
-  // ---- spinning friction (Bullet skips the row while the normal impulse is 0)
-  PRB_D void spins(int t_spin, int ns) const {
-    float4 h = m.g(t_spin);
-#pragma unroll 1
-    for (int i = 0; i < ns; i++) {
-      const float4 hc = h;
-      h = m.g(t_spin + i + 1);                                      // next entry (readable slack after the last)
-      const int t = __float_as_int(hc.x);
-      const float4 q0 = m.g(t), q1 = m.g(t + 1), q2 = m.g(t + 2);
-      const float tot = q1.w;
-      if (!(tot > 0.f)) continue;
-      PSide P, Sd;
-      sides_of(__float_as_int(q0.x), t, q2, P, Sd);
-      const v3 n = V3(q1.x, q1.y, q1.z);
-      PVel VP, VS;
-      load(P, VP);
-      float u = jdot(P, VP, n, 1, true);
-      if (Sd.kind != K_STATIC) { load(Sd, VS); u += jdot(Sd, VS, n, 1, true); }
-      const float lim = hc.y * tot;
-      float& lam1 = m.g(t + 3).w;
-      const float l0 = lam1;
-      const float nl = clampf(l0 + (hc.z - u * hc.w), -lim, lim);
-      const float dl = nl - l0;
-      if (dl != 0.f) {
-        lam1 = nl;
-        apply<false>(P, VP, n * dl, true, 1, dl, 1, 0.f);
-        if (Sd.kind != K_STATIC) {
-          if (same_body(P, Sd)) load(Sd, VS);
-          apply<false>(Sd, VS, n * dl, true, 1, dl, 1, 0.f);
-        }
-      }
-    }
-  }
-  // ---- lateral friction: the two rows of a contact are solved together (implicit cone)
-  PRB_D void frictions(int t_ct, int nc) const {
-    int t = t_ct;
-    float4 q0 = m.g(t), q1 = m.g(t + 1), q2 = m.g(t + 2), q3 = m.g(t + 3), q4 = m.g(t + 4), q5 = m.g(t + 5);
-#pragma unroll 1
-    for (int c = 0; c < nc; c++) {
-      const int pk = __float_as_int(q0.x);
-      const int tn = t + ((pk >> 12) & 255);
-      const float4 n0 = m.g(tn), n1 = m.g(tn + 1), n2 = m.g(tn + 2), n3 = m.g(tn + 3), n4 = m.g(tn + 4), n5 = m.g(tn + 5);
-      PSide P, Sd;
-      sides_of(pk, t, q2, P, Sd);
-      const v3 n = V3(q1.x, q1.y, q1.z), t1 = V3(q3.x, q3.y, q3.z), t2 = cross(n, t1);
-      PVel VP, VS;
-      load(P, VP);
-      float ua = jdot(P, VP, t1, 2, false), ub = jdot(P, VP, t2, 3, false);
-      if (Sd.kind != K_STATIC) {
-        load(Sd, VS);
-        ua += jdot(Sd, VS, t1, 2, false); ub += jdot(Sd, VS, t2, 3, false);
-      }
-      const float lim = q2.w * q1.w;
-      const float la = q5.x, lb = q5.y;
-      const float sumA = la + (q4.x - ua * q4.z);
-      const float sumB = lb + (q4.y - ub * q4.w);
-      float na = sumA, nb = sumB;
-      if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
-        const float ss = sumA * sumA + sumB * sumB;
-        const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
-        const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
-        na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
-      }
-      const float d1 = na - la, d2 = nb - lb;
-      if (d1 != 0.f || d2 != 0.f) {
-        m.g(t + 5) = make_float4(na, nb, 0.f, 0.f);
-        const v3 Pv = t1 * d1 + t2 * d2;
-        apply<true>(P, VP, Pv, false, 2, d1, 3, d2);
-        if (Sd.kind != K_STATIC) {
-          if (same_body(P, Sd)) load(Sd, VS);
-          apply<true>(Sd, VS, Pv, false, 2, d1, 3, d2);
-        }
-      }
-      t = tn; q0 = n0; q1 = n1; q2 = n2; q3 = n3; q4 = n4; q5 = n5;
-    }
-  }
-};
-
-// ---- non-contact rows (limits, motors, gear), sweep direction alternating per iteration.
-// region 0 staged in m; dv q array at t = dvt: arm at q 0..2, slide DoFs at q SLQ
-template <int ND, int SLQ, int LW>
-PRB_D void pgs_joint_rows(const DevModel& M, const PgsMem<LW>& m, int dvt, int njr, int it, float ratio) {
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int t_jlam = T_JROW + njr;
-#pragma unroll 1
-  for (int i = 0; i < njr; i++) {
-    const int j = (it & 1) ? i : njr - 1 - i;
-    const float4 r = m.s(T_JROW + j);
-    const int pk = __float_as_int(r.x);
-    int pd = pk & 0xff, pd2 = (pk >> 8) & 0xff;
-    const int a = (pk >> 16) & 15, a2 = (pk >> 20) & 15;
-    const int sidx = pd - DVW_SLIDE(0);                              // slide index when a == 15
-    if (a == 15) pd = 4 * SLQ + sidx;
-    const float sg = ((pk >> 24) & 1) ? -1.0f : 1.0f;
-    // the M^-1 rows are needed only if the impulse changes; issue their loads now anyway
-    float4 m0[3], m1[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      m0[k] = z4; m1[k] = z4;
-      if (a != 15) m0[k] = m.s(T_MINV + 3 * a + k);
-      if (a2 != 15) m1[k] = m.s(T_MINV + 3 * a2 + k);
-    }
-    float& ru = m.sw(dvt, pd);
-    float u = ru;
-    if (pd2 != 0xff) u = fmaf(ratio, m.sw(dvt, pd2), u);
-    u *= sg;
-    float& rl = m.sw(t_jlam, j);
-    const float l0 = rl;
-    const float hi = r.w, lo = ((pk >> 25) & 1) ? -hi : 0.f;
-    const float nl = clampf(l0 + (r.y - u * r.z), lo, hi);
-    const float dl = (nl - l0) * sg;
-    if (dl != 0.f) {
-      rl = nl;
-      if (a != 15) {
-        const float dl2 = dl * ratio;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          if (4 * k < ND) {
-            float4 y = m.s(dvt + k);
-            axpy4(y, m0[k], dl);
-            axpy4(y, m1[k], dl2);
-            m.s(dvt + k) = y;
-          }
-        }
-      } else {
-        ru = fmaf(M.slide_minv[sidx], dl, ru);
-      }
-    }
-  }
-}
-
-// solver dv words of the arm and the slide bodies -> stream (linear DoF order)
-template <int LW>
-PRB_D void pgs_store_arm(const DevModel& M, float4* G, const PgsMem<LW>& m, int dvt, int slq) {
-  float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
-  const int nd = M.nd, o = nd + 6 * M.n_free;
-#pragma unroll 1
-  for (int i = 0; i < nd; i++) gd[(i >> 2) * 128 + (i & 3)] = m.sw(dvt, i);
-#pragma unroll 1
-  for (int s = 0; s < M.n_slide; s++) gd[((o + s) >> 2) * 128 + ((o + s) & 3)] = m.sw(dvt + slq, s);
-}
-template <int LW>
-PRB_D void pgs_store_free(const DevModel& M, float4* G, const PgsMem<LW>& m, int t0, int b) {
-  float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
-  const float4 x = m.s(t0 + 2 * b), y = m.s(t0 + 2 * b + 1);
-  const float v[6] = {x.x, x.y, x.z, x.w, y.x, y.y};
-  const int o = M.nd + 6 * b;
-#pragma unroll
-  for (int k = 0; k < 6; k++) gd[((o + k) >> 2) * 128 + ((o + k) & 3)] = v[k];
-}
 PRB_D float4* stream_col(float* sbuf, int e) { return reinterpret_cast<float4*>(sbuf) + (size_t)(e >> 5) * (SB_Q * 32) + (e & 31); }
 
-// ---- slot 0, arm island without contacts: joint rows only
+// ---- slot 0, arm island without contacts: joint rows only.  sl: this env's column (row t = q t of region 0)
 template <int ND>
 __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N) {
   PRB_PGS_SMEM_DECL;
   const int lane = threadIdx.x;
-  const int e = blockIdx.x * PGS_BLOCK + lane;
-  if (e >= N) return;
   const DevModel& M = *Mp;
+  // persistent blocks: a block walks groups of 32 envs (launching one block per group costs more than
+  // the solve: each block launch allocates its shared memory)
+  for (int e = blockIdx.x * PGS_BLOCK + lane; e < N; e += gridDim.x * PGS_BLOCK) {
   float4* G = stream_col(sbuf, e);
-  const float4 hdr = G[Q_HDR * 32];
-  const int njr = __float_as_int(hdr.x), nc0 = __float_as_int(hdr.y);
-  if (nc0 > 0 || njr > PGS_MAXJROW_J) return;            // on a heavy list: prb_pgs_kernel solves it
-  PgsMem<0> m;
-  m.sl = sm + lane; m.Gr = G + Q_ST * 32; m.cap = PGS_STAGE_J;
-  const int dvt = PGS_STAGE_J;
+  const int h0 = __float_as_int(G[Q_HDR * 32].x);
+  const int njr = h0 & 0xff, nc0 = (h0 >> 8) & 0xff;
+  if (nc0 > 0 || njr > PGS_MAXJROW_J) continue;          // on a heavy list: prb_pgs_arm_kernel solves it
+  float4* sl = sm + lane;
+  const float4* Gr = G + Q_ST * 32;
+  float4* dvq = sl + PGS_STAGE_J * 32;                   // arm q 0..2, slides q 3
   {
     const int tq = T_JROW + njr;
 #pragma unroll 8
-    for (int q = T_MINV; q < tq; q++) m.s(q) = m.Gr[q * 32];
+    for (int q = T_MINV; q < tq; q++) sl[q * 32] = Gr[q * 32];
   }
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < PGS_J_DVQ; i++) m.s(dvt + i) = z4;
-  for (int i = 0; i < ((njr + 3) >> 2); i++) m.s(T_JROW + njr + i) = z4;
+  for (int i = 0; i < PGS_J_DVQ; i++) dvq[i * 32] = z4;
+  for (int i = 0; i < ((njr + 3) >> 2); i++) sl[(T_JROW + njr + i) * 32] = z4;
+  const float4* minv = sl + T_MINV * 32;
+  float* jlam = reinterpret_cast<float*>(sl + (T_JROW + njr) * 32);  // word j at jlam[(j >> 2) * 128 + (j & 3)]
+  float* dvw = reinterpret_cast<float*>(dvq);                        // word i at dvw[(i >> 2) * 128 + (i & 3)]
   const float ratio = M.params[P_GEAR_RATIO];
   const int iters = M.solver_iters;
 #pragma unroll 1
-  for (int it = 0; it < iters; it++) pgs_joint_rows<ND, 3, 0>(M, m, dvt, njr, it, ratio);
-  pgs_store_arm(M, G, m, dvt, 3);
+  for (int it = 0; it < iters; it++) {
+    // non-contact rows, sweep direction alternating per iteration
+#pragma unroll 1
+    for (int i = 0; i < njr; i++) {
+      const int j = (it & 1) ? i : njr - 1 - i;
+      const float4 r = sl[(T_JROW + j) * 32];
+      const int pk = __float_as_int(r.x);
+      int pd = pk & 0xff;
+      const int pd2 = (pk >> 8) & 0xff, a = (pk >> 16) & 15, a2 = (pk >> 20) & 15;
+      const int sidx = pd - DVW_SLIDE(0);                            // slide index when a == 15
+      if (a == 15) pd = 12 + sidx;
+      const float sg = ((pk >> 24) & 1) ? -1.0f : 1.0f;
+      // the M^-1 rows are needed only if the impulse changes; issue their loads now anyway
+      float4 m0[3], m1[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        m0[k] = z4; m1[k] = z4;
+        if (a != 15) m0[k] = minv[(3 * a + k) * 32];
+        if (a2 != 15) m1[k] = minv[(3 * a2 + k) * 32];
+      }
+      float* pu = &dvw[(pd >> 2) * 128 + (pd & 3)];
+      float u = *pu;
+      if (pd2 != 0xff) u = fmaf(ratio, dvw[(pd2 >> 2) * 128 + (pd2 & 3)], u);
+      u *= sg;
+      float* pl = &jlam[(j >> 2) * 128 + (j & 3)];
+      const float l0 = *pl;
+      const float hi = r.w, lo = ((pk >> 25) & 1) ? -hi : 0.f;
+      const float nl = clampf(l0 + (r.y - u * r.z), lo, hi);
+      const float dl = (nl - l0) * sg;
+      if (dl != 0.f) {
+        *pl = nl;
+        if (a != 15) {
+          const float dl2 = dl * ratio;
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            if (4 * k < ND) {
+              float4 y = dvq[k * 32];
+              axpy4(y, m0[k], dl);
+              axpy4(y, m1[k], dl2);
+              dvq[k * 32] = y;
+            }
+          }
+        } else {
+          *pu = fmaf(M.slide_minv[sidx], dl, *pu);
+        }
+      }
+    }
+  }
+  float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
+  const int nd = M.nd, o = nd + 6 * M.n_free;
+#pragma unroll 1
+  for (int i = 0; i < nd; i++) gd[(i >> 2) * 128 + (i & 3)] = dvw[(i >> 2) * 128 + (i & 3)];
+#pragma unroll 1
+  for (int s = 0; s < M.n_slide; s++) gd[((o + s) >> 2) * 128 + ((o + s) & 3)] = dvw[3 * 128 + s];
+  }
 }
 
-// ---- slots 1 and 2 (blockIdx.y + 1): islands of free bodies against static geometry / each other
+// ---- slots 1 and 2 (blockIdx.y + 1): islands of free bodies against static geometry / each other.
+// dv of free body b at dvq q 2b, 2b+1 (6 words used)
+struct FSide { int idx; float sgn; v3 r; };
+struct FVel { v3 v, w, pv; };
+PRB_D void fside_load(const FSide& s, const float4* dvq, FVel& V) {
+  const float4 x = dvq[(2 * s.idx) * 32], y = dvq[(2 * s.idx + 1) * 32];
+  V.v = V3(x.x, x.y, x.z); V.w = V3(x.w, y.x, y.y);
+  V.pv = V.v + cross(V.w, s.r);
+}
+// dv += B P: P = sum of direction * impulse (linear rows) or the angular impulse (spin row)
+PRB_D void fside_apply(const FSide& s, const FVel& V, float4* dvq, const float4* body, v3 P, bool ang) {
+  const float4 i0 = body[(2 * s.idx) * 32], i1 = body[(2 * s.idx + 1) * 32];
+  const float I[6] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y};
+  const v3 Ps = P * s.sgn;
+  v3 v = V.v, w = V.w;
+  if (ang) w = w + symmul(I, Ps);
+  else { v = v + Ps * i1.z; w = w + symmul(I, cross(s.r, Ps)); }
+  dvq[(2 * s.idx) * 32] = make_float4(v.x, v.y, v.z, w.x);
+  dvq[(2 * s.idx + 1) * 32] = make_float4(w.y, w.z, 0.f, 0.f);
+}
+PRB_D bool fsides_of(int pk, const float4* rec, const float4& q2, FSide& P, FSide& Sd) {
+  P.idx = (pk >> 4) & 7; Sd.idx = (pk >> 7) & 7;
+  P.sgn = ((pk >> 10) & 1) ? -1.0f : 1.0f; Sd.sgn = -P.sgn;
+  P.r = V3(q2.x, q2.y, q2.z);
+  Sd.r = V3(0, 0, 0);
+  const bool two = ((pk >> 2) & 3) == K_FREE;
+  if (two) { const float4 g = rec[CT_BASE_Q * 32]; Sd.r = V3(g.x, g.y, g.z); }
+  return two;
+}
+
 __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N) {
   PRB_PGS_SMEM_DECL;
   const int lane = threadIdx.x;
-  const int e = blockIdx.x * PGS_BLOCK + lane;
   const int slot = blockIdx.y + 1;
-  if (e >= N) return;
   const DevModel& M = *Mp;
+  for (int e = blockIdx.x * PGS_BLOCK + lane; e < N; e += gridDim.x * PGS_BLOCK) {     // persistent blocks
   float4* G = stream_col(sbuf, e);
   const float4 h1 = G[(Q_HDR + 1) * 32], hs = G[(Q_HDR + slot) * 32];
   const int info = __float_as_int(h1.x);
@@ -813,76 +650,344 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
   const int nc = cnt & 0xff, ns = (cnt >> 8) & 0xff, start = __float_as_int(hs.y), t_spin = __float_as_int(hs.z);
   bool owner = false;
   for (int b = 0; b < M.n_free; b++) owner = owner || ((info >> (16 + 2 * b)) & 3) == slot;
-  if (!owner) return;                                    // merged into another island
-  PgsSweep<true, 0> sw;
-  sw.m.sl = sm + lane; sw.m.Gr = G + (Q_ST + start) * 32; sw.m.cap = PGS_STAGE_F;
-  sw.dvt = PGS_STAGE_F; sw.bodyt = PGS_STAGE_F + 4; sw.M = Mp;
+  if (!owner) continue;                                  // merged into another island
+  float4* sl = sm + lane;
+  float4* Gr = G + (Q_ST + start) * 32;
+  float4* dvq = sl + PGS_STAGE_F * 32;
+  float4* body = dvq + 4 * 32;
   {
     const int tq = min(t_spin + ns, PGS_STAGE_F);
 #pragma unroll 8
-    for (int q = 0; q < tq; q++) sw.m.s(q) = sw.m.Gr[q * 32];
+    for (int q = 0; q < tq; q++) sl[q * 32] = Gr[q * 32];
   }
+#define PGS_PTR(t_) ((t_) < PGS_STAGE_F ? sl + (t_) * 32 : Gr + (t_) * 32)
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 4; i++) { sw.m.s(sw.dvt + i) = z4; sw.m.s(sw.bodyt + i) = G[(Q_ST + T_BODY + i) * 32]; }
+  for (int i = 0; i < 4; i++) { dvq[i * 32] = z4; body[i * 32] = G[(Q_ST + T_BODY + i) * 32]; }
   const int iters = M.solver_iters;
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
-    sw.normals(0, nc);
-    sw.spins(t_spin, ns);
-    sw.frictions(0, nc);
+    // ---- contact normals
+    {
+      int t = 0;
+      float4* rec = PGS_PTR(t);
+      float4 q0 = rec[0], q1 = rec[32], q2 = rec[64];
+#pragma unroll 1
+      for (int c = 0; c < nc; c++) {
+        const int pk = __float_as_int(q0.x);
+        const int tn = t + ((pk >> 12) & 255);
+        float4* recn = PGS_PTR(tn);
+        const float4 n0 = recn[0], n1 = recn[32], n2 = recn[64];     // next record (readable slack after the last)
+        FSide P, Sd;
+        const bool two = fsides_of(pk, rec, q2, P, Sd);
+        const v3 n = V3(q1.x, q1.y, q1.z);
+        FVel VP, VS;
+        fside_load(P, dvq, VP);
+        float u = P.sgn * dot(n, VP.pv);
+        if (two) { fside_load(Sd, dvq, VS); u += Sd.sgn * dot(n, VS.pv); }
+        const float l0 = q1.w;
+        const float nl = fmaxf(l0 + (q0.z - l0 * q0.y - u * q0.w), 0.f);
+        const float dl = nl - l0;
+        if (dl != 0.f) {
+          reinterpret_cast<float*>(rec + 32)[3] = nl;
+          fside_apply(P, VP, dvq, body, n * dl, false);
+          if (two) fside_apply(Sd, VS, dvq, body, n * dl, false);
+        }
+        t = tn; rec = recn; q0 = n0; q1 = n1; q2 = n2;
+      }
+    }
+    // ---- spinning friction (Bullet skips the row while the normal impulse is 0)
+#pragma unroll 1
+    for (int i = 0; i < ns; i++) {
+      const float4 h = *PGS_PTR(t_spin + i);
+      float4* rec = PGS_PTR(__float_as_int(h.x));
+      const float4 q0 = rec[0], q1 = rec[32], q2 = rec[64];
+      const float tot = q1.w;
+      if (!(tot > 0.f)) continue;
+      FSide P, Sd;
+      const bool two = fsides_of(__float_as_int(q0.x), rec, q2, P, Sd);
+      const v3 n = V3(q1.x, q1.y, q1.z);
+      FVel VP, VS;
+      fside_load(P, dvq, VP);
+      float u = P.sgn * dot(n, VP.w);
+      if (two) { fside_load(Sd, dvq, VS); u += Sd.sgn * dot(n, VS.w); }
+      const float lim = h.y * tot;
+      float* pl = reinterpret_cast<float*>(rec + 96) + 3;
+      const float l0 = *pl;
+      const float nl = clampf(l0 + (h.z - u * h.w), -lim, lim);
+      const float dl = nl - l0;
+      if (dl != 0.f) {
+        *pl = nl;
+        fside_apply(P, VP, dvq, body, n * dl, true);
+        if (two) fside_apply(Sd, VS, dvq, body, n * dl, true);
+      }
+    }
+    // ---- lateral friction: the two rows of a contact are solved together (implicit cone)
+    {
+      int t = 0;
+      float4* rec = PGS_PTR(t);
+      float4 q0 = rec[0], q1 = rec[32], q2 = rec[64], q3 = rec[96], q4 = rec[128], q5 = rec[160];
+#pragma unroll 1
+      for (int c = 0; c < nc; c++) {
+        const int pk = __float_as_int(q0.x);
+        const int tn = t + ((pk >> 12) & 255);
+        float4* recn = PGS_PTR(tn);
+        const float4 n0 = recn[0], n1 = recn[32], n2 = recn[64], n3 = recn[96], n4 = recn[128], n5 = recn[160];
+        FSide P, Sd;
+        const bool two = fsides_of(pk, rec, q2, P, Sd);
+        const v3 n = V3(q1.x, q1.y, q1.z), t1 = V3(q3.x, q3.y, q3.z), t2 = cross(n, t1);
+        FVel VP, VS;
+        fside_load(P, dvq, VP);
+        float ua = P.sgn * dot(t1, VP.pv), ub = P.sgn * dot(t2, VP.pv);
+        if (two) {
+          fside_load(Sd, dvq, VS);
+          ua += Sd.sgn * dot(t1, VS.pv); ub += Sd.sgn * dot(t2, VS.pv);
+        }
+        const float lim = q2.w * q1.w;
+        const float la = q5.x, lb = q5.y;
+        const float sumA = la + (q4.x - ua * q4.z);
+        const float sumB = lb + (q4.y - ub * q4.w);
+        float na = sumA, nb = sumB;
+        if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
+          const float ss = sumA * sumA + sumB * sumB;
+          const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+          const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
+          na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
+        }
+        const float d1 = na - la, d2 = nb - lb;
+        if (d1 != 0.f || d2 != 0.f) {
+          rec[160] = make_float4(na, nb, 0.f, 0.f);
+          const v3 Pv = t1 * d1 + t2 * d2;
+          fside_apply(P, VP, dvq, body, Pv, false);
+          if (two) fside_apply(Sd, VS, dvq, body, Pv, false);
+        }
+        t = tn; rec = recn; q0 = n0; q1 = n1; q2 = n2; q3 = n3; q4 = n4; q5 = n5;
+      }
+    }
   }
+#undef PGS_PTR
+  float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
   for (int b = 0; b < M.n_free; b++)
-    if (((info >> (16 + 2 * b)) & 3) == slot) pgs_store_free(M, G, sw.m, sw.dvt, b);
+    if (((info >> (16 + 2 * b)) & 3) == slot) {
+      const float4 x = dvq[(2 * b) * 32], y = dvq[(2 * b + 1) * 32];
+      const float v[6] = {x.x, x.y, x.z, x.w, y.x, y.y};
+      const int o = M.nd + 6 * b;
+#pragma unroll
+      for (int k = 0; k < 6; k++) gd[((o + k) >> 2) * 128 + ((o + k) & 3)] = v[k];
+    }
+  }
 }
 
-// ---- slot 0 of the envs whose arm island has contacts (a heavy list): joint rows + all record kinds.
-// 8 envs per warp: lanes 4k..4k+3 stage the four columns of env k, lane 4k solves it.
-template <int ND>
-__global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf,
-                                                            const int* __restrict__ heavy_list, const int* __restrict__ heavy_cnt, int rows) {
-  PRB_PGS_SMEM_DECL;
-  const int lane = threadIdx.x, col = lane & ((1 << PGS_G_LW) - 1);
-  const int i = blockIdx.x * PGS_G_EPW + (lane >> PGS_G_LW);
-  const int cnt = *heavy_cnt;
-  if (blockIdx.x * PGS_G_EPW >= cnt) return;             // whole warp
-  const bool have = i < cnt;
-  const int e = have ? heavy_list[i] : 0;
-  const DevModel& M = *Mp;
-  float4* G = stream_col(sbuf, e);
-  int njr = 0, nc = 0, ns = 0, t_spin = 0, info = 0;
-  if (have) {
-    const float4 hdr = G[Q_HDR * 32], h1 = G[(Q_HDR + 1) * 32];
-    njr = __float_as_int(hdr.x); nc = __float_as_int(hdr.y); ns = __float_as_int(hdr.z); t_spin = __float_as_int(hdr.w);
-    info = __float_as_int(h1.x);
-  }
-  PgsSweep<false, PGS_G_LW> sw;
-  sw.m.sl = sm + (lane - col); sw.m.Gr = G + Q_ST * 32; sw.m.cap = rows << PGS_G_LW;
-  sw.dvt = rows << PGS_G_LW; sw.bodyt = T_BODY; sw.M = Mp;
-  {
-    const int tq = min(t_spin + ns, sw.m.cap);
-#pragma unroll 4
-    for (int q = col; q < tq; q += (1 << PGS_G_LW)) sw.m.s(q) = sw.m.Gr[q * 32];
-  }
+// ---- slot 0 of the envs whose arm island has contacts (a heavy list): joint rows + explicit rows.
+// Four lanes per env (quad): lane c of the quad keeps words 4c..4c+3 of the island's velocity change
+// (A: arm, F: free bodies + slides) in registers and owns column c of the env's four shared-memory
+// columns: q number t of region 0 sits in row t >> 2, column t & 3, so a row's J (B) slices are one
+// conflict-free LDS.128 per lane and its header a quad broadcast.  J . dv = 4 FMAs per lane + a 2-step
+// quad shuffle reduction.
+struct QuadMem {
+  float4* base;            // column 0 of this env in shared memory
+  float4* Gr;              // this env's column of region 0 in the stream
+  int cap;                 // staged q count; rows that do not end below it are read from the stream in place
+  PRB_D float4* sp(int t) const { return base + (t >> 2) * 32 + (t & 3); }     // always-staged q (fixed part of region 0)
+  PRB_D bool staged(int t) const { return t + 2 * XROW_Q <= cap; }            // explicit row starting at t
+};
+// an explicit row in shared memory (q k of the row at rp[(k >> 2) * 32 + (k & 3)]) or in the stream (gp[k * 32])
+struct RowS {
+  float4* rp;
+  template <int K0> PRB_D float4 ld(int c) const { return rp[(K0 >> 2) * 32 + c]; }
+  PRB_D float* lam() const { return reinterpret_cast<float*>(rp + 3) + 3; }
+};
+struct RowG {
+  float4* gp;
+  template <int K0> PRB_D float4 ld(int c) const { return gp[(K0 + c) * 32]; }
+  PRB_D float* lam() const { return reinterpret_cast<float*>(gp + 3 * 32) + 3; }
+};
+PRB_D float quad_sum(unsigned qmask, float v) {
+  v += __shfl_xor_sync(qmask, v, 1);
+  v += __shfl_xor_sync(qmask, v, 2);
+  return v;
+}
+PRB_D float* quad_lam(const QuadMem& m, int t) {          // accumulated impulse of the explicit row at t
+  return m.staged(t) ? RowS{m.sp(t)}.lam() : RowG{m.Gr + t * 32}.lam();
+}
+// one row visit; kind 0: contact normal (lambda >= 0, soft CFM), 1: spin (|lambda| <= coefficient * normal impulse)
+template <int KIND, class Row>
+PRB_D bool quad_row(const Row& r, int c, unsigned qmask, float4& A, float4& F, float tot) {
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (col == 0) {
-#pragma unroll
-    for (int k = 0; k < PGS_DVQ; k++) sw.m.s(sw.dvt + k) = z4;
+  const float4 H1 = r.template ld<0>(3), H2 = r.template ld<4>(3);
+  const bool hasF = __float_as_int(H1.x) & 1;
+  const float4 J = r.template ld<0>(c), B = r.template ld<4>(c);
+  float4 JF = z4, BF = z4;
+  if (hasF) { JF = r.template ld<8>(c); BF = r.template ld<12>(c); }
+  float p = c < 3 ? dot4(J, A, 0.f) : 0.f;
+  p = dot4(JF, F, p);
+  const float u = quad_sum(qmask, p);
+  const float l0 = H1.w;
+  float nl;
+  if (KIND == 0) nl = fmaxf(l0 + (H1.y - l0 * H2.x - u * H1.z), 0.f);
+  else { const float lim = H2.x * tot; nl = clampf(l0 + (H1.y - u * H1.z), -lim, lim); }
+  const float dl = nl - l0;
+  __syncwarp(qmask);                                     // every lane of the quad has read lambda
+  if (dl != 0.f) {
+    if (c == 3) *r.lam() = nl;
+    if (c < 3) axpy4(A, B, dl);
+    axpy4(F, BF, dl);
   }
-  __syncwarp();
-  if (col != 0 || !have) return;
-  for (int k = 0; k < ((njr + 3) >> 2); k++) sw.m.s(T_JROW + njr + k) = z4;
-  const int t_ct = T_JROW + njr + ((njr + 3) >> 2);
+  __syncwarp(qmask);                                     // the new impulse is visible to the quad
+  return hasF;
+}
+// lateral friction: the two rows of a contact are solved together (implicit cone)
+template <class Row>
+PRB_D bool quad_friction(const Row& r, const Row& r2f, const Row& r2n, const QuadMem& m, int c, unsigned qmask, float4& A, float4& F) {
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 H1 = r.template ld<0>(3), H2 = r.template ld<4>(3);
+  const bool hasF = __float_as_int(H1.x) & 1;
+  const Row& r2 = hasF ? r2f : r2n;                      // second row of the pair: 16 or 8 q further
+  const float4 G1 = r2.template ld<0>(3);
+  const float4 J1 = r.template ld<0>(c), B1 = r.template ld<4>(c), J2 = r2.template ld<0>(c), B2 = r2.template ld<4>(c);
+  float4 JF1 = z4, BF1 = z4, JF2 = z4, BF2 = z4;
+  if (hasF) { JF1 = r.template ld<8>(c); BF1 = r.template ld<12>(c); JF2 = r2.template ld<8>(c); BF2 = r2.template ld<12>(c); }
+  const float tot = *quad_lam(m, __float_as_int(H2.y));
+  float pa = c < 3 ? dot4(J1, A, 0.f) : 0.f, pb = c < 3 ? dot4(J2, A, 0.f) : 0.f;
+  pa = dot4(JF1, F, pa); pb = dot4(JF2, F, pb);
+  const float ua = quad_sum(qmask, pa), ub = quad_sum(qmask, pb);
+  const float lim = H2.x * tot;
+  const float la = H1.w, lb = G1.w;
+  const float sumA = la + (H1.y - ua * H1.z);
+  const float sumB = lb + (G1.y - ub * G1.z);
+  float na = sumA, nb = sumB;
+  if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
+    const float ss = sumA * sumA + sumB * sumB;
+    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+    const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
+    na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
+  }
+  const float d1 = na - la, d2 = nb - lb;
+  __syncwarp(qmask);
+  if (d1 != 0.f || d2 != 0.f) {
+    if (c == 3) { *r.lam() = na; *r2.lam() = nb; }
+    if (c < 3) { axpy4(A, B1, d1); axpy4(A, B2, d2); }
+    axpy4(F, BF1, d1); axpy4(F, BF2, d2);
+  }
+  __syncwarp(qmask);
+  return hasF;
+}
+
+template <int ND>
+__global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_arm_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf,
+                                                                const int* __restrict__ heavy_list, const int* __restrict__ heavy_cnt, int rows) {
+  PRB_PGS_SMEM_DECL;
+  const int lane = threadIdx.x, c = lane & 3, qb = lane & ~3;
+  const unsigned qmask = 0xfu << qb;
+  const int cnt = *heavy_cnt;
+  const DevModel& M = *Mp;
+  // persistent blocks: every quad walks the list with the grid's stride (quads of a warp are independent)
+  for (int i = blockIdx.x * PGS_G_EPW + (lane >> 2); i < cnt; i += gridDim.x * PGS_G_EPW) {
+  const int e = heavy_list[i];
+  float4* G = stream_col(sbuf, e);
+  const float4 hdr = G[Q_HDR * 32];
+  const int h0 = __float_as_int(hdr.x), info = __float_as_int(G[(Q_HDR + 1) * 32].x);
+  const int njr = h0 & 0xff, nc = (h0 >> 8) & 0xff, ns = (h0 >> 16) & 0xff;
+  const int tS0 = __float_as_int(hdr.y), tT0 = __float_as_int(hdr.z), tEnd = __float_as_int(hdr.w);
+  const int tN0 = (T_JROW + njr + ((njr + 3) >> 2) + 3) & ~3;
+  QuadMem m;
+  m.base = sm + qb; m.Gr = G + Q_ST * 32; m.cap = rows << 2;
+  {
+    const int tq = min(tEnd, m.cap);
+#pragma unroll 4
+    for (int q = T_MINV + c; q < tq; q += 4) *m.sp(q) = m.Gr[q * 32];
+  }
+  __syncwarp(qmask);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c == 0) for (int k = 0; k < ((njr + 3) >> 2); k++) *m.sp(T_JROW + njr + k) = z4;
+  __syncwarp(qmask);
+  float4 A = z4, F = z4;
   const float ratio = M.params[P_GEAR_RATIO];
   const int iters = M.solver_iters;
+  const int t_jlam = T_JROW + njr;
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
-    pgs_joint_rows<ND, 3 + 2 * PRB_MAXFREE, PGS_G_LW>(M, sw.m, sw.dvt, njr, it, ratio);
-    sw.normals(t_ct, nc);
-    sw.spins(t_spin, ns);
-    sw.frictions(t_ct, nc);
+    // ---- non-contact rows, sweep direction alternating per iteration
+#pragma unroll 1
+    for (int ii = 0; ii < njr; ii++) {
+      const int j = (it & 1) ? ii : njr - 1 - ii;
+      const float4 r = *m.sp(T_JROW + j);
+      const int pk = __float_as_int(r.x);
+      const int pd = pk & 0xff, a = (pk >> 16) & 15, a2 = (pk >> 20) & 15;
+      const int sidx = pd - DVW_SLIDE(0);                            // slide index when a == 15
+      const float sg = ((pk >> 24) & 1) ? -1.0f : 1.0f;
+      float4 m0 = z4, m1 = z4;                                       // this lane's slice of the M^-1 rows
+      if (a != 15 && c < 3) m0 = *m.sp(T_MINV + 3 * a + c);
+      if (a2 != 15 && c < 3) m1 = *m.sp(T_MINV + 3 * a2 + c);
+      // u = J . dv: J = e_a (+ ratio e_a2) or e_slide: the owning lane contributes its word
+      float p = 0.f;
+      if (a != 15) { if (c == (a >> 2)) p = f4comp(A, a & 3); }
+      else if (c == 3) p = f4comp(F, sidx);
+      if (a2 != 15 && c == (a2 >> 2)) p = fmaf(ratio, f4comp(A, a2 & 3), p);
+      const float u = quad_sum(qmask, p) * sg;
+      float* pl = reinterpret_cast<float*>(m.sp(t_jlam + (j >> 2))) + (j & 3);
+      const float l0 = *pl;
+      const float hi = r.w, lo = ((pk >> 25) & 1) ? -hi : 0.f;
+      const float nl = clampf(l0 + (r.y - u * r.z), lo, hi);
+      const float dl = (nl - l0) * sg;
+      __syncwarp(qmask);                                             // every lane of the quad has read l0
+      if (dl != 0.f) {
+        if (c == 0) *pl = nl;
+        if (a != 15) { axpy4(A, m0, dl); axpy4(A, m1, dl * ratio); }
+        else if (c == 3) f4add(F, sidx, M.slide_minv[sidx] * dl);
+      }
+      __syncwarp(qmask);                                             // the new impulse is visible to the quad
+    }
+    // ---- contact normals
+    {
+      int t = tN0;
+#pragma unroll 1
+      for (int k = 0; k < nc; k++) {
+        const bool hasF = m.staged(t) ? quad_row<0>(RowS{m.sp(t)}, c, qmask, A, F, 0.f) : quad_row<0>(RowG{m.Gr + t * 32}, c, qmask, A, F, 0.f);
+        t += hasF ? 2 * XROW_Q : XROW_Q;
+      }
+    }
+    // ---- spinning friction (Bullet skips the row while the normal impulse is 0)
+    {
+      int t = tS0;
+#pragma unroll 1
+      for (int k = 0; k < ns; k++) {
+        const bool st = m.staged(t);
+        const float4 H1 = st ? RowS{m.sp(t)}.ld<0>(3) : RowG{m.Gr + t * 32}.ld<0>(3);
+        const float4 H2 = st ? RowS{m.sp(t)}.ld<4>(3) : RowG{m.Gr + t * 32}.ld<4>(3);
+        const float tot = *quad_lam(m, __float_as_int(H2.y));        // normal impulse of the contact
+        if (tot > 0.f) {
+          if (st) quad_row<1>(RowS{m.sp(t)}, c, qmask, A, F, tot); else quad_row<1>(RowG{m.Gr + t * 32}, c, qmask, A, F, tot);
+        }
+        t += (__float_as_int(H1.x) & 1) ? 2 * XROW_Q : XROW_Q;
+      }
+    }
+    // ---- lateral friction
+    {
+      int t = tT0;
+#pragma unroll 1
+      for (int k = 0; k < nc; k++) {
+        bool hasF;
+        if (m.staged(t + 2 * XROW_Q)) hasF = quad_friction(RowS{m.sp(t)}, RowS{m.sp(t + 2 * XROW_Q)}, RowS{m.sp(t + XROW_Q)}, m, c, qmask, A, F);
+        else hasF = quad_friction(RowG{m.Gr + t * 32}, RowG{m.Gr + (t + 2 * XROW_Q) * 32}, RowG{m.Gr + (t + XROW_Q) * 32}, m, c, qmask, A, F);
+        t += hasF ? 4 * XROW_Q : 2 * XROW_Q;
+      }
+    }
   }
-  pgs_store_arm(M, G, sw.m, sw.dvt, 3 + 2 * PRB_MAXFREE);
-  for (int b = 0; b < M.n_free; b++)
-    if (((info >> (16 + 2 * b)) & 3) == 0) pgs_store_free(M, G, sw.m, sw.dvt + 3, b);
+  // ---- velocity change -> stream (linear DoF order): arm, slides, and the free bodies this island owns
+  float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
+  const int nd = M.nd, nf = M.n_free;
+  const float a4[4] = {A.x, A.y, A.z, A.w}, f4[4] = {F.x, F.y, F.z, F.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int wa = 4 * c + k;                    // word of A: arm DoF
+    if (c < 3 && wa < nd) gd[(wa >> 2) * 128 + (wa & 3)] = a4[k];
+    const int wf = 4 * c + k;                    // word of F
+    int d = -1;
+    if (wf < 12) { const int b = wf / 6; if (b < nf && ((info >> (16 + 2 * b)) & 3) == 0) d = nd + wf; }
+    else if (wf - 12 < M.n_slide) d = nd + 6 * nf + (wf - 12);
+    if (d >= 0) gd[(d >> 2) * 128 + (d & 3)] = f4[k];
+  }
+  __syncwarp(qmask);                                     // the quad's columns are re-staged by the next env
+  }
 }

@@ -53,6 +53,7 @@ struct Warp {
   unsigned gen = 0, arrived = 0;
   uint32_t buf[32];
   unsigned ballot = 0;
+  unsigned ggen[32] = {0}, garr[32] = {0};   // sub-warp groups (partial masks), keyed by the mask's lowest lane
 };
 static std::vector<Fiber> fibers;
 static std::vector<Warp> warps;
@@ -82,6 +83,15 @@ static inline void block_barrier() {
   unsigned g = block_gen;
   if (++block_arrived == (unsigned)nthreads) { block_arrived = 0; block_gen++; }
   else while (block_gen == g) yield();
+}
+// barrier among the lanes of a partial mask (e.g. a quad): exited lanes of other groups do not take part
+static inline void group_barrier(unsigned mask) {
+  Warp& w = warps[cur / 32];
+  const int key = __builtin_ctz(mask);
+  const unsigned width = __builtin_popcount(mask);
+  unsigned g = w.ggen[key];
+  if (++w.garr[key] == width) { w.garr[key] = 0; w.ggen[key]++; }
+  else while (w.ggen[key] == g) yield();
 }
 static const size_t STACK = 256 * 1024;
 
@@ -131,8 +141,19 @@ void launch(emu_dim3 grid, emu_dim3 block, F f) { launch_y(grid, block, 0, f); }
 using std::min;
 using std::max;
 
-static inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)mask; emu::warp_barrier(); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { if (mask == 0xffffffffu) emu::warp_barrier(); else emu::group_barrier(mask); }
 static inline void __syncthreads() { emu::block_barrier(); }
+template <class T>
+static inline T emu_shfl_group(unsigned mask, T v, int src) {
+  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  emu::Warp& w = emu::warps[emu::cur / 32];
+  int lane = emu::cur % 32;
+  memcpy(&w.buf[lane], &v, 4);
+  emu::group_barrier(mask);
+  T r; memcpy(&r, &w.buf[src & 31], 4);
+  emu::group_barrier(mask);
+  return r;
+}
 template <class T>
 static inline T emu_shfl(T v, int src) {
   static_assert(sizeof(T) == 4, "32-bit shuffles only");
@@ -145,7 +166,9 @@ static inline T emu_shfl(T v, int src) {
   return r;
 }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, src); }
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, (emu::cur % 32) ^ m); }
+template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int m) {
+  return mask == 0xffffffffu ? emu_shfl(v, (emu::cur % 32) ^ m) : emu_shfl_group(mask, v, (emu::cur % 32) ^ m);
+}
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { int l = emu::cur % 32; return emu_shfl(v, l + d < 32 ? l + d : l); }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { int l = emu::cur % 32; return emu_shfl(v, l - d >= 0 ? l - d : l); }
 static inline unsigned __ballot_sync(unsigned, int pred) {

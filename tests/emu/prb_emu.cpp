@@ -33,8 +33,8 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
         emu::launch_y(gy, bp, y, [&]() { prb_pgs_free_kernel(&g_M, g_sbuf.data(), N); });
       }
       emu_dim3 gh; gh.x = (N + PGS_G_EPW - 1) / PGS_G_EPW;
-      emu::launch(gh, bp, [&]() { prb_pgs_kernel<ND>(&g_M, g_sbuf.data(), heavy.data() + N, heavy_cnt + 1, PGS_ROWS_GB); });
-      emu::launch(gh, bp, [&]() { prb_pgs_kernel<ND>(&g_M, g_sbuf.data(), heavy.data(), heavy_cnt, PGS_ROWS_GA); });
+      emu::launch(gh, bp, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data() + N, heavy_cnt + 1, PGS_ROWS_GB); });
+      emu::launch(gh, bp, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data(), heavy_cnt, PGS_ROWS_GA); });
     }
   }
 }
