@@ -26,38 +26,82 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENV_ID = 'UR5PlayAbsRPY1Obj-v0'
+RELABEL_EVERY, RELABEL_PHASE = 64, 8       # goal relabelling cadence and its phase in the timed region
 BYTES_PER_ENV_STEP = {'UR5Reach-v0': 416, 'pandaPick-v0': 560, 'UR5PlayAbsRPY1Obj-v0': 1044}
 METRIC = 'UR5PlayAbsRPY1Obj-v0 env-steps/s'
 
 
-def synth_actions(rng, n, steps, env_id):
-    """Teleop-shaped synthetic actions: per env a piecewise-linear end-effector
-    trajectory between random workspace waypoints at <= 0.015 m / 0.1 rad per 25 Hz step, gripper
-    toggling at waypoints; 5% of the steps jump to a point of the full +-6 clip box."""
+# Interaction regions of the playroom scene (scenes.py:46-426), arm base frame.  Round 1: the block
+# sub-tasks make real contact (reach, grasp, lift, carry); the drawer / door / button / dial sub-tasks
+# trace their gestures a few centimetres clear of the furniture (handle geometry is not scripted yet).
+_ANCHORS = {'drawer': (-0.10, 0.06, 0.08), 'door': (0.05, 0.32, 0.10), 'button': (-0.20, 0.33, 0.12), 'dial': (0.20, 0.10, 0.07)}
+# sub-task scripts: waypoints (dx, dy, dz relative to the anchor, yaw, gripper, dwell steps)
+_SCRIPTS = [
+    ('block', [(0, 0, 0.15, 0, -1, 0), (0, 0, 0.03, 0, -1, 4)]),                                             # reach block
+    ('block', [(0, 0, 0.15, 0, -1, 0), (0, 0, -0.01, 0, -1, 2), (0, 0, -0.01, 0, 1, 10), (0, 0, 0.2, 0, 1, 6),
+               (0.05, 0.05, 0.2, 0, 1, 2), (0.05, 0.05, 0.03, 0, -1, 4)]),                                    # grasp, lift, carry, release
+    ('drawer', [(0, 0, 0.06, 0, -1, 0), (0, 0, 0.0, 0, 1, 6), (0, -0.08, 0.0, 0, 1, 4)]),                        # drawer pull gesture (-y)
+    ('door', [(-0.08, 0, 0.0, 0, -1, 0), (0.08, 0.0, 0.0, 0, -1, 4)]),                                          # door slide gesture (+x)
+    ('button', [(0, 0, 0.06, 0, 1, 0), (0, 0, 0.0, 0, 1, 6), (0, 0, 0.06, 0, 1, 2)]),                           # button press gesture
+    ('dial', [(0, 0, 0.06, 0, -1, 0), (0, 0, 0.0, 0, 1, 6), (0, 0, 0.0, 1.0, 1, 4)]),                           # dial turn gesture
+]
+
+
+def synth_actions(rng, n, steps, env_id, block_xyz=None, ee_xyz=None, jump_frac=0.0):
+    """Scripted teleop-shaped synthetic actions: every env runs a random
+    sub-task {reach block, grasp + lift, pull drawer, slide door, press button, turn dial} as
+    piecewise-linear end-effector waypoints at <= 0.015 m / 0.1 rad per 25 Hz step, the gripper closing
+    at contact, then draws the next sub-task.  jump_frac > 0 adds the Random stream's tail (that
+    fraction of the steps targets a point of the full +-6 clip box: exercises the +-inc clamp and
+    drives arms into the furniture)."""
     if env_id == 'UR5PlayAbsRPY1Obj-v0':
         lo, hi = np.array([-0.30, -0.05, 0.0]), np.array([0.30, 0.50, 0.35])
     else:
         lo, hi = np.array([-0.18, -0.18, -0.05]), np.array([0.18, 0.18, 0.2])
-    pos = rng.uniform(lo, hi, (n, 3))
-    rpy = rng.uniform(-0.5, 0.5, (n, 3))
-    grip = rng.choice([-1.0, 1.0], (n, 1))
-    tgt_p, tgt_r = rng.uniform(lo, hi, (n, 3)), rng.uniform(-0.5, 0.5, (n, 3))
+    play = env_id == 'UR5PlayAbsRPY1Obj-v0'
+    blk = np.asarray(block_xyz, np.float64) if block_xyz is not None else rng.uniform(lo, hi, (n, 3))
+    pos = np.asarray(ee_xyz, np.float64).copy() if ee_xyz is not None else rng.uniform(lo, hi, (n, 3))
+    rpy = np.zeros((n, 3))
+    grip = -np.ones((n, 1))
+    nscripts = len(_SCRIPTS) if play else 2
+    task = rng.integers(0, nscripts, n)
+    stage = np.zeros(n, np.int64)
+    dwell = np.zeros(n, np.int64)
+    maxw = max(len(w) for _, w in _SCRIPTS)
+    wp = np.zeros((len(_SCRIPTS), maxw, 6))
+    nwp = np.zeros(len(_SCRIPTS), np.int64)
+    for i, (_, w) in enumerate(_SCRIPTS):
+        wp[i, :len(w)] = w
+        nwp[i] = len(w)
+    anchors = np.zeros((len(_SCRIPTS), n, 3))
+    for i, (name, _) in enumerate(_SCRIPTS):
+        anchors[i] = blk if name == 'block' else np.asarray(_ANCHORS[name])[None]
     out = np.zeros((steps, n, 7), np.float32)
+    idx = np.arange(n)
     for s in range(steps):
+        w = wp[task, stage]                                   # [n, 6]
+        tgt_p = anchors[task, idx] + w[:, :3]
+        tgt_yaw = w[:, 3]
         dp = tgt_p - pos
         dist = np.linalg.norm(dp, axis=1, keepdims=True)
         pos = pos + dp * np.minimum(1.0, 0.015 / np.maximum(dist, 1e-9))
-        rpy = rpy + np.clip(tgt_r - rpy, -0.1, 0.1)
-        arrived = dist[:, 0] < 0.015
-        k = int(arrived.sum())
+        rpy[:, 2] += np.clip(tgt_yaw - rpy[:, 2], -0.1, 0.1)
+        arrived = (dist[:, 0] < 0.015) & (np.abs(tgt_yaw - rpy[:, 2]) < 0.1)
+        grip[arrived, 0] = w[arrived, 4]                      # the gripper acts once the waypoint is reached
+        dwell = np.where(arrived, dwell + 1, 0)
+        adv = arrived & (dwell > w[:, 5])
+        stage = np.where(adv, stage + 1, stage)
+        dwell = np.where(adv, 0, dwell)
+        done = stage >= nwp[task]
+        k = int(done.sum())
         if k:
-            tgt_p[arrived] = rng.uniform(lo, hi, (k, 3))
-            tgt_r[arrived] = rng.uniform(-0.5, 0.5, (k, 3))
-            grip[arrived] = -grip[arrived]
+            task[done] = rng.integers(0, nscripts, k)
+            stage[done] = 0
         a = np.concatenate([pos, rpy, grip], 1)
-        jump = rng.random(n) < 0.05
-        if jump.any():
-            a[jump, :6] = rng.uniform(-6, 6, (int(jump.sum()), 6))
+        if jump_frac > 0:
+            jump = rng.random(n) < jump_frac
+            if jump.any():
+                a[jump, :6] = rng.uniform(-6, 6, (int(jump.sum()), 6))
         out[s] = a
     return out
 
@@ -104,18 +148,22 @@ def _cpu_worker(args):
     from oracle.oracle import Oracle
     m = load_model(env_id)
     o = Oracle(m, seed=seed + wid, env_id=wid)
-    o.reset()
-    acts = synth_actions(np.random.default_rng(seed + wid), 1, 4096, env_id)[:, 0, :]
+    d0 = o.reset()
+    blk = d0['achieved_goal'][None, :3] if env_id == ENV_ID else None
+    ee = d0['obs_quat'][None, :3]
+    acts = synth_actions(np.random.default_rng(seed + wid), 1, 4096, env_id, block_xyz=blk, ee_xyz=ee)[:, 0, :]
+    # the same scripted stream as the GPU arm; the CPU sample starts inside the contact phases too
+    # (the pre-roll is skipped through by stepping, untimed, every 4th action: cheap approach to the objects)
     for i in range(warm):
-        o.step(acts[i])
+        o.step(acts[min(4 * i, 95)])
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s:
-        o.step(acts[(warm + n) % len(acts)])
+        o.step(acts[(96 + n) % len(acts)])
         n += 1
     return n, time.perf_counter() - t0
 
 
-def cpu_baseline(env_id, seed, budget_s=12.0, warm=20):
+def cpu_baseline(env_id, seed, budget_s=12.0, warm=24):
     """Oracle (kind 'port') on every host core, one process per core, bounded to ~budget_s."""
     cores = os.cpu_count() or 1
     ctx = mp.get_context('fork')
@@ -136,7 +184,7 @@ def run_reference(args):
     per = []
     # each "step" = one bounded sample: ~ (budget / steps) seconds of oracle stepping on all cores
     total_budget = min(150.0, max(10.0, 3.0 * (args.steps + args.warmup)))
-    b = cpu_baseline(args.env, args.seed, budget_s=total_budget, warm=20)
+    b = cpu_baseline(args.env, args.seed, budget_s=total_budget, warm=24)
     v = b['value']
     line = {'impl': 'reference', 'metric': METRIC if args.env == ENV_ID else args.env + ' env-steps/s',
             'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -167,8 +215,7 @@ def run_gpu(args):
     N = args.envs_per_gpu
     K, W = args.steps, args.warmup
     env = make(args.env, num_envs=N, device=local, seed=args.seed, env_offset=rank * N)
-    acts_host = synth_actions(np.random.default_rng(args.seed + rank), N, K + W, args.env)
-    acts_dev = torch.as_tensor(acts_host).to(dev)
+    P = args.preroll
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -176,12 +223,21 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    env.reset_device()
+    obs0 = env.reset_device()
     torch.cuda.synchronize()
+    play = args.env == ENV_ID
+    blk = obs0['achieved_goal'][:, :3].cpu().numpy() if play else None
+    ee = obs0['obs_quat'][:, :3].cpu().numpy()
+    acts_host = synth_actions(np.random.default_rng(args.seed + rank), N, P + K + W, args.env, block_xyz=blk, ee_xyz=ee,
+                              jump_frac=args.jump_frac)
+    acts_dev = torch.as_tensor(acts_host).to(dev)
     env.enable_kernel_timing(True)
-    for s in range(W):
+    # untimed pre-roll: the scripted sub-tasks need ~100 steps to reach their contact phases, so that the
+    # timed steps sample the steady state of scripted play rather than the approach from the rest pose
+    for s in range(P + W):
         env.step_device(acts_dev[s])
     torch.cuda.synchronize()
+    acts_host, acts_dev = acts_host[P:], acts_dev[P:]
     sampler = ClockSampler(local)
     sampler.start()
     # ---- device-resident timed region: exactly K steps, CUDA events on the launching stream,
@@ -191,12 +247,26 @@ def run_gpu(args):
     kern_ms, ik_ms, tier_ms = [], [], []
     succ = torch.zeros((), device=dev)
     rsum = torch.zeros((), device=dev)
+    relabel_r = torch.zeros((), device=dev)
+    n_relabel, n_reset = 0, 0
+    ag_hist = env.dev['achieved_goal'].clone() if play else None
     barrier()
     t_wall0 = time.perf_counter()
     for s in range(K):
         flush.fill_(float(s))
         ev[s][0].record()
         obs, r, _, info = env.step_device(acts_dev[W + s])
+        if play and s % RELABEL_EVERY == RELABEL_PHASE:
+            # goal relabelling (SURVEY.md \u00a78d): the stored achieved goals are rewarded against a LATER
+            # achieved goal of the same env, which also becomes the env's desired goal (reset_goal_pos)
+            new_goal = obs['achieved_goal'].clone()
+            relabel_r += env.compute_reward_device(ag_hist, new_goal).sum()
+            env.reset_goal_pos_device(new_goal)
+            ag_hist.copy_(new_goal)
+            n_relabel += 1
+        if (P + W + s + 1) % args.episode_steps == 0:
+            env.reset_device(torch.ones(N, dtype=torch.uint8, device=dev))      # episode end (masked reset path)
+            n_reset += 1
         ev[s][1].record()
         a, b = env.last_kernel_ms()
         ik_ms.append(a)
@@ -245,12 +315,16 @@ def run_gpu(args):
                 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
                 'ms_per_step': 1000.0 * dev_s / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': '%s, %d envs per GPU (%d total), sharded by env index; teleop-shaped synthetic '
-                                       'actions; L2 flushed (256 MB fill) between timed steps' % (args.env, N, N * world),
-                           'envs_per_gpu': N, 'substeps_per_step': 12, 'solver_iterations': 50, 'seed': args.seed},
+                'config': {'workload': '%s, %d envs per GPU (%d total), sharded by env index; scripted teleop-shaped synthetic '
+                                       'sub-task trajectories (reach / grasp+lift / drawer / door / button / dial), goal '
+                                       'relabelling every %d steps, %d untimed pre-roll steps; L2 flushed (256 MB fill) '
+                                       'between timed steps' % (args.env, N, N * world, RELABEL_EVERY, P),
+                           'envs_per_gpu': N, 'substeps_per_step': 12, 'solver_iterations': 50, 'seed': args.seed,
+                           'jump_frac': args.jump_frac, 'preroll_steps': P, 'relabel_events': n_relabel,
+                           'episode_resets': n_reset},
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                              'frac': achieved / peak_gbs, 'traffic': None,
-                             'kernel': 'step pipeline: 13 x prb_setup_kernel + 12 x prb_pgs_kernel per env step',
+                             'kernel': 'step pipeline per env step: 13 x prb_setup_kernel + 12 x (prb_pgs_joint_kernel, prb_pgs_free_kernel, 2 x prb_pgs_arm_kernel)',
                              'setup_kernels_ms': float(np.mean([t[0] for t in tier_ms])),
                              'pgs_kernels_ms': float(np.mean([t[1] for t in tier_ms])),
                              'kernel_ms': kms, 'ik_kernel_ms': float(np.mean(ik_ms)), 'peak_source': which,
@@ -286,6 +360,9 @@ def main():
     ap.add_argument('--seed', type=int, default=1234)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--preroll', type=int, default=96, help='untimed scripted steps before the warm-up')
+    ap.add_argument('--jump-frac', type=float, default=0.0, help='fraction of steps that target the full +-6 clip box (Random-stream tail)')
+    ap.add_argument('--episode-steps', type=int, default=512, help='masked reset of every env after this many steps')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

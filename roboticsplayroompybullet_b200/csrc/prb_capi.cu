@@ -73,7 +73,7 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
     int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
     if (flags == 0) break;
     if (h->timing && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
-    if (i < nsub) CK(h, cudaMemsetAsync(h->heavy_cnt, 0, 2 * sizeof(int), s));
+    if (i < nsub) CK(h, cudaMemsetAsync(h->heavy_cnt, 0, 8 * sizeof(int), s));
     prb_setup_kernel<ND><<<gs, bs, h->smem, s>>>(h->dm, h->state, h->sbuf, h->O, h->N, flags, h->heavy_list, h->heavy_cnt);
     h->launches++;
     if (i < nsub) {
@@ -85,7 +85,7 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
       CK(h, cudaEventRecord(h->ev_fork, s));
       CK(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
       CK(h, cudaStreamWaitEvent(h->side2, h->ev_fork, 0));
-      prb_pgs_arm_kernel<ND><<<ghb, bp, PGS_SMEM_G(PGS_ROWS_GB), h->side2>>>(h->dm, h->sbuf, h->heavy_list + h->N, h->heavy_cnt + 1, PGS_ROWS_GB);
+      prb_pgs_arm_kernel<ND><<<ghb, bp, PGS_SMEM_G(PGS_ROWS_GB), h->side2>>>(h->dm, h->sbuf, h->heavy_list + h->N, h->heavy_cnt + 4, PGS_ROWS_GB);
       prb_pgs_arm_kernel<ND><<<gha, bp, PGS_SMEM_G(PGS_ROWS_GA), h->side>>>(h->dm, h->sbuf, h->heavy_list, h->heavy_cnt, PGS_ROWS_GA);
       CK(h, cudaEventRecord(h->ev_join, h->side));
       CK(h, cudaEventRecord(h->ev_join2, h->side2));
@@ -176,7 +176,7 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
     CK(h, cudaMalloc(&h->sbuf, sb_bytes));
     CK(h, cudaMemset(h->sbuf, 0, sb_bytes));
     CK(h, cudaMalloc(&h->heavy_list, sizeof(int) * 2 * N));
-    CK(h, cudaMalloc(&h->heavy_cnt, 2 * sizeof(int)));
+    CK(h, cudaMalloc(&h->heavy_cnt, 8 * sizeof(int)));   // {list length, -, work counter, -} x 2 classes
     int lo_pri = 0, hi_pri = 0;
     CK(h, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
     CK(h, cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi_pri));

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
     if (lane == 0 && W.overflow && O.overflow) atomicAdd(O.overflow, 1ull);
     if (lane == 0 && W.dbg_u) {                      // order within a list is immaterial: envs are independent
       const int cls = W.dbg_u - 1;                   // 0: region 0 fits class A's stage, 1: larger
-      heavy_list[(size_t)cls * N + atomicAdd(heavy_cnt + cls, 1)] = e;
+      heavy_list[(size_t)cls * N + atomicAdd(heavy_cnt + 4 * cls, 1)] = e;    // heavy_cnt: {length, -, work counter, -} per class
     }
     if (lane == 0 && O.dbg) { O.dbg[4 * e] = 0; O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.n_jrow; }
   }
@@ -875,14 +875,19 @@ PRB_D bool quad_friction(const Row& r, const Row& r2f, const Row& r2n, const Qua
 
 template <int ND>
 __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_arm_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf,
-                                                                const int* __restrict__ heavy_list, const int* __restrict__ heavy_cnt, int rows) {
+                                                                const int* __restrict__ heavy_list, int* __restrict__ heavy_cnt, int rows) {
   PRB_PGS_SMEM_DECL;
   const int lane = threadIdx.x, c = lane & 3, qb = lane & ~3;
   const unsigned qmask = 0xfu << qb;
   const int cnt = *heavy_cnt;
   const DevModel& M = *Mp;
-  // persistent blocks: every quad walks the list with the grid's stride (quads of a warp are independent)
-  for (int i = blockIdx.x * PGS_G_EPW + (lane >> 2); i < cnt; i += gridDim.x * PGS_G_EPW) {
+  // persistent blocks, dynamic scheduling: every quad (the quads of a warp are independent) draws the
+  // next env of the list from a device counter (heavy_cnt[2]), so long islands do not queue behind each other
+  for (;;) {
+  int i = 0;
+  if (c == 0) i = atomicAdd(heavy_cnt + 2, 1);
+  i = __shfl_sync(qmask, i, qb);
+  if (i >= cnt) break;
   const int e = heavy_list[i];
   float4* G = stream_col(sbuf, e);
   const float4 hdr = G[Q_HDR * 32];

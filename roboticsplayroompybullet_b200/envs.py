@@ -169,6 +169,18 @@ class VecPlayEnv:
         self._g_keep = g
         _lib.check(self.L, self._h, self.L.prb_set_goal(self._h, ctypes.c_void_p(g.data_ptr()), None, self._stream()))
 
+    def reset_goal_pos_device(self, goal, mask=None):
+        """Device-resident reset_goal_pos (environments.py:190-191) for goal relabelling inside a rollout loop:
+        goal float32 CUDA tensor [N, goal_dim], optional uint8 mask [N]."""
+        t = self.torch
+        g = goal.to(self.device, t.float32).reshape(self.num_envs, -1).contiguous()
+        self._g_keep = g
+        mp = None
+        if mask is not None:
+            self._gmask = mask.to(self.device, t.uint8).contiguous()
+            mp = ctypes.c_void_p(self._gmask.data_ptr())
+        _lib.check(self.L, self._h, self.L.prb_set_goal(self._h, ctypes.c_void_p(g.data_ptr()), mp, self._stream()))
+
     def compute_reward(self, achieved_goal, desired_goal, info=None):
         """Batched compute_reward_sparse (sparse=True) or dense -||ag-dg|| (environments.py:274-304)."""
         t = self.torch

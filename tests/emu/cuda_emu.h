@@ -165,7 +165,7 @@ static inline T emu_shfl(T v, int src) {
   emu::warp_barrier();
   return r;
 }
-template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, src); }
+template <class T> static inline T __shfl_sync(unsigned mask, T v, int src) { return mask == 0xffffffffu ? emu_shfl(v, src) : emu_shfl_group(mask, v, src); }
 template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int m) {
   return mask == 0xffffffffu ? emu_shfl(v, (emu::cur % 32) ^ m) : emu_shfl_group(mask, v, (emu::cur % 32) ^ m);
 }

@@ -17,14 +17,14 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
   }
   g_sbuf.assign(sbuf_bytes(N) / sizeof(float), 0.f);
   std::vector<int> heavy(2 * N);
-  int heavy_cnt[2] = {0, 0};
+  int heavy_cnt[8] = {0};
   emu_dim3 gs, bs, gp, bp;
   bs.x = 32 * SetupCfg::WPB; gs.x = (N + SetupCfg::WPB - 1) / SetupCfg::WPB;
   bp.x = PGS_BLOCK; gp.x = (N + PGS_BLOCK - 1) / PGS_BLOCK;
   for (int i = 0; i <= nsub; i++) {
     int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
     if (flags == 0) break;
-    heavy_cnt[0] = heavy_cnt[1] = 0;
+    memset(heavy_cnt, 0, sizeof(heavy_cnt));
     emu::launch(gs, bs, [&]() { prb_setup_kernel<ND>(&g_M, state, g_sbuf.data(), O, N, flags, heavy.data(), heavy_cnt); });
     if (i < nsub) {
       emu::launch(gp, bp, [&]() { prb_pgs_joint_kernel<ND>(&g_M, g_sbuf.data(), N); });
@@ -33,7 +33,7 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
         emu::launch_y(gy, bp, y, [&]() { prb_pgs_free_kernel(&g_M, g_sbuf.data(), N); });
       }
       emu_dim3 gh; gh.x = (N + PGS_G_EPW - 1) / PGS_G_EPW;
-      emu::launch(gh, bp, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data() + N, heavy_cnt + 1, PGS_ROWS_GB); });
+      emu::launch(gh, bp, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data() + N, heavy_cnt + 4, PGS_ROWS_GB); });
       emu::launch(gh, bp, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data(), heavy_cnt, PGS_ROWS_GA); });
     }
   }

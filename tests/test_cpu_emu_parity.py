@@ -66,3 +66,52 @@ def test_emu_box_box_matches_oracle():
             n_hit += 1
             assert np.abs(a - b).max() < 5e-5
     assert n_hit > 20
+
+
+def _stream_headers(env=0):
+    """Decode the three header float4 of one env's record stream (csrc/prb_stream.cuh, Q_HDR)."""
+    import ctypes
+    from emu_lib import lib
+    L = lib()
+    L.emu_sbuf.restype = ctypes.POINTER(ctypes.c_float)
+    sbq = L.emu_sbuf_q()
+    buf = np.ctypeslib.as_array(L.emu_sbuf(), shape=(sbq, 32, 4))
+    h = [buf[i, env].view(np.int32).copy() for i in range(3)]
+    return {'njr': int(h[0][0] & 0xff), 'nc0': int((h[0][0] >> 8) & 0xff), 'ns0': int((h[0][0] >> 16) & 0xff),
+            'nc1': int(h[1][0] & 0xff), 'nc2': int(h[2][0] & 0xff),
+            'slot_free0': int((h[1][0] >> 16) & 3), 'slot_free1': int((h[1][0] >> 18) & 3)}
+
+
+def test_emu_grasp_sequence_islands_and_arm_solver():
+    """Scripted reach-close-lift of the block, every env step started from the oracle's state.  While the
+    gripper is away the block and the drawer are their own constraint islands (slots 1, 2: free-body
+    solver) and the arm island has joint rows only; once the fingers touch the block its island merges
+    into slot 0 and is solved by the four-lanes-per-env arm-island kernel.  Both paths must match the
+    fp64 oracle to the one-step pose tolerance."""
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    sim, o = EmuSim(m, 1, seed=3), Oracle(m, seed=3)
+    o.reset()
+    blk = o.state[60:63].copy()
+    act = lambda z, g: np.array([blk[0], blk[1], z, 0, 0, 0, g])
+    seq = [act(0.15, -1)] * 3 + [act(-0.01, -1)] * 12 + [act(-0.01, 1)] * 10 + [act(0.2, 1)] * 8
+    errs, merged, separate = [], 0, 0
+    for a in seq:
+        _sync(sim, o)
+        sim.step(a[None]); o.step(a)
+        sd = o.state_dim
+        d = np.abs(sim.state[0, :sd - 1] - o.state[:sd - 1])
+        errs.append(max(d[:12].max(), d[60:63].max(), d[73:76].max()))
+        h = _stream_headers()
+        assert h['njr'] >= 12                                    # 12 motors (+ gear, limits)
+        if h['slot_free0'] == 0:
+            merged += 1
+            assert h['nc0'] > 0 and h['nc1'] == 0                # block contacts moved to the arm island
+        else:
+            separate += 1
+            assert h['slot_free0'] == 1 and h['nc1'] >= 1
+        assert h['slot_free1'] == 2 and h['nc2'] >= 4            # drawer rests on its blockers throughout
+    assert merged >= 8 and separate >= 8
+    errs = np.array(errs)
+    assert np.median(errs) < 1e-6
+    assert (errs < 1e-4).sum() >= len(errs) - 2                  # contact onset may flip by one substep (fp32 vs fp64)
+    assert o.state[62] > 0.1                                     # lifted

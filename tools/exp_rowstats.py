@@ -13,25 +13,18 @@ acts = bench.synth_actions(np.random.default_rng(1234), N, T, 'UR5PlayAbsRPY1Obj
 L = lib(); L.emu_sbuf.restype = ctypes.POINTER(ctypes.c_float)
 SBQ = L.emu_sbuf_q()
 rows = []
-for s in range(T):
-    sim.step(acts[s])
-    buf = np.ctypeslib.as_array(L.emu_sbuf(), shape=(SBQ * 32 // 2, 32, 2, 4))   # [q>>1][lane][q&1][4]
+QST = 19
+for s_ in range(T):
+    sim.step(acts[s_])
+    buf = np.ctypeslib.as_array(L.emu_sbuf(), shape=(SBQ, 32, 4))            # [q][lane][4]
     for e in range(N):
-        q = lambda i: buf[i >> 1, e, i & 1]
-        hdr = q(0).view(np.int32)
-        njr, nc, ns = int(hdr[0]), int(hdr[1]), int(hdr[2])
-        types = {}
-        for c in range(nc):
-            pk = int(q(134 + c).view(np.int32)[0])
-            nA, nB = (pk >> 5) & 15, (pk >> 14) & 15
-            k = tuple(sorted((nA, nB)))
-            types[k] = types.get(k, 0) + 1
-        rows.append((njr, nc, ns, types))
-njr = np.array([r[0] for r in rows]); nc = np.array([r[1] for r in rows]); ns = np.array([r[2] for r in rows])
-for nm, x in (('jrows', njr), ('contacts', nc), ('spin', ns)):
+        h = [buf[i, e].view(np.int32) for i in range(3)]
+        rows.append((int(h[0][0] & 0xff), int((h[0][0] >> 8) & 0xff), int(h[1][0] & 0xff), int(h[2][0] & 0xff),
+                     int((h[1][0] >> 16) & 3), int((h[1][0] >> 18) & 3), int(h[0][3])))
+r = np.array(rows)
+for i, nm in enumerate(['joint rows', 'slot-0 contacts', 'slot-1 contacts', 'slot-2 contacts']):
+    x = r[:, i]
     print(nm, 'mean %.1f' % x.mean(), 'pct 50/90/99/max', [int(np.percentile(x, p)) for p in (50, 90, 99, 100)])
-tot = {}
-for r in rows:
-    for k, v in r[3].items(): tot[k] = tot.get(k, 0) + v
-print('contact types (nA,nB) per env-substep:', {k: round(v / len(rows), 2) for k, v in sorted(tot.items())})
+print('free body 0 merged into the arm island: %.3f   free body 1: %.3f' % ((r[:, 4] == 0).mean(), (r[:, 5] == 0).mean()))
+print('arm island needs the general solver: %.3f   region-0 q pct 50/90/99/max' % (r[:, 1] > 0).mean(), [int(np.percentile(r[:, 6], p)) for p in (50, 90, 99, 100)])
 print('step time', (time.time() - t0) / T)
