@@ -15,6 +15,7 @@ struct prb_handle {
   DevModel hm;
   DevModel* dm = nullptr;
   int N = 0, device = 0, sms = 148;
+  int arm_threads = 32;            // threads per block of the arm-island kernel (4 per env)
   unsigned env_offset = 0;
   unsigned long long seed = 0;
   float* state = nullptr;
@@ -67,7 +68,13 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
   // persistent solver blocks: resident blocks per SM (shared-memory limited) x SMs, grid-stride inside
   const int ng = (h->N + PGS_BLOCK - 1) / PGS_BLOCK, nq = (h->N + PGS_G_EPW - 1) / PGS_G_EPW;
   dim3 gp(ng < 6 * h->sms ? ng : 6 * h->sms), gf(ng < 3 * h->sms ? ng : 3 * h->sms, h->hm.n_free), bp(PGS_BLOCK);
-  dim3 gha(nq < 4 * h->sms ? nq : 4 * h->sms), ghb(nq < 2 * h->sms ? nq : 2 * h->sms);
+  // arm-island kernel: one env (4 threads) per block, up to 32 / 16 resident blocks per SM for the two size classes
+  const int at = h->arm_threads;
+  const int smA = PGS_ROWS_GA * at * 16, smB = PGS_ROWS_GB * at * 16;
+  int bpsA = (227 * 1024) / (smA + 1024), bpsB = (227 * 1024) / (smB + 1024);
+  if (bpsA > 24) bpsA = 24;
+  if (bpsB > 24) bpsB = 24;
+  dim3 gha(bpsA * h->sms), ghb(bpsB * h->sms), bq(at);
   h->n_evk = 0;
   for (int i = 0; i <= nsub; i++) {
     int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
@@ -85,8 +92,8 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
       CK(h, cudaEventRecord(h->ev_fork, s));
       CK(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
       CK(h, cudaStreamWaitEvent(h->side2, h->ev_fork, 0));
-      prb_pgs_arm_kernel<ND><<<ghb, bp, PGS_SMEM_G(PGS_ROWS_GB), h->side2>>>(h->dm, h->sbuf, h->heavy_list + h->N, h->heavy_cnt + 4, PGS_ROWS_GB);
-      prb_pgs_arm_kernel<ND><<<gha, bp, PGS_SMEM_G(PGS_ROWS_GA), h->side>>>(h->dm, h->sbuf, h->heavy_list, h->heavy_cnt, PGS_ROWS_GA);
+      prb_pgs_arm_kernel<ND><<<ghb, bq, smB, h->side2>>>(h->dm, h->sbuf, h->heavy_list + h->N, h->heavy_cnt + 4, PGS_ROWS_GB);
+      prb_pgs_arm_kernel<ND><<<gha, bq, smA, h->side>>>(h->dm, h->sbuf, h->heavy_list, h->heavy_cnt, PGS_ROWS_GA);
       CK(h, cudaEventRecord(h->ev_join, h->side));
       CK(h, cudaEventRecord(h->ev_join2, h->side2));
       prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, s>>>(h->dm, h->sbuf, h->N);
@@ -115,7 +122,7 @@ static int setup_kernels(prb_handle* h) {
   cudaFuncAttributes fa;
   CK(h, cudaFuncGetAttributes(&fa, prb_setup_kernel<ND>));
   h->regs = fa.numRegs;
-  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_G(PGS_ROWS_GB)));
+  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_ROWS_GB * 32 * 16));
   CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_J));
   CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -170,6 +177,8 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
   {
     const char* p = getenv("PRB_PIPELINE");
     h->fused = (p && strcmp(p, "fused") == 0) ? 1 : 0;
+    const char* a = getenv("PRB_ARM_THREADS");
+    if (a) { int v = atoi(a); if (v == 4 || v == 8 || v == 16 || v == 32) h->arm_threads = v; }
   }
   if (!h->fused) {
     const size_t sb_bytes = sbuf_bytes(N);   // whole 32-env groups + prefetch slack

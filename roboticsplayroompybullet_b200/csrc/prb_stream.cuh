@@ -52,15 +52,23 @@
                          // then ceil(n_jrow / 4) q of accumulated impulses, then (4-q aligned) slot 0's contact rows
 #define SB_MAXJROW 40
 #define SB_MAXCONTACT 32
-// slot 0 contact rows are EXPLICIT.  The island's velocity change is two 16-float vectors:
-//   A: arm DoF 0..11 (words 12..15 unused)      F: free body b at words 6 b .. 6 b + 5, slide body s at word 12 + s
-// A row is 8 q: {JA[0..3], JA[4..7], JA[8..11], H1} {BA[0..3], BA[4..7], BA[8..11], H2}, followed, when
-// bit 0 of the flags is set, by 8 q {JF[0..15]} {BF[0..15]}.   J: Jacobian, B = M^-1 J^T.
-//   H1 = {flags, rhs, invD, lambda}      H2 = normal: {cfm * invD, -, -, -}; spin: {coefficient, t of the normal row, -, -};
-//                                             friction 1: {mu, t of the normal row, -, -}; friction 2: unused
-// Rows are grouped by pass: all normal rows (contact order), all spin rows, all friction pairs (rows of a
-// pair adjacent).  The solver kernel gives an env four lanes: lane c holds words 4c..4c+3 of A and F in
-// registers and column c of the rows.
+// slot 0 contacts.  The arm part of a row is EXPLICIT (12-wide J and B = M^-1 J^T); a free-body side is
+// rebuilt from the contact frame like in slots 1, 2; a slide-body side is one scalar.  Items are multiples of
+// 4 q, grouped by pass (all normal items in contact order, all spin items, all friction items); the first
+// header of an item is its q 3:  H1 = {flags, rhs, invD, lambda},
+//   flags: bits 0-1 item type (0 row, 1 normal row + geometry, 2 compact record, 3 pointer), bit 2 slide side,
+//          bits 3-4 slide index, bit 5 free-body side, bit 6 free body index, bit 7 sign of the free side is -1
+//   row (8 q):   {JA[0..3], JA[4..7], JA[8..11], H1} {BA[0..3], BA[4..7], BA[8..11], H2}
+//                H2 = {cfm * invD (normal) | spin coefficient | mu (friction 1), t of the contact's normal item,
+//                      J of the slide side, B of the slide side}
+//   normal row + geometry (12 q): the row, then {n.xyz,-} {t1.xyz,-} {r.xyz,-} {-} of the free-body side
+//                (spin and friction rows of the contact read it through H2.y)
+//   friction item (16 q): the two friction rows of a contact
+//   compact record (8 q; both sides free body / static, as in slots 1, 2): q 0..2 = record +0..+2, q 3 = {flags},
+//                q 4..7 = record +3..+6
+//   pointer (4 q; spin / friction item of a compact record): {t of the record, spin coefficient, rhs1, invD1} - - {flags}
+// The solver kernel gives an env four lanes: lane c holds arm words 4c..4c+3 in registers and column c of the
+// items; free-body and slide velocities are replicated in the registers of all four lanes.
 #define XROW_Q 8
 // ---- slots 1, 2: compact contact record (6 q, +1 q when the second side is the other free body):
 //   +0 {packed, cfm * invD0, rhs0, invD0}     +1 {n.xyz, lambda0}        +2 {rP.xyz, mu}
@@ -71,7 +79,7 @@
 //   record — a record never straddles the stage boundary PGS_STAGE_F)
 // spin list entry (1 q): {t of the contact record, spin coefficient, rhs1, invD1}
 #define CT_BASE_Q 6
-#define SB_Q (Q_ST + 96 + SB_MAXCONTACT * 4 * 2 * XROW_Q + SB_MAXCONTACT + 64 + 8)
+#define SB_Q (Q_ST + 96 + SB_MAXCONTACT * (12 + 8 + 16) + 3 * 4 + SB_MAXCONTACT * 8 + 64 + 8)
 #define SB_PAD_Q 48      // readable slack after the last group (the solvers prefetch one record ahead)
 // stage capacities (q of shared memory per env) of the solver kernels
 #ifndef PGS_STAGE_J
@@ -304,15 +312,19 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
     slotf[1] = c02 ? 0 : (c12 ? 1 : 2);
   }
   const int slot = lane < nc ? (grpP == 0 ? 0 : slotf[grpP - 1]) : -1;
-  // ---- placement.  Slot 0: explicit rows grouped by pass
+  // ---- placement.  Slot 0: items grouped by pass
   const bool s0 = slot == 0;
-  const bool hasF = s0 && (kP != K_ARM || kS != K_STATIC);
-  const int su = s0 ? (hasF ? 2 * XROW_Q : XROW_Q) : 0;
-  int totN, totS;
-  const int offN = warp_excl_scan(su, lane, &totN);
-  const int offS = warp_excl_scan((s0 && has_spin) ? su : 0, lane, &totS);
+  const bool cmp0 = s0 && kP == K_FREE;                              // both sides free body / static: compact record
+  const bool freeS = s0 && !cmp0 && kS == K_FREE;                    // row items with a free-body side
+  const int szN = s0 ? (freeS ? 12 : 8) : 0;
+  const int szS = (s0 && has_spin) ? (cmp0 ? 4 : 8) : 0;
+  const int szT = s0 ? (cmp0 ? 4 : 16) : 0;
+  int totN, totS, totT;
+  const int offN = warp_excl_scan(szN, lane, &totN);
+  const int offS = warp_excl_scan(szS, lane, &totS);
+  const int offT = warp_excl_scan(szT, lane, &totT);
   const int tN0 = (T_JROW + njr + ((njr + 3) >> 2) + 3) & ~3;
-  const int tS0 = tN0 + totN, tT0 = tS0 + totS, tEnd0 = tT0 + 2 * totN;
+  const int tS0 = tN0 + totN, tT0 = tS0 + totS, tEnd0 = tT0 + totT;
   const int nc0 = __popc(__ballot_sync(FULL, s0)), ns0 = __popc(__ballot_sync(FULL, s0 && has_spin));
   // slots 1, 2: compact records + spin list per region
   const int size = (lane < nc && !s0) ? CT_BASE_Q + (kS == K_FREE ? 1 : 0) : 0;
@@ -375,15 +387,16 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
       const bool ang = (k == 1);
       if (k == 1 && !has_spin) continue;      // no torsional row: never visited by the solver
       float JA[12], BA[12], JF[16], BF[16];
-      if (s0) {
+      const bool xrow = s0 && !cmp0;
+      if (xrow) {
 #pragma unroll
         for (int i = 0; i < 12; i++) { JA[i] = 0.f; BA[i] = 0.f; }
 #pragma unroll
         for (int i = 0; i < 16; i++) { JF[i] = 0.f; BF[i] = 0.f; }
       }
       float rel = 0.f, D = 0.f;
-      D += side_row<ND>(M, W, colP, pP, dir, sP, ang, s0 ? JA : nullptr, BA, s0 ? JF : nullptr, BF, &rel);
-      if (kS != K_STATIC) D += side_row<ND>(M, W, colS, pS, dir, -sP, ang, s0 ? JA : nullptr, BA, s0 ? JF : nullptr, BF, &rel);
+      D += side_row<ND>(M, W, colP, pP, dir, sP, ang, xrow ? JA : nullptr, BA, xrow ? JF : nullptr, BF, &rel);
+      if (kS != K_STATIC) D += side_row<ND>(M, W, colS, pS, dir, -sP, ang, xrow ? JA : nullptr, BA, xrow ? JF : nullptr, BF, &rel);
       if (k == 0) D += cfm;
       const float invD = D > 1.1920929e-7f ? 1.0f / D : 0.f;
       if (k == 0) {
@@ -394,38 +407,53 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
         cfms = cfm * invD;
       } else rhs[k] = -rel * invD;
       invDs[k] = invD;
-      if (s0) {                                // explicit row
-        const int tr = k == 0 ? tN : (k == 1 ? tS0 + offS : tT0 + 2 * offN + (k == 3 ? su : 0));
+      if (xrow) {                              // explicit arm part; slide side as a scalar; free side through the geometry
+        const int sld = kP == K_SLIDE ? M.col_body[colP] - 1 - M.n_free : (kS == K_SLIDE ? M.col_body[colS] - 1 - M.n_free : -1);
+        if (kP == K_SLIDE && kS == K_SLIDE) W.overflow = 1;          // two slide bodies in one contact: not representable
+        const int fb = freeS ? M.col_body[colS] - 1 : 0;
+        const int flags = (k == 0 && freeS ? 1 : 0) | (sld >= 0 ? (4 | (sld << 3)) : 0) | (freeS ? (32 | (fb << 6) | (sP > 0.f ? 128 : 0)) : 0);
+        const int tr = k == 0 ? tN : (k == 1 ? tS0 + offS : tT0 + offT + (k == 3 ? 8 : 0));
         float4* row = &S.q(Q_ST + tr);
 #pragma unroll
         for (int j = 0; j < 3; j++) {
           row[j * 32] = make_float4(JA[4 * j], JA[4 * j + 1], JA[4 * j + 2], JA[4 * j + 3]);
           row[(4 + j) * 32] = make_float4(BA[4 * j], BA[4 * j + 1], BA[4 * j + 2], BA[4 * j + 3]);
         }
-        row[3 * 32] = make_float4(__int_as_float(hasF ? 1 : 0), rhs[k], invD, 0.f);
-        row[7 * 32] = make_float4(k == 0 ? cfms : (k == 1 ? spin : (k == 2 ? mu : 0.f)), __int_as_float(tN), 0.f, 0.f);
-        if (hasF) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            row[(8 + j) * 32] = make_float4(JF[4 * j], JF[4 * j + 1], JF[4 * j + 2], JF[4 * j + 3]);
-            row[(12 + j) * 32] = make_float4(BF[4 * j], BF[4 * j + 1], BF[4 * j + 2], BF[4 * j + 3]);
-          }
+        row[3 * 32] = make_float4(__int_as_float(flags), rhs[k], invD, 0.f);
+        row[7 * 32] = make_float4(k == 0 ? cfms : (k == 1 ? spin : (k == 2 ? mu : 0.f)), __int_as_float(tN),
+                                  sld >= 0 ? JF[12 + sld] : 0.f, sld >= 0 ? BF[12 + sld] : 0.f);
+        if (k == 0 && freeS) {
+          const v3 rS = pS - ld3(W.fpos[fb]);
+          row[8 * 32] = make_float4(n.x, n.y, n.z, 0.f);
+          row[9 * 32] = make_float4(t1.x, t1.y, t1.z, 0.f);
+          row[10 * 32] = make_float4(rS.x, rS.y, rS.z, 0.f);
+          row[11 * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
-    if (!s0) {                                 // compact record (both sides are free bodies or static)
+    if (!s0 || cmp0) {                         // compact record (both sides are free bodies or static)
       const int iP = M.col_body[colP] - 1, iS = kS == K_FREE ? M.col_body[colS] - 1 : 0;
       const v3 rP = pP - ld3(W.fpos[iP]);
-      float4* rec = &S.q(Q_ST + region_mine + t);
       const int packed = (kS << 2) | (iP << 4) | (iS << 7) | ((swapped ? 1 : 0) << 10) | ((has_spin ? 1 : 0) << 11) | (stride << 12);
-      rec[0] = make_float4(__int_as_float(packed), cfms, rhs[0], invDs[0]);
-      rec[32] = make_float4(n.x, n.y, n.z, 0.f);
-      rec[64] = make_float4(rP.x, rP.y, rP.z, mu);
-      rec[96] = make_float4(t1.x, t1.y, t1.z, 0.f);
-      rec[128] = make_float4(rhs[2], rhs[3], invDs[2], invDs[3]);
-      rec[160] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kS == K_FREE) { const v3 rS = pS - ld3(W.fpos[iS]); rec[192] = make_float4(rS.x, rS.y, rS.z, 0.f); }
-      if (has_spin) S.q(Q_ST + region_mine + t_spin_mine + spin_rank) = make_float4(__int_as_float(t), spin, rhs[1], invDs[1]);
+      const float4 r0 = make_float4(__int_as_float(packed), cfms, rhs[0], invDs[0]), r1 = make_float4(n.x, n.y, n.z, 0.f);
+      const float4 r2 = make_float4(rP.x, rP.y, rP.z, mu), r3 = make_float4(t1.x, t1.y, t1.z, 0.f);
+      const float4 r4 = make_float4(rhs[2], rhs[3], invDs[2], invDs[3]), r5 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 r6 = r5;
+      if (kS == K_FREE) { const v3 rS = pS - ld3(W.fpos[iS]); r6 = make_float4(rS.x, rS.y, rS.z, 0.f); }
+      if (!s0) {
+        float4* rec = &S.q(Q_ST + region_mine + t);
+        rec[0] = r0; rec[32] = r1; rec[64] = r2; rec[96] = r3; rec[128] = r4; rec[160] = r5;
+        if (kS == K_FREE) rec[192] = r6;
+        if (has_spin) S.q(Q_ST + region_mine + t_spin_mine + spin_rank) = make_float4(__int_as_float(t), spin, rhs[1], invDs[1]);
+      } else {                                 // slot 0: compact item + pointer items in the spin / friction passes
+        float4* it = &S.q(Q_ST + tN);
+        it[0] = r0; it[32] = r1; it[64] = r2; it[96] = make_float4(__int_as_float(2), 0.f, 0.f, 0.f);
+        it[128] = r3; it[160] = r4; it[192] = r5; it[224] = r6;
+        const float4 ph = make_float4(__int_as_float(3), 0.f, 0.f, 0.f);
+        if (has_spin) { float4* ps = &S.q(Q_ST + tS0 + offS); ps[0] = make_float4(__int_as_float(tN), spin, rhs[1], invDs[1]); ps[96] = ph; }
+        float4* pt_ = &S.q(Q_ST + tT0 + offT);
+        pt_[0] = make_float4(__int_as_float(tN), 0.f, 0.f, 0.f); pt_[96] = ph;
+      }
     }
   }
   __syncwarp();
@@ -504,7 +532,8 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
 #define PGS_G_EPW (32 >> PGS_G_LW)                      // envs per warp of the arm-island kernel
 #define PGS_SMEM_J ((PGS_STAGE_J + PGS_J_DVQ) * 32 * 16)
 #define PGS_SMEM_F ((PGS_STAGE_F + PGS_F_TAILQ) * 32 * 16)
-#define PGS_SMEM_G(rows) ((rows) * 32 * 16)
+#define PGS_G_THREADS 4                                 // threads per block of the arm-island kernel
+#define PGS_SMEM_G(rows) ((rows) * PGS_G_THREADS * 16)
 
 #ifdef PRB_EMU
 static float4 g_emu_pgs_smem[(PGS_ROWS_GB + 2) * 32 + (PGS_STAGE_J + PGS_STAGE_F + 16) * 32];
@@ -787,41 +816,81 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
 struct QuadMem {
   float4* base;            // column 0 of this env in shared memory
   float4* Gr;              // this env's column of region 0 in the stream
-  int cap;                 // staged q count; rows that do not end below it are read from the stream in place
-  PRB_D float4* sp(int t) const { return base + (t >> 2) * 32 + (t & 3); }     // always-staged q (fixed part of region 0)
-  PRB_D bool staged(int t) const { return t + 2 * XROW_Q <= cap; }            // explicit row starting at t
+  int cap;                 // staged q count; items that do not end below it are read from the stream in place
+  int rs;                  // row stride = columns of the block's stage = threads per block
+  PRB_D float4* sp(int t) const { return base + (t >> 2) * rs + (t & 3); }     // always-staged q (fixed part of region 0)
+  PRB_D bool staged(int t) const { return t + 16 <= cap; }                    // item starting at t (items are <= 16 q)
+  PRB_D float4 ldq(int t) const { return t < cap ? *sp(t) : Gr[t * 32]; }     // immutable data (geometry)
 };
-// an explicit row in shared memory (q k of the row at rp[(k >> 2) * 32 + (k & 3)]) or in the stream (gp[k * 32])
+// an item in shared memory (q k of the item at rp[(k >> 2) * 32 + (k & 3)]) or in the stream (gp[k * 32])
 struct RowS {
   float4* rp;
-  template <int K0> PRB_D float4 ld(int c) const { return rp[(K0 >> 2) * 32 + c]; }
-  PRB_D float* lam() const { return reinterpret_cast<float*>(rp + 3) + 3; }
+  int rs;
+  template <int K0> PRB_D float4 ld(int c) const { return rp[(K0 >> 2) * rs + c]; }
+  template <int K> PRB_D float4* q() const { return rp + (K >> 2) * rs + (K & 3); }
 };
 struct RowG {
   float4* gp;
   template <int K0> PRB_D float4 ld(int c) const { return gp[(K0 + c) * 32]; }
-  PRB_D float* lam() const { return reinterpret_cast<float*>(gp + 3 * 32) + 3; }
+  template <int K> PRB_D float4* q() const { return gp + K * 32; }
 };
 PRB_D float quad_sum(unsigned qmask, float v) {
   v += __shfl_xor_sync(qmask, v, 1);
   v += __shfl_xor_sync(qmask, v, 2);
   return v;
 }
-PRB_D float* quad_lam(const QuadMem& m, int t) {          // accumulated impulse of the explicit row at t
-  return m.staged(t) ? RowS{m.sp(t)}.lam() : RowG{m.Gr + t * 32}.lam();
+// velocities of the non-arm bodies of the island, replicated in the four lanes of the quad
+struct QuadFree {
+  v3 v[PRB_MAXFREE], w[PRB_MAXFREE];
+  float4 sl;                                     // slide bodies
+  float I[PRB_MAXFREE][6], invm[PRB_MAXFREE];    // world inverse inertia, 1 / mass
+  PRB_D v3 vel(int b) const { return b ? v[PRB_MAXFREE - 1] : v[0]; }
+  PRB_D v3 ang(int b) const { return b ? w[PRB_MAXFREE - 1] : w[0]; }
+  // J . dv of a free-body side: unit force d at lever arm r (or unit torque d), times sgn
+  PRB_D float jdot(int b, float sgn, v3 r, v3 d, bool angular) const {
+    const v3 ww = ang(b);
+    return sgn * (angular ? dot(d, ww) : dot(d, vel(b) + cross(ww, r)));
+  }
+  // dv += B P: P = sum of direction * impulse (linear rows) or the angular impulse (spin row)
+  PRB_D void apply(int b, float sgn, v3 r, v3 P, bool angular) {
+    const v3 Ps = P * sgn;
+    // register selects (no runtime-indexed arrays: they would live in local memory)
+    float Ib[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) Ib[k] = b ? I[PRB_MAXFREE - 1][k] : I[0][k];
+    const float im = b ? invm[PRB_MAXFREE - 1] : invm[0];
+    v3 dv = V3(0, 0, 0), dw;
+    if (angular) dw = symmul(Ib, Ps);
+    else { dv = Ps * im; dw = symmul(Ib, cross(r, Ps)); }
+    const float m0 = b ? 0.f : 1.f, m1 = b ? 1.f : 0.f;
+    v[0] = v[0] + dv * m0; w[0] = w[0] + dw * m0;
+    v[PRB_MAXFREE - 1] = v[PRB_MAXFREE - 1] + dv * m1; w[PRB_MAXFREE - 1] = w[PRB_MAXFREE - 1] + dw * m1;
+  }
+};
+PRB_D float* quad_lam0(const QuadMem& m, int tN) {        // normal impulse of the contact whose normal item is at tN
+  float4* h = m.staged(tN) ? m.sp(tN + 3) : m.Gr + (tN + 3) * 32;
+  const int type = __float_as_int(h->x) & 3;
+  if (type == 2) { float4* q1 = m.staged(tN) ? m.sp(tN + 1) : m.Gr + (tN + 1) * 32; return reinterpret_cast<float*>(q1) + 3; }
+  return reinterpret_cast<float*>(h) + 3;
 }
-// one row visit; kind 0: contact normal (lambda >= 0, soft CFM), 1: spin (|lambda| <= coefficient * normal impulse)
+// one explicit row; KIND 0: contact normal (lambda >= 0, soft CFM), 1: spin (|lambda| <= coefficient * normal impulse)
 template <int KIND, class Row>
-PRB_D bool quad_row(const Row& r, int c, unsigned qmask, float4& A, float4& F, float tot) {
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 H1 = r.template ld<0>(3), H2 = r.template ld<4>(3);
-  const bool hasF = __float_as_int(H1.x) & 1;
+PRB_D void quad_xrow(const Row& r, const QuadMem& m, int c, unsigned qmask, float4& A, QuadFree& Fr, float tot) {
+  const float4 H1 = *r.template q<3>(), H2 = *r.template q<7>();
+  const int flags = __float_as_int(H1.x);
   const float4 J = r.template ld<0>(c), B = r.template ld<4>(c);
-  float4 JF = z4, BF = z4;
-  if (hasF) { JF = r.template ld<8>(c); BF = r.template ld<12>(c); }
-  float p = c < 3 ? dot4(J, A, 0.f) : 0.f;
-  p = dot4(JF, F, p);
-  const float u = quad_sum(qmask, p);
+  float u = quad_sum(qmask, c < 3 ? dot4(J, A, 0.f) : 0.f);
+  const int sidx = (flags >> 3) & 3, fb = (flags >> 6) & 1;
+  const float fs = (flags & 128) ? -1.0f : 1.0f;
+  v3 n = V3(0, 0, 0), rr = n;
+  if (flags & 4) u = fmaf(H2.z, f4comp(Fr.sl, sidx), u);
+  if (flags & 32) {
+    const int tg = (KIND == 0 ? 0 : __float_as_int(H2.y)) + 8;      // geometry of the contact: after its normal row
+    float4 g0, g2;
+    if (KIND == 0) { g0 = *r.template q<8>(); g2 = *r.template q<10>(); } else { g0 = m.ldq(tg); g2 = m.ldq(tg + 2); }
+    n = V3(g0.x, g0.y, g0.z); rr = V3(g2.x, g2.y, g2.z);
+    u += Fr.jdot(fb, fs, rr, n, KIND == 1);
+  }
   const float l0 = H1.w;
   float nl;
   if (KIND == 0) nl = fmaxf(l0 + (H1.y - l0 * H2.x - u * H1.z), 0.f);
@@ -829,28 +898,32 @@ PRB_D bool quad_row(const Row& r, int c, unsigned qmask, float4& A, float4& F, f
   const float dl = nl - l0;
   __syncwarp(qmask);                                     // every lane of the quad has read lambda
   if (dl != 0.f) {
-    if (c == 3) *r.lam() = nl;
+    if (c == 3) reinterpret_cast<float*>(r.template q<3>())[3] = nl;
     if (c < 3) axpy4(A, B, dl);
-    axpy4(F, BF, dl);
+    if (flags & 4) f4add(Fr.sl, sidx, H2.w * dl);
+    if (flags & 32) Fr.apply(fb, fs, rr, n * dl, KIND == 1);
   }
   __syncwarp(qmask);                                     // the new impulse is visible to the quad
-  return hasF;
 }
-// lateral friction: the two rows of a contact are solved together (implicit cone)
+// lateral friction of an explicit contact: the two rows are solved together (implicit cone)
 template <class Row>
-PRB_D bool quad_friction(const Row& r, const Row& r2f, const Row& r2n, const QuadMem& m, int c, unsigned qmask, float4& A, float4& F) {
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 H1 = r.template ld<0>(3), H2 = r.template ld<4>(3);
-  const bool hasF = __float_as_int(H1.x) & 1;
-  const Row& r2 = hasF ? r2f : r2n;                      // second row of the pair: 16 or 8 q further
-  const float4 G1 = r2.template ld<0>(3);
-  const float4 J1 = r.template ld<0>(c), B1 = r.template ld<4>(c), J2 = r2.template ld<0>(c), B2 = r2.template ld<4>(c);
-  float4 JF1 = z4, BF1 = z4, JF2 = z4, BF2 = z4;
-  if (hasF) { JF1 = r.template ld<8>(c); BF1 = r.template ld<12>(c); JF2 = r2.template ld<8>(c); BF2 = r2.template ld<12>(c); }
-  const float tot = *quad_lam(m, __float_as_int(H2.y));
-  float pa = c < 3 ? dot4(J1, A, 0.f) : 0.f, pb = c < 3 ? dot4(J2, A, 0.f) : 0.f;
-  pa = dot4(JF1, F, pa); pb = dot4(JF2, F, pb);
-  const float ua = quad_sum(qmask, pa), ub = quad_sum(qmask, pb);
+PRB_D void quad_xfriction(const Row& r, const QuadMem& m, int c, unsigned qmask, float4& A, QuadFree& Fr) {
+  const float4 H1 = *r.template q<3>(), H2 = *r.template q<7>(), G1 = *r.template q<11>(), G2 = *r.template q<15>();
+  const int flags = __float_as_int(H1.x);
+  const float4 J1 = r.template ld<0>(c), B1 = r.template ld<4>(c), J2 = r.template ld<8>(c), B2 = r.template ld<12>(c);
+  const int tN = __float_as_int(H2.y);
+  const float tot = *quad_lam0(m, tN);
+  float ua = quad_sum(qmask, c < 3 ? dot4(J1, A, 0.f) : 0.f), ub = quad_sum(qmask, c < 3 ? dot4(J2, A, 0.f) : 0.f);
+  const int sidx = (flags >> 3) & 3, fb = (flags >> 6) & 1;
+  const float fs = (flags & 128) ? -1.0f : 1.0f;
+  v3 t1 = V3(0, 0, 0), t2 = t1, rr = t1;
+  if (flags & 4) { const float vs = f4comp(Fr.sl, sidx); ua = fmaf(H2.z, vs, ua); ub = fmaf(G2.z, vs, ub); }
+  if (flags & 32) {
+    const float4 g0 = m.ldq(tN + 8), g1 = m.ldq(tN + 9), g2 = m.ldq(tN + 10);
+    const v3 n = V3(g0.x, g0.y, g0.z);
+    t1 = V3(g1.x, g1.y, g1.z); t2 = cross(n, t1); rr = V3(g2.x, g2.y, g2.z);
+    ua += Fr.jdot(fb, fs, rr, t1, false); ub += Fr.jdot(fb, fs, rr, t2, false);
+  }
   const float lim = H2.x * tot;
   const float la = H1.w, lb = G1.w;
   const float sumA = la + (H1.y - ua * H1.z);
@@ -865,18 +938,88 @@ PRB_D bool quad_friction(const Row& r, const Row& r2f, const Row& r2n, const Qua
   const float d1 = na - la, d2 = nb - lb;
   __syncwarp(qmask);
   if (d1 != 0.f || d2 != 0.f) {
-    if (c == 3) { *r.lam() = na; *r2.lam() = nb; }
+    if (c == 3) { reinterpret_cast<float*>(r.template q<3>())[3] = na; reinterpret_cast<float*>(r.template q<11>())[3] = nb; }
     if (c < 3) { axpy4(A, B1, d1); axpy4(A, B2, d2); }
-    axpy4(F, BF1, d1); axpy4(F, BF2, d2);
+    if (flags & 4) f4add(Fr.sl, sidx, H2.w * d1 + G2.w * d2);
+    if (flags & 32) Fr.apply(fb, fs, rr, t1 * d1 + t2 * d2, false);
   }
   __syncwarp(qmask);
-  return hasF;
+}
+// a compact record (both sides free body / static) inside the arm island: the free-body solver's arithmetic
+// on the replicated velocities.  PASS 0 normal, 1 spin (h: its pointer item), 2 friction
+template <int PASS, class Row>
+PRB_D void quad_compact(const Row& r, float4 h, int c, unsigned qmask, QuadFree& Fr) {
+  const float4 q0 = *r.template q<0>(), q1 = *r.template q<1>(), q2 = *r.template q<2>();
+  const int pk = __float_as_int(q0.x);
+  const int iP = (pk >> 4) & 7, iS = (pk >> 7) & 7;
+  const float sP = ((pk >> 10) & 1) ? -1.0f : 1.0f;
+  const bool two = ((pk >> 2) & 3) == K_FREE;
+  const v3 n = V3(q1.x, q1.y, q1.z), rP = V3(q2.x, q2.y, q2.z);
+  v3 rS = V3(0, 0, 0);
+  if (two) { const float4 g = *r.template q<7>(); rS = V3(g.x, g.y, g.z); }
+  if (PASS == 0) {
+    float u = Fr.jdot(iP, sP, rP, n, false);
+    if (two) u += Fr.jdot(iS, -sP, rS, n, false);
+    const float l0 = q1.w;
+    const float nl = fmaxf(l0 + (q0.z - l0 * q0.y - u * q0.w), 0.f);
+    const float dl = nl - l0;
+    __syncwarp(qmask);
+    if (dl != 0.f) {
+      if (c == 3) reinterpret_cast<float*>(r.template q<1>())[3] = nl;
+      Fr.apply(iP, sP, rP, n * dl, false);
+      if (two) Fr.apply(iS, -sP, rS, n * dl, false);
+    }
+  } else if (PASS == 1) {
+    const float tot = q1.w;
+    if (tot > 0.f) {                                   // Bullet skips the row while the normal impulse is 0
+      float u = Fr.jdot(iP, sP, rP, n, true);
+      if (two) u += Fr.jdot(iS, -sP, rS, n, true);
+      const float lim = h.y * tot;
+      float* pl = reinterpret_cast<float*>(r.template q<4>()) + 3;
+      const float l0 = *pl;
+      const float nl = clampf(l0 + (h.z - u * h.w), -lim, lim);
+      const float dl = nl - l0;
+      __syncwarp(qmask);
+      if (dl != 0.f) {
+        if (c == 3) *pl = nl;
+        Fr.apply(iP, sP, rP, n * dl, true);
+        if (two) Fr.apply(iS, -sP, rS, n * dl, true);
+      }
+    }
+  } else {
+    const float4 q3 = *r.template q<4>(), q4 = *r.template q<5>(), q5 = *r.template q<6>();
+    const v3 t1 = V3(q3.x, q3.y, q3.z), t2 = cross(n, t1);
+    float ua = Fr.jdot(iP, sP, rP, t1, false), ub = Fr.jdot(iP, sP, rP, t2, false);
+    if (two) { ua += Fr.jdot(iS, -sP, rS, t1, false); ub += Fr.jdot(iS, -sP, rS, t2, false); }
+    const float lim = q2.w * q1.w;
+    const float la = q5.x, lb = q5.y;
+    const float sumA = la + (q4.x - ua * q4.z);
+    const float sumB = lb + (q4.y - ub * q4.w);
+    float na = sumA, nb = sumB;
+    if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
+      const float ss = sumA * sumA + sumB * sumB;
+      const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+      const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
+      na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
+    }
+    const float d1 = na - la, d2 = nb - lb;
+    __syncwarp(qmask);
+    if (d1 != 0.f || d2 != 0.f) {
+      if (c == 3) *r.template q<6>() = make_float4(na, nb, 0.f, 0.f);
+      const v3 Pv = t1 * d1 + t2 * d2;
+      Fr.apply(iP, sP, rP, Pv, false);
+      if (two) Fr.apply(iS, -sP, rS, Pv, false);
+    }
+  }
+  __syncwarp(qmask);
 }
 
 template <int ND>
-__global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_arm_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf,
+__global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf,
                                                                 const int* __restrict__ heavy_list, int* __restrict__ heavy_cnt, int rows) {
   PRB_PGS_SMEM_DECL;
+  // any multiple of 4 threads per block (<= 32); 4 = one env per block: the warps of an SM then are
+  // independent envs (no divergence between the quads of a warp, 32 latency-hiding warps per SM)
   const int lane = threadIdx.x, c = lane & 3, qb = lane & ~3;
   const unsigned qmask = 0xfu << qb;
   const int cnt = *heavy_cnt;
@@ -896,17 +1039,26 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_arm_kernel(const DevModel* 
   const int tS0 = __float_as_int(hdr.y), tT0 = __float_as_int(hdr.z), tEnd = __float_as_int(hdr.w);
   const int tN0 = (T_JROW + njr + ((njr + 3) >> 2) + 3) & ~3;
   QuadMem m;
-  m.base = sm + qb; m.Gr = G + Q_ST * 32; m.cap = rows << 2;
+  m.base = sm + qb; m.Gr = G + Q_ST * 32; m.cap = rows << 2; m.rs = blockDim.x;
   {
     const int tq = min(tEnd, m.cap);
 #pragma unroll 4
-    for (int q = T_MINV + c; q < tq; q += 4) *m.sp(q) = m.Gr[q * 32];
+    for (int q = c; q < tq; q += 4) *m.sp(q) = m.Gr[q * 32];
   }
   __syncwarp(qmask);
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c == 0) for (int k = 0; k < ((njr + 3) >> 2); k++) *m.sp(T_JROW + njr + k) = z4;
   __syncwarp(qmask);
-  float4 A = z4, F = z4;
+  float4 A = z4;
+  QuadFree Fr;
+  Fr.sl = z4;
+#pragma unroll
+  for (int b = 0; b < PRB_MAXFREE; b++) {
+    Fr.v[b] = V3(0, 0, 0); Fr.w[b] = V3(0, 0, 0);
+    const float4 i0 = *m.sp(T_BODY + 2 * b), i1 = *m.sp(T_BODY + 2 * b + 1);
+    Fr.I[b][0] = i0.x; Fr.I[b][1] = i0.y; Fr.I[b][2] = i0.z; Fr.I[b][3] = i0.w; Fr.I[b][4] = i1.x; Fr.I[b][5] = i1.y;
+    Fr.invm[b] = i1.z;
+  }
   const float ratio = M.params[P_GEAR_RATIO];
   const int iters = M.solver_iters;
   const int t_jlam = T_JROW + njr;
@@ -924,12 +1076,13 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_arm_kernel(const DevModel* 
       float4 m0 = z4, m1 = z4;                                       // this lane's slice of the M^-1 rows
       if (a != 15 && c < 3) m0 = *m.sp(T_MINV + 3 * a + c);
       if (a2 != 15 && c < 3) m1 = *m.sp(T_MINV + 3 * a2 + c);
-      // u = J . dv: J = e_a (+ ratio e_a2) or e_slide: the owning lane contributes its word
+      // u = J . dv: J = e_a (+ ratio e_a2): the owning lane contributes its word; slide rows are replicated
       float p = 0.f;
-      if (a != 15) { if (c == (a >> 2)) p = f4comp(A, a & 3); }
-      else if (c == 3) p = f4comp(F, sidx);
+      if (a != 15 && c == (a >> 2)) p = f4comp(A, a & 3);
       if (a2 != 15 && c == (a2 >> 2)) p = fmaf(ratio, f4comp(A, a2 & 3), p);
-      const float u = quad_sum(qmask, p) * sg;
+      float u = quad_sum(qmask, p);
+      if (a == 15) u = f4comp(Fr.sl, sidx);
+      u *= sg;
       float* pl = reinterpret_cast<float*>(m.sp(t_jlam + (j >> 2))) + (j & 3);
       const float l0 = *pl;
       const float hi = r.w, lo = ((pk >> 25) & 1) ? -hi : 0.f;
@@ -939,7 +1092,7 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_arm_kernel(const DevModel* 
       if (dl != 0.f) {
         if (c == 0) *pl = nl;
         if (a != 15) { axpy4(A, m0, dl); axpy4(A, m1, dl * ratio); }
-        else if (c == 3) f4add(F, sidx, M.slide_minv[sidx] * dl);
+        else f4add(Fr.sl, sidx, M.slide_minv[sidx] * dl);
       }
       __syncwarp(qmask);                                             // the new impulse is visible to the quad
     }
@@ -948,8 +1101,12 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_arm_kernel(const DevModel* 
       int t = tN0;
 #pragma unroll 1
       for (int k = 0; k < nc; k++) {
-        const bool hasF = m.staged(t) ? quad_row<0>(RowS{m.sp(t)}, c, qmask, A, F, 0.f) : quad_row<0>(RowG{m.Gr + t * 32}, c, qmask, A, F, 0.f);
-        t += hasF ? 2 * XROW_Q : XROW_Q;
+        const bool st = m.staged(t);
+        const int type = __float_as_int((st ? m.sp(t + 3) : m.Gr + (t + 3) * 32)->x) & 3;
+        if (type == 2) { if (st) quad_compact<0>(RowS{m.sp(t), m.rs}, z4, c, qmask, Fr); else quad_compact<0>(RowG{m.Gr + t * 32}, z4, c, qmask, Fr); }
+        else if (st) quad_xrow<0>(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr, 0.f);
+        else quad_xrow<0>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, 0.f);
+        t += type == 1 ? 12 : 8;
       }
     }
     // ---- spinning friction (Bullet skips the row while the normal impulse is 0)
@@ -958,13 +1115,20 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_arm_kernel(const DevModel* 
 #pragma unroll 1
       for (int k = 0; k < ns; k++) {
         const bool st = m.staged(t);
-        const float4 H1 = st ? RowS{m.sp(t)}.ld<0>(3) : RowG{m.Gr + t * 32}.ld<0>(3);
-        const float4 H2 = st ? RowS{m.sp(t)}.ld<4>(3) : RowG{m.Gr + t * 32}.ld<4>(3);
-        const float tot = *quad_lam(m, __float_as_int(H2.y));        // normal impulse of the contact
-        if (tot > 0.f) {
-          if (st) quad_row<1>(RowS{m.sp(t)}, c, qmask, A, F, tot); else quad_row<1>(RowG{m.Gr + t * 32}, c, qmask, A, F, tot);
+        const int type = __float_as_int((st ? m.sp(t + 3) : m.Gr + (t + 3) * 32)->x) & 3;
+        if (type == 3) {
+          const float4 h = *(st ? m.sp(t) : m.Gr + t * 32);
+          const int tr = __float_as_int(h.x);
+          if (m.staged(tr)) quad_compact<1>(RowS{m.sp(tr), m.rs}, h, c, qmask, Fr); else quad_compact<1>(RowG{m.Gr + tr * 32}, h, c, qmask, Fr);
+          t += 4;
+        } else {
+          const float4 H2 = *(st ? m.sp(t + 7) : m.Gr + (t + 7) * 32);
+          const float tot = *quad_lam0(m, __float_as_int(H2.y));     // normal impulse of the contact
+          if (tot > 0.f) {
+            if (st) quad_xrow<1>(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr, tot); else quad_xrow<1>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, tot);
+          }
+          t += 8;
         }
-        t += (__float_as_int(H1.x) & 1) ? 2 * XROW_Q : XROW_Q;
       }
     }
     // ---- lateral friction
@@ -972,26 +1136,37 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_arm_kernel(const DevModel* 
       int t = tT0;
 #pragma unroll 1
       for (int k = 0; k < nc; k++) {
-        bool hasF;
-        if (m.staged(t + 2 * XROW_Q)) hasF = quad_friction(RowS{m.sp(t)}, RowS{m.sp(t + 2 * XROW_Q)}, RowS{m.sp(t + XROW_Q)}, m, c, qmask, A, F);
-        else hasF = quad_friction(RowG{m.Gr + t * 32}, RowG{m.Gr + (t + 2 * XROW_Q) * 32}, RowG{m.Gr + (t + XROW_Q) * 32}, m, c, qmask, A, F);
-        t += hasF ? 4 * XROW_Q : 2 * XROW_Q;
+        const bool st = m.staged(t);
+        const int type = __float_as_int((st ? m.sp(t + 3) : m.Gr + (t + 3) * 32)->x) & 3;
+        if (type == 3) {
+          const int tr = __float_as_int((st ? m.sp(t) : m.Gr + t * 32)->x);
+          if (m.staged(tr)) quad_compact<2>(RowS{m.sp(tr), m.rs}, z4, c, qmask, Fr); else quad_compact<2>(RowG{m.Gr + tr * 32}, z4, c, qmask, Fr);
+          t += 4;
+        } else {
+          if (st) quad_xfriction(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr); else quad_xfriction(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr);
+          t += 16;
+        }
       }
     }
   }
   // ---- velocity change -> stream (linear DoF order): arm, slides, and the free bodies this island owns
   float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
   const int nd = M.nd, nf = M.n_free;
-  const float a4[4] = {A.x, A.y, A.z, A.w}, f4[4] = {F.x, F.y, F.z, F.w};
+  const float a4[4] = {A.x, A.y, A.z, A.w};
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int wa = 4 * c + k;                    // word of A: arm DoF
+    const int wa = 4 * c + k;                    // arm DoF of this lane's word k
     if (c < 3 && wa < nd) gd[(wa >> 2) * 128 + (wa & 3)] = a4[k];
-    const int wf = 4 * c + k;                    // word of F
-    int d = -1;
-    if (wf < 12) { const int b = wf / 6; if (b < nf && ((info >> (16 + 2 * b)) & 3) == 0) d = nd + wf; }
-    else if (wf - 12 < M.n_slide) d = nd + 6 * nf + (wf - 12);
-    if (d >= 0) gd[(d >> 2) * 128 + (d & 3)] = f4[k];
+  }
+  if (c == 3) {
+    for (int s_ = 0; s_ < M.n_slide; s_++) { const int d = nd + 6 * nf + s_; gd[(d >> 2) * 128 + (d & 3)] = f4comp(Fr.sl, s_); }
+#pragma unroll
+    for (int b = 0; b < PRB_MAXFREE; b++)
+      if (b < nf && ((info >> (16 + 2 * b)) & 3) == 0) {
+        const float v6[6] = {Fr.v[b].x, Fr.v[b].y, Fr.v[b].z, Fr.w[b].x, Fr.w[b].y, Fr.w[b].z};
+#pragma unroll
+        for (int k = 0; k < 6; k++) { const int d = nd + 6 * b + k; gd[(d >> 2) * 128 + (d & 3)] = v6[k]; }
+      }
   }
   __syncwarp(qmask);                                     // the quad's columns are re-staged by the next env
   }
