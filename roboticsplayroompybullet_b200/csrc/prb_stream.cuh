@@ -143,17 +143,18 @@ PRB_D int body_kind(const DevModel& M, int body) { return body < 0 ? K_STATIC : 
 PRB_D int kind_rank(int k) { return k == K_ARM ? 3 : (k == K_SLIDE ? 2 : (k == K_FREE ? 1 : 0)); }
 
 // One side of one constraint row: J = unit force `dir` at world point pt (or unit torque when angular)
-// on the body of collider col, times sign; B = M^-1 J^T.  Returns J.B and accumulates J.v*.  When JA is
-// given the explicit row is accumulated: arm sides into JA / BA (12 floats), free and slide sides into
-// JF / BF (16 floats, layout F above).
+// on the body of collider col, times sign; B = M^-1 J^T.  Returns J.B and accumulates J.v*.  When gJ is
+// given, an arm side writes (accum: adds to) its explicit J and B, 3 q each at stride 32; a slide side
+// returns its scalar J and B in *js, *bs; free-body sides store nothing (the solvers rebuild them from the
+// contact geometry).
 template <int ND, class WM>
 PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, float sign, bool angular,
-                     float* JA, float* BA, float* JF, float* BF, float* rel) {
+                     float4* gJ, float4* gB, bool accum, float* js, float* bs, float* rel) {
   const int body = M.col_body[col];
   float d = 0.f;
   if (body == 0) {
     const int link = M.col_link[col];
-    float J[12];
+    float J[12], B[12];
     const unsigned anc = M.anc_mask[link];
 #pragma unroll
     for (int j = 0; j < 12; j++) {
@@ -174,7 +175,20 @@ PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, flo
         for (int j = 0; j < ND; j++) s = fmaf(W.Minv[i][j], J[j], s);
         d = fmaf(J[i], s, d); r = fmaf(J[i], W.vs[i], r);
       }
-      if (JA) { JA[i] += J[i]; BA[i] += s; }
+      B[i] = s;
+    }
+    if (gJ) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        float4 j4 = make_float4(J[4 * k], J[4 * k + 1], J[4 * k + 2], J[4 * k + 3]);
+        float4 b4 = make_float4(B[4 * k], B[4 * k + 1], B[4 * k + 2], B[4 * k + 3]);
+        if (accum) {                           // second arm side of an arm-arm contact
+          const float4 pj = gJ[k * 32], pb = gB[k * 32];
+          j4 = make_float4(j4.x + pj.x, j4.y + pj.y, j4.z + pj.z, j4.w + pj.w);
+          b4 = make_float4(b4.x + pb.x, b4.y + pb.y, b4.z + pb.z, b4.w + pb.w);
+        }
+        gJ[k * 32] = j4; gB[k * 32] = b4;
+      }
     }
     *rel += r;
   } else if (body <= M.n_free) {
@@ -186,10 +200,7 @@ PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, flo
     float J[6] = {jl.x, jl.y, jl.z, ja.x, ja.y, ja.z}, B[6] = {bl.x, bl.y, bl.z, ba.x, ba.y, ba.z};
     float r = 0.f;
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-      d = fmaf(J[k], B[k], d); r = fmaf(J[k], W.vs[o + k], r);
-      if (JF) { JF[6 * b + k] += J[k]; BF[6 * b + k] += B[k]; }
-    }
+    for (int k = 0; k < 6; k++) { d = fmaf(J[k], B[k], d); r = fmaf(J[k], W.vs[o + k], r); }
     *rel += r;
   } else {
     const int s = body - 1 - M.n_free, o = M.nd + 6 * M.n_free + s;
@@ -198,7 +209,7 @@ PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, flo
     if (M.slide_jtype[s] == 0) g = angular ? dot(a, dir) : dot(a, cross(pt - ld3(W.sp[s]), dir));
     else g = angular ? 0.f : dot(a, dir);
     const float j = sign * g, bb = j * M.slide_minv[s];
-    if (JF) { JF[12 + s] += j; BF[12 + s] += bb; }
+    *js = j; *bs = bb;
     d = j * bb; *rel += j * W.vs[o];
   }
   return d;
@@ -386,17 +397,17 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
       v3 dir = k == 0 ? n : (k == 1 ? n : (k == 2 ? t1 : t2));
       const bool ang = (k == 1);
       if (k == 1 && !has_spin) continue;      // no torsional row: never visited by the solver
-      float JA[12], BA[12], JF[16], BF[16];
       const bool xrow = s0 && !cmp0;
-      if (xrow) {
+      const int tr = k == 0 ? tN : (k == 1 ? tS0 + offS : tT0 + offT + (k == 3 ? 8 : 0));
+      float4* row = &S.q(Q_ST + tr);
+      float js = 0.f, bs = 0.f;
+      if (xrow && kP != K_ARM) {               // no arm side: zero arm part
 #pragma unroll
-        for (int i = 0; i < 12; i++) { JA[i] = 0.f; BA[i] = 0.f; }
-#pragma unroll
-        for (int i = 0; i < 16; i++) { JF[i] = 0.f; BF[i] = 0.f; }
+        for (int j = 0; j < 3; j++) { row[j * 32] = make_float4(0.f, 0.f, 0.f, 0.f); row[(4 + j) * 32] = make_float4(0.f, 0.f, 0.f, 0.f); }
       }
       float rel = 0.f, D = 0.f;
-      D += side_row<ND>(M, W, colP, pP, dir, sP, ang, xrow ? JA : nullptr, BA, xrow ? JF : nullptr, BF, &rel);
-      if (kS != K_STATIC) D += side_row<ND>(M, W, colS, pS, dir, -sP, ang, xrow ? JA : nullptr, BA, xrow ? JF : nullptr, BF, &rel);
+      D += side_row<ND>(M, W, colP, pP, dir, sP, ang, xrow ? row : nullptr, row + 4 * 32, false, &js, &bs, &rel);
+      if (kS != K_STATIC) D += side_row<ND>(M, W, colS, pS, dir, -sP, ang, xrow ? row : nullptr, row + 4 * 32, true, &js, &bs, &rel);
       if (k == 0) D += cfm;
       const float invD = D > 1.1920929e-7f ? 1.0f / D : 0.f;
       if (k == 0) {
@@ -407,21 +418,13 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
         cfms = cfm * invD;
       } else rhs[k] = -rel * invD;
       invDs[k] = invD;
-      if (xrow) {                              // explicit arm part; slide side as a scalar; free side through the geometry
+      if (xrow) {                              // arm part written above; slide side as a scalar; free side through the geometry
         const int sld = kP == K_SLIDE ? M.col_body[colP] - 1 - M.n_free : (kS == K_SLIDE ? M.col_body[colS] - 1 - M.n_free : -1);
         if (kP == K_SLIDE && kS == K_SLIDE) W.overflow = 1;          // two slide bodies in one contact: not representable
         const int fb = freeS ? M.col_body[colS] - 1 : 0;
         const int flags = (k == 0 && freeS ? 1 : 0) | (sld >= 0 ? (4 | (sld << 3)) : 0) | (freeS ? (32 | (fb << 6) | (sP > 0.f ? 128 : 0)) : 0);
-        const int tr = k == 0 ? tN : (k == 1 ? tS0 + offS : tT0 + offT + (k == 3 ? 8 : 0));
-        float4* row = &S.q(Q_ST + tr);
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-          row[j * 32] = make_float4(JA[4 * j], JA[4 * j + 1], JA[4 * j + 2], JA[4 * j + 3]);
-          row[(4 + j) * 32] = make_float4(BA[4 * j], BA[4 * j + 1], BA[4 * j + 2], BA[4 * j + 3]);
-        }
         row[3 * 32] = make_float4(__int_as_float(flags), rhs[k], invD, 0.f);
-        row[7 * 32] = make_float4(k == 0 ? cfms : (k == 1 ? spin : (k == 2 ? mu : 0.f)), __int_as_float(tN),
-                                  sld >= 0 ? JF[12 + sld] : 0.f, sld >= 0 ? BF[12 + sld] : 0.f);
+        row[7 * 32] = make_float4(k == 0 ? cfms : (k == 1 ? spin : (k == 2 ? mu : 0.f)), __int_as_float(tN), js, bs);
         if (k == 0 && freeS) {
           const v3 rS = pS - ld3(W.fpos[fb]);
           row[8 * 32] = make_float4(n.x, n.y, n.z, 0.f);
@@ -580,6 +583,9 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel
   const int iters = M.solver_iters;
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
+    // A sweep that changes no impulse leaves the state untouched, so every later sweep repeats it
+    // exactly: stopping there is bit-identical to running all the iterations.
+    bool changed = false;
     // non-contact rows, sweep direction alternating per iteration
 #pragma unroll 1
     for (int i = 0; i < njr; i++) {
@@ -609,6 +615,7 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel
       const float nl = clampf(l0 + (r.y - u * r.z), lo, hi);
       const float dl = (nl - l0) * sg;
       if (dl != 0.f) {
+        changed = true;
         *pl = nl;
         if (a != 15) {
           const float dl2 = dl * ratio;
@@ -626,6 +633,7 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel
         }
       }
     }
+    if (!changed) break;
   }
   float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
   const int nd = M.nd, o = nd + 6 * M.n_free;
@@ -696,6 +704,7 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
   const int iters = M.solver_iters;
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
+    bool changed = false;                                  // fixed point reached: later sweeps are exact repeats
     // ---- contact normals
     {
       int t = 0;
@@ -718,6 +727,7 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
         const float nl = fmaxf(l0 + (q0.z - l0 * q0.y - u * q0.w), 0.f);
         const float dl = nl - l0;
         if (dl != 0.f) {
+          changed = true;
           reinterpret_cast<float*>(rec + 32)[3] = nl;
           fside_apply(P, VP, dvq, body, n * dl, false);
           if (two) fside_apply(Sd, VS, dvq, body, n * dl, false);
@@ -746,6 +756,7 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
       const float nl = clampf(l0 + (h.z - u * h.w), -lim, lim);
       const float dl = nl - l0;
       if (dl != 0.f) {
+        changed = true;
         *pl = nl;
         fside_apply(P, VP, dvq, body, n * dl, true);
         if (two) fside_apply(Sd, VS, dvq, body, n * dl, true);
@@ -785,6 +796,7 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
         }
         const float d1 = na - la, d2 = nb - lb;
         if (d1 != 0.f || d2 != 0.f) {
+          changed = true;
           rec[160] = make_float4(na, nb, 0.f, 0.f);
           const v3 Pv = t1 * d1 + t2 * d2;
           fside_apply(P, VP, dvq, body, Pv, false);
@@ -793,6 +805,7 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
         t = tn; rec = recn; q0 = n0; q1 = n1; q2 = n2; q3 = n3; q4 = n4; q5 = n5;
       }
     }
+    if (!changed) break;
   }
 #undef PGS_PTR
   float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
@@ -875,7 +888,7 @@ PRB_D float* quad_lam0(const QuadMem& m, int tN) {        // normal impulse of t
 }
 // one explicit row; KIND 0: contact normal (lambda >= 0, soft CFM), 1: spin (|lambda| <= coefficient * normal impulse)
 template <int KIND, class Row>
-PRB_D void quad_xrow(const Row& r, const QuadMem& m, int c, unsigned qmask, float4& A, QuadFree& Fr, float tot) {
+PRB_D bool quad_xrow(const Row& r, const QuadMem& m, int c, unsigned qmask, float4& A, QuadFree& Fr, float tot) {
   const float4 H1 = *r.template q<3>(), H2 = *r.template q<7>();
   const int flags = __float_as_int(H1.x);
   const float4 J = r.template ld<0>(c), B = r.template ld<4>(c);
@@ -904,10 +917,11 @@ PRB_D void quad_xrow(const Row& r, const QuadMem& m, int c, unsigned qmask, floa
     if (flags & 32) Fr.apply(fb, fs, rr, n * dl, KIND == 1);
   }
   __syncwarp(qmask);                                     // the new impulse is visible to the quad
+  return dl != 0.f;
 }
 // lateral friction of an explicit contact: the two rows are solved together (implicit cone)
 template <class Row>
-PRB_D void quad_xfriction(const Row& r, const QuadMem& m, int c, unsigned qmask, float4& A, QuadFree& Fr) {
+PRB_D bool quad_xfriction(const Row& r, const QuadMem& m, int c, unsigned qmask, float4& A, QuadFree& Fr) {
   const float4 H1 = *r.template q<3>(), H2 = *r.template q<7>(), G1 = *r.template q<11>(), G2 = *r.template q<15>();
   const int flags = __float_as_int(H1.x);
   const float4 J1 = r.template ld<0>(c), B1 = r.template ld<4>(c), J2 = r.template ld<8>(c), B2 = r.template ld<12>(c);
@@ -944,11 +958,13 @@ PRB_D void quad_xfriction(const Row& r, const QuadMem& m, int c, unsigned qmask,
     if (flags & 32) Fr.apply(fb, fs, rr, t1 * d1 + t2 * d2, false);
   }
   __syncwarp(qmask);
+  return d1 != 0.f || d2 != 0.f;
 }
 // a compact record (both sides free body / static) inside the arm island: the free-body solver's arithmetic
 // on the replicated velocities.  PASS 0 normal, 1 spin (h: its pointer item), 2 friction
 template <int PASS, class Row>
-PRB_D void quad_compact(const Row& r, float4 h, int c, unsigned qmask, QuadFree& Fr) {
+PRB_D bool quad_compact(const Row& r, float4 h, int c, unsigned qmask, QuadFree& Fr) {
+  bool changed = false;
   const float4 q0 = *r.template q<0>(), q1 = *r.template q<1>(), q2 = *r.template q<2>();
   const int pk = __float_as_int(q0.x);
   const int iP = (pk >> 4) & 7, iS = (pk >> 7) & 7;
@@ -964,6 +980,7 @@ PRB_D void quad_compact(const Row& r, float4 h, int c, unsigned qmask, QuadFree&
     const float nl = fmaxf(l0 + (q0.z - l0 * q0.y - u * q0.w), 0.f);
     const float dl = nl - l0;
     __syncwarp(qmask);
+    changed = dl != 0.f;
     if (dl != 0.f) {
       if (c == 3) reinterpret_cast<float*>(r.template q<1>())[3] = nl;
       Fr.apply(iP, sP, rP, n * dl, false);
@@ -980,6 +997,7 @@ PRB_D void quad_compact(const Row& r, float4 h, int c, unsigned qmask, QuadFree&
       const float nl = clampf(l0 + (h.z - u * h.w), -lim, lim);
       const float dl = nl - l0;
       __syncwarp(qmask);
+      changed = dl != 0.f;
       if (dl != 0.f) {
         if (c == 3) *pl = nl;
         Fr.apply(iP, sP, rP, n * dl, true);
@@ -1004,6 +1022,7 @@ PRB_D void quad_compact(const Row& r, float4 h, int c, unsigned qmask, QuadFree&
     }
     const float d1 = na - la, d2 = nb - lb;
     __syncwarp(qmask);
+    changed = d1 != 0.f || d2 != 0.f;
     if (d1 != 0.f || d2 != 0.f) {
       if (c == 3) *r.template q<6>() = make_float4(na, nb, 0.f, 0.f);
       const v3 Pv = t1 * d1 + t2 * d2;
@@ -1012,6 +1031,7 @@ PRB_D void quad_compact(const Row& r, float4 h, int c, unsigned qmask, QuadFree&
     }
   }
   __syncwarp(qmask);
+  return changed;
 }
 
 template <int ND>
@@ -1064,6 +1084,7 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
   const int t_jlam = T_JROW + njr;
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
+    bool changed = false;                                  // fixed point reached: later sweeps are exact repeats
     // ---- non-contact rows, sweep direction alternating per iteration
 #pragma unroll 1
     for (int ii = 0; ii < njr; ii++) {
@@ -1090,6 +1111,7 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
       const float dl = (nl - l0) * sg;
       __syncwarp(qmask);                                             // every lane of the quad has read l0
       if (dl != 0.f) {
+        changed = true;
         if (c == 0) *pl = nl;
         if (a != 15) { axpy4(A, m0, dl); axpy4(A, m1, dl * ratio); }
         else f4add(Fr.sl, sidx, M.slide_minv[sidx] * dl);
@@ -1103,9 +1125,8 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
       for (int k = 0; k < nc; k++) {
         const bool st = m.staged(t);
         const int type = __float_as_int((st ? m.sp(t + 3) : m.Gr + (t + 3) * 32)->x) & 3;
-        if (type == 2) { if (st) quad_compact<0>(RowS{m.sp(t), m.rs}, z4, c, qmask, Fr); else quad_compact<0>(RowG{m.Gr + t * 32}, z4, c, qmask, Fr); }
-        else if (st) quad_xrow<0>(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr, 0.f);
-        else quad_xrow<0>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, 0.f);
+        if (type == 2) changed |= st ? quad_compact<0>(RowS{m.sp(t), m.rs}, z4, c, qmask, Fr) : quad_compact<0>(RowG{m.Gr + t * 32}, z4, c, qmask, Fr);
+        else changed |= st ? quad_xrow<0>(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr, 0.f) : quad_xrow<0>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, 0.f);
         t += type == 1 ? 12 : 8;
       }
     }
@@ -1119,13 +1140,13 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
         if (type == 3) {
           const float4 h = *(st ? m.sp(t) : m.Gr + t * 32);
           const int tr = __float_as_int(h.x);
-          if (m.staged(tr)) quad_compact<1>(RowS{m.sp(tr), m.rs}, h, c, qmask, Fr); else quad_compact<1>(RowG{m.Gr + tr * 32}, h, c, qmask, Fr);
+          changed |= m.staged(tr) ? quad_compact<1>(RowS{m.sp(tr), m.rs}, h, c, qmask, Fr) : quad_compact<1>(RowG{m.Gr + tr * 32}, h, c, qmask, Fr);
           t += 4;
         } else {
           const float4 H2 = *(st ? m.sp(t + 7) : m.Gr + (t + 7) * 32);
           const float tot = *quad_lam0(m, __float_as_int(H2.y));     // normal impulse of the contact
           if (tot > 0.f) {
-            if (st) quad_xrow<1>(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr, tot); else quad_xrow<1>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, tot);
+            changed |= st ? quad_xrow<1>(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr, tot) : quad_xrow<1>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, tot);
           }
           t += 8;
         }
@@ -1140,14 +1161,15 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
         const int type = __float_as_int((st ? m.sp(t + 3) : m.Gr + (t + 3) * 32)->x) & 3;
         if (type == 3) {
           const int tr = __float_as_int((st ? m.sp(t) : m.Gr + t * 32)->x);
-          if (m.staged(tr)) quad_compact<2>(RowS{m.sp(tr), m.rs}, z4, c, qmask, Fr); else quad_compact<2>(RowG{m.Gr + tr * 32}, z4, c, qmask, Fr);
+          changed |= m.staged(tr) ? quad_compact<2>(RowS{m.sp(tr), m.rs}, z4, c, qmask, Fr) : quad_compact<2>(RowG{m.Gr + tr * 32}, z4, c, qmask, Fr);
           t += 4;
         } else {
-          if (st) quad_xfriction(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr); else quad_xfriction(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr);
+          changed |= st ? quad_xfriction(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr) : quad_xfriction(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr);
           t += 16;
         }
       }
     }
+    if (!changed) break;
   }
   // ---- velocity change -> stream (linear DoF order): arm, slides, and the free bodies this island owns
   float* gd = reinterpret_cast<float*>(G + Q_DV * 32);

@@ -103,12 +103,21 @@ def test_stats_gather_gloo_world2():
 
 
 def test_synthetic_actions_shape_and_rate():
+    """Scripted teleop-shaped stream: bounded end-effector speed, gripper toggles,
+    every sub-task reached; the optional Random-stream tail jumps into the +-6 clip box."""
     sys.path.insert(0, ROOT)
     import bench
-    a = bench.synth_actions(np.random.default_rng(0), 64, 50, 'UR5PlayAbsRPY1Obj-v0')
-    assert a.shape == (50, 64, 7) and a.dtype == np.float32
-    inside = np.abs(a[..., :3]).max(-1) < 0.6
+    blk = np.random.default_rng(1).uniform([-0.18, 0.0, 0.0], [0.18, 0.3, 0.0], (64, 3))
+    a = bench.synth_actions(np.random.default_rng(0), 64, 400, 'UR5PlayAbsRPY1Obj-v0', block_xyz=blk, ee_xyz=np.tile([0.0, 0.2, 0.25], (64, 1)))
+    assert a.shape == (400, 64, 7) and a.dtype == np.float32
     step = np.linalg.norm(np.diff(a[..., :3], axis=0), axis=-1)
-    both = inside[1:] & inside[:-1]
-    assert step[both].max() <= 0.0151          # teleop-shaped: <= 0.015 m per 25 Hz step
-    assert 0.01 < (~inside).mean() < 0.12      # ~5% jumps into the +-6 clip box
+    assert step.max() <= 0.0151                # teleop-shaped: <= 0.015 m per 25 Hz step
+    assert np.abs(np.diff(a[..., 5], axis=0)).max() <= 0.1001
+    assert set(np.unique(a[..., 6])) == {-1.0, 1.0}            # gripper opens and closes
+    assert np.abs(a[..., :3]).max() < 0.6
+    # grasp sub-task reaches the block: some step targets a point within 2 cm above a block
+    d = np.linalg.norm(a[..., :2] - blk[None, :, :2], axis=-1)
+    assert ((d < 0.01) & (a[..., 2] < 0.02)).any()
+    j = bench.synth_actions(np.random.default_rng(0), 64, 200, 'UR5PlayAbsRPY1Obj-v0', jump_frac=0.05)
+    outside = np.abs(j[..., :3]).max(-1) > 0.6
+    assert 0.01 < outside.mean() < 0.12        # ~5% jumps into the +-6 clip box
