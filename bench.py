@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENV_ID = 'UR5PlayAbsRPY1Obj-v0'
-RELABEL_EVERY, RELABEL_PHASE = 64, 8       # goal relabelling cadence and its phase in the timed region
+RELABEL_EVERY, RELABEL_PHASE = 64, 2       # goal relabelling cadence and its phase in the timed region
 # DRAM bytes (read + write) of the step pipeline per env step at 65536 envs, from the ncu --set full capture in
 # profiles/r1_v23_ncu.md (12 substeps x 1.02 GB + the final setup launch); None for configurations not captured
 MEASURED_TRAFFIC_BYTES = {('UR5PlayAbsRPY1Obj-v0', 65536): 12.5e9}

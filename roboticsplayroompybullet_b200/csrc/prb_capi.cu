@@ -177,8 +177,7 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
   {
     const char* p = getenv("PRB_PIPELINE");
     h->fused = (p && strcmp(p, "fused") == 0) ? 1 : 0;
-    const char* a = getenv("PRB_ARM_THREADS");
-    if (a) { int v = atoi(a); if (v == 4 || v == 8 || v == 16 || v == 32) h->arm_threads = v; }
+
   }
   if (!h->fused) {
     const size_t sb_bytes = sbuf_bytes(N);   // whole 32-env groups + prefetch slack

@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
 #define PGS_G_EPW (32 >> PGS_G_LW)                      // envs per warp of the arm-island kernel
 #define PGS_SMEM_J ((PGS_STAGE_J + PGS_J_DVQ) * 32 * 16)
 #define PGS_SMEM_F ((PGS_STAGE_F + PGS_F_TAILQ) * 32 * 16)
-#define PGS_G_THREADS 4                                 // threads per block of the arm-island kernel
+#define PGS_G_THREADS 32                                // threads per block of the arm-island kernel
 #define PGS_SMEM_G(rows) ((rows) * PGS_G_THREADS * 16)
 
 #ifdef PRB_EMU
@@ -830,7 +830,7 @@ struct QuadMem {
   float4* base;            // column 0 of this env in shared memory
   float4* Gr;              // this env's column of region 0 in the stream
   int cap;                 // staged q count; items that do not end below it are read from the stream in place
-  int rs;                  // row stride = columns of the block's stage = threads per block
+  static constexpr int rs = 32;   // row stride = columns of the block's stage = threads per block
   PRB_D float4* sp(int t) const { return base + (t >> 2) * rs + (t & 3); }     // always-staged q (fixed part of region 0)
   PRB_D bool staged(int t) const { return t + 16 <= cap; }                    // item starting at t (items are <= 16 q)
   PRB_D float4 ldq(int t) const { return t < cap ? *sp(t) : Gr[t * 32]; }     // immutable data (geometry)
@@ -838,7 +838,7 @@ struct QuadMem {
 // an item in shared memory (q k of the item at rp[(k >> 2) * 32 + (k & 3)]) or in the stream (gp[k * 32])
 struct RowS {
   float4* rp;
-  int rs;
+  static constexpr int rs = 32;
   template <int K0> PRB_D float4 ld(int c) const { return rp[(K0 >> 2) * rs + c]; }
   template <int K> PRB_D float4* q() const { return rp + (K >> 2) * rs + (K & 3); }
 };
@@ -1038,8 +1038,8 @@ template <int ND>
 __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf,
                                                                 const int* __restrict__ heavy_list, int* __restrict__ heavy_cnt, int rows) {
   PRB_PGS_SMEM_DECL;
-  // any multiple of 4 threads per block (<= 32); 4 = one env per block: the warps of an SM then are
-  // independent envs (no divergence between the quads of a warp, 32 latency-hiding warps per SM)
+  // 32 threads = 8 envs per block.  (Smaller blocks were measured: 16 threads equal, 8 and 4 slower — the
+  // kernel is bound by the instruction count per row visit, which a warp amortises over its converged quads.)
   const int lane = threadIdx.x, c = lane & 3, qb = lane & ~3;
   const unsigned qmask = 0xfu << qb;
   const int cnt = *heavy_cnt;
@@ -1059,7 +1059,7 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
   const int tS0 = __float_as_int(hdr.y), tT0 = __float_as_int(hdr.z), tEnd = __float_as_int(hdr.w);
   const int tN0 = (T_JROW + njr + ((njr + 3) >> 2) + 3) & ~3;
   QuadMem m;
-  m.base = sm + qb; m.Gr = G + Q_ST * 32; m.cap = rows << 2; m.rs = blockDim.x;
+  m.base = sm + qb; m.Gr = G + Q_ST * 32; m.cap = rows << 2;
   {
     const int tq = min(tEnd, m.cap);
 #pragma unroll 4
@@ -1097,11 +1097,9 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
       float4 m0 = z4, m1 = z4;                                       // this lane's slice of the M^-1 rows
       if (a != 15 && c < 3) m0 = *m.sp(T_MINV + 3 * a + c);
       if (a2 != 15 && c < 3) m1 = *m.sp(T_MINV + 3 * a2 + c);
-      // u = J . dv: J = e_a (+ ratio e_a2): the owning lane contributes its word; slide rows are replicated
-      float p = 0.f;
-      if (a != 15 && c == (a >> 2)) p = f4comp(A, a & 3);
-      if (a2 != 15 && c == (a2 >> 2)) p = fmaf(ratio, f4comp(A, a2 & 3), p);
-      float u = quad_sum(qmask, p);
+      // u = J . dv: J = e_a (+ ratio e_a2): broadcast of the owning lane's word; slide rows are replicated
+      float u = __shfl_sync(qmask, f4comp(A, a & 3), qb + ((a >> 2) & 3));
+      if (a2 != 15) u = fmaf(ratio, __shfl_sync(qmask, f4comp(A, a2 & 3), qb + (a2 >> 2)), u);
       if (a == 15) u = f4comp(Fr.sl, sidx);
       u *= sg;
       float* pl = reinterpret_cast<float*>(m.sp(t_jlam + (j >> 2))) + (j & 3);
@@ -1125,8 +1123,8 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
       for (int k = 0; k < nc; k++) {
         const bool st = m.staged(t);
         const int type = __float_as_int((st ? m.sp(t + 3) : m.Gr + (t + 3) * 32)->x) & 3;
-        if (type == 2) changed |= st ? quad_compact<0>(RowS{m.sp(t), m.rs}, z4, c, qmask, Fr) : quad_compact<0>(RowG{m.Gr + t * 32}, z4, c, qmask, Fr);
-        else changed |= st ? quad_xrow<0>(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr, 0.f) : quad_xrow<0>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, 0.f);
+        if (type == 2) changed |= st ? quad_compact<0>(RowS{m.sp(t)}, z4, c, qmask, Fr) : quad_compact<0>(RowG{m.Gr + t * 32}, z4, c, qmask, Fr);
+        else changed |= st ? quad_xrow<0>(RowS{m.sp(t)}, m, c, qmask, A, Fr, 0.f) : quad_xrow<0>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, 0.f);
         t += type == 1 ? 12 : 8;
       }
     }
@@ -1140,13 +1138,13 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
         if (type == 3) {
           const float4 h = *(st ? m.sp(t) : m.Gr + t * 32);
           const int tr = __float_as_int(h.x);
-          changed |= m.staged(tr) ? quad_compact<1>(RowS{m.sp(tr), m.rs}, h, c, qmask, Fr) : quad_compact<1>(RowG{m.Gr + tr * 32}, h, c, qmask, Fr);
+          changed |= m.staged(tr) ? quad_compact<1>(RowS{m.sp(tr)}, h, c, qmask, Fr) : quad_compact<1>(RowG{m.Gr + tr * 32}, h, c, qmask, Fr);
           t += 4;
         } else {
           const float4 H2 = *(st ? m.sp(t + 7) : m.Gr + (t + 7) * 32);
           const float tot = *quad_lam0(m, __float_as_int(H2.y));     // normal impulse of the contact
           if (tot > 0.f) {
-            changed |= st ? quad_xrow<1>(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr, tot) : quad_xrow<1>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, tot);
+            changed |= st ? quad_xrow<1>(RowS{m.sp(t)}, m, c, qmask, A, Fr, tot) : quad_xrow<1>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, tot);
           }
           t += 8;
         }
@@ -1161,10 +1159,10 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
         const int type = __float_as_int((st ? m.sp(t + 3) : m.Gr + (t + 3) * 32)->x) & 3;
         if (type == 3) {
           const int tr = __float_as_int((st ? m.sp(t) : m.Gr + t * 32)->x);
-          changed |= m.staged(tr) ? quad_compact<2>(RowS{m.sp(tr), m.rs}, z4, c, qmask, Fr) : quad_compact<2>(RowG{m.Gr + tr * 32}, z4, c, qmask, Fr);
+          changed |= m.staged(tr) ? quad_compact<2>(RowS{m.sp(tr)}, z4, c, qmask, Fr) : quad_compact<2>(RowG{m.Gr + tr * 32}, z4, c, qmask, Fr);
           t += 4;
         } else {
-          changed |= st ? quad_xfriction(RowS{m.sp(t), m.rs}, m, c, qmask, A, Fr) : quad_xfriction(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr);
+          changed |= st ? quad_xfriction(RowS{m.sp(t)}, m, c, qmask, A, Fr) : quad_xfriction(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr);
           t += 16;
         }
       }

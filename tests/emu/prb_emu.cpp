@@ -32,7 +32,7 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
         emu_dim3 gy = gp;
         emu::launch_y(gy, bp, y, [&]() { prb_pgs_free_kernel(&g_M, g_sbuf.data(), N); });
       }
-      emu_dim3 gh, bq; gh.x = N; bq.x = PGS_G_THREADS;
+      emu_dim3 gh, bq; gh.x = (N + 7) / 8; bq.x = PGS_G_THREADS;
       emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data() + N, heavy_cnt + 4, PGS_ROWS_GB); });
       emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data(), heavy_cnt, PGS_ROWS_GA); });
     }

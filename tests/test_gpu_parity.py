@@ -182,3 +182,40 @@ def test_grasp_and_lift_statistics():
     lifted = obs['achieved_goal'][:, 2] > 0.1
     assert lifted.mean() > 0.7, lifted.mean()
     env.close()
+
+
+def test_step_parity_scripted_steady_state():
+    """One-step parity from identical states in the contact-rich steady state of the scripted workload
+    (gripper on the block, block island merged into the arm island: the four-lanes-per-env solver and the
+    compact free-body records), 64 envs after 60 scripted steps."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle
+    env_id = 'UR5PlayAbsRPY1Obj-v0'
+    n = 64
+    env = _mk(env_id, n, seed=13)
+    obs = env.reset()
+    acts = bench.synth_actions(np.random.default_rng(2), n, 64, env_id, block_xyz=obs['achieved_goal'][:, :3],
+                               ee_xyz=obs['obs_quat'][:, :3])
+    for s in range(60):
+        env.step(acts[s])
+    m = load_model(env_id)
+    total_bad, merged, worst_all = 0, 0, 0.0
+    for s in range(60, 63):
+        st = env.get_state()
+        obs, r, done, info = env.step(acts[s])
+        merged += int((env.debug_usage()[:, 2] > 200).sum())       # envs whose record stream shows an arm island in contact
+        outs = [oracle_step_from(m, st[i], acts[s][i], Oracle)[0] for i in range(n)]
+        bad, worst = compare_step(obs, r, info, outs)
+        total_bad += bad
+        worst_all = max(worst_all, worst)
+    assert merged >= 6, merged                                      # the heavy path was exercised
+    # Envs with the fingers closed on the block are stiff (soft-contact CFM of the pads, 4 rows per point): fp32 vs
+    # fp64 differs by up to ~5e-3 m after one step in ~7 % of them.  The fused A/B solver (PRB_PIPELINE=fused,
+    # impulse space, different arithmetic) is off by the same amount on the same envs (tools/exp_parity_steady.py),
+    # so this is conditioning, not the solver: bound the outlier count and their size.
+    assert total_bad <= int(0.12 * 3 * n), total_bad
+    assert worst_all < 2e-2, worst_all
+    env.close()
