@@ -15,7 +15,6 @@ struct prb_handle {
   DevModel hm;
   DevModel* dm = nullptr;
   int N = 0, device = 0, sms = 148;
-  int arm_threads = 32;            // threads per block of the arm-island kernel (4 per env)
   unsigned env_offset = 0;
   unsigned long long seed = 0;
   float* state = nullptr;
@@ -28,9 +27,9 @@ struct prb_handle {
   float* sbuf = nullptr;           // constraint-row record stream of the split pipeline (prb_stream.cuh)
   int* heavy_list = nullptr;       // env ids whose arm island has contacts this substep (general solver kernel)
   int* heavy_cnt = nullptr;
-  cudaStream_t side = nullptr;     // high-priority side stream: the arm-island solver overlaps the joint / free-body solvers
-  cudaStream_t side2 = nullptr;    // second side stream: the two size classes of the arm-island solver overlap too
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  // high-priority side streams: the size classes of the arm-island solver overlap each other and the joint / free-body solvers
+  cudaStream_t side[PGS_NCLASS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[PGS_NCLASS] = {};
   int smem = 0, regs = 0;          // setup kernel (reported)
   int regs_pgs = 0;
   int smem_fused = 0, smem_reset = 0;
@@ -66,41 +65,39 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
   }
   dim3 gs((h->N + SetupCfg::WPB - 1) / SetupCfg::WPB), bs(32 * SetupCfg::WPB);
   // persistent solver blocks: resident blocks per SM (shared-memory limited) x SMs, grid-stride inside
-  const int ng = (h->N + PGS_BLOCK - 1) / PGS_BLOCK, nq = (h->N + PGS_G_EPW - 1) / PGS_G_EPW;
+  const int ng = (h->N + PGS_BLOCK - 1) / PGS_BLOCK;
   dim3 gp(ng < 6 * h->sms ? ng : 6 * h->sms), gf(ng < 3 * h->sms ? ng : 3 * h->sms, h->hm.n_free), bp(PGS_BLOCK);
-  // arm-island kernel: one env (4 threads) per block, up to 32 / 16 resident blocks per SM for the two size classes
-  const int at = h->arm_threads;
-  const int smA = PGS_ROWS_GA * at * 16, smB = PGS_ROWS_GB * at * 16;
-  int bpsA = (227 * 1024) / (smA + 1024), bpsB = (227 * 1024) / (smB + 1024);
-  if (bpsA > 24) bpsA = 24;
-  if (bpsB > 24) bpsB = 24;
-  dim3 gha(bpsA * h->sms), ghb(bpsB * h->sms), bq(at);
+  // arm-island kernel: 8 envs (4 lanes each) per block, one launch per size class
+  dim3 bq(PGS_G_THREADS);
+  int gcls[PGS_NCLASS], smcls[PGS_NCLASS];
+  for (int k = 0; k < PGS_NCLASS; k++) {
+    smcls[k] = PGS_SMEM_G(pgs_class_rows(k));
+    gcls[k] = ((227 * 1024) / (smcls[k] + 1024)) * h->sms;     // resident blocks per SM x SMs
+  }
   h->n_evk = 0;
   for (int i = 0; i <= nsub; i++) {
     int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
     if (flags == 0) break;
     if (h->timing && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
-    if (i < nsub) CK(h, cudaMemsetAsync(h->heavy_cnt, 0, 8 * sizeof(int), s));
+    if (i < nsub) CK(h, cudaMemsetAsync(h->heavy_cnt, 0, 4 * PGS_NCLASS * sizeof(int), s));
     prb_setup_kernel<ND><<<gs, bs, h->smem, s>>>(h->dm, h->state, h->sbuf, h->O, h->N, flags, h->heavy_list, h->heavy_cnt);
     h->launches++;
     if (i < nsub) {
       if (h->timing && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
-      // the islands of a substep are independent: three solver kernels, any order
       // the islands of a substep are independent: the arm-island solver (few envs, long dependent
-      // chains) goes first on the high-priority side stream, the two throughput kernels fill the
+      // chains) goes first on high-priority side streams, the two throughput kernels fill the
       // machine behind it; the streams join before the next setup launch
       CK(h, cudaEventRecord(h->ev_fork, s));
-      CK(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-      CK(h, cudaStreamWaitEvent(h->side2, h->ev_fork, 0));
-      prb_pgs_arm_kernel<ND><<<ghb, bq, smB, h->side2>>>(h->dm, h->sbuf, h->heavy_list + h->N, h->heavy_cnt + 4, PGS_ROWS_GB);
-      prb_pgs_arm_kernel<ND><<<gha, bq, smA, h->side>>>(h->dm, h->sbuf, h->heavy_list, h->heavy_cnt, PGS_ROWS_GA);
-      CK(h, cudaEventRecord(h->ev_join, h->side));
-      CK(h, cudaEventRecord(h->ev_join2, h->side2));
+      for (int k = PGS_NCLASS - 1; k >= 0; k--) {        // largest islands first
+        CK(h, cudaStreamWaitEvent(h->side[k], h->ev_fork, 0));
+        prb_pgs_arm_kernel<ND><<<gcls[k], bq, smcls[k], h->side[k]>>>(h->dm, h->sbuf, h->heavy_list + (size_t)k * h->N, h->heavy_cnt + 4 * k,
+                                                                         pgs_class_rows(k));
+        CK(h, cudaEventRecord(h->ev_join[k], h->side[k]));
+      }
       prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, s>>>(h->dm, h->sbuf, h->N);
       if (h->hm.n_free > 0) prb_pgs_free_kernel<<<gf, bp, PGS_SMEM_F, s>>>(h->dm, h->sbuf, h->N);
-      CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
-      CK(h, cudaStreamWaitEvent(s, h->ev_join2, 0));
-      h->launches += h->hm.n_free > 0 ? 4 : 3;
+      for (int k = 0; k < PGS_NCLASS; k++) CK(h, cudaStreamWaitEvent(s, h->ev_join[k], 0));
+      h->launches += (h->hm.n_free > 0 ? 2 : 1) + PGS_NCLASS;
     }
   }
   if (h->timing && h->n_evk < 64) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
@@ -122,7 +119,7 @@ static int setup_kernels(prb_handle* h) {
   cudaFuncAttributes fa;
   CK(h, cudaFuncGetAttributes(&fa, prb_setup_kernel<ND>));
   h->regs = fa.numRegs;
-  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_ROWS_GB * 32 * 16));
+  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_G(PGS_ROWS_GMAX)));
   CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_J));
   CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -183,15 +180,15 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
     const size_t sb_bytes = sbuf_bytes(N);   // whole 32-env groups + prefetch slack
     CK(h, cudaMalloc(&h->sbuf, sb_bytes));
     CK(h, cudaMemset(h->sbuf, 0, sb_bytes));
-    CK(h, cudaMalloc(&h->heavy_list, sizeof(int) * 2 * N));
-    CK(h, cudaMalloc(&h->heavy_cnt, 8 * sizeof(int)));   // {list length, -, work counter, -} x 2 classes
+    CK(h, cudaMalloc(&h->heavy_list, sizeof(int) * PGS_NCLASS * N));
+    CK(h, cudaMalloc(&h->heavy_cnt, 4 * PGS_NCLASS * sizeof(int)));   // {list length, -, work counter, -} per class
     int lo_pri = 0, hi_pri = 0;
     CK(h, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-    CK(h, cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi_pri));
-    CK(h, cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, hi_pri));
-    CK(h, cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
     CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    for (int k = 0; k < PGS_NCLASS; k++) {
+      CK(h, cudaStreamCreateWithPriority(&h->side[k], cudaStreamNonBlocking, hi_pri));
+      CK(h, cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
+    }
   }
   {
     int rc = M.nd == 12 ? setup_kernels<12>(h) : setup_kernels<9>(h);
@@ -208,11 +205,11 @@ int prb_destroy(prb_handle* h) {
   if (!h) return PRB_ERR_INVALID;
   cudaSetDevice(h->device);
   cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->sbuf); cudaFree(h->heavy_list); cudaFree(h->heavy_cnt);
-  if (h->side) cudaStreamDestroy(h->side);
-  if (h->side2) cudaStreamDestroy(h->side2);
-  if (h->ev_join2) cudaEventDestroy(h->ev_join2);
+  for (int k = 0; k < PGS_NCLASS; k++) {
+    if (h->side[k]) cudaStreamDestroy(h->side[k]);
+    if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+  }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return PRB_OK;
 }

@@ -89,9 +89,13 @@
 #define PGS_STAGE_F 64   // free-body kernel: 10 contact records; 6 blocks per SM
 #endif
 #define PGS_G_LW 2       // arm-island kernel: an env owns 4 shared-memory columns (8 envs per warp)
-#define PGS_ROWS_GA 104  // class A: 416 q per env, 4 blocks per SM
-#define PGS_ROWS_GB 216  // class B: 864 q per env, 2 blocks per SM
-#define PGS_CLASS_A_MAXQ (PGS_ROWS_GA << PGS_G_LW)
+#define PGS_NCLASS 4      // size classes of the arm-island kernel (by the q count of region 0): rows of 4 q per env
+#define PGS_ROWS_G0 56   // class 0: 224 q per env, 7 blocks per SM (56 envs)
+#define PGS_ROWS_G1 80   // class 1: 320 q per env, 5 blocks per SM (40 envs)
+#define PGS_ROWS_G2 104  // class 2: 416 q per env, 4 blocks per SM (32 envs)
+#define PGS_ROWS_G3 216  // class 3: 864 q per env (larger islands read the rest in place), 2 blocks per SM (16 envs)
+#define PGS_ROWS_GMAX PGS_ROWS_G3
+PRB_HD int pgs_class_rows(int cls) { return cls == 0 ? PGS_ROWS_G0 : (cls == 1 ? PGS_ROWS_G1 : (cls == 2 ? PGS_ROWS_G2 : PGS_ROWS_G3)); }
 #define PGS_MAXJROW_J ((PGS_STAGE_J - T_JROW) * 4 / 5)     // njr + ceil(njr / 4) <= PGS_STAGE_J - T_JROW
 #define DVW_SLIDE(s) (28 + (s))
 enum { K_STATIC = 0, K_FREE = 1, K_SLIDE = 2, K_ARM = 3 };
@@ -467,7 +471,7 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
     S.q(Q_HDR + 2) = make_float4(__int_as_float(ncs[2] | (nss[2] << 8)), __int_as_float(start[2]), __int_as_float(tsp[2]), 0.f);
     if (nc > W.dbg_c) W.dbg_c = nc;
     // island of the arm needs the arm-island solver: size class by the q count of region 0
-    W.dbg_u = (nc0 > 0 || njr > PGS_MAXJROW_J) ? ((tEnd0 <= PGS_CLASS_A_MAXQ) ? 1 : 2) : 0;
+    W.dbg_u = (nc0 > 0 || njr > PGS_MAXJROW_J) ? (tEnd0 <= 4 * PGS_ROWS_G0 ? 1 : (tEnd0 <= 4 * PGS_ROWS_G1 ? 2 : (tEnd0 <= 4 * PGS_ROWS_G2 ? 3 : 4))) : 0;
   }
   if (lane < M.nv) S.w(4 * Q_VSTAR + lane) = W.vs[lane];
 }
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
     __syncwarp();
     if (lane == 0 && W.overflow && O.overflow) atomicAdd(O.overflow, 1ull);
     if (lane == 0 && W.dbg_u) {                      // order within a list is immaterial: envs are independent
-      const int cls = W.dbg_u - 1;                   // 0: region 0 fits class A's stage, 1: larger
+      const int cls = W.dbg_u - 1;                   // size class of region 0
       heavy_list[(size_t)cls * N + atomicAdd(heavy_cnt + 4 * cls, 1)] = e;    // heavy_cnt: {length, -, work counter, -} per class
     }
     if (lane == 0 && O.dbg) { O.dbg[4 * e] = 0; O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.n_jrow; }
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
 #define PGS_SMEM_G(rows) ((rows) * PGS_G_THREADS * 16)
 
 #ifdef PRB_EMU
-static float4 g_emu_pgs_smem[(PGS_ROWS_GB + 2) * 32 + (PGS_STAGE_J + PGS_STAGE_F + 16) * 32];
+static float4 g_emu_pgs_smem[(PGS_ROWS_GMAX + 2) * 32 + (PGS_STAGE_J + PGS_STAGE_F + 16) * 32];
 #define PRB_PGS_SMEM_DECL float4* sm = g_emu_pgs_smem
 #else
 #define PRB_PGS_SMEM_DECL extern __shared__ __align__(16) float4 prb_pgs_smem[]; float4* sm = prb_pgs_smem

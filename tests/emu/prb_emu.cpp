@@ -16,8 +16,8 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
     return;
   }
   g_sbuf.assign(sbuf_bytes(N) / sizeof(float), 0.f);
-  std::vector<int> heavy(2 * N);
-  int heavy_cnt[8] = {0};
+  std::vector<int> heavy(PGS_NCLASS * N);
+  int heavy_cnt[4 * PGS_NCLASS] = {0};
   emu_dim3 gs, bs, gp, bp;
   bs.x = 32 * SetupCfg::WPB; gs.x = (N + SetupCfg::WPB - 1) / SetupCfg::WPB;
   bp.x = PGS_BLOCK; gp.x = (N + PGS_BLOCK - 1) / PGS_BLOCK;
@@ -33,8 +33,8 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
         emu::launch_y(gy, bp, y, [&]() { prb_pgs_free_kernel(&g_M, g_sbuf.data(), N); });
       }
       emu_dim3 gh, bq; gh.x = (N + 7) / 8; bq.x = PGS_G_THREADS;
-      emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data() + N, heavy_cnt + 4, PGS_ROWS_GB); });
-      emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data(), heavy_cnt, PGS_ROWS_GA); });
+      for (int k = 0; k < PGS_NCLASS; k++)
+        emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data() + (size_t)k * N, heavy_cnt + 4 * k, pgs_class_rows(k)); });
     }
   }
 }
