@@ -879,9 +879,8 @@ struct QuadFree {
     v3 dv = V3(0, 0, 0), dw;
     if (angular) dw = symmul(Ib, Ps);
     else { dv = Ps * im; dw = symmul(Ib, cross(r, Ps)); }
-    const float m0 = b ? 0.f : 1.f, m1 = b ? 1.f : 0.f;
-    v[0] = v[0] + dv * m0; w[0] = w[0] + dw * m0;
-    v[PRB_MAXFREE - 1] = v[PRB_MAXFREE - 1] + dv * m1; w[PRB_MAXFREE - 1] = w[PRB_MAXFREE - 1] + dw * m1;
+    if (b) { v[PRB_MAXFREE - 1] = v[PRB_MAXFREE - 1] + dv; w[PRB_MAXFREE - 1] = w[PRB_MAXFREE - 1] + dw; }
+    else { v[0] = v[0] + dv; w[0] = w[0] + dw; }
   }
 };
 PRB_D float* quad_lam0(const QuadMem& m, int tN) {        // normal impulse of the contact whose normal item is at tN
