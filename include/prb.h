@@ -78,7 +78,8 @@ int prb_reset(prb_handle* h, const uint8_t* mask_dev, void* stream);
 /* playEnv.reset_goal_pos(goal) (environments.py:190-191, 492-501): goal_dev is [N, goal_dim]. */
 int prb_set_goal(prb_handle* h, const float* goal_dev, const uint8_t* mask_dev, void* stream);
 
-/* playEnv.step(action) (environments.py:206-214): action_dev is [N,7] absolute xyz + rpy +
+/* playEnv.step(action) (environments.py:206-214): action_dev is [N,A]; A = 7 (8 for the quaternion decoders), the
+ * decoder is the model's action_type parameter (environments.py:915-981).  Default [N,7] absolute xyz + rpy +
  * gripper; clip -> IK -> motor targets -> 12 substeps -> calc_state -> reward / is_success. */
 int prb_step(prb_handle* h, const float* action_dev, void* stream);
 
@@ -102,7 +103,7 @@ int prb_compute_reward(prb_handle* h, const float* ag_dev, const float* dg_dev, 
 int prb_get_state(prb_handle* h, float* host_out);
 int prb_set_state(prb_handle* h, const float* host_in);
 
-/* Same as prb_step, but through HOST buffers: copies action_host [N,7] to the device, steps,
+/* Same as prb_step, but through HOST buffers: copies action_host [N,A] to the device, steps,
  * copies the whole output block (out_floats floats) back into out_host and synchronises the
  * stream.  This is the call the Python gym mirror makes for numpy in / numpy out stepping. */
 int prb_step_host(prb_handle* h, const float* action_host, float* out_host, void* stream);

@@ -1222,14 +1222,37 @@ static real clampr(real x, real lo, real hi) { return x < lo ? lo : (x > hi ? hi
 void orc_step(const prb_model* M, real* state, const real* action, real* out) {
   State S; state_unpack(M, state, &S);
   Out O; memset(&O, 0, sizeof(O));
-  real a[7];
-  for (int k = 0; k < 6; k++) a[k] = clampr(action[k], -M->params[PRB_P_ACTION_HIGH_XYZ], M->params[PRB_P_ACTION_HIGH_XYZ]);
-  a[6] = clampr(action[6], -M->params[PRB_P_ACTION_HIGH_GRIP], M->params[PRB_P_ACTION_HIGH_GRIP]);
-  /* absolute_rpy_step :955-961 -> goto :984-1007 */
-  real tq[4]; orc_quat_from_euler(a + 3, tq);
+  /* perform_action :915-934: 0 absolute_rpy, 1 relative_rpy, 2 absolute_quat, 3 relative_quat, 4 absolute_joints,
+   * 5 relative_joints; clip to the action space first (:207, bounds :88-112) */
+  const int atype = (int)(M->params[PRB_P_ACTION_TYPE] + 0.5), adim = (atype == 2 || atype == 3) ? 8 : 7;
+  real a[8] = {0};
+  for (int k = 0; k < adim - 1; k++) a[k] = clampr(action[k], -M->params[PRB_P_ACTION_HIGH_XYZ], M->params[PRB_P_ACTION_HIGH_XYZ]);
+  const real grip = clampr(action[adim - 1], -M->params[PRB_P_ACTION_HIGH_GRIP], M->params[PRB_P_ACTION_HIGH_GRIP]);
   real jp[MAXD];
-  if (M->arm_kind == 0) orc_calc_angles(M, S.q, a, tq, jp);
-  else orc_ik(M, S.q, a, tq, M->ik_iters, jp);     /* Panda: one call on the live arm, 200 iterations (:995-997) */
+  if (atype >= 4) {                                  /* relative / absolute_joint_step :973-981 (6-joint arms) */
+    for (int i = 0; i < M->n_ik; i++) jp[i] = (atype == 5 ? S.q[i] : 0) + a[i];
+  } else {
+    real tp[3] = {a[0], a[1], a[2]}, tq[4];
+    if (atype == 0) orc_quat_from_euler(a + 3, tq);  /* absolute_rpy_step :955-961 */
+    else if (atype == 2) { for (int k = 0; k < 4; k++) tq[k] = a[3 + k]; }   /* absolute_quat_step :936-943 */
+    else {                                           /* relative to getLinkState(arm, ee) :945-953, 962-970 */
+      real sites[28];
+      orc_fk_sites(M, S.q, sites);
+      for (int k = 0; k < 3; k++) tp[k] += sites[k];
+      if (atype == 1) {
+        real rpy[3]; orc_euler_from_quat(sites + 3, rpy);
+        for (int k = 0; k < 3; k++) rpy[k] += a[3 + k];
+        orc_quat_from_euler(rpy, tq);
+      } else for (int k = 0; k < 4; k++) tq[k] = sites[3 + k] + a[3 + k];
+    }
+    if (atype >= 2) {                                /* commanded quaternions are used normalised */
+      real nrm = sqrt(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]);
+      if (nrm > 1e-12) for (int k = 0; k < 4; k++) tq[k] /= nrm; else { tq[0] = tq[1] = tq[2] = 0; tq[3] = 1; }
+    }
+    /* goto :984-1007 */
+    if (M->arm_kind == 0) orc_calc_angles(M, S.q, tp, tq, jp);
+    else orc_ik(M, S.q, tp, tq, M->ik_iters, jp);     /* Panda: one call on the live arm, 200 iterations (:995-997) */
+  }
   /* goto_joint_poses :1010-1034 */
   real dt = M->params[PRB_P_DT];
   for (int i = 0; i < M->n_ik; i++) {
@@ -1241,7 +1264,7 @@ void orc_step(const prb_model* M, real* state, const real* action, real* out) {
   /* close_gripper :1037-1073 (mimic entries read the CURRENT position of their source joint) */
   for (int k = 0; k < M->n_grip; k++) {
     int d = M->grip_dof[k];
-    real t = M->grip_mimic[k] >= 0 ? S.q[M->grip_mimic[k]] : M->grip_scale[k] * a[6] + M->grip_offset[k];
+    real t = M->grip_mimic[k] >= 0 ? S.q[M->grip_mimic[k]] : M->grip_scale[k] * grip + M->grip_offset[k];
     S.mtarget[d] = t; S.mkp[d] = M->params[PRB_P_MOTOR_KP]; S.mmaximp[d] = M->grip_force[k] * dt;
   }
   for (int i = 0; i < M->n_substeps; i++) substep(M, &S);   /* runSimulation :485-490 */

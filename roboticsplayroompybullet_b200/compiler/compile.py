@@ -245,7 +245,7 @@ def compile_env(env_id, ref_envs):
              reset_z_offset=0.0, default_motor_impulse=1.0, motor_kp=0.1, motor_kd=1.0,
              limit_max_impulse=100.0, gear_ratio=-1.0, gear_erp=0.1, gear_max_impulse=50.0 / 300,
              max_coord_vel=100.0, action_high_xyz=6.0, action_high_grip=1.0, obj_reset_dz=0.03,
-             arm_lin_damp=0.0, arm_ang_damp=0.0, contact_breaking=0.02, reserved=0.0)
+             arm_lin_damp=0.0, arm_ang_damp=0.0, contact_breaking=0.02, action_type=0.0)
     if env_id == 'UR5Reach-v0':                             # envList.py:89-91
         arm_kind = 0
         d = build_arm(world, ref_envs, arm_kind)

@@ -29,7 +29,7 @@ enum {
   P_ARM_FORCE, P_SPARSE_THRESH, P_RESET_Z_OFFSET, P_DEFAULT_MOTOR_IMPULSE, P_MOTOR_KP, P_MOTOR_KD,
   P_LIMIT_MAX_IMPULSE, P_GEAR_RATIO, P_GEAR_ERP, P_GEAR_MAX_IMPULSE, P_MAX_COORD_VEL,
   P_ACTION_HIGH_XYZ, P_ACTION_HIGH_GRIP, P_OBJ_RESET_DZ, P_ARM_LIN_DAMP, P_ARM_ANG_DAMP,
-  P_CONTACT_BREAKING, P_RESERVED
+  P_CONTACT_BREAKING, P_ACTION_TYPE
 };
 
 struct DevModel {

@@ -250,19 +250,63 @@ PRB_D void ik_world(const DevModel& M, float* q, const float* tpos_w, const floa
   for (int c = 0; c < calls; c++) ik_call<NJ>(M, q, tp, tq, iters);
 }
 
+// world pose of the end-effector site for joint angles q (the pose calc_actor_state reports,
+// environments.py:746-764): serial chain of NJ joints, site 0 on the last link
+template <int NJ>
+PRB_D void ee_world(const DevModel& M, const float* q, v3& pos, float* quat) {
+  m3 R = ldm(M.base_rot);
+  v3 p = ld3(M.base_pos);
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    p = p + mul(R, ld3(M.jpos[j]));
+    R = mul(mul(R, ldm(M.jrot[j])), axis_angle(ld3(M.axis[j]), q[j]));
+  }
+  pos = p + mul(R, ld3(M.site_pos[0]));
+  mat_to_quat(mul(R, ldm(M.site_rot[0])), quat);
+}
+PRB_HD int action_dim_of(int action_type) { return (action_type == 2 || action_type == 3) ? 8 : 7; }
+
+// perform_action (environments.py:915-981) -> goto / goto_joint_poses (:984-1034) -> close_gripper (:1037-1073).
+// action_type: 0 absolute_rpy, 1 relative_rpy, 2 absolute_quat, 3 relative_quat, 4 absolute_joints, 5 relative_joints
 template <int NJ>
 PRB_D void ik_action_env(const DevModel& M, float* st /* this env's state */, const float* act, float* target_out) {
   const int nd = M.nd;
-  float a[7];
+  const int atype = (int)(M.params[P_ACTION_TYPE] + 0.5f), adim = action_dim_of(atype);
+  float a[8];
 #pragma unroll
-  for (int k = 0; k < 6; k++) a[k] = clampf(act[k], -M.params[P_ACTION_HIGH_XYZ], M.params[P_ACTION_HIGH_XYZ]);
-  a[6] = clampf(act[6], -M.params[P_ACTION_HIGH_GRIP], M.params[P_ACTION_HIGH_GRIP]);
-  float tq[4];
-  quat_from_euler(a + 3, tq);
+  for (int k = 0; k < 8; k++) {
+    a[k] = 0.f;
+    if (k < adim - 1) a[k] = clampf(act[k], -M.params[P_ACTION_HIGH_XYZ], M.params[P_ACTION_HIGH_XYZ]);
+  }
+  const float grip = clampf(act[adim - 1], -M.params[P_ACTION_HIGH_GRIP], M.params[P_ACTION_HIGH_GRIP]);
   float q[NJ], q0[NJ];
 #pragma unroll
   for (int i = 0; i < NJ; i++) { q0[i] = st[i]; q[i] = q0[i]; }
-  ik_world<NJ>(M, q, a, tq, M.ik_calls, M.ik_iters);
+  if (atype >= 4) {                            // joint space: no IK (:973-981)
+#pragma unroll
+    for (int i = 0; i < NJ; i++) q[i] = (atype == 5 ? q0[i] : 0.f) + a[i];
+  } else {
+    float tp[3] = {a[0], a[1], a[2]}, tq[4];
+    if (atype == 0) quat_from_euler(a + 3, tq);
+    else if (atype == 2) { tq[0] = a[3]; tq[1] = a[4]; tq[2] = a[5]; tq[3] = a[6]; }
+    else {                                     // relative to the current end-effector pose (:945-953, 962-970)
+      v3 cp; float cq[4];
+      ee_world<NJ>(M, q0, cp, cq);
+      tp[0] += cp.x; tp[1] += cp.y; tp[2] += cp.z;
+      if (atype == 1) {
+        float rpy[3];
+        euler_from_quat(cq, rpy);
+        rpy[0] += a[3]; rpy[1] += a[4]; rpy[2] += a[5];
+        quat_from_euler(rpy, tq);
+      } else { tq[0] = cq[0] + a[3]; tq[1] = cq[1] + a[4]; tq[2] = cq[2] + a[5]; tq[3] = cq[3] + a[6]; }
+    }
+    if (atype >= 2) {                          // commanded quaternions are used normalised
+      const float nrm = sqrtf(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]);
+      const float inv = nrm > 1e-12f ? 1.0f / nrm : 0.f;
+      if (nrm > 1e-12f) { tq[0] *= inv; tq[1] *= inv; tq[2] *= inv; tq[3] *= inv; } else { tq[0] = tq[1] = tq[2] = 0.f; tq[3] = 1.f; }
+    }
+    ik_world<NJ>(M, q, tp, tq, M.ik_calls, M.ik_iters);
+  }
   const float dt = M.params[P_DT];
 #pragma unroll
   for (int i = 0; i < NJ; i++) {
@@ -275,7 +319,7 @@ PRB_D void ik_action_env(const DevModel& M, float* st /* this env's state */, co
   }
   for (int k = 0; k < M.n_grip; k++) {
     int d = M.grip_dof[k];
-    float t = M.grip_mimic[k] >= 0 ? st[M.grip_mimic[k]] : M.grip_scale[k] * a[6] + M.grip_offset[k];
+    float t = M.grip_mimic[k] >= 0 ? st[M.grip_mimic[k]] : M.grip_scale[k] * grip + M.grip_offset[k];
     st[2 * nd + d] = t;
     st[3 * nd + d] = M.params[P_MOTOR_KP];
     st[4 * nd + d] = M.grip_force[k] * dt;
@@ -288,8 +332,9 @@ __global__ void __launch_bounds__(128) prb_ik_kernel(const DevModel* __restrict_
   if (e >= N) return;
   const DevModel& M = *Mp;
   float* st = state + (size_t)e * M.state_stride;
-  if (M.n_ik == 6) ik_action_env<6>(M, st, action + (size_t)e * 7, target_poses + (size_t)e * 6);
-  else ik_action_env<7>(M, st, action + (size_t)e * 7, target_poses + (size_t)e * 7);
+  const int adim = action_dim_of((int)(M.params[P_ACTION_TYPE] + 0.5f));
+  if (M.n_ik == 6) ik_action_env<6>(M, st, action + (size_t)e * adim, target_poses + (size_t)e * 6);
+  else ik_action_env<7>(M, st, action + (size_t)e * adim, target_poses + (size_t)e * 7);
 }
 
 // ============================================================================ state <-> shared memory

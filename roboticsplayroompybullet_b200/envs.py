@@ -20,7 +20,7 @@ import ctypes
 import numpy as np
 
 from . import lib as _lib
-from .model import ENV_KINDS, load_model
+from .model import ACTION_VARIANTS, ENV_KINDS, action_dim, load_model
 
 OUT_KEYS = ['obs_quat', 'achieved_goal', 'desired_goal', 'controllable_achieved_goal', 'full_positional_state',
             'joints', 'velocity', 'observation', 'gripper_proprioception', 'reward', 'is_success', 'target_poses']
@@ -43,7 +43,7 @@ class VecPlayEnv:
         import torch  # device memory / streams only
         self.torch = torch
         env_id = env_id or self.env_id
-        if env_id not in ENV_KINDS:
+        if env_id not in ENV_KINDS and env_id not in ACTION_VARIANTS:
             raise NotImplementedError(env_id)           # environments.py:376,416,933
         self.env_id = env_id
         self.model = model if model is not None else load_model(env_id)
@@ -71,7 +71,8 @@ class VecPlayEnv:
                         for k in OUT_KEYS}
             self.state_dev = torch.as_tensor(_DevArray(b.state, (N, b.state_stride), self), device=self.device)
         # pinned host staging for the numpy path
-        self._h_action = torch.empty((N, 7), dtype=torch.float32).pin_memory()
+        self.action_dim = action_dim(self.model)
+        self._h_action = torch.empty((N, self.action_dim), dtype=torch.float32).pin_memory()
         self._h_out = torch.empty((self.out_floats,), dtype=torch.float32).pin_memory()
         self._h_views = {}
         off = 0
@@ -81,11 +82,11 @@ class VecPlayEnv:
             off += n
         # gym-like metadata (environments.py:84,108-117)
         self._max_episode_steps = None if m['play'] else 250
-        high = np.array([6, 6, 6, 6, 6, 6, 1], np.float32)
+        high = np.array([m.param('action_high_xyz')] * (self.action_dim - 1) + [m.param('action_high_grip')], np.float32)   # :88-112
         self.action_low, self.action_high = -high, high
         self.play = bool(m['play'])
         self.sparse = sparse
-        self.h2d_bytes_per_step = N * 7 * 4
+        self.h2d_bytes_per_step = N * self.action_dim * 4
         self.d2h_bytes_per_step = self.out_floats * 4
 
     # ------------------------------------------------------------------ helpers
@@ -124,7 +125,7 @@ class VecPlayEnv:
     def step_device(self, action):
         """action: float32 CUDA tensor [N,7].  Returns views of the library's output buffers."""
         a = action.to(self.device, self.torch.float32).contiguous()
-        assert a.shape == (self.num_envs, 7), 'action must be [num_envs, 7]'   # environments.py:956
+        assert a.shape == (self.num_envs, self.action_dim), 'action must be [num_envs, %d]' % self.action_dim   # environments.py:937,956
         self._a_keep = a
         _lib.check(self.L, self._h, self.L.prb_step(self._h, ctypes.c_void_p(a.data_ptr()), self._stream()))
         info = {'is_success': self.dev['is_success'][:, 0], 'target_poses': self.dev['target_poses']}
@@ -153,7 +154,7 @@ class VecPlayEnv:
 
     def step(self, action):
         a = np.asarray(action, np.float32)
-        assert a.shape == (self.num_envs, 7), 'action must be [num_envs, 7]'
+        assert a.shape == (self.num_envs, self.action_dim), 'action must be [num_envs, %d]' % self.action_dim
         self._h_action.numpy()[...] = a
         _lib.check(self.L, self._h, self.L.prb_step_host(self._h, ctypes.c_void_p(self._h_action.data_ptr()),
                                                         ctypes.c_void_p(self._h_out.data_ptr()), self._stream()))
@@ -275,7 +276,29 @@ class UR5PlayAbsRPY1Obj(VecPlayEnv):
     env_id = 'UR5PlayAbsRPY1Obj-v0'
 
 
-_REGISTRY = {c.env_id: c for c in (UR5Reach, pandaPick, UR5PlayAbsRPY1Obj)}
+# the other UR5 playroom ids: same world, other action decoder (envList.py:101-140, environments.py:915-981)
+class UR5Play1Obj(VecPlayEnv):
+    env_id = 'UR5Play1Obj-v0'               # absolute_quat, 8-D action
+
+
+class UR5PlayRel1Obj(VecPlayEnv):
+    env_id = 'UR5PlayRel1Obj-v0'            # relative_quat, 8-D action
+
+
+class UR5PlayRelRPY1Obj(VecPlayEnv):
+    env_id = 'UR5PlayRelRPY1Obj-v0'         # relative_rpy
+
+
+class UR5PlayAbsJoints1Obj(VecPlayEnv):
+    env_id = 'UR5PlayAbsJoints1Obj-v0'      # absolute_joints
+
+
+class UR5PlayRelJoints1Obj(VecPlayEnv):
+    env_id = 'UR5PlayRelJoints1Obj-v0'      # relative_joints
+
+
+_REGISTRY = {c.env_id: c for c in (UR5Reach, pandaPick, UR5PlayAbsRPY1Obj, UR5Play1Obj, UR5PlayRel1Obj, UR5PlayRelRPY1Obj,
+                                   UR5PlayAbsJoints1Obj, UR5PlayRelJoints1Obj)}
 
 
 def make(env_id, num_envs=1, **kw):

@@ -75,7 +75,7 @@ PARAM_NAMES = [
     'arm_force', 'sparse_thresh', 'reset_z_offset', 'default_motor_impulse', 'motor_kp', 'motor_kd',
     'limit_max_impulse', 'gear_ratio', 'gear_erp', 'gear_max_impulse', 'max_coord_vel',
     'action_high_xyz', 'action_high_grip', 'obj_reset_dz', 'arm_lin_damp', 'arm_ang_damp',
-    'contact_breaking', 'reserved',
+    'contact_breaking', 'action_type',
 ]
 N_PARAMS = len(PARAM_NAMES)
 
@@ -148,7 +148,34 @@ def asset_path(env_id):
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'assets', env_id + '.npz')
 
 
+# action decoders of the reference (environments.py:915-981); value of the `action_type` parameter
+ACTION_TYPES = {'absolute_rpy': 0, 'relative_rpy': 1, 'absolute_quat': 2, 'relative_quat': 3,
+                'absolute_joints': 4, 'relative_joints': 5}
+# env ids that differ from a compiled asset only by the action decoder (envList.py:101-140): base asset,
+# action type, bound of the non-gripper action entries (environments.py:88-112)
+ACTION_VARIANTS = {
+    'UR5Play1Obj-v0': ('UR5PlayAbsRPY1Obj-v0', 'absolute_quat', 1.0),
+    'UR5PlayRel1Obj-v0': ('UR5PlayAbsRPY1Obj-v0', 'relative_quat', 1.0),
+    'UR5PlayRelRPY1Obj-v0': ('UR5PlayAbsRPY1Obj-v0', 'relative_rpy', 1.0),
+    'UR5PlayAbsJoints1Obj-v0': ('UR5PlayAbsRPY1Obj-v0', 'absolute_joints', 6.0),
+    'UR5PlayRelJoints1Obj-v0': ('UR5PlayAbsRPY1Obj-v0', 'relative_joints', 1.0),
+}
+
+
+def action_dim(model):
+    """Length of one action: 8 for the quaternion decoders (xyz + quat + gripper), else 7."""
+    return 8 if int(round(model.param('action_type'))) in (2, 3) else 7
+
+
 def load_model(env_id):
+    if env_id in ACTION_VARIANTS:
+        base, atype, high = ACTION_VARIANTS[env_id]
+        m = load_model(base)
+        prm = m.d['params'].copy()
+        prm[PARAM_NAMES.index('action_type')] = float(ACTION_TYPES[atype])
+        prm[PARAM_NAMES.index('action_high_xyz')] = high
+        m.d['params'] = prm
+        return m
     p = asset_path(env_id)
     if not os.path.exists(p):
         raise FileNotFoundError(

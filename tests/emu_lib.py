@@ -64,7 +64,8 @@ class EmuSim:
 
     def step(self, action):
         self._sel()
-        a = np.ascontiguousarray(action, np.float32).reshape(self.N, 7)
+        from roboticsplayroompybullet_b200.model import action_dim
+        a = np.ascontiguousarray(action, np.float32).reshape(self.N, action_dim(self.m))
         self.L.emu_step(self.state.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p),
                         ctypes.byref(self.O), self.N)
         return {k: v.copy() for k, v in self.out.items()}
@@ -86,7 +87,8 @@ class EmuSim:
 
     def ik(self, action):
         self._sel()
-        a = np.ascontiguousarray(action, np.float32).reshape(self.N, 7)
+        from roboticsplayroompybullet_b200.model import action_dim
+        a = np.ascontiguousarray(action, np.float32).reshape(self.N, action_dim(self.m))
         t = np.zeros((self.N, self.m['n_ik']), np.float32)
         self.L.emu_ik(self.state.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p),
                       t.ctypes.data_as(ctypes.c_void_p), self.N)

@@ -219,3 +219,40 @@ def test_step_parity_scripted_steady_state():
     assert total_bad <= int(0.12 * 3 * n), total_bad
     assert worst_all < 2e-2, worst_all
     env.close()
+
+
+@pytest.mark.parametrize('env_id', ['UR5Play1Obj-v0', 'UR5PlayRel1Obj-v0', 'UR5PlayRelRPY1Obj-v0',
+                                    'UR5PlayAbsJoints1Obj-v0', 'UR5PlayRelJoints1Obj-v0'])
+def test_action_decoder_variants(env_id):
+    """The other UR5 playroom ids (same world, other action decoder: environments.py:915-981) against the oracle
+    from identical states: decoded motor targets and the one-step poses."""
+    from roboticsplayroompybullet_b200.model import load_model, action_dim
+    from oracle.oracle import Oracle
+    n = 32
+    env = _mk(env_id, n, seed=17)
+    obs = env.reset()
+    m = load_model(env_id)
+    A = action_dim(m)
+    assert env.action_dim == A and env.action_high.shape == (A,)
+    rng = np.random.default_rng(4)
+    total_bad = 0
+    for step in range(3):
+        st = env.get_state()
+        ee = obs['obs_quat'][:, :7]
+        if 'Joints' in env_id:
+            a = np.concatenate([rng.uniform(-0.05, 0.05, (n, 6)) + (st[:, :6] if 'Abs' in env_id else 0), rng.uniform(-1, 1, (n, 1))], 1)
+        elif A == 8:
+            rel = 'Rel' in env_id
+            a = np.concatenate([(0 if rel else ee[:, :3]) + rng.uniform(-0.03, 0.03, (n, 3)),
+                                (0 if rel else ee[:, 3:7]) + rng.uniform(-0.05, 0.05, (n, 4)), rng.uniform(-1, 1, (n, 1))], 1)
+        else:
+            a = np.concatenate([rng.uniform(-0.03, 0.03, (n, 3)), rng.uniform(-0.1, 0.1, (n, 3)), rng.uniform(-1, 1, (n, 1))], 1)
+        a = a.astype(np.float32)
+        obs, r, done, info = env.step(a)
+        outs = [oracle_step_from(m, st[i], a[i], Oracle)[0] for i in range(n)]
+        tp = np.array([o['target_poses'] for o in outs])
+        assert np.abs(info['target_poses'] - tp).max() < 2e-4
+        bad, worst = compare_step(obs, r, info, outs)
+        total_bad += bad
+    assert total_bad <= 4, total_bad
+    env.close()
