@@ -90,10 +90,12 @@
 #endif
 #define PGS_G_LW 2       // arm-island kernel: an env owns 4 shared-memory columns (8 envs per warp)
 #define PGS_NCLASS 4      // size classes of the arm-island kernel (by the q count of region 0): rows of 4 q per env
+#ifndef PGS_ROWS_G0       // (overridable: the CPU tests build a variant with tiny stages to exercise the read-in-place path)
 #define PGS_ROWS_G0 56   // class 0: 224 q per env, 7 blocks per SM (56 envs)
 #define PGS_ROWS_G1 80   // class 1: 320 q per env, 5 blocks per SM (40 envs)
 #define PGS_ROWS_G2 104  // class 2: 416 q per env, 4 blocks per SM (32 envs)
 #define PGS_ROWS_G3 216  // class 3: 864 q per env (larger islands read the rest in place), 2 blocks per SM (16 envs)
+#endif
 #define PGS_ROWS_GMAX PGS_ROWS_G3
 PRB_HD int pgs_class_rows(int cls) { return cls == 0 ? PGS_ROWS_G0 : (cls == 1 ? PGS_ROWS_G1 : (cls == 2 ? PGS_ROWS_G2 : PGS_ROWS_G3)); }
 #define PGS_MAXJROW_J ((PGS_STAGE_J - T_JROW) * 4 / 5)     // njr + ceil(njr / 4) <= PGS_STAGE_J - T_JROW

@@ -25,6 +25,19 @@ def out_dims(m):
             'target_poses': m['n_ik']}
 
 
+def lib_variant(tag, defines):
+    """A second build of the emulated kernels with other compile-time constants (e.g. tiny solver stages)."""
+    so = os.path.join(_HERE, 'libprb_emu_%s.so' % tag)
+    deps = [os.path.join(_HERE, f) for f in ('prb_emu.cpp', 'cuda_emu.h')] + \
+           [os.path.join(_SRC, f) for f in ('prb_kernels.cuh', 'prb_stream.cuh', 'prb_device.h', 'prb_convert.h')]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-U_FORTIFY_SOURCE', '-Wno-unknown-pragmas'] +
+                              ['-D%s' % d for d in defines] + ['-o', so, os.path.join(_HERE, 'prb_emu.cpp')])
+    L = ctypes.CDLL(so)
+    L.emu_error.restype = ctypes.c_char_p
+    return L
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -40,9 +53,9 @@ def lib():
 
 
 class EmuSim:
-    def __init__(self, model, N, seed=1234, env_offset=0):
+    def __init__(self, model, N, seed=1234, env_offset=0, library=None):
         self.m = model
-        self.L = lib()
+        self.L = library if library is not None else lib()
         self.ms = model.as_struct()
         if self.L.emu_set_model(ctypes.byref(self.ms)) != 0:
             raise RuntimeError(self.L.emu_error().decode())

@@ -146,3 +146,25 @@ def test_emu_action_decoders_match_oracle(env_id):
         assert np.abs(de['obs_quat'][0][:7] - do['obs_quat'][:7]).max() < 2e-5
         # the command moved the arm the way its decoder says
         assert np.abs(do['target_poses'] - o.state[:6]).max() < 0.3
+
+
+def test_emu_records_read_in_place_when_stage_is_small():
+    """Capacity only costs speed, never contacts: with tiny solver stages (arm-island classes of 112-160 q, free-body
+    stage of 16 q) most records are read from the stream in place; the grasp sequence must give the SAME states as
+    the normal build, bit for bit."""
+    from emu_lib import lib_variant
+    small = lib_variant('smallstage', ['PGS_ROWS_G0=28', 'PGS_ROWS_G1=32', 'PGS_ROWS_G2=36', 'PGS_ROWS_G3=40', 'PGS_STAGE_F=16'])
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    a_sim, b_sim, o = EmuSim(m, 1, seed=3), EmuSim(m, 1, seed=3, library=small), Oracle(m, seed=3)
+    o.reset()
+    blk = o.state[60:63].copy()
+    act = lambda z, g: np.array([blk[0], blk[1], z, 0, 0, 0, g])
+    seq = [act(-0.01, -1)] * 14 + [act(-0.01, 1)] * 8 + [act(0.15, 1)] * 4
+    a_sim.state[0, :o.state_dim] = o.state.astype(np.float32)
+    b_sim.state[0, :o.state_dim] = o.state.astype(np.float32)
+    for a in seq:
+        da, db = a_sim.step(a[None]), b_sim.step(a[None])
+        assert np.array_equal(a_sim.state, b_sim.state)
+        for k in da:
+            assert np.array_equal(da[k], db[k]), k
+    assert a_sim.state[0, 62] > 0.05            # the block was grasped and lifted on the way

@@ -256,3 +256,21 @@ def test_action_decoder_variants(env_id):
         total_bad += bad
     assert total_bad <= 4, total_bad
     env.close()
+
+
+def test_batched_stepping_bit_identical(monkeypatch):
+    """PRB_BATCHES=2 steps the envs as two pipelined stream chains; envs are independent, so the results must be
+    bit-identical to the single-chain default."""
+    n = 96
+    act = random_actions(np.random.default_rng(8), n, 'UR5PlayAbsRPY1Obj-v0')
+    outs = []
+    for nb in ('1', '2'):
+        monkeypatch.setenv('PRB_BATCHES', nb)
+        env = _mk('UR5PlayAbsRPY1Obj-v0', n, seed=4)
+        env.reset()
+        for _ in range(3):
+            obs, r, _, info = env.step(act)
+        outs.append((obs['obs_quat'].copy(), r.copy(), info['target_poses'].copy(), env.get_state()))
+        env.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
