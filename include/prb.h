@@ -11,7 +11,8 @@
  * ABI); prb_last_error() gives the message.  All `*_dev` pointers are device pointers on the
  * handle's GPU; calls are asynchronous on the given CUDA stream (a cudaStream_t passed as
  * void*; NULL = legacy default stream) and serialised per handle; one handle per GPU/process.
- * No host synchronisation happens inside prb_step / prb_reset / prb_observe.
+ * No host synchronisation happens inside prb_step / prb_observe / prb_substeps / prb_set_goal; prb_reset
+ * synchronises the stream (once per reset round, see below), like the reference's reset() it replaces.
  */
 #ifndef PRB_H
 #define PRB_H
@@ -72,8 +73,11 @@ int prb_destroy(prb_handle* h);
 /* playEnv.reset() (environments.py:173-187 -> instance.reset :599-603): for every env whose
  * mask byte is non-zero (NULL = all) re-seat objects, settle 100 substeps, reset the arm through
  * one IK call, sample a goal, and repeat while the sampled state already satisfies the goal.
- * Refreshes all output buffers of the reset envs. */
+ * Refreshes all output buffers of the reset envs.  Runs as rounds of {seat objects, settle on the masked step
+ * pipeline, finish} over the envs still pending and reads one device counter per round (synchronous on `stream`);
+ * prb_reset_rounds returns the number of rounds the most recent call needed. */
 int prb_reset(prb_handle* h, const uint8_t* mask_dev, void* stream);
+int prb_reset_rounds(prb_handle* h);
 
 /* playEnv.reset_goal_pos(goal) (environments.py:190-191, 492-501): goal_dev is [N, goal_dim]. */
 int prb_set_goal(prb_handle* h, const float* goal_dev, const uint8_t* mask_dev, void* stream);
@@ -119,8 +123,9 @@ int prb_last_tier_ms(prb_handle* h, float* setup_ms, float* pgs_ms);
 
 /* Number of kernels launched by this handle since creation (bench.py reports it). */
 int64_t prb_launch_count(prb_handle* h);
-/* Env-steps (since creation) in which a contact had to be dropped because the per-env on-chip
- * capacity (contacts, packed Jacobians or one island's Delassus block) was exceeded; synchronous. */
+/* Env steps (since creation; a reset counts as one) in which a contact had to be dropped because the per-env
+ * capacity (overlapping pairs, contacts, joint rows) was exceeded: an env is counted once per step however many of
+ * its 12 substeps dropped one.  Synchronises the device. */
 int64_t prb_overflow_count(prb_handle* h);
 /* Per-env maxima over the last env step of the on-chip resources used: [N,4] int32 =
  * {Delassus floats, contacts, packed-Jacobian floats, sweep units}; synchronous; for sizing reports. */

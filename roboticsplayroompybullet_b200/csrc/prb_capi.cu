@@ -9,7 +9,7 @@
 #include "prb_convert.h"
 #include <stdlib.h>
 #include <string.h>
-#include "prb_stream.cuh"
+#include "prb_reset.cuh"
 
 struct prb_handle {
   DevModel hm;
@@ -43,7 +43,13 @@ struct prb_handle {
   cudaEvent_t ev_begin = nullptr;
   int smem = 0, regs = 0;          // setup kernel (reported)
   int regs_pgs = 0;
-  int smem_fused = 0, smem_reset = 0;
+  int smem_fused = 0;
+  // reset rounds (prb_reset.cuh)
+  unsigned char* pending = nullptr;
+  int* reset_ctl = nullptr;
+  int* n_pending = nullptr;        // device counter
+  int* n_pending_host = nullptr;   // pinned
+  int reset_rounds = 0;            // rounds of the most recent prb_reset
   int timing = 0;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t evk[64];             // per-launch events of the most recent step (timing mode)
@@ -52,6 +58,18 @@ struct prb_handle {
 };
 
 static std::string g_err;  // errors before a handle exists
+
+// Every entry point runs on the handle's device and leaves the caller's current device untouched
+// (several handles on different GPUs may live in one process).
+struct DevGuard {
+  int prev = -1;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 #define CK(h, call)                                                              \
   do {                                                                           \
@@ -66,8 +84,8 @@ static std::string g_err;  // errors before a handle exists
 // (integrate previous solution + build rows) and one thread-per-env solver launch; a final setup
 // launch integrates the last solution and writes the observation.  No host synchronisation.
 template <int ND>
-static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
-  if (h->fused) {
+static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s, const unsigned char* active = nullptr) {
+  if (h->fused && active == nullptr) {
     dim3 gl((h->N + CfgL::WPB - 1) / CfgL::WPB), bl(32 * CfgL::WPB);
     prb_step_kernel<ND, CfgL><<<gl, bl, h->smem_fused, s>>>(h->dm, h->state, h->O, nullptr, nullptr, nullptr, nullptr, h->N, nsub, observe);
     h->launches++;
@@ -102,7 +120,8 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
       if (flags == 0) break;
       if (timed && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], ms));
       if (i < nsub) CK(h, cudaMemsetAsync(B.heavy_cnt, 0, 4 * PGS_NCLASS * sizeof(int), ms));
-      prb_setup_kernel<ND><<<gs, bs, h->smem, ms>>>(h->dm, state, sbuf, B.O, B.n, flags, B.heavy_list, B.heavy_cnt);
+      const unsigned char* act = active ? active + B.off : nullptr;
+      prb_setup_kernel<ND><<<gs, bs, h->smem, ms>>>(h->dm, state, sbuf, B.O, B.n, flags, B.heavy_list, B.heavy_cnt, act);
       h->launches++;
       if (i < nsub) {
         if (timed && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], ms));
@@ -116,8 +135,8 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
                                                                          pgs_class_rows(k));
           CK(h, cudaEventRecord(B.ev_join[k], B.side[k]));
         }
-        prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, ms>>>(h->dm, sbuf, B.n);
-        if (h->hm.n_free > 0) prb_pgs_free_kernel<<<gf, bp, PGS_SMEM_F, ms>>>(h->dm, sbuf, B.n);
+        prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, ms>>>(h->dm, sbuf, B.n, act);
+        if (h->hm.n_free > 0) prb_pgs_free_kernel<<<gf, bp, PGS_SMEM_F, ms>>>(h->dm, sbuf, B.n, act);
         for (int k = 0; k < PGS_NCLASS; k++) CK(h, cudaStreamWaitEvent(ms, B.ev_join[k], 0));
         h->launches += (h->hm.n_free > 0 ? 2 : 1) + PGS_NCLASS;
       }
@@ -128,18 +147,17 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
   CK(h, cudaGetLastError());
   return PRB_OK;
 }
-static int run_step(prb_handle* h, int nsub, int observe, cudaStream_t s) {
-  return h->hm.nd == 12 ? launch_step<12>(h, nsub, observe, s) : launch_step<9>(h, nsub, observe, s);
+static int run_step(prb_handle* h, int nsub, int observe, cudaStream_t s, const unsigned char* active = nullptr) {
+  return h->hm.nd == 12 ? launch_step<12>(h, nsub, observe, s, active) : launch_step<9>(h, nsub, observe, s, active);
 }
 
 template <int ND>
 static int setup_kernels(prb_handle* h) {
   h->smem = SetupCfg::WPB * (int)sizeof(SetupMemT<SetupCfg>);
   h->smem_fused = CfgL::WPB * (int)sizeof(WarpMemT<CfgL>);
-  h->smem_reset = (int)sizeof(WarpMemT<CfgL>);
   CK(h, cudaFuncSetAttribute(prb_setup_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
   CK(h, cudaFuncSetAttribute(prb_step_kernel<ND, CfgL>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_fused));
-  CK(h, cudaFuncSetAttribute(prb_reset_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_reset));
+  CK(h, cudaFuncSetAttribute(prb_reset_finish_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
   cudaFuncAttributes fa;
   CK(h, cudaFuncGetAttributes(&fa, prb_setup_kernel<ND>));
   h->regs = fa.numRegs;
@@ -151,6 +169,32 @@ static int setup_kernels(prb_handle* h) {
   CK(h, cudaFuncSetAttribute(prb_pgs_free_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(h, cudaFuncGetAttributes(&fa, prb_pgs_arm_kernel<ND>));
   h->regs_pgs = fa.numRegs;
+  return PRB_OK;
+}
+
+// Rounds of {seat objects, settle on the masked step pipeline, finish} until no env is pending (prb_reset.cuh).
+// Synchronises the stream once per round (one 4-byte read), like the reference's reset, which is synchronous.
+template <int ND>
+static int reset_rounds(prb_handle* h, const uint8_t* mask_dev, cudaStream_t s) {
+  const int N = h->N;
+  const int max_rounds = RESET_MAX_ATTEMPTS * RESET_MAX_TRIES;
+  dim3 gf((N + SetupCfg::WPB - 1) / SetupCfg::WPB), bf(32 * SetupCfg::WPB);
+  h->reset_rounds = 0;
+  for (int round = 0; round < max_rounds; round++) {
+    prb_reset_place_kernel<<<(N + 127) / 128, 128, 0, s>>>(h->dm, h->state, h->reset_ctl, mask_dev, h->pending, N, h->seed, h->env_offset, round == 0);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    int rc = launch_step<ND>(h, h->hm.settle_steps, 0, s, h->pending);
+    if (rc != PRB_OK) return rc;
+    CK(h, cudaMemsetAsync(h->n_pending, 0, sizeof(int), s));
+    prb_reset_finish_kernel<ND><<<gf, bf, h->smem, s>>>(h->dm, h->state, h->O, h->reset_ctl, h->pending, h->n_pending, N, h->seed, h->env_offset);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(h->n_pending_host, h->n_pending, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(h, cudaStreamSynchronize(s));
+    h->reset_rounds = round + 1;
+    if (*h->n_pending_host == 0) break;
+  }
   return PRB_OK;
 }
 
@@ -173,7 +217,8 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
   if (h->hm.nd != 12 && h->hm.nd != 9) { g_err = "prb_create: arm must have 12 (UR5+Robotiq) or 9 (Panda) DoF"; delete h; return PRB_ERR_INVALID; }
   h->N = cfg->num_envs; h->device = cfg->device; h->env_offset = (unsigned)cfg->env_offset; h->seed = cfg->seed;
   *out = h;
-  CK(h, cudaSetDevice(h->device));
+  if (h->device < 0 || h->device >= ndev) { h->err = "prb_create: device ordinal out of range"; return PRB_ERR_INVALID; }
+  DevGuard guard(h->device);
   CK(h, cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device));
   CK(h, cudaMalloc(&h->dm, sizeof(DevModel)));
   CK(h, cudaMemcpy(h->dm, &h->hm, sizeof(DevModel), cudaMemcpyHostToDevice));
@@ -191,6 +236,14 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
   CK(h, cudaMemset(h->O.overflow, 0, sizeof(unsigned long long)));
   CK(h, cudaMalloc(&h->O.dbg, sizeof(int) * 4 * N));
   CK(h, cudaMemset(h->O.dbg, 0, sizeof(int) * 4 * N));
+  CK(h, cudaMalloc(&h->O.ovf_env, N));
+  CK(h, cudaMemset(h->O.ovf_env, 0, N));
+  CK(h, cudaMalloc(&h->pending, N));
+  CK(h, cudaMemset(h->pending, 0, N));
+  CK(h, cudaMalloc(&h->reset_ctl, sizeof(int) * 2 * N));
+  CK(h, cudaMemset(h->reset_ctl, 0, sizeof(int) * 2 * N));
+  CK(h, cudaMalloc(&h->n_pending, sizeof(int)));
+  CK(h, cudaMallocHost(&h->n_pending_host, sizeof(int)));
   float** slots[12] = {&h->O.obs_quat, &h->O.achieved_goal, &h->O.desired_goal, &h->O.cag, &h->O.fps, &h->O.joints,
                        &h->O.velocity, &h->O.observation, &h->O.proprio, &h->O.reward, &h->O.success, &h->O.target_poses};
   int64_t off = 0;
@@ -200,7 +253,7 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
     h->fused = (p && strcmp(p, "fused") == 0) ? 1 : 0;
 
   }
-  if (!h->fused) {
+  {                                            // the split pipeline's buffers are always needed (reset runs on it)
     const size_t sb_bytes = sbuf_bytes(N);   // whole 32-env groups + prefetch slack
     CK(h, cudaMalloc(&h->sbuf, sb_bytes));
     CK(h, cudaMemset(h->sbuf, 0, sb_bytes));
@@ -245,8 +298,12 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
 
 int prb_destroy(prb_handle* h) {
   if (!h) return PRB_ERR_INVALID;
-  cudaSetDevice(h->device);
+  {
+  DevGuard guard(h->device);
+  cudaDeviceSynchronize();
   cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->sbuf);
+  cudaFree(h->O.ovf_env); cudaFree(h->pending); cudaFree(h->reset_ctl); cudaFree(h->n_pending);
+  if (h->n_pending_host) cudaFreeHost(h->n_pending_host);
   for (int bi = 0; bi < 4; bi++) {
     prb_handle::Batch& B = h->batch[bi];
     for (int k = 0; k < PGS_NCLASS; k++) {
@@ -259,6 +316,9 @@ int prb_destroy(prb_handle* h) {
     cudaFree(B.heavy_list); cudaFree(B.heavy_cnt);
   }
   if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+  for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->ev[0]) for (int i = 0; i < 64; i++) cudaEventDestroy(h->evk[i]);
+  }
   delete h;
   return PRB_OK;
 }
@@ -278,6 +338,7 @@ int prb_get_buffers(prb_handle* h, prb_buffers* b) {
 
 int prb_step(prb_handle* h, const float* action_dev, void* stream) {
   if (!h || !action_dev) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   if (h->timing) CK(h, cudaEventRecord(h->ev[0], s));
   prb_ik_kernel<<<(h->N + 127) / 128, 128, 0, s>>>(h->dm, h->state, action_dev, h->O.target_poses, h->N);
@@ -291,6 +352,7 @@ int prb_step(prb_handle* h, const float* action_dev, void* stream) {
 
 int prb_enable_kernel_timing(prb_handle* h, int32_t enable) {
   if (!h) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   if (enable && !h->ev[0]) {
     for (int i = 0; i < 3; i++) CK(h, cudaEventCreate(&h->ev[i]));
     for (int i = 0; i < 64; i++) CK(h, cudaEventCreate(&h->evk[i]));
@@ -301,6 +363,7 @@ int prb_enable_kernel_timing(prb_handle* h, int32_t enable) {
 
 int prb_last_kernel_ms(prb_handle* h, float* ik_ms, float* step_ms) {
   if (!h || !h->ev[0]) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   CK(h, cudaEventSynchronize(h->ev[2]));
   if (ik_ms) CK(h, cudaEventElapsedTime(ik_ms, h->ev[0], h->ev[1]));
   if (step_ms) CK(h, cudaEventElapsedTime(step_ms, h->ev[1], h->ev[2]));
@@ -309,6 +372,7 @@ int prb_last_kernel_ms(prb_handle* h, float* ik_ms, float* step_ms) {
 
 int prb_last_tier_ms(prb_handle* h, float* setup_ms, float* pgs_ms) {
   if (!h || !h->ev[0]) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   CK(h, cudaEventSynchronize(h->ev[2]));
   float a = 0.f, b = 0.f;
   // per-launch events alternate setup, solver, setup, solver, ..., setup, end
@@ -324,24 +388,24 @@ int prb_last_tier_ms(prb_handle* h, float* setup_ms, float* pgs_ms) {
 
 int prb_observe(prb_handle* h, void* stream) {
   if (!h) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   return run_step(h, 0, 1, (cudaStream_t)stream);
 }
 
 int prb_substeps(prb_handle* h, int32_t n, void* stream) {
   if (!h || n < 0) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   return run_step(h, n, 0, (cudaStream_t)stream);
 }
 
 int prb_reset(prb_handle* h, const uint8_t* mask_dev, void* stream) {
   if (!h) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid(h->N), block(32);
-  if (h->hm.nd == 12) prb_reset_kernel<12><<<grid, block, h->smem_reset, s>>>(h->dm, h->state, h->O, mask_dev, h->N, h->seed, h->env_offset);
-  else prb_reset_kernel<9><<<grid, block, h->smem_reset, s>>>(h->dm, h->state, h->O, mask_dev, h->N, h->seed, h->env_offset);
-  h->launches++;
-  CK(h, cudaGetLastError());
-  return PRB_OK;
+  return h->hm.nd == 12 ? reset_rounds<12>(h, mask_dev, s) : reset_rounds<9>(h, mask_dev, s);
 }
+
+int prb_reset_rounds(prb_handle* h) { return h ? h->reset_rounds : -1; }
 
 __global__ void prb_set_goal_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state, const float* __restrict__ goal,
                                     const unsigned char* __restrict__ mask, int N) {
@@ -355,6 +419,7 @@ __global__ void prb_set_goal_kernel(const DevModel* __restrict__ Mp, float* __re
 
 int prb_set_goal(prb_handle* h, const float* goal_dev, const uint8_t* mask_dev, void* stream) {
   if (!h || !goal_dev) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   int n = h->N * h->hm.goal_dim;
   prb_set_goal_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->dm, h->state, goal_dev, mask_dev, h->N);
   h->launches++;
@@ -364,6 +429,7 @@ int prb_set_goal(prb_handle* h, const float* goal_dev, const uint8_t* mask_dev, 
 
 int prb_compute_reward(prb_handle* h, const float* ag_dev, const float* dg_dev, int64_t B, float* out_dev, void* stream) {
   if (!h || !ag_dev || !dg_dev || !out_dev || B < 0) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   if (B == 0) return PRB_OK;
   prb_reward_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->dm, ag_dev, dg_dev, (long long)B, out_dev);
   h->launches++;
@@ -373,6 +439,7 @@ int prb_compute_reward(prb_handle* h, const float* ag_dev, const float* dg_dev, 
 
 int prb_get_state(prb_handle* h, float* host_out) {
   if (!h || !host_out) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   const DevModel& M = h->hm;
   CK(h, cudaDeviceSynchronize());
   CK(h, cudaMemcpy2D(host_out, sizeof(float) * M.state_dim, h->state, sizeof(float) * M.state_stride,
@@ -382,6 +449,7 @@ int prb_get_state(prb_handle* h, float* host_out) {
 
 int prb_set_state(prb_handle* h, const float* host_in) {
   if (!h || !host_in) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   const DevModel& M = h->hm;
   CK(h, cudaDeviceSynchronize());
   CK(h, cudaMemcpy2D(h->state, sizeof(float) * M.state_stride, host_in, sizeof(float) * M.state_dim,
@@ -391,6 +459,7 @@ int prb_set_state(prb_handle* h, const float* host_in) {
 
 int prb_step_host(prb_handle* h, const float* action_host, float* out_host, void* stream) {
   if (!h || !action_host || !out_host) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   const int adim = action_dim_of((int)(h->hm.params[P_ACTION_TYPE] + 0.5f));
   CK(h, cudaMemcpyAsync(h->action_stage, action_host, sizeof(float) * h->N * adim, cudaMemcpyHostToDevice, s));
@@ -405,6 +474,7 @@ int64_t prb_launch_count(prb_handle* h) { return h ? h->launches : 0; }
 
 int prb_debug_usage(prb_handle* h, int32_t* host_out /* [N,4] */) {
   if (!h || !host_out) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
   CK(h, cudaDeviceSynchronize());
   CK(h, cudaMemcpy(host_out, h->O.dbg, sizeof(int) * 4 * h->N, cudaMemcpyDeviceToHost));
   return PRB_OK;
@@ -412,7 +482,9 @@ int prb_debug_usage(prb_handle* h, int32_t* host_out /* [N,4] */) {
 
 int64_t prb_overflow_count(prb_handle* h) {
   if (!h) return -1;
+  DevGuard guard(h->device);
   unsigned long long v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;      // orders the read against non-blocking user streams
   if (cudaMemcpy(&v, h->O.overflow, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (int64_t)v;
 }

@@ -78,8 +78,9 @@ struct DevModel {
 struct DevOut {
   float *obs_quat, *achieved_goal, *desired_goal, *cag, *fps, *joints, *velocity, *observation;
   float *proprio, *reward, *success, *target_poses;
-  unsigned long long* overflow;
-  int* dbg;                       // optional [N,4] per-env-step maxima: A floats, contacts, pool floats, units   // [1] env-steps in which some contact had to be dropped (capacity)
+  unsigned long long* overflow;   // env steps (since creation) in which a contact had to be dropped (capacity)
+  unsigned char* ovf_env;         // optional [N]: env dropped a contact since its last observation (counted once per env step)
+  int* dbg;                       // optional [N,4] per-env-step maxima: A floats, contacts, pool floats, units
 };
 
 // ------------------------------------------------------------------ vector algebra

@@ -14,7 +14,8 @@
 //                        DoF in the projected-Gauss-Seidel sweeps (J.dv by warp-shuffle
 //                        reduction).  Ends with the fused observation/reward write.  Reference
 //                        path: environments.py:209-214 (runSimulation, calc_state, reward).
-//   * prb_reset_kernel   one WARP per env, masked: environments.py:173-187, 492-603.
+//   * reset              rounds of {seat objects, settle on the masked step pipeline, finish}: prb_reset.cuh
+//                        (environments.py:173-187, 492-603).
 //   * prb_reward_kernel  stateless batched compute_reward (relabelling): environments.py:278-304,
 //                        playRewardFunc.py:66-77.
 //
@@ -1734,89 +1735,6 @@ __global__ void __launch_bounds__(32 * CFG::WPB, CFG::MINBLOCKS) prb_step_kernel
   if (observe) phase_observe(M, W, lane, O, (size_t)e, true);
   __syncwarp();
   if (lane == 0 && W.overflow && O.overflow) atomicAdd(O.overflow, 1ull);
-  store_state(M, W, st, lane);
-}
-
-// ============================================================================ reset kernel (warp per env, masked)
-template <int ND>
-__global__ void __launch_bounds__(32) prb_reset_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
-                                                                  DevOut O, const unsigned char* __restrict__ mask, int N,
-                                                                  unsigned long long seed, unsigned env_offset) {
-  typedef WarpMemT<CfgL> WM;
-  PRB_SMEM_DECL;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int e = blockIdx.x + wib;
-  if (e >= N) return;
-  if (mask != nullptr && mask[e] == 0) return;
-  const DevModel& M = *Mp;
-  WM& W = wm[wib];
-  float* st = state + (size_t)e * M.state_stride;
-  load_state(M, W, st, lane);
-  if (lane == 0) W.overflow = 0;
-  const LaneMap lm = make_lanemap(M, lane);
-  const int nobj = M.n_free > 0 ? 1 : 0;
-  float r = 0.f;
-  for (int guard = 0; guard < 16 && r > -1.f; guard++) {
-    const uint32_t attempt = (uint32_t)W.reset_count;
-    __syncwarp();
-    if (lane == 0) W.reset_count += 1.0f;
-    float u[4];
-    // reset_object_pos (environments.py:519-556)
-    for (int t = 0; t < 4; t++) {
-      __syncwarp();
-      if (lane == 0) {
-        if (M.play) {
-          for (int k = 0; k < 3; k++) { W.fpos[1][k] = M.free_pos0[1][k]; W.fvel[1][k] = 0.f; W.fang[1][k] = 0.f; }
-          for (int k = 0; k < 4; k++) W.fquat[1][k] = M.free_quat0[1][k];
-          for (int s = 0; s < M.n_slide; s++) { W.sq[s] = 0.f; W.sqd[s] = 0.f; }
-        }
-        if (nobj) {
-          rng4(seed, env_offset + (uint32_t)e, attempt, (uint32_t)t, u);
-          for (int k = 0; k < 3; k++) { W.fpos[0][k] = M.obj_lo[k] + (M.obj_hi[k] - M.obj_lo[k]) * u[k]; W.fvel[0][k] = 0.f; W.fang[0][k] = 0.f; }
-          W.fpos[0][2] += M.params[P_OBJ_RESET_DZ];
-          W.fquat[0][0] = 0.f; W.fquat[0][1] = 0.f; W.fquat[0][2] = 0.7071f; W.fquat[0][3] = 0.7071f;
-        }
-      }
-      __syncwarp();
-      for (int i = 0; i < M.settle_steps; i++) substep<ND>(M, W, lane, lm);
-      bool oob = false;
-      if (nobj) for (int k = 0; k < 3; k++) if (W.fpos[0][k] > M.env_hi[k]) oob = true;
-      if (!oob) break;   // uniform: every lane reads the same shared values
-    }
-    // reset_arm (environments.py:575-596): rest pose -> one IK call on the live arm -> hard reset of joints [0:6]
-    __syncwarp();
-    if (lane == 0) {
-      rng4(seed, env_offset + (uint32_t)e, attempt, 4u, u);
-      float np_[3];
-      for (int k = 0; k < 3; k++) np_[k] = M.goal_lo[k] + (M.goal_hi[k] - M.goal_lo[k]) * u[k];
-      np_[2] += M.params[P_RESET_Z_OFFSET];
-      float qq[7];
-      for (int i = 0; i < M.n_ik; i++) { qq[i] = M.rest[i]; W.q[i] = M.rest[i]; W.qd[i] = 0.f; }
-      if (M.arm_kind == 1) { W.q[M.n_ik] = 0.f; W.qd[M.n_ik] = 0.f; }
-      if (M.n_ik == 6) ik_world<6>(M, qq, np_, M.default_orn, 1, M.ik_reset_iters);
-      else ik_world<7>(M, qq, np_, M.default_orn, 1, M.ik_reset_iters);
-      for (int i = 0; i < 6; i++) { W.q[i] = qq[i]; W.qd[i] = 0.f; }
-    }
-    __syncwarp();
-    // reset_goal_pos (environments.py:492-516)
-    rng4(seed, env_offset + (uint32_t)e, attempt, 5u, u);
-    if (!M.play) {
-      if (lane < 3) W.goal[lane] = M.goal_lo[lane] + (M.goal_hi[lane] - M.goal_lo[lane]) * u[lane];
-      __syncwarp();
-    } else {
-      phase_observe(M, W, lane, O, (size_t)e, true);   // writes achieved_goal for this env
-      __syncwarp();
-      int idx = (int)(u[0] * M.goal_dim);
-      if (idx >= M.goal_dim) idx = M.goal_dim - 1;
-      if (lane < M.goal_dim) {
-        float g = O.achieved_goal[(size_t)e * M.goal_dim + lane];
-        if (lane == idx) g = g + u[1];
-        W.goal[lane] = g;
-      }
-      __syncwarp();
-    }
-    r = phase_observe(M, W, lane, O, (size_t)e, true);
-  }
   store_state(M, W, st, lane);
 }
 

@@ -491,12 +491,14 @@ static char g_emu_smem2[8 * sizeof(SetupMemT<SetupCfg>) + 256];
 template <int ND>
 __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
                                                                          float* __restrict__ sbuf, DevOut O, int N, int flags,
-                                                                         int* __restrict__ heavy_list, int* __restrict__ heavy_cnt) {
+                                                                         int* __restrict__ heavy_list, int* __restrict__ heavy_cnt,
+                                                                         const unsigned char* __restrict__ active) {
   typedef SetupMemT<SetupCfg> WM;
   PRB_SMEM_DECL2;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int e = blockIdx.x * SetupCfg::WPB + wib;
   if (e >= N) return;
+  if (active != nullptr && active[e] == 0) return;       // masked stepping (reset: only the envs being reset settle)
   const DevModel& M = *Mp;
   WM& W = wm[wib];
   float* st = state + (size_t)e * M.state_stride;
@@ -517,14 +519,18 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
     phase_vstar(M, W, lane);
     phase_rows_stream<ND>(M, W, lane, S);
     __syncwarp();
-    if (lane == 0 && W.overflow && O.overflow) atomicAdd(O.overflow, 1ull);
+    // a dropped contact marks the env; the mark is counted (once per env step) by the launch that observes
+    if (lane == 0 && W.overflow) { if (O.ovf_env) O.ovf_env[e] = 1; else if (O.overflow) atomicAdd(O.overflow, 1ull); }
     if (lane == 0 && W.dbg_u) {                      // order within a list is immaterial: envs are independent
       const int cls = W.dbg_u - 1;                   // size class of region 0
       heavy_list[(size_t)cls * N + atomicAdd(heavy_cnt + 4 * cls, 1)] = e;    // heavy_cnt: {length, -, work counter, -} per class
     }
     if (lane == 0 && O.dbg) { O.dbg[4 * e] = 0; O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.n_jrow; }
   }
-  if (flags & SETUP_OBSERVE) phase_observe(M, W, lane, O, (size_t)e, true);
+  if (flags & SETUP_OBSERVE) {
+    phase_observe(M, W, lane, O, (size_t)e, true);
+    if (lane == 0 && O.ovf_env && O.ovf_env[e]) { O.ovf_env[e] = 0; if (O.overflow) atomicAdd(O.overflow, 1ull); }
+  }
   __syncwarp();
   if (flags & (SETUP_INTEGRATE | SETUP_OBSERVE)) store_state(M, W, st, lane);
 }
@@ -559,13 +565,15 @@ PRB_D float4* stream_col(float* sbuf, int e) { return reinterpret_cast<float4*>(
 
 // ---- slot 0, arm island without contacts: joint rows only.  sl: this env's column (row t = q t of region 0)
 template <int ND>
-__global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N) {
+__global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N,
+                                                                 const unsigned char* __restrict__ active) {
   PRB_PGS_SMEM_DECL;
   const int lane = threadIdx.x;
   const DevModel& M = *Mp;
   // persistent blocks: a block walks groups of 32 envs (launching one block per group costs more than
   // the solve: each block launch allocates its shared memory)
   for (int e = blockIdx.x * PGS_BLOCK + lane; e < N; e += gridDim.x * PGS_BLOCK) {
+  if (active != nullptr && active[e] == 0) continue;
   float4* G = stream_col(sbuf, e);
   const int h0 = __float_as_int(G[Q_HDR * 32].x);
   const int njr = h0 & 0xff, nc0 = (h0 >> 8) & 0xff;
@@ -680,12 +688,14 @@ PRB_D bool fsides_of(int pk, const float4* rec, const float4& q2, FSide& P, FSid
   return two;
 }
 
-__global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N) {
+__global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N,
+                                                                const unsigned char* __restrict__ active) {
   PRB_PGS_SMEM_DECL;
   const int lane = threadIdx.x;
   const int slot = blockIdx.y + 1;
   const DevModel& M = *Mp;
   for (int e = blockIdx.x * PGS_BLOCK + lane; e < N; e += gridDim.x * PGS_BLOCK) {     // persistent blocks
+  if (active != nullptr && active[e] == 0) continue;
   float4* G = stream_col(sbuf, e);
   const float4 h1 = G[(Q_HDR + 1) * 32], hs = G[(Q_HDR + slot) * 32];
   const int info = __float_as_int(h1.x);

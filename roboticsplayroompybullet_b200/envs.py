@@ -43,6 +43,12 @@ class VecPlayEnv:
         import torch  # device memory / streams only
         self.torch = torch
         env_id = env_id or self.env_id
+        if not sparse:
+            # The reference binds compute_reward once and uses it in step() AND in the reset retry loop
+            # (environments.py:169-170, 185, 210); with the dense reward that loop only ends when the sampled goal
+            # is >= 1 m away.  No registered id uses it; the in-kernel reward is the sparse one.
+            raise NotImplementedError('sparse=False (dense reward inside step/reset) is not supported; '
+                                      'use dense_reward(ag, dg) for the dense metric')
         if env_id not in ENV_KINDS and env_id not in ACTION_VARIANTS:
             raise NotImplementedError(env_id)           # environments.py:376,416,933
         self.env_id = env_id
@@ -167,6 +173,7 @@ class VecPlayEnv:
     def reset_goal_pos(self, goal):
         t = self.torch
         g = t.as_tensor(np.asarray(goal, np.float32)).reshape(self.num_envs, -1).to(self.device).contiguous()
+        assert g.shape == (self.num_envs, self.dims['desired_goal']), 'goal must be [num_envs, %d]' % self.dims['desired_goal']
         self._g_keep = g
         _lib.check(self.L, self._h, self.L.prb_set_goal(self._h, ctypes.c_void_p(g.data_ptr()), None, self._stream()))
 
@@ -175,6 +182,7 @@ class VecPlayEnv:
         goal float32 CUDA tensor [N, goal_dim], optional uint8 mask [N]."""
         t = self.torch
         g = goal.to(self.device, t.float32).reshape(self.num_envs, -1).contiguous()
+        assert g.shape == (self.num_envs, self.dims['desired_goal']), 'goal must be [num_envs, %d]' % self.dims['desired_goal']
         self._g_keep = g
         mp = None
         if mask is not None:
@@ -189,9 +197,7 @@ class VecPlayEnv:
         dg = np.asarray(desired_goal, np.float32)
         single = ag.ndim == 1
         G = self.dims['achieved_goal']
-        if not self.sparse:
-            d = -np.linalg.norm(ag.reshape(-1, G) - dg.reshape(-1, G), axis=1)
-            return d[0] if single else d
+        assert ag.shape[-1] == G and dg.shape == ag.shape, 'goals must be [..., %d]' % G
         agd = t.as_tensor(ag.reshape(-1, G)).to(self.device).contiguous()
         dgd = t.as_tensor(dg.reshape(-1, G)).to(self.device).contiguous()
         out = t.empty(agd.shape[0], dtype=t.float32, device=self.device)
@@ -202,6 +208,13 @@ class VecPlayEnv:
         return r[0] if single else r
 
     compute_reward_sparse = compute_reward
+
+    def dense_reward(self, achieved_goal, desired_goal):
+        """playEnv.compute_reward before the sparse rebinding (environments.py:269-275): -||ag - dg|| (host numpy)."""
+        G = self.dims['achieved_goal']
+        ag = np.asarray(achieved_goal, np.float32)
+        d = -np.linalg.norm(ag.reshape(-1, G) - np.asarray(desired_goal, np.float32).reshape(-1, G), axis=1)
+        return d[0] if ag.ndim == 1 else d
 
     def compute_reward_device(self, ag, dg):
         t = self.torch

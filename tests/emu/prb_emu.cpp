@@ -1,6 +1,6 @@
 // prb_emu.cpp — runs the product's kernel source under the CPU SIMT emulator (tests only).
 #include "cuda_emu.h"
-#include "../../roboticsplayroompybullet_b200/csrc/prb_stream.cuh"
+#include "../../roboticsplayroompybullet_b200/csrc/prb_reset.cuh"
 #include "../../roboticsplayroompybullet_b200/csrc/prb_convert.h"
 
 static DevModel g_M;
@@ -9,8 +9,8 @@ static std::string g_err;
 static std::vector<float> g_sbuf;
 static int g_fused = 0;     // 1: run the fused warp-per-env kernel instead of the split pipeline
 template <int ND>
-static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
-  if (g_fused) {
+static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe, const unsigned char* active = nullptr) {
+  if (g_fused && active == nullptr) {
     emu_dim3 g, b; b.x = 32 * CfgL::WPB; g.x = (N + CfgL::WPB - 1) / CfgL::WPB;
     emu::launch(g, b, [&]() { prb_step_kernel<ND, CfgL>(&g_M, state, O, nullptr, nullptr, nullptr, nullptr, N, nsub, observe); });
     return;
@@ -25,12 +25,12 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe) {
     int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
     if (flags == 0) break;
     memset(heavy_cnt, 0, sizeof(heavy_cnt));
-    emu::launch(gs, bs, [&]() { prb_setup_kernel<ND>(&g_M, state, g_sbuf.data(), O, N, flags, heavy.data(), heavy_cnt); });
+    emu::launch(gs, bs, [&]() { prb_setup_kernel<ND>(&g_M, state, g_sbuf.data(), O, N, flags, heavy.data(), heavy_cnt, active); });
     if (i < nsub) {
-      emu::launch(gp, bp, [&]() { prb_pgs_joint_kernel<ND>(&g_M, g_sbuf.data(), N); });
+      emu::launch(gp, bp, [&]() { prb_pgs_joint_kernel<ND>(&g_M, g_sbuf.data(), N, active); });
       for (int y = 0; y < g_M.n_free; y++) {
         emu_dim3 gy = gp;
-        emu::launch_y(gy, bp, y, [&]() { prb_pgs_free_kernel(&g_M, g_sbuf.data(), N); });
+        emu::launch_y(gy, bp, y, [&]() { prb_pgs_free_kernel(&g_M, g_sbuf.data(), N, active); });
       }
       emu_dim3 gh, bq; gh.x = (N + 7) / 8; bq.x = PGS_G_THREADS;
       for (int k = 0; k < PGS_NCLASS; k++)
@@ -42,7 +42,29 @@ static void run_step(float* state, DevOut O, int N, int nsub, int observe) {
   if (g_M.nd == 12) run_step_nd<12>(state, O, N, nsub, observe); else run_step_nd<9>(state, O, N, nsub, observe);
 }
 
+static unsigned long long g_overflow = 0;
+static int g_reset_rounds = 0;
+// mirrors reset_rounds() of prb_capi.cu
+template <int ND>
+static void emu_reset_nd(float* state, DevOut o, const unsigned char* mask, int N, unsigned long long seed, unsigned env_offset) {
+  std::vector<unsigned char> pending(N, 0), ovf(N, 0);
+  std::vector<int> ctl(2 * N, 0);
+  o.ovf_env = ovf.data();
+  emu_dim3 gp, bp, gf, bf;
+  bp.x = 128; gp.x = (N + 127) / 128;
+  bf.x = 32 * SetupCfg::WPB; gf.x = (N + SetupCfg::WPB - 1) / SetupCfg::WPB;
+  g_reset_rounds = 0;
+  for (int round = 0; round < RESET_MAX_ATTEMPTS * RESET_MAX_TRIES; round++) {
+    emu::launch(gp, bp, [&]() { prb_reset_place_kernel(&g_M, state, ctl.data(), mask, pending.data(), N, seed, env_offset, round == 0); });
+    run_step_nd<ND>(state, o, N, g_M.settle_steps, 0, pending.data());
+    int n_pending = 0;
+    emu::launch(gf, bf, [&]() { prb_reset_finish_kernel<ND>(&g_M, state, o, ctl.data(), pending.data(), &n_pending, N, seed, env_offset); });
+    g_reset_rounds = round + 1;
+    if (n_pending == 0) break;
+  }
+}
 extern "C" {
+int emu_reset_rounds() { return g_reset_rounds; }
 int emu_set_model(const prb_model* m) { g_err = prb_convert_model(m, &g_M); return g_err.empty() ? 0 : -1; }
 const char* emu_error() { return g_err.c_str(); }
 int emu_state_stride() { return g_M.state_stride; }
@@ -62,21 +84,19 @@ void emu_ik(float* state, const float* action, float* target, int N) {
 void emu_set_fused(int f) { g_fused = f; }
 float* emu_sbuf() { return g_sbuf.data(); }
 int emu_sbuf_q() { return SB_Q; }
-static unsigned long long g_overflow = 0;
 unsigned long long emu_overflow() { return g_overflow; }
-void emu_substeps(float* state, int N, int nsub) { DevOut O; memset(&O, 0, sizeof(O)); O.overflow = &g_overflow; O.dbg = nullptr; run_step(state, O, N, nsub, 0); }
+void emu_substeps(float* state, int N, int nsub) { DevOut O; memset(&O, 0, sizeof(O)); O.overflow = &g_overflow; O.dbg = nullptr; O.ovf_env = nullptr; run_step(state, O, N, nsub, 0); }
 void emu_step(float* state, const float* action, DevOut* O, int N) {
-  O->overflow = &g_overflow; O->dbg = nullptr;
+  O->overflow = &g_overflow; O->dbg = nullptr; O->ovf_env = nullptr;
   emu_ik(state, action, O->target_poses, N);
   run_step(state, *O, N, g_M.n_substeps, 1);
 }
-void emu_observe(float* state, DevOut* O, int N) { O->overflow = &g_overflow; O->dbg = nullptr; run_step(state, *O, N, 0, 1); }
+void emu_observe(float* state, DevOut* O, int N) { O->overflow = &g_overflow; O->dbg = nullptr; O->ovf_env = nullptr; run_step(state, *O, N, 0, 1); }
 void emu_reset(float* state, DevOut* O, const unsigned char* mask, int N, unsigned long long seed, unsigned env_offset) {
-  emu_dim3 g, b; b.x = 32; g.x = N;
   DevOut o = *O;
   o.overflow = &g_overflow; o.dbg = nullptr;
-  if (g_M.nd == 12) emu::launch(g, b, [&]() { prb_reset_kernel<12>(&g_M, state, o, mask, N, seed, env_offset); });
-  else emu::launch(g, b, [&]() { prb_reset_kernel<9>(&g_M, state, o, mask, N, seed, env_offset); });
+  if (g_M.nd == 12) emu_reset_nd<12>(state, o, mask, N, seed, env_offset);
+  else emu_reset_nd<9>(state, o, mask, N, seed, env_offset);
 }
 void emu_reward(const float* ag, const float* dg, long long B, float* out) {
   emu_dim3 g, b; b.x = 128; g.x = (unsigned)((B + 127) / 128);

@@ -15,7 +15,7 @@ OUT_KEYS = ['obs_quat', 'achieved_goal', 'desired_goal', 'controllable_achieved_
 
 
 class DevOut(ctypes.Structure):
-    _fields_ = [(k, ctypes.c_void_p) for k in OUT_KEYS] + [('overflow', ctypes.c_void_p), ('dbg', ctypes.c_void_p)]
+    _fields_ = [(k, ctypes.c_void_p) for k in OUT_KEYS] + [('overflow', ctypes.c_void_p), ('ovf_env', ctypes.c_void_p), ('dbg', ctypes.c_void_p)]
 
 
 def out_dims(m):
@@ -29,7 +29,7 @@ def lib_variant(tag, defines):
     """A second build of the emulated kernels with other compile-time constants (e.g. tiny solver stages)."""
     so = os.path.join(_HERE, 'libprb_emu_%s.so' % tag)
     deps = [os.path.join(_HERE, f) for f in ('prb_emu.cpp', 'cuda_emu.h')] + \
-           [os.path.join(_SRC, f) for f in ('prb_kernels.cuh', 'prb_stream.cuh', 'prb_device.h', 'prb_convert.h')]
+           [os.path.join(_SRC, f) for f in ('prb_kernels.cuh', 'prb_stream.cuh', 'prb_reset.cuh', 'prb_device.h', 'prb_convert.h')]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-U_FORTIFY_SOURCE', '-Wno-unknown-pragmas'] +
                               ['-D%s' % d for d in defines] + ['-o', so, os.path.join(_HERE, 'prb_emu.cpp')])
@@ -43,7 +43,7 @@ def lib():
     if _LIB is None:
         so = os.path.join(_HERE, 'libprb_emu.so')
         deps = [os.path.join(_HERE, f) for f in ('prb_emu.cpp', 'cuda_emu.h')] + \
-               [os.path.join(_SRC, f) for f in ('prb_kernels.cuh', 'prb_stream.cuh', 'prb_device.h', 'prb_convert.h')]
+               [os.path.join(_SRC, f) for f in ('prb_kernels.cuh', 'prb_stream.cuh', 'prb_reset.cuh', 'prb_device.h', 'prb_convert.h')]
         if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
             subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-U_FORTIFY_SOURCE',
                                    '-Wno-unknown-pragmas', '-o', so, os.path.join(_HERE, 'prb_emu.cpp')])
