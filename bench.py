@@ -290,16 +290,26 @@ def run_gpu(args):
         obs, r, done, info = env.step(acts_host[W + s])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # ---- reset cost (environments.py:173-187 on the masked step pipeline): one full-batch reset, device events around the
+    #      call (it synchronises once per round), reported beside the step time and amortised over an episode
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    r0.record()
+    env.reset_device(torch.ones(N, dtype=torch.uint8, device=dev))
+    r1.record()
+    torch.cuda.synchronize()
+    reset_ms = r0.elapsed_time(r1)
+    reset_rounds = env.reset_rounds()
     sampler.stop_flag = True
     sampler.join(timeout=2)
     clocks = sampler.summary()
     # ---- max over ranks, whole-job aggregate
-    t = torch.tensor([dev_s, e2e_s], device=dev, dtype=torch.float64)
+    t = torch.tensor([dev_s, e2e_s, reset_ms], device=dev, dtype=torch.float64)
     stats = torch.stack([succ.double(), rsum.double(), torch.tensor(float(N * K), device=dev, dtype=torch.float64)])
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)       # the only collective: episode statistics
-    dev_s, e2e_s = float(t[0]), float(t[1])
+    dev_s, e2e_s, reset_ms = float(t[0]), float(t[1]), float(t[2])
     total_env_steps = float(stats[2])
     value = total_env_steps / dev_s
     e2e = total_env_steps / e2e_s
@@ -342,6 +352,10 @@ def run_gpu(args):
                 'episode_stats': {'success_rate': float(stats[0]) / total_env_steps,
                                   'mean_reward': float(stats[1]) / total_env_steps},
                 'capacity_overflow_env_steps': env.overflow_count(),
+                'reset': {'full_batch_ms': reset_ms, 'rounds': reset_rounds, 'episode_steps': args.episode_steps,
+                          'value_amortised': total_env_steps / K * args.episode_steps /
+                          (args.episode_steps * dev_s / K + reset_ms / 1000.0),
+                          'note': 'env-steps/s of a whole episode: episode_steps steps + one full-batch reset'},
                 'wall_s_timed_region': t_wall}
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(args.env, args.seed, budget_s=args.cpu_seconds)

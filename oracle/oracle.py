@@ -8,6 +8,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_LIB32 = None
 
 
 def build():
@@ -30,6 +31,20 @@ def lib():
     return _LIB
 
 
+def lib32():
+    """The same restatement built with ORC_REAL=float: conditioning probe for the parity tests only."""
+    global _LIB32
+    if _LIB32 is None:
+        so = os.path.join(_HERE, 'libprb_oracle_f32.so')
+        src = os.path.join(_HERE, 'prb_oracle.c')
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            build()
+        _LIB32 = ctypes.CDLL(so)
+        _LIB32.orc_state_dim.restype = ctypes.c_int
+        _LIB32.orc_out_dim.restype = ctypes.c_int
+    return _LIB32
+
+
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
@@ -41,14 +56,15 @@ def _d(x):
 class Oracle:
     """One environment stepped by the fp64 restatement."""
 
-    def __init__(self, model, seed=1234, env_id=0):
+    def __init__(self, model, seed=1234, env_id=0, f32=False):
         self.model = model
         self.ms = model.as_struct()
         self.mp = ctypes.byref(self.ms)
-        self.L = lib()
+        self.L = lib32() if f32 else lib()
+        self.dtype = np.float32 if f32 else np.float64
         self.state_dim = self.L.orc_state_dim(self.mp)
         self.out_dim = self.L.orc_out_dim(self.mp)
-        self.state = np.zeros(self.state_dim)
+        self.state = np.zeros(self.state_dim, self.dtype)
         self.seed = seed
         self.env_id = env_id
         self.L.orc_init_state(self.mp, _p(self.state))
@@ -66,18 +82,18 @@ class Oracle:
         return d
 
     def reset(self):
-        out = np.zeros(self.out_dim)
+        out = np.zeros(self.out_dim, self.dtype)
         self.L.orc_reset(self.mp, _p(self.state), ctypes.c_uint64(self.seed), ctypes.c_uint32(self.env_id), _p(out))
         return self.split_out(out)
 
     def step(self, action):
-        out = np.zeros(self.out_dim)
-        a = _d(action)
+        out = np.zeros(self.out_dim, self.dtype)
+        a = np.ascontiguousarray(np.asarray(action, dtype=self.dtype))
         self.L.orc_step(self.mp, _p(self.state), _p(a), _p(out))
         return self.split_out(out)
 
     def calc_state(self):
-        out = np.zeros(self.out_dim)
+        out = np.zeros(self.out_dim, self.dtype)
         self.L.orc_calc_state(self.mp, _p(self.state), _p(out))
         return self.split_out(out)
 

@@ -39,7 +39,12 @@
 #define MAXROW (2 * MAXD + MAXD + MAXSLIDE + 1 + 4 * MAXCONTACT)
 #define PI 3.14159265358979323846
 
-typedef double real;
+/* ORC_REAL=float builds the SAME restatement in single precision (liborc f32): used only by the conditioning tests,
+ * which bound |CUDA - oracle| on stiff contact states by |oracle(fp32) - oracle(fp64)| of this independent algorithm. */
+#ifndef ORC_REAL
+#define ORC_REAL double
+#endif
+typedef ORC_REAL real;
 typedef struct { real x, y, z; } v3;
 typedef struct { real m[3][3]; } m3;
 
@@ -73,6 +78,8 @@ static m3 mmul(const m3* A, const m3* B) {
 static m3 mtrans(const m3* A) { m3 C; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C.m[i][j] = A->m[j][i]; return C; }
 static m3 mload(const double* p) { m3 C; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C.m[i][j] = p[3 * i + j]; return C; }
 static v3 vload(const double* p) { return V(p[0], p[1], p[2]); }
+static m3 mloadr(const real* p) { m3 C; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C.m[i][j] = p[3 * i + j]; return C; }
+static v3 vloadr(const real* p) { return V(p[0], p[1], p[2]); }
 static v3 mcol(const m3* A, int j) { return V(A->m[0][j], A->m[1][j], A->m[2][j]); }
 static m3 axis_angle(v3 a, real q) {
   real c = cos(q), s = sin(q), t = 1 - c;
@@ -285,7 +292,7 @@ void orc_ik(const prb_model* M, const real* q_in, const real* tpos_w, const real
   real lambda = M->params[PRB_P_IK_DAMPING], thresh = M->params[PRB_P_IK_THRESHOLD];
   m3 bR = mload(M->arm_base_rot); v3 bp = vload(M->arm_base_pos);
   /* target into base coordinates */
-  v3 tp = mtmulv(&bR, vsub(vload(tpos_w), bp));
+  v3 tp = mtmulv(&bR, vsub(vloadr(tpos_w), bp));
   real bq[4], bqi[4], tq[4];
   mat_to_quat(&bR, bq);
   bqi[0] = -bq[0]; bqi[1] = -bq[1]; bqi[2] = -bq[2]; bqi[3] = bq[3];
@@ -536,8 +543,8 @@ int orc_box_box_impl(v3 p1, const m3* R1, v3 side1h, v3 p2, const m3* R2, v3 sid
 }
 /* test entry: boxes given as pos3, rot9 (row-major), half3; out = n x (pos3, normal3, depth) */
 int orc_box_box(const real* p1, const real* R1, const real* h1, const real* p2, const real* R2, const real* h2, real* out) {
-  CPoint c[8]; m3 Ra = mload(R1), Rb = mload(R2);
-  int n = orc_box_box_impl(vload(p1), &Ra, vload(h1), vload(p2), &Rb, vload(h2), c);
+  CPoint c[8]; m3 Ra = mloadr(R1), Rb = mloadr(R2);
+  int n = orc_box_box_impl(vloadr(p1), &Ra, vloadr(h1), vloadr(p2), &Rb, vloadr(h2), c);
   for (int i = 0; i < n; i++) {
     out[7 * i] = c[i].pos.x; out[7 * i + 1] = c[i].pos.y; out[7 * i + 2] = c[i].pos.z;
     out[7 * i + 3] = c[i].n.x; out[7 * i + 4] = c[i].n.y; out[7 * i + 5] = c[i].n.z; out[7 * i + 6] = c[i].depth;
@@ -558,7 +565,7 @@ static void body_frame(const prb_model* M, const State* S, const Poses* P, int b
   if (body < 0) { m3 I = {{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}}; *R = I; *p = V(0, 0, 0); }
   else if (body == 0 && link < 0) { *R = mload(M->arm_base_rot); *p = vload(M->arm_base_pos); }
   else if (body == 0) { *R = P->K.R[link]; *p = P->K.p[link]; }
-  else if (body <= M->n_free) { *R = P->fR[body - 1]; *p = vload(S->fpos[body - 1]); }
+  else if (body <= M->n_free) { *R = P->fR[body - 1]; *p = vloadr(S->fpos[body - 1]); }
   else { *R = P->sR[body - 1 - M->n_free]; *p = P->sp[body - 1 - M->n_free]; }
 }
 static void compute_poses(const prb_model* M, const State* S, Poses* P) {
@@ -807,7 +814,7 @@ static void add_point_jac(const SolveCtx* X, int col, v3 pt, v3 dir, real sign, 
     }
   } else if (body <= M->n_free) {
     int b = body - 1, o = nd + 6 * b;
-    v3 r = vsub(pt, vload(X->S->fpos[b]));
+    v3 r = vsub(pt, vloadr(X->S->fpos[b]));
     v3 t = angular_only ? dir : vcross(r, dir);
     if (!angular_only) { J[o] += sign * dir.x; J[o + 1] += sign * dir.y; J[o + 2] += sign * dir.z; }
     J[o + 3] += sign * t.x; J[o + 4] += sign * t.y; J[o + 5] += sign * t.z;
@@ -897,7 +904,7 @@ static void substep(const prb_model* M, State* S) {
   for (int b = 0; b < M->n_free; b++) {
     int o = nd + 6 * b;
     real kl = M->free_lin_damp[b], ka = M->free_ang_damp[b];
-    v3 vl = vload(S->fvel[b]), w = vload(S->fang[b]);
+    v3 vl = vloadr(S->fvel[b]), w = vloadr(S->fang[b]);
     v3 acc = vadd(V(0, 0, g), vscale(vl, -(kl + kl * vnorm(vl))));
     v3 wb = mtmulv(&P.fR[b], w);
     v3 Id = vload(M->free_inertia + 3 * b);
@@ -951,7 +958,7 @@ static void substep(const prb_model* M, State* S) {
   }
   for (int s = 0; s < M->n_slide; s++) {
     int o = nd + 6 * M->n_free + s;
-    const real* mot = M->slide_motor + 4 * s;
+    const double* mot = M->slide_motor + 4 * s;
     real maximp = mot[3] < 0 ? M->params[PRB_P_DEFAULT_MOTOR_IMPULSE] : mot[3];
     if (maximp <= 0) continue;
     Row* r = &rows[nr++]; memset(r, 0, sizeof(*r));
@@ -1050,7 +1057,7 @@ static void substep(const prb_model* M, State* S) {
   for (int b = 0; b < M->n_free; b++) {
     int o = nd + 6 * b;
     for (int k = 0; k < 3; k++) { S->fvel[b][k] = X.v[o + k]; S->fang[b][k] = X.v[o + 3 + k]; S->fpos[b][k] += dt * S->fvel[b][k]; }
-    v3 w = vload(S->fang[b]);
+    v3 w = vloadr(S->fang[b]);
     real ang = vnorm(w);
     if (ang * dt > 0.7853981633974483) ang = 0.5 * 1.5707963267948966 / dt;   /* ANGULAR_MOTION_THRESHOLD */
     v3 ax;
@@ -1324,7 +1331,8 @@ void orc_reset(const prb_model* M, real* state, uint64_t seed, uint32_t env_id, 
     for (int i = 0; i < M->n_ik; i++) { S.q[i] = M->arm_rest[i]; S.qd[i] = 0; }
     if (M->arm_kind == 1) { S.q[M->n_ik] = 0; S.qd[M->n_ik] = 0; }
     real jp[MAXD];
-    orc_ik(M, S.q, np_, M->default_orn, M->ik_reset_iters, jp);
+    real dorn[4] = {(real)M->default_orn[0], (real)M->default_orn[1], (real)M->default_orn[2], (real)M->default_orn[3]};
+    orc_ik(M, S.q, np_, dorn, M->ik_reset_iters, jp);
     for (int i = 0; i < 6; i++) { S.q[i] = jp[i]; S.qd[i] = 0; }      /* [0:6] for both arms (:593) */
     /* reset_goal_pos :492-516 */
     rng4(seed, env_id, attempt, 5, u);

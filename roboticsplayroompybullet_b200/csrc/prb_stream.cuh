@@ -375,7 +375,7 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
       ncs[sidx] = __popc(mask); nss[sidx] = __popc(smask); tsp[sidx] = tend; start[sidx] = region;
       region += tend + nss[sidx];
     }
-    if (lane == 0) W.dbg_p = region;
+    if (lane == 0) { W.dbg_p = region; W.dbg_a = tEnd0; }
   }
   if (lane < nc) {
     const int ca = c.cols & 0xff, cb = (c.cols >> 8) & 0xff;
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
       const int cls = W.dbg_u - 1;                   // size class of region 0
       heavy_list[(size_t)cls * N + atomicAdd(heavy_cnt + 4 * cls, 1)] = e;    // heavy_cnt: {length, -, work counter, -} per class
     }
-    if (lane == 0 && O.dbg) { O.dbg[4 * e] = 0; O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.n_jrow; }
+    if (lane == 0 && O.dbg) { O.dbg[4 * e] = W.dbg_u | (W.dbg_a << 8); O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.n_jrow; }
   }
   if (flags & SETUP_OBSERVE) {
     phase_observe(M, W, lane, O, (size_t)e, true);

@@ -259,6 +259,10 @@ class VecPlayEnv:
         _lib.check(self.L, self._h, self.L.prb_last_tier_ms(self._h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def reset_rounds(self):
+        """Rounds (seat objects, settle, finish) the most recent reset needed."""
+        return int(self.L.prb_reset_rounds(self._h))
+
     def launch_count(self):
         return int(self.L.prb_launch_count(self._h))
 

@@ -168,3 +168,53 @@ def test_emu_records_read_in_place_when_stage_is_small():
         for k in da:
             assert np.array_equal(da[k], db[k]), k
     assert a_sim.state[0, 62] > 0.05            # the block was grasped and lifted on the way
+
+
+def test_emu_reset_rounds_match_oracle():
+    """reset() as rounds on the masked step pipeline (prb_reset.cuh): same counter-based draws as the oracle's
+    orc_reset, including the envs that need a second attempt because the sampled goal is already satisfied
+    (environments.py:180-185), and a masked reset that leaves the other envs untouched."""
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    n = 6
+    sim = EmuSim(m, n, seed=21)
+    sd = Oracle(m).state_dim
+    d = sim.reset()
+    rounds = sim.L.emu_reset_rounds()
+    attempts = sim.state[:, sd - 1].copy()
+    assert rounds >= 2 and attempts.max() >= 2, (rounds, attempts)      # seed chosen so that a retry happens
+    for i in range(n):
+        o = Oracle(m, seed=21, env_id=i)
+        do = o.reset()
+        assert o.state[-1] == attempts[i]
+        for k in ['achieved_goal', 'desired_goal']:
+            assert np.abs(d[k][i] - do[k]).max() < 2e-3, (i, k)
+        assert np.abs(d['obs_quat'][i][:7] - do['obs_quat'][:7]).max() < 1e-5       # end-effector pose after reset_arm
+        assert abs(d['obs_quat'][i][7] - do['obs_quat'][7]) < 1e-3                  # gripper reading (23 x the pad joint)
+    before = sim.state.copy()
+    mask = np.zeros(n, np.uint8); mask[2] = 1
+    sim.reset(mask)
+    keep = np.arange(n) != 2
+    assert np.array_equal(sim.state[keep], before[keep])
+    assert sim.state[2, sd - 1] > before[2, sd - 1]
+
+
+@pytest.mark.parametrize('env_id', ['UR5Reach-v0', 'pandaPick-v0', 'UR5PlayAbsRPY1Obj-v0'])
+def test_emu_every_key_matches_oracle(env_id):
+    """The all-key comparison the GPU parity tests use (tests/helpers.py: pose / velocity / flag groups, dial and Euler
+    wrap, conditioning rule) run on the emulated kernels: no env may need the conditioning allowance here."""
+    from helpers import compare_step, random_actions, oracle_step_from, OBS_KEYS
+    m = load_model(env_id)
+    n = 4
+    sim = EmuSim(m, n, seed=7)
+    sim.reset()
+    rng = np.random.default_rng(3)
+    sd = Oracle(m).state_dim
+    for step in range(2):
+        st = sim.state[:, :sd].copy()
+        a = random_actions(rng, n, env_id)
+        de = sim.step(a)
+        outs = [oracle_step_from(m, st[i], a[i], Oracle)[0] for i in range(n)]
+        res = compare_step(m, {k: de[k] for k in OBS_KEYS}, de['reward'][:, 0], {'is_success': de['is_success'][:, 0]}, outs,
+                           st, a, Oracle)
+        assert res['bad_pose'] == res['bad_vel'] == res['bad_flags'] == res['bad_reward'] == res['stiff'] == 0, res
+        assert res['worst_pose'] < 2e-5 and res['worst_vel'] < 0.1, res

@@ -3,7 +3,7 @@ same seeded inputs, started from identical states."""
 import numpy as np
 import pytest
 
-from helpers import compare_step, random_actions, oracle_step_from, POS_TOL
+from helpers import compare_step, random_actions, oracle_step_from, POS_TOL, OBS_KEYS
 
 pytestmark = pytest.mark.gpu
 
@@ -57,6 +57,8 @@ def test_reset_matches_oracle(env_id):
 
 @pytest.mark.parametrize('env_id', ENVS)
 def test_step_parity_identical_states(env_id):
+    """Every key of the observation dict, reward, success and target poses after one env step from identical states
+    (tolerances and the conditioning rule: tests/helpers.py)."""
     from roboticsplayroompybullet_b200.model import load_model
     from oracle.oracle import Oracle
     n = 48
@@ -64,26 +66,25 @@ def test_step_parity_identical_states(env_id):
     env.reset()
     m = load_model(env_id)
     rng = np.random.default_rng(3)
-    total_bad, worst_all = 0, 0.0
+    tot = {'bad_pose': 0, 'bad_vel': 0, 'bad_flags': 0, 'bad_reward': 0, 'stiff': 0}
     for step in range(4):
         st = env.get_state()
         a = random_actions(rng, n, env_id)
         obs, r, done, info = env.step(a)
         outs = [oracle_step_from(m, st[i], a[i], Oracle)[0] for i in range(n)]
-        bad, worst = compare_step(obs, r, info, outs)
-        total_bad += bad
-        worst_all = max(worst_all, worst)
+        res = compare_step(m, obs, r, info, outs, st, a, Oracle)
+        for k in tot:
+            tot[k] += res[k]
         tp = np.array([o['target_poses'] for o in outs])
         # IK + clipping, fp32 vs fp64.  The iteration loop exits on |position error| < 1e-4, so a
         # sample sitting exactly on that boundary may run one DLS iteration more or less (seen
         # with the Panda's 200-iteration call): bound the bulk tightly and the tail loosely.
         terr = np.abs(info['target_poses'] - tp).max(axis=1)
         assert np.quantile(terr, 0.9) < 2e-5 and terr.max() < 2e-3, (np.quantile(terr, 0.9), terr.max())
-        rr = np.array([o['reward'][0] for o in outs])
-        agree = (r == rr) | (np.abs(r - rr) < 1e-4)
-        assert agree.mean() > 0.97
-    # contact onset can flip by one substep between fp32 and fp64: allow a few outlier envs
-    assert total_bad <= max(2, int(0.04 * 4 * n)), (total_bad, worst_all)
+    # a contact that appears one substep earlier or later in fp32 than in fp64 is the one legitimate source of
+    # unexplained outliers: <= 2 % of the env steps
+    lim = max(1, int(0.02 * 4 * n))
+    assert tot['bad_pose'] <= lim and tot['bad_vel'] <= lim and tot['bad_flags'] <= lim and tot['bad_reward'] <= lim, tot
     env.close()
 
 
@@ -185,9 +186,12 @@ def test_grasp_and_lift_statistics():
 
 
 def test_step_parity_scripted_steady_state():
-    """One-step parity from identical states in the contact-rich steady state of the scripted workload
-    (gripper on the block, block island merged into the arm island: the four-lanes-per-env solver and the
-    compact free-body records), 64 envs after 60 scripted steps."""
+    """One-step parity from identical states in the contact-rich steady state of the scripted workload (gripper on the
+    block, block island merged into the arm island: the arm-island solver and the compact free-body records), 64 envs
+    after 60 scripted steps.  Envs with the fingers closed on the block are stiff (soft-contact CFM of the pads against
+    240 N motor rows): there fp32 and fp64 differ by up to several mm after one step.  That this is conditioning and not
+    the solver is PROVEN per env: the oracle's own fp64 step moves by the same amount when its input state is perturbed
+    by one fp32 ulp (helpers.ulp_spread); an env beyond the pose tolerance must be within COND_K x that spread."""
     import os, sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
@@ -202,22 +206,84 @@ def test_step_parity_scripted_steady_state():
     for s in range(60):
         env.step(acts[s])
     m = load_model(env_id)
-    total_bad, merged, worst_all = 0, 0, 0.0
+    tot = {'bad_pose': 0, 'bad_vel': 0, 'bad_flags': 0, 'bad_reward': 0, 'stiff': 0}
+    merged = 0
     for s in range(60, 63):
         st = env.get_state()
         obs, r, done, info = env.step(acts[s])
-        merged += int((env.debug_usage()[:, 2] > 200).sum())       # envs whose record stream shows an arm island in contact
+        merged += int(((env.debug_usage()[:, 0] & 0x7f) > 0).sum())       # envs solved by the arm-island kernel in the last substep
         outs = [oracle_step_from(m, st[i], acts[s][i], Oracle)[0] for i in range(n)]
-        bad, worst = compare_step(obs, r, info, outs)
-        total_bad += bad
-        worst_all = max(worst_all, worst)
+        res = compare_step(m, obs, r, info, outs, st, acts[s], Oracle)
+        for k in tot:
+            tot[k] += res[k]
     assert merged >= 6, merged                                      # the heavy path was exercised
-    # Envs with the fingers closed on the block are stiff (soft-contact CFM of the pads, 4 rows per point): fp32 vs
-    # fp64 differs by up to ~5e-3 m after one step in ~7 % of them.  The fused A/B solver (PRB_PIPELINE=fused,
-    # impulse space, different arithmetic) is off by the same amount on the same envs (tools/exp_parity_steady.py),
-    # so this is conditioning, not the solver: bound the outlier count and their size.
-    assert total_bad <= int(0.12 * 3 * n), total_bad
-    assert worst_all < 2e-2, worst_all
+    lim = int(0.02 * 3 * n)
+    assert tot['bad_pose'] <= lim and tot['bad_vel'] <= lim and tot['bad_flags'] <= lim and tot['bad_reward'] <= lim, tot
+    env.close()
+
+
+BASELINE_SIZES = [('UR5Reach-v0', 4096), ('pandaPick-v0', 16384), ('UR5PlayAbsRPY1Obj-v0', 8192), ('UR5PlayAbsRPY1Obj-v0', 65536)]
+
+
+@pytest.mark.parametrize('env_id,N', BASELINE_SIZES)
+def test_parity_at_baseline_size(env_id, N):
+    """BASELINE.json configs 2-5 at their full sizes (more envs than persistent solver blocks: grid-stride loops, the
+    device work counters of the heavy lists, every size class and the read-in-place path all run with real queues).
+    After a scripted pre-roll, one env step of all N envs is checked two ways on a seeded sample of >= 256 envs that
+    contains envs of EVERY arm-island size class (largest islands first, so read-in-place ones when they exist):
+      * against the oracle from identical states (all keys, conditioning rule of tests/helpers.py);
+      * bit for bit against a 256-env handle stepped from the same states (envs are independent, so which block, list
+        slot or queue position served an env must not matter: catches work-counter / list / staging races)."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import torch
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle
+    play = env_id.startswith('UR5Play')
+    env = _mk(env_id, N, seed=31)
+    obs = env.reset()
+    pre = 40 if play else 12
+    acts = bench.synth_actions(np.random.default_rng(6), N, pre + 1, env_id,
+                               block_xyz=obs['achieved_goal'][:, :3] if env_id != 'UR5Reach-v0' else None, ee_xyz=obs['obs_quat'][:, :3],
+                               jump_frac=0.02)
+    acts_dev = torch.as_tensor(acts).cuda()
+    for s in range(pre):
+        env.step_device(acts_dev[s])
+    st = env.get_state()
+    obs, r, done, info = env.step(acts[pre])
+    st_after = env.get_state()
+    use = env.debug_usage()
+    cls, region = use[:, 0] & 0x7f, use[:, 0] >> 8
+    rng = np.random.default_rng(9)
+    pick = []
+    for c in (4, 3, 2, 1):
+        idx = np.nonzero(cls == c)[0]
+        idx = idx[np.argsort(-region[idx], kind='stable')][:48]
+        pick += list(idx)
+    if play and N >= 8192:
+        assert len(set(cls[pick])) >= 3, np.bincount(cls)            # the sample really spans the solver's size classes
+    rest = np.setdiff1d(np.arange(N), pick)
+    pick += list(rng.choice(rest, 256 - len(pick), replace=False))
+    pick = np.array(sorted(pick))
+    assert len(pick) == 256
+    m = load_model(env_id)
+    # (1) oracle
+    outs = [oracle_step_from(m, st[i], acts[pre][i], Oracle)[0] for i in pick]
+    sub_obs = {k: obs[k][pick] for k in OBS_KEYS}
+    res = compare_step(m, sub_obs, r[pick], {'is_success': info['is_success'][pick]}, outs, st[pick], acts[pre][pick], Oracle)
+    lim = max(2, int(0.02 * 256))
+    assert res['bad_pose'] <= lim and res['bad_vel'] <= lim and res['bad_flags'] <= lim and res['bad_reward'] <= lim, res
+    # (2) the same envs in a small handle
+    small = _mk(env_id, 256, seed=31)
+    small.set_state(st[pick])
+    o2, r2, _, i2 = small.step(acts[pre][pick])
+    for k in OBS_KEYS:
+        assert np.array_equal(o2[k], obs[k][pick]), k
+    assert np.array_equal(r2, r[pick]) and np.array_equal(i2['target_poses'], info['target_poses'][pick])
+    assert np.array_equal(small.get_state(), st_after[pick])
+    assert np.isfinite(st_after).all()
+    small.close()
     env.close()
 
 
@@ -252,9 +318,9 @@ def test_action_decoder_variants(env_id):
         outs = [oracle_step_from(m, st[i], a[i], Oracle)[0] for i in range(n)]
         tp = np.array([o['target_poses'] for o in outs])
         assert np.abs(info['target_poses'] - tp).max() < 2e-4
-        bad, worst = compare_step(obs, r, info, outs)
-        total_bad += bad
-    assert total_bad <= 4, total_bad
+        res = compare_step(m, obs, r, info, outs, st, a, Oracle)
+        total_bad += res['bad_pose'] + res['bad_vel'] + res['bad_flags'] + res['bad_reward']
+    assert total_bad <= 2, total_bad
     env.close()
 
 
