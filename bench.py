@@ -254,6 +254,8 @@ def run_gpu(args):
     n_relabel, n_reset = 0, 0
     ag_hist = env.dev['achieved_goal'].clone() if play else None
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.start()          # ncu --profile-from-start off: capture starts with the timed steps
     t_wall0 = time.perf_counter()
     for s in range(K):
         flush.fill_(float(s))
@@ -279,6 +281,8 @@ def run_gpu(args):
         rsum += r.sum()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     launches = env.launch_count() - l0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     dev_s = sum(step_ms) / 1000.0
@@ -338,7 +342,7 @@ def run_gpu(args):
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                              'frac': achieved / peak_gbs, 'traffic': MEASURED_TRAFFIC_BYTES.get((args.env, N)),
                              'traffic_note': 'bytes per launch set of one env step (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_v27_ncu.md)',
-                             'kernel': 'step pipeline per env step: 13 x prb_setup_kernel + 12 x (prb_pgs_joint_kernel, prb_pgs_free_kernel, 2 x prb_pgs_arm_kernel)',
+                             'kernel': 'step pipeline per env step: 13 x prb_setup_kernel + 12 x (prb_pgs_joint_kernel, prb_pgs_free_kernel, 5 size classes of prb_pgs_arm_kernel)',
                              'setup_kernels_ms': float(np.mean([t[0] for t in tier_ms])),
                              'pgs_kernels_ms': float(np.mean([t[1] for t in tier_ms])),
                              'kernel_ms': kms, 'ik_kernel_ms': float(np.mean(ik_ms)), 'peak_source': which,
@@ -380,6 +384,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--preroll', type=int, default=96, help='untimed scripted steps before the warm-up')
     ap.add_argument('--jump-frac', type=float, default=0.0, help='fraction of steps that target the full +-6 clip box (Random-stream tail)')
+    ap.add_argument('--profiler-range', action='store_true', help='cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)')
     ap.add_argument('--episode-steps', type=int, default=512, help='masked reset of every env after this many steps')
     args = ap.parse_args()
     if args.warmup < 3:

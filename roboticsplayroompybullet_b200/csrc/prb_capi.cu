@@ -24,23 +24,13 @@ struct prb_handle {
   DevOut O;
   int64_t launches = 0;
   int fused = 0;                   // PRB_PIPELINE=fused: A/B reference path (warp-per-env kernel, 12 substeps in one launch)
-  float* sbuf = nullptr;           // constraint-row record stream of the split pipeline (prb_stream.cuh)
-  // The envs can be stepped as `nb` independent batches, each a stream chain of its own, so that one batch's
-  // setup launch (register-bound) overlaps another's solve (shared-memory-bound).  Measured slower than one batch
-  // (the persistent solver grids then share the SMs); kept as an experiment knob (PRB_BATCHES), default 1.
-  int nb = 1;
+  float* sbuf = nullptr;           // record stream of the split pipeline (prb_stream.cuh)
+  float4* hbuf = nullptr;          // arm-island ("heavy") class buffers
+  int* heavy_cnt = nullptr;        // {bundle-list length, -, work counter, -} per class
+  // high-priority side streams: the size classes of the arm-island solver overlap each other and the joint / free-body solvers
+  cudaStream_t side[ARM_NCLASS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[ARM_NCLASS] = {};
   int dims[12] = {};
-  struct Batch {
-    int off = 0, n = 0;                        // env range (multiple of 32)
-    cudaStream_t main = nullptr;               // batch 0 runs on the caller's stream
-    // high-priority side streams: the size classes of the arm-island solver overlap each other and the joint / free-body solvers
-    cudaStream_t side[PGS_NCLASS] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[PGS_NCLASS] = {}, ev_end = nullptr;
-    int* heavy_list = nullptr;
-    int* heavy_cnt = nullptr;
-    DevOut O;
-  } batch[4];
-  cudaEvent_t ev_begin = nullptr;
   int smem = 0, regs = 0;          // setup kernel (reported)
   int regs_pgs = 0;
   int smem_fused = 0;
@@ -81,7 +71,7 @@ struct DevGuard {
   } while (0)
 
 // One env step (or n raw substeps).  Split pipeline: per substep one warp-per-env setup launch
-// (integrate previous solution + build rows) and one thread-per-env solver launch; a final setup
+// (integrate previous solution + build rows) and the thread-per-env solver launches; a final setup
 // launch integrates the last solution and writes the observation.  No host synchronisation.
 template <int ND>
 static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s, const unsigned char* active = nullptr) {
@@ -93,57 +83,50 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s, con
     return PRB_OK;
   }
   h->n_evk = 0;
-  if (h->nb > 1) CK(h, cudaEventRecord(h->ev_begin, s));
-  for (int bi = 0; bi < h->nb; bi++) {
-    prb_handle::Batch& B = h->batch[bi];
-    if (B.n <= 0) continue;
-    cudaStream_t ms = bi == 0 ? s : B.main;
-    if (bi > 0) CK(h, cudaStreamWaitEvent(ms, h->ev_begin, 0));
-    float* state = h->state + (size_t)B.off * h->hm.state_stride;
-    float* sbuf = h->sbuf + (size_t)(B.off / 32) * (SB_Q * 32) * 4;
-    dim3 gs((B.n + SetupCfg::WPB - 1) / SetupCfg::WPB), bs(32 * SetupCfg::WPB);
-    // persistent solver blocks: resident blocks per SM (shared-memory limited, shared between the batches) x SMs
-    const int ng = (B.n + PGS_BLOCK - 1) / PGS_BLOCK;
-    const int pj = (6 / h->nb > 0 ? 6 / h->nb : 1) * h->sms, pf = (3 / h->nb > 0 ? 3 / h->nb : 1) * h->sms;
-    dim3 gp(ng < pj ? ng : pj), gf(ng < pf ? ng : pf, h->hm.n_free), bp(PGS_BLOCK);
-    // arm-island kernel: 8 envs (4 lanes each) per block, one launch per size class
-    dim3 bq(PGS_G_THREADS);
-    int gcls[PGS_NCLASS], smcls[PGS_NCLASS];
-    for (int k = 0; k < PGS_NCLASS; k++) {
-      smcls[k] = PGS_SMEM_G(pgs_class_rows(k));
-      int per_sm = ((227 * 1024) / (smcls[k] + 1024)) / h->nb;
-      gcls[k] = (per_sm > 0 ? per_sm : 1) * h->sms;
-    }
-    const bool timed = h->timing && bi == 0;
-    for (int i = 0; i <= nsub; i++) {
-      int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
-      if (flags == 0) break;
-      if (timed && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], ms));
-      if (i < nsub) CK(h, cudaMemsetAsync(B.heavy_cnt, 0, 4 * PGS_NCLASS * sizeof(int), ms));
-      const unsigned char* act = active ? active + B.off : nullptr;
-      prb_setup_kernel<ND><<<gs, bs, h->smem, ms>>>(h->dm, state, sbuf, B.O, B.n, flags, B.heavy_list, B.heavy_cnt, act);
-      h->launches++;
-      if (i < nsub) {
-        if (timed && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], ms));
-        // the islands of a substep are independent: the arm-island solver (few envs, long dependent
-        // chains) goes first on high-priority side streams, the two throughput kernels fill the
-        // machine behind it; the streams join before the next setup launch
-        CK(h, cudaEventRecord(B.ev_fork, ms));
-        for (int k = PGS_NCLASS - 1; k >= 0; k--) {        // largest islands first
-          CK(h, cudaStreamWaitEvent(B.side[k], B.ev_fork, 0));
-          prb_pgs_arm_kernel<ND><<<gcls[k], bq, smcls[k], B.side[k]>>>(h->dm, sbuf, B.heavy_list + (size_t)k * B.n, B.heavy_cnt + 4 * k,
-                                                                         pgs_class_rows(k));
-          CK(h, cudaEventRecord(B.ev_join[k], B.side[k]));
-        }
-        prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, ms>>>(h->dm, sbuf, B.n, act);
-        if (h->hm.n_free > 0) prb_pgs_free_kernel<<<gf, bp, PGS_SMEM_F, ms>>>(h->dm, sbuf, B.n, act);
-        for (int k = 0; k < PGS_NCLASS; k++) CK(h, cudaStreamWaitEvent(ms, B.ev_join[k], 0));
-        h->launches += (h->hm.n_free > 0 ? 2 : 1) + PGS_NCLASS;
-      }
-    }
-    if (timed && h->n_evk < 64) CK(h, cudaEventRecord(h->evk[h->n_evk++], ms));
-    if (bi > 0) { CK(h, cudaEventRecord(B.ev_end, ms)); CK(h, cudaStreamWaitEvent(s, B.ev_end, 0)); }
+  const int N = h->N;
+  dim3 gs((N + SetupCfg::WPB - 1) / SetupCfg::WPB), bs(32 * SetupCfg::WPB);
+  // persistent solver blocks: resident blocks per SM (shared-memory limited) x SMs
+  const int ng = (N + PGS_BLOCK - 1) / PGS_BLOCK;
+  const int pj = 6 * h->sms, pf = 3 * h->sms;
+  dim3 gp(ng < pj ? ng : pj), gf(ng < pf ? ng : pf, h->hm.n_free), bp(PGS_BLOCK);
+  int gcls[ARM_NCLASS], smcls[ARM_NCLASS];
+  for (int k = 0; k < ARM_NCLASS; k++) {
+    smcls[k] = PGS_SMEM_ARM(k);
+    const int per_sm = (227 * 1024) / (smcls[k] + 1024);
+    const int want = (N + arm_lanes(k) - 1) / arm_lanes(k);       // bundles if every env were in this class
+    gcls[k] = (per_sm > 0 ? per_sm : 1) * h->sms;
+    if (gcls[k] > want) gcls[k] = want;
   }
+  const bool timed = h->timing != 0;
+  for (int i = 0; i <= nsub; i++) {
+    int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
+    if (flags == 0) break;
+    if (timed && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
+    if (i < nsub) CK(h, cudaMemsetAsync(h->heavy_cnt, 0, 4 * ARM_NCLASS * sizeof(int), s));
+    prb_setup_kernel<ND><<<gs, bs, h->smem, s>>>(h->dm, h->state, h->sbuf, h->O, N, flags, h->hbuf, h->heavy_cnt, active);
+    h->launches++;
+    if (i < nsub) {
+      if (timed && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
+      // the islands of a substep are independent: the arm-island solver (few envs, long dependent
+      // chains) goes first on high-priority side streams, the two light kernels fill the
+      // machine behind it; the streams join before the next setup launch
+      CK(h, cudaEventRecord(h->ev_fork, s));
+      for (int k = ARM_NCLASS - 1; k >= 0; k--) {        // largest islands first
+        CK(h, cudaStreamWaitEvent(h->side[k], h->ev_fork, 0));
+        float4* hc = h->hbuf + arm_class_base(k, N);
+        if (k == ARM_NCLASS - 1)
+          prb_pgs_arm_kernel<ND, true><<<gcls[k], 32, smcls[k], h->side[k]>>>(h->dm, h->sbuf, hc, h->heavy_cnt + 4 * k, arm_lanes(k), arm_capq(k), arm_bufq(k));
+        else
+          prb_pgs_arm_kernel<ND, false><<<gcls[k], 32, smcls[k], h->side[k]>>>(h->dm, h->sbuf, hc, h->heavy_cnt + 4 * k, arm_lanes(k), arm_capq(k), arm_bufq(k));
+        CK(h, cudaEventRecord(h->ev_join[k], h->side[k]));
+      }
+      prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, s>>>(h->dm, h->sbuf, N, active);
+      if (h->hm.n_free > 0) prb_pgs_free_kernel<<<gf, bp, PGS_SMEM_F, s>>>(h->dm, h->sbuf, N, active);
+      for (int k = 0; k < ARM_NCLASS; k++) CK(h, cudaStreamWaitEvent(s, h->ev_join[k], 0));
+      h->launches += (h->hm.n_free > 0 ? 2 : 1) + ARM_NCLASS;
+    }
+  }
+  if (timed && h->n_evk < 64) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
   CK(h, cudaGetLastError());
   return PRB_OK;
 }
@@ -161,13 +144,17 @@ static int setup_kernels(prb_handle* h) {
   cudaFuncAttributes fa;
   CK(h, cudaFuncGetAttributes(&fa, prb_setup_kernel<ND>));
   h->regs = fa.numRegs;
-  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_G(PGS_ROWS_GMAX)));
-  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int smax = 0;
+  for (int k = 0; k < ARM_NCLASS; k++) smax = PGS_SMEM_ARM(k) > smax ? PGS_SMEM_ARM(k) : smax;
+  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_J));
   CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(h, cudaFuncSetAttribute(prb_pgs_free_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_F));
   CK(h, cudaFuncSetAttribute(prb_pgs_free_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(h, cudaFuncGetAttributes(&fa, prb_pgs_arm_kernel<ND>));
+  CK(h, cudaFuncGetAttributes(&fa, prb_pgs_arm_kernel<ND, false>));
   h->regs_pgs = fa.numRegs;
   return PRB_OK;
 }
@@ -257,32 +244,15 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
     const size_t sb_bytes = sbuf_bytes(N);   // whole 32-env groups + prefetch slack
     CK(h, cudaMalloc(&h->sbuf, sb_bytes));
     CK(h, cudaMemset(h->sbuf, 0, sb_bytes));
+    CK(h, cudaMalloc(&h->hbuf, hbuf_bytes(N)));
+    CK(h, cudaMemset(h->hbuf, 0, hbuf_bytes(N)));
+    CK(h, cudaMalloc(&h->heavy_cnt, 4 * ARM_NCLASS * sizeof(int)));
     int lo_pri = 0, hi_pri = 0;
     CK(h, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-    h->nb = 1;                                     // measured at 65536 envs: 1 batch 632k, 2 batches 524k, 4 batches 363k env-steps/s
-    { const char* e = getenv("PRB_BATCHES"); if (e) { int v = atoi(e); if (v >= 1 && v <= 4) h->nb = v; } }
-    if ((N + 31) / 32 < h->nb) h->nb = 1;
-    CK(h, cudaEventCreateWithFlags(&h->ev_begin, cudaEventDisableTiming));
-    const int groups = (int)((N + 31) / 32);
-    for (int bi = 0; bi < h->nb; bi++) {
-      prb_handle::Batch& B = h->batch[bi];
-      const int g0 = (int)((int64_t)groups * bi / h->nb), g1 = (int)((int64_t)groups * (bi + 1) / h->nb);
-      B.off = g0 * 32;
-      B.n = (int)((g1 * 32 < N ? g1 * 32 : N) - B.off);
-      if (bi > 0) CK(h, cudaStreamCreateWithFlags(&B.main, cudaStreamNonBlocking));
-      CK(h, cudaMalloc(&B.heavy_list, sizeof(int) * PGS_NCLASS * (B.n > 0 ? B.n : 1)));
-      CK(h, cudaMalloc(&B.heavy_cnt, 4 * PGS_NCLASS * sizeof(int)));   // {list length, -, work counter, -} per class
-      CK(h, cudaEventCreateWithFlags(&B.ev_fork, cudaEventDisableTiming));
-      CK(h, cudaEventCreateWithFlags(&B.ev_end, cudaEventDisableTiming));
-      for (int k = 0; k < PGS_NCLASS; k++) {
-        CK(h, cudaStreamCreateWithPriority(&B.side[k], cudaStreamNonBlocking, hi_pri));
-        CK(h, cudaEventCreateWithFlags(&B.ev_join[k], cudaEventDisableTiming));
-      }
-      B.O = h->O;                                  // this batch's rows of every output array
-      float** src[12] = {&B.O.obs_quat, &B.O.achieved_goal, &B.O.desired_goal, &B.O.cag, &B.O.fps, &B.O.joints,
-                         &B.O.velocity, &B.O.observation, &B.O.proprio, &B.O.reward, &B.O.success, &B.O.target_poses};
-      for (int i = 0; i < 12; i++) *src[i] += (size_t)B.off * h->dims[i];
-      B.O.dbg = h->O.dbg + 4 * (size_t)B.off;
+    CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int k = 0; k < ARM_NCLASS; k++) {
+      CK(h, cudaStreamCreateWithPriority(&h->side[k], cudaStreamNonBlocking, hi_pri));
+      CK(h, cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
     }
   }
   {
@@ -304,18 +274,12 @@ int prb_destroy(prb_handle* h) {
   cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->sbuf);
   cudaFree(h->O.ovf_env); cudaFree(h->pending); cudaFree(h->reset_ctl); cudaFree(h->n_pending);
   if (h->n_pending_host) cudaFreeHost(h->n_pending_host);
-  for (int bi = 0; bi < 4; bi++) {
-    prb_handle::Batch& B = h->batch[bi];
-    for (int k = 0; k < PGS_NCLASS; k++) {
-      if (B.side[k]) cudaStreamDestroy(B.side[k]);
-      if (B.ev_join[k]) cudaEventDestroy(B.ev_join[k]);
-    }
-    if (B.main) cudaStreamDestroy(B.main);
-    if (B.ev_fork) cudaEventDestroy(B.ev_fork);
-    if (B.ev_end) cudaEventDestroy(B.ev_end);
-    cudaFree(B.heavy_list); cudaFree(B.heavy_cnt);
+  for (int k = 0; k < ARM_NCLASS; k++) {
+    if (h->side[k]) cudaStreamDestroy(h->side[k]);
+    if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
   }
-  if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  cudaFree(h->hbuf); cudaFree(h->heavy_cnt);
   for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->ev[0]) for (int i = 0; i < 64; i++) cudaEventDestroy(h->evk[i]);
   }

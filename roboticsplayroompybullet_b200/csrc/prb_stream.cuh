@@ -3,31 +3,27 @@
 // One stepSimulation() substep = one setup launch + the constraint solve:
 //   prb_setup_kernel   one WARP per env: integrate the previous substep's solution, then kinematics,
 //                      collision detection, mass matrix and its inverse, unconstrained velocities and
-//                      the constraint rows of this substep, written as records to a per-env record
-//                      stream in HBM (~2-3 kB per env-substep).  The last launch of an env step also
-//                      runs the fused observation / reward write.
+//                      the constraint rows of this substep, written as records to HBM.  The last launch
+//                      of an env step also runs the fused observation / reward write.
 //   solver kernels     the 50 projected-Gauss-Seidel sweeps, in velocity space, in
-//                      btMultiBodyConstraintSolver::solveSingleIteration order.  Every kernel stages its
-//                      envs' records ONCE into shared memory (one warp per block, lane-interleaved
-//                      float4 columns, conflict-free) and sweeps them there; the constraint islands of
-//                      an env are solved by different kernels concurrently (see "Constraint islands").
+//                      btMultiBodyConstraintSolver::solveSingleIteration order.  All three are ONE THREAD
+//                      PER ENV: the island's velocity change lives in registers, the records are staged
+//                      once into shared memory (lane-interleaved float4 columns, conflict-free) and swept
+//                      there; no shuffles or barriers inside the sweeps.  The constraint islands of an env
+//                      are solved by different kernels concurrently (see "Constraint islands").
 //
-// Why (profiles/r1_v9_ncu.md): the first thread-per-env solver re-streamed 4.5 kB of explicit Jacobian
-// rows per env per iteration from HBM (14.7 GB of DRAM reads per launch at 65536 envs) and was
-// latency-bound on dependent global loads.  95 % of the contacts in the playroom are a free body
-// (block, drawer) against static geometry: their three rows are fully described by the contact frame
-// (n, t1), the lever arm r and the body's inverse inertia, so the record is 6 float4 instead of 15 and
-// the Jacobians are rebuilt in registers.  Rows that involve the arm keep explicit J and M^-1 J^T and are
-// solved by four lanes per env.
+// History (profiles/): r1 v9 re-streamed 4.5 kB of explicit Jacobian rows per env per iteration from HBM;
+// r1 v27 staged the records once and gave an arm island four lanes (quad shuffles, ~125 warp instructions per
+// row visit for 8 envs: 66 % of the step's kernel time for 28 % of the envs); r2 gives every island one thread
+// (~80 instructions per contact visit for up to 32 envs) and hands the arm islands to the solver through
+// per-size-class "heavy" buffers that are contiguous per thread block, so a block stages its envs with one
+// bulk async copy (cp.async.bulk + mbarrier).
 //
 // Reference path: environments.py:485-490 (12 x stepSimulation), Bullet btMultiBodyDynamicsWorld.
 #pragma once
 #include "prb_kernels.cuh"
 
-// ---- record stream.  Envs are grouped by 32; float4 number q of env (g, l) lives at float4 index
-// g * 32 * SB_Q + q * 32 + l.  All offsets are in float4 units ("q").
-//
-// Constraint islands.  Rows that share no dynamic body never exchange data in Gauss-Seidel, so the
+// ---- Constraint islands.  Rows that share no dynamic body never exchange data in Gauss-Seidel, so the
 // sweep order BETWEEN islands is immaterial (bit-identical results) and islands can be solved
 // concurrently.  Bodies are grouped as {arm + door/button/dial}, {free body 0}, {free body 1}; a
 // contact between two groups merges them.  Each island is solved by the "slot" of its lowest group:
@@ -35,42 +31,48 @@
 //   slot 1, 2: contacts of a free body (block, drawer) that touches only static geometry (or the
 //              other free body) — the common case; these records need no arm data at all.
 // Within a slot the contacts keep Bullet's order.
-#define Q_HDR 0          // ints {n_jrow | n_contact[0] << 8 | n_spin[0] << 16, t of slot 0's spin rows, t of its friction rows, t end of region 0}
+//
+// ---- Record stream.  Envs are grouped by 32; float4 number q of env (g, l) lives at float4 index
+// g * 32 * SB_Q + q * 32 + l.  All offsets are in float4 units ("q").
+#define Q_HDR 0          // ints {njr | nc0 << 8 | canon << 24 | (arm class + 1) << 25, -, -, end of region 0}
                          //      {n_contact[1] | n_spin[1] << 8 | slot of free body 0 << 16 | slot of free body 1 << 18, start[1], t_spin[1], -}
                          //      {n_contact[2] | n_spin[2] << 8, start[2], t_spin[2], -}
 #define Q_VSTAR 3        // 8 q: unconstrained velocities v* of the substep (word i = DoF i)
 #define Q_DV 11          // 8 q: solver output M^-1 J^T lambda (word i = DoF i)
-#define Q_ST 19          // start of the slot regions; region 0 starts here, region s at Q_ST + start[s];
-                         // "t" offsets are relative to the start of the slot's region
-// ---- region 0
-#define T_BODY 0         // 2 q per free body: world inverse inertia {xx xy xz yy} {yz zz 1/m -}
-#define T_MINV 4         // 12 rows x 3 q: arm inverse mass matrix (row d at T_MINV + 3 d, zero padded)
-#define T_JROW 40        // n_jrow x 1 q: {packed, rhs, invD, hi}
+#define Q_ST 19          // region 0 of a LIGHT env (arm island without contacts); a heavy env's region 0 is in its class buffer
+// ---- region 0 (same layout in the stream and in the heavy buffers; offsets relative to its start)
+#define R0_HQ 0          // ints {env, njr | nc << 8 | canon << 24, slot owners of the free bodies (as Q_HDR+1 .x), end of region}
+#define R0_BODY 1        // 2 q per free body: world inverse inertia {xx xy xz yy} {yz zz 1/m -}
+#define R0_MINV 5        // 12 rows x 3 q: arm inverse mass matrix (row d at R0_MINV + 3 d, zero padded)
+#define R0_JROW 41       // njr x 1 q: {packed, rhs, invD, hi}
                          //   packed: pd | pd2 << 8 | a << 16 | a2 << 20 | neg << 24 | sym << 25
                          //   pd/pd2: dv word of the DoF (arm: d, slide s: DVW_SLIDE(s); pd2 = 0xff: none);
                          //   a/a2: arm row (15: not arm); neg: J = -e_d; sym: lo = -hi (else lo = 0)
-                         // then ceil(n_jrow / 4) q of accumulated impulses, then (4-q aligned) slot 0's contact rows
-#define SB_MAXJROW 40
+                         // rows are ordered [limits][arm motors by DoF][slide motors][gear]; "canon": every arm DoF and
+                         // every slide body has a motor row (always, once an action was applied) — the solvers then run
+                         // the motor rows fully unrolled with compile-time register indices;
+                         // then ceil(njr / 4) q of accumulated impulses (zeroed by the solver), then the contacts
+#define SB_MAXJROW 40    // 2 limit rows + 1 motor per arm DoF, 3 slide motors, gear
 #define SB_MAXCONTACT 32
-// slot 0 contacts.  The arm part of a row is EXPLICIT (12-wide J and B = M^-1 J^T); a free-body side is
-// rebuilt from the contact frame like in slots 1, 2; a slide-body side is one scalar.  Items are multiples of
-// 4 q, grouped by pass (all normal items in contact order, all spin items, all friction items); the first
-// header of an item is its q 3:  H1 = {flags, rhs, invD, lambda},
-//   flags: bits 0-1 item type (0 row, 1 normal row + geometry, 2 compact record, 3 pointer), bit 2 slide side,
-//          bits 3-4 slide index, bit 5 free-body side, bit 6 free body index, bit 7 sign of the free side is -1
-//   row (8 q):   {JA[0..3], JA[4..7], JA[8..11], H1} {BA[0..3], BA[4..7], BA[8..11], H2}
-//                H2 = {cfm * invD (normal) | spin coefficient | mu (friction 1), t of the contact's normal item,
-//                      J of the slide side, B of the slide side}
-//   normal row + geometry (12 q): the row, then {n.xyz,-} {t1.xyz,-} {r.xyz,-} {-} of the free-body side
-//                (spin and friction rows of the contact read it through H2.y)
-//   friction item (16 q): the two friction rows of a contact
-//   compact record (8 q; both sides free body / static, as in slots 1, 2): q 0..2 = record +0..+2, q 3 = {flags},
-//                q 4..7 = record +3..+6
-//   pointer (4 q; spin / friction item of a compact record): {t of the record, spin coefficient, rhs1, invD1} - - {flags}
-// The solver kernel gives an env four lanes: lane c holds arm words 4c..4c+3 in registers and column c of the
-// items; free-body and slide velocities are replicated in the registers of all four lanes.
-#define XROW_Q 8
-// ---- slots 1, 2: compact contact record (6 q, +1 q when the second side is the other free body):
+// slot 0 contact record, fixed layout (the solver issues every load of a visit at a fixed offset before it has
+// decoded the flags, so nothing depends on a previous load):
+//   +0 H0 {flags, rhs n, invD n, cfm * invD n}     +1 H1 {rhs spin, invD spin, spin coefficient, mu}
+//   +2 H2 {rhs t1, rhs t2, invD t1, invD t2}        +3 L  {lambda n, lambda spin, lambda t1, lambda t2}
+//   +4 G0 {n.xyz, rS.x}  +5 G1 {t1.xyz, rS.y}  +6 G2 {rF.xyz, rS.z}   (free-body side: lever arm rF; second free body: rS)
+//   +7 SL {J of the slide side for the rows n, spin, t1, t2}            (B = J * slide_minv)
+//   +8 ... arm side, explicit 12-wide J and B = M^-1 J^T, 6 q per row: n, t1, t2, [spin] (fixed offsets 8, 14, 20, 26)
+//   flags: 1 arm side | 2 free-body side | 4 its body index | 8 its sign is -1 | 16 second free body (index 1 - first)
+//          | 32 slide side | slide index << 6 | 256 spin row | size in q << 16
+#define CR_ARM 1
+#define CR_FREE 2
+#define CR_FB 4
+#define CR_FNEG 8
+#define CR_TWO 16
+#define CR_SLIDE 32
+#define CR_SPIN 256
+#define CR_BASE_Q 8
+#define CR_MAX_Q 32      // 8 + 4 rows x 6 q; also the look-ahead of the solver's fixed-offset loads
+// ---- slots 1, 2 (stream, from Q_S12): compact contact record (6 q, +1 q when the second side is the other free body):
 //   +0 {packed, cfm * invD0, rhs0, invD0}     +1 {n.xyz, lambda0}        +2 {rP.xyz, mu}
 //   +3 {t1.xyz, lambda1 (spin)}               +4 {rhs2, rhs3, invD2, invD3}   +5 {lambda2, lambda3, -, -}
 //   +6 {rS.xyz, -} when side S is a free body
@@ -79,37 +81,68 @@
 //   record — a record never straddles the stage boundary PGS_STAGE_F)
 // spin list entry (1 q): {t of the contact record, spin coefficient, rhs1, invD1}
 #define CT_BASE_Q 6
-#define SB_Q (Q_ST + 96 + SB_MAXCONTACT * (12 + 8 + 16) + 3 * 4 + SB_MAXCONTACT * 8 + 64 + 8)
+#define R0_LIGHT_END (R0_JROW + SB_MAXJROW + SB_MAXJROW / 4)
+#define Q_S12 (Q_ST + R0_LIGHT_END + 1)
+#define SB_Q (Q_S12 + SB_MAXCONTACT * 7 + SB_MAXCONTACT + 2 * 8 + 12)
 #define SB_PAD_Q 48      // readable slack after the last group (the solvers prefetch one record ahead)
-// stage capacities (q of shared memory per env) of the solver kernels
+// stage capacities (q of shared memory per env) of the light solver kernels
 #ifndef PGS_STAGE_J
-#define PGS_STAGE_J 68   // joint-row kernel: region 0 up to the impulses of <= 22 joint rows; 6 blocks per SM
+#define PGS_STAGE_J 72   // joint-row kernel: region 0 up to the impulses of <= 24 joint rows; 6 blocks per SM
 #endif
 #ifndef PGS_STAGE_F
 #define PGS_STAGE_F 64   // free-body kernel: 10 contact records; 6 blocks per SM
 #endif
-#define PGS_G_LW 2       // arm-island kernel: an env owns 4 shared-memory columns (8 envs per warp)
-#define PGS_NCLASS 4      // size classes of the arm-island kernel (by the q count of region 0): rows of 4 q per env
-#ifndef PGS_ROWS_G0       // (overridable: the CPU tests build a variant with tiny stages to exercise the read-in-place path)
-#define PGS_ROWS_G0 56   // class 0: 224 q per env, 7 blocks per SM (56 envs)
-#define PGS_ROWS_G1 80   // class 1: 320 q per env, 5 blocks per SM (40 envs)
-#define PGS_ROWS_G2 104  // class 2: 416 q per env, 4 blocks per SM (32 envs)
-#define PGS_ROWS_G3 216  // class 3: 864 q per env (larger islands read the rest in place), 2 blocks per SM (16 envs)
+#define PGS_MAXJROW_J ((PGS_STAGE_J - R0_JROW) * 4 / 5)     // njr + ceil(njr / 4) <= PGS_STAGE_J - R0_JROW
+// ---- arm-island ("heavy") size classes: class k gives an env ARM_CAPQ(k) q of shared memory and a thread block
+// ARM_LANES(k) envs, so that every class keeps 3-4 blocks (one warp each) resident per SM; class 4 stages the first
+// ARM_CAPQ(4) q and reads the records beyond that in place.  The heavy buffer of a class is an array of bundles of
+// ARM_LANES(k) envs, lane-interleaved like the stage: a block stages its bundle with ONE bulk copy.
+#define ARM_NCLASS 5
+#ifndef ARM_CAPQ0         // (overridable: the CPU tests build a variant with tiny stages to exercise the read-in-place path)
+#define ARM_CAPQ0 136
+#define ARM_CAPQ1 220
+#define ARM_CAPQ2 288
+#define ARM_CAPQ3 440
+#define ARM_CAPQ4 880
 #endif
-#define PGS_ROWS_GMAX PGS_ROWS_G3
-PRB_HD int pgs_class_rows(int cls) { return cls == 0 ? PGS_ROWS_G0 : (cls == 1 ? PGS_ROWS_G1 : (cls == 2 ? PGS_ROWS_G2 : PGS_ROWS_G3)); }
-#define PGS_MAXJROW_J ((PGS_STAGE_J - T_JROW) * 4 / 5)     // njr + ceil(njr / 4) <= PGS_STAGE_J - T_JROW
+#define ARM_BUFQ_MAX (R0_LIGHT_END + SB_MAXCONTACT * CR_MAX_Q + CR_MAX_Q + 4)
+PRB_HD int arm_lanes(int k) { return k == 0 ? 32 : (k <= 2 ? 16 : (k == 3 ? 8 : 4)); }
+PRB_HD int arm_capq(int k) { return k == 0 ? ARM_CAPQ0 : (k == 1 ? ARM_CAPQ1 : (k == 2 ? ARM_CAPQ2 : (k == 3 ? ARM_CAPQ3 : ARM_CAPQ4))); }
+PRB_HD int arm_bufq(int k) { return k == ARM_NCLASS - 1 ? ARM_BUFQ_MAX : arm_capq(k); }
+// float4 offset of class k's buffer inside the heavy allocation for N envs (every class can take all N)
+PRB_HD size_t arm_class_base(int k, int64_t N) {
+  size_t o = 0;
+  for (int j = 0; j < k; j++) o += (size_t)((N + arm_lanes(j) - 1) / arm_lanes(j)) * arm_lanes(j) * arm_bufq(j);
+  return o;
+}
+PRB_HD size_t hbuf_bytes(int64_t N) { return (arm_class_base(ARM_NCLASS, N) + 64) * sizeof(float4); }
+// class of an arm island whose region ends at tEnd (the solver's fixed-offset loads look CR_MAX_Q - CR_BASE_Q q ahead)
+PRB_HD int arm_class_of(int tEnd) {
+  const int need = tEnd + CR_MAX_Q - CR_BASE_Q;
+  for (int k = 0; k < ARM_NCLASS - 1; k++) if (need <= arm_capq(k)) return k;
+  return ARM_NCLASS - 1;
+}
 #define DVW_SLIDE(s) (28 + (s))
 enum { K_STATIC = 0, K_FREE = 1, K_SLIDE = 2, K_ARM = 3 };
 
-struct SV {              // one env's column of its group
+struct SV {              // one env's column: q i at b[i * stride]
   float4* b;
-  PRB_D float4& q(int i) const { return b[i * 32]; }
-  PRB_D float& w(int i) const { return reinterpret_cast<float*>(&b[(i >> 2) * 32])[i & 3]; }
+  int stride;
+  PRB_D float4& q(int i) const { return b[(size_t)i * stride]; }
+  PRB_D float& w(int i) const { return reinterpret_cast<float*>(&b[(size_t)(i >> 2) * stride])[i & 3]; }
 };
 PRB_D SV sv_of(float* sbuf, int e) {
   SV s;
   s.b = reinterpret_cast<float4*>(sbuf) + (size_t)(e >> 5) * (SB_Q * 32) + (e & 31);
+  s.stride = 32;
+  return s;
+}
+// column of list slot i of class k in the heavy allocation
+PRB_D SV hv_of(float4* hbuf, int k, int i, int N) {
+  const int L = arm_lanes(k);
+  SV s;
+  s.b = hbuf + arm_class_base(k, N) + (size_t)(i / L) * ((size_t)arm_bufq(k) * L) + (i % L);
+  s.stride = L;
   return s;
 }
 PRB_HD size_t sbuf_bytes(int64_t N) { return ((size_t)((N + 31) / 32) * 32 * SB_Q + 32 * SB_PAD_Q) * sizeof(float4); }
@@ -150,12 +183,12 @@ PRB_D int kind_rank(int k) { return k == K_ARM ? 3 : (k == K_SLIDE ? 2 : (k == K
 
 // One side of one constraint row: J = unit force `dir` at world point pt (or unit torque when angular)
 // on the body of collider col, times sign; B = M^-1 J^T.  Returns J.B and accumulates J.v*.  When gJ is
-// given, an arm side writes (accum: adds to) its explicit J and B, 3 q each at stride 32; a slide side
-// returns its scalar J and B in *js, *bs; free-body sides store nothing (the solvers rebuild them from the
+// given, an arm side writes (accum: adds to) its explicit J and B, 3 q each at `stride`; a slide side
+// returns its scalar J in *js; free-body sides store nothing (the solvers rebuild them from the
 // contact geometry).
 template <int ND, class WM>
 PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, float sign, bool angular,
-                     float4* gJ, float4* gB, bool accum, float* js, float* bs, float* rel) {
+                     float4* gJ, float4* gB, int stride, bool accum, float* js, float* rel) {
   const int body = M.col_body[col];
   float d = 0.f;
   if (body == 0) {
@@ -189,11 +222,11 @@ PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, flo
         float4 j4 = make_float4(J[4 * k], J[4 * k + 1], J[4 * k + 2], J[4 * k + 3]);
         float4 b4 = make_float4(B[4 * k], B[4 * k + 1], B[4 * k + 2], B[4 * k + 3]);
         if (accum) {                           // second arm side of an arm-arm contact
-          const float4 pj = gJ[k * 32], pb = gB[k * 32];
+          const float4 pj = gJ[(size_t)k * stride], pb = gB[(size_t)k * stride];
           j4 = make_float4(j4.x + pj.x, j4.y + pj.y, j4.z + pj.z, j4.w + pj.w);
           b4 = make_float4(b4.x + pb.x, b4.y + pb.y, b4.z + pb.z, b4.w + pb.w);
         }
-        gJ[k * 32] = j4; gB[k * 32] = b4;
+        gJ[(size_t)k * stride] = j4; gB[(size_t)k * stride] = b4;
       }
     }
     *rel += r;
@@ -215,7 +248,7 @@ PRB_D float side_row(const DevModel& M, const WM& W, int col, v3 pt, v3 dir, flo
     if (M.slide_jtype[s] == 0) g = angular ? dot(a, dir) : dot(a, cross(pt - ld3(W.sp[s]), dir));
     else g = angular ? 0.f : dot(a, dir);
     const float j = sign * g, bb = j * M.slide_minv[s];
-    *js = j; *bs = bb;
+    *js = j;
     d = j * bb; *rel += j * W.vs[o];
   }
   return d;
@@ -225,81 +258,72 @@ PRB_D int dvw_of(const DevModel& M, int d) {     // velocity DoF -> dv word of a
   if (d < M.nd) return d;
   return DVW_SLIDE(d - M.nd - 6 * M.n_free);
 }
+PRB_D float4 jrow_q(const DevModel& M, int d, int d2, int neg, int sym, float rhs, float invD, float hi) {
+  const int nd = M.nd;
+  const int pk = dvw_of(M, d) | ((d2 < 0 ? 0xff : dvw_of(M, d2)) << 8) | ((d < nd ? d : 15) << 16) |
+                 (((d2 >= 0 && d2 < nd) ? d2 : 15) << 20) | (neg << 24) | (sym << 25);
+  return make_float4(__int_as_float(pk), rhs, invD, hi);
+}
 
-// constraint rows of the substep -> record stream
+// constraint rows of the substep -> record stream / heavy buffers
 template <int ND, class WM>
-PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
+PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, int e, int N, const SV& S, float4* __restrict__ hbuf,
+                             int* __restrict__ heavy_cnt) {
   const float dt = M.params[P_DT], erp = M.params[P_ERP_JOINT], erp2 = M.params[P_ERP_CONTACT];
   const int nd = M.nd;
-  // ---- joint rows (lane 0, serial: <= 40 rows of a few flops each): limits, motors, gear
-  if (lane == 0) {
-    int nr = 0;
-#define PRB_PUT_JROW(d_, d2_, neg_, sym_, rhs_, invD_, hi_)                                                \
-    do {                                                                                                  \
-      if (nr >= SB_MAXJROW) { W.overflow = 1; }                                                            \
-      else {                                                                                              \
-        const int d__ = (d_), d2__ = (d2_);                                                               \
-        const int pk__ = dvw_of(M, d__) | ((d2__ < 0 ? 0xff : dvw_of(M, d2__)) << 8) | ((d__ < nd ? d__ : 15) << 16) | \
-                         (((d2__ >= 0 && d2__ < nd) ? d2__ : 15) << 20) | ((neg_) << 24) | ((sym_) << 25); \
-        S.q(Q_ST + T_JROW + nr) = make_float4(__int_as_float(pk__), rhs_, invD_, hi_);                    \
-        nr++;                                                                                             \
-      }                                                                                                   \
-    } while (0)
-    for (int i = 0; i < nd; i++) {
-      if (M.lo[i] > M.hi[i]) continue;
+  // ---- joint rows, one lane per DoF: limits (lane = arm DoF), motors (lane = arm DoF; lanes 16.. = slide bodies), gear (lane 20).
+  // Row order (Bullet's): [limits by DoF, lower side first][arm motors by DoF][slide motors][gear]
+  float4 jr_lim[2], jr_mot = make_float4(0.f, 0.f, 0.f, 0.f);
+  int n_lim = 0, n_mot = 0, n_sl = 0, n_gear = 0;
+  jr_lim[0] = jr_mot; jr_lim[1] = jr_mot;
+  if (lane < nd) {
+    const int i = lane;
+    const float invD = 1.0f / W.Minv[i][i];
+    if (!(M.lo[i] > M.hi[i])) {
+#pragma unroll
       for (int side = 0; side < 2; side++) {
-        float pen = side == 0 ? W.q[i] - M.lo[i] : M.hi[i] - W.q[i];
+        const float pen = side == 0 ? W.q[i] - M.lo[i] : M.hi[i] - W.q[i];
         if (pen > 0.f) continue;
-        float sg = side == 0 ? 1.0f : -1.0f;
-        float invD = 1.0f / W.Minv[i][i];
-        float rel = sg * W.vs[i];
-        float e = pen > -0.04f ? erp : erp2;
-        PRB_PUT_JROW(i, -1, side, 0, (-pen * e / dt - rel) * invD, invD, M.params[P_LIMIT_MAX_IMPULSE]);
+        const float sg = side == 0 ? 1.0f : -1.0f;
+        const float rel = sg * W.vs[i];
+        const float er = pen > -0.04f ? erp : erp2;
+        const float4 row = jrow_q(M, i, -1, side, 0, (-pen * er / dt - rel) * invD, invD, M.params[P_LIMIT_MAX_IMPULSE]);
+        if (n_lim == 0) jr_lim[0] = row; else jr_lim[1] = row;
+        n_lim++;
       }
     }
-    for (int i = 0; i < nd; i++) {
-      if (W.mmaximp[i] <= 0.f) continue;
-      float invD = 1.0f / W.Minv[i][i];
-      float v = W.vs[i];
-      float target_v = W.mkp[i] * (W.mtarget[i] - W.q[i]) / dt + v + M.params[P_MOTOR_KD] * (0.f - v);
-      PRB_PUT_JROW(i, -1, 0, 1, (target_v - v) * invD, invD, W.mmaximp[i]);
+    if (W.mmaximp[i] > 0.f) {
+      const float v = W.vs[i];
+      const float target_v = W.mkp[i] * (W.mtarget[i] - W.q[i]) / dt + v + M.params[P_MOTOR_KD] * (0.f - v);
+      jr_mot = jrow_q(M, i, -1, 0, 1, (target_v - v) * invD, invD, W.mmaximp[i]);
+      n_mot = 1;
     }
-    for (int s = 0; s < M.n_slide; s++) {
-      int o = nd + 6 * M.n_free + s;
-      float maximp = M.slide_motor[s][3] < 0 ? M.params[P_DEFAULT_MOTOR_IMPULSE] : M.slide_motor[s][3];
-      if (maximp <= 0.f) continue;
-      float invD = 1.0f / M.slide_minv[s];
-      float v = W.vs[o];
-      float target_v = M.slide_motor[s][1] * (M.slide_motor[s][0] - W.sq[s]) / dt + v + M.slide_motor[s][2] * (0.f - v);
-      PRB_PUT_JROW(o, -1, 0, 1, (target_v - v) * invD, invD, maximp);
+  } else if (lane >= 16 && lane - 16 < M.n_slide) {
+    const int s = lane - 16, o = nd + 6 * M.n_free + s;
+    const float maximp = M.slide_motor[s][3] < 0 ? M.params[P_DEFAULT_MOTOR_IMPULSE] : M.slide_motor[s][3];
+    if (maximp > 0.f) {
+      const float invD = 1.0f / M.slide_minv[s];
+      const float v = W.vs[o];
+      const float target_v = M.slide_motor[s][1] * (M.slide_motor[s][0] - W.sq[s]) / dt + v + M.slide_motor[s][2] * (0.f - v);
+      jr_mot = jrow_q(M, o, -1, 0, 1, (target_v - v) * invD, invD, maximp);
+      n_sl = 1;
     }
-    if (M.gear_a >= 0) {
-      int a = M.gear_a, b = M.gear_b;
-      float r = M.params[P_GEAR_RATIO];
-      float D = W.Minv[a][a] + 2.f * r * W.Minv[a][b] + r * r * W.Minv[b][b];
-      float invD = 1.0f / D;
-      float rel = W.vs[a] + r * W.vs[b];
-      PRB_PUT_JROW(a, b, 0, 1, (-rel * M.params[P_GEAR_ERP]) * invD, invD, M.params[P_GEAR_MAX_IMPULSE]);
-    }
-#undef PRB_PUT_JROW
-    W.n_jrow = nr;
+  } else if (lane == 20 && M.gear_a >= 0) {
+    const int a = M.gear_a, b = M.gear_b;
+    const float r = M.params[P_GEAR_RATIO];
+    const float D = W.Minv[a][a] + 2.f * r * W.Minv[a][b] + r * r * W.Minv[b][b];
+    const float invD = 1.0f / D;
+    const float rel = W.vs[a] + r * W.vs[b];
+    jr_mot = jrow_q(M, a, b, 0, 1, (-rel * M.params[P_GEAR_ERP]) * invD, invD, M.params[P_GEAR_MAX_IMPULSE]);
+    n_gear = 1;
   }
-  // ---- arm inverse mass matrix (lane = row), zero padded to 12 columns; free-body table
-  if (lane < ND) {
-    float r[12];
-#pragma unroll
-    for (int j = 0; j < 12; j++) r[j] = j < ND ? W.Minv[lane][j] : 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; k++) S.q(Q_ST + T_MINV + 3 * lane + k) = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
-  }
-  if (lane >= 16 && lane - 16 < M.n_free) {
-    const int b = lane - 16;
-    S.q(Q_ST + T_BODY + 2 * b) = make_float4(W.fIinv[b][0], W.fIinv[b][1], W.fIinv[b][2], W.fIinv[b][3]);
-    S.q(Q_ST + T_BODY + 2 * b + 1) = make_float4(W.fIinv[b][4], W.fIinv[b][5], 1.0f / M.free_mass[b], 0.f);
-  }
-  __syncwarp();
+  int jtot;
+  const int jpre = warp_excl_scan(n_lim | (n_mot << 8) | (n_sl << 16) | (n_gear << 24), lane, &jtot);
+  const int nL = jtot & 0xff, nMo = (jtot >> 8) & 0xff, nSl = (jtot >> 16) & 0xff, nGe = (jtot >> 24) & 0xff;
+  const int njr = nL + nMo + nSl + nGe;            // <= 2 nd + nd + n_slide + 1 <= SB_MAXJROW
+  const bool canon = nMo == nd && nSl == M.n_slide;
   // ---- contacts: lane = contact
-  const int nc = W.n_contact, njr = W.n_jrow;
+  const int nc = W.n_contact;
   int colP = 0, colS = 0, kP = K_STATIC, kS = K_STATIC, grpP = 0, grpS = -1;
   bool swapped = false, has_spin = false;
   float spin = 0.f;
@@ -329,26 +353,21 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
     slotf[1] = c02 ? 0 : (c12 ? 1 : 2);
   }
   const int slot = lane < nc ? (grpP == 0 ? 0 : slotf[grpP - 1]) : -1;
-  // ---- placement.  Slot 0: items grouped by pass
+  // ---- placement.  Slot 0: one record per contact, in contact order
   const bool s0 = slot == 0;
-  const bool cmp0 = s0 && kP == K_FREE;                              // both sides free body / static: compact record
-  const bool freeS = s0 && !cmp0 && kS == K_FREE;                    // row items with a free-body side
-  const int szN = s0 ? (freeS ? 12 : 8) : 0;
-  const int szS = (s0 && has_spin) ? (cmp0 ? 4 : 8) : 0;
-  const int szT = s0 ? (cmp0 ? 4 : 16) : 0;
-  int totN, totS, totT;
-  const int offN = warp_excl_scan(szN, lane, &totN);
-  const int offS = warp_excl_scan(szS, lane, &totS);
-  const int offT = warp_excl_scan(szT, lane, &totT);
-  const int tN0 = (T_JROW + njr + ((njr + 3) >> 2) + 3) & ~3;
-  const int tS0 = tN0 + totN, tT0 = tS0 + totS, tEnd0 = tT0 + totT;
-  const int nc0 = __popc(__ballot_sync(FULL, s0)), ns0 = __popc(__ballot_sync(FULL, s0 && has_spin));
+  const bool armP = s0 && kP == K_ARM;
+  const int size0 = s0 ? CR_BASE_Q + (armP ? (has_spin ? 24 : 18) : 0) : 0;
+  int tot0;
+  const int off0 = warp_excl_scan(size0, lane, &tot0);
+  const int tC0 = R0_JROW + njr + ((njr + 3) >> 2);
+  const int tEnd0 = tC0 + tot0;
+  const int nc0 = __popc(__ballot_sync(FULL, s0));
   // slots 1, 2: compact records + spin list per region
   const int size = (lane < nc && !s0) ? CT_BASE_Q + (kS == K_FREE ? 1 : 0) : 0;
-  int t = 0, stride = size, t_spin_mine = 0, spin_rank = 0, region_mine = 0;
-  int ncs[3] = {nc0, 0, 0}, nss[3] = {ns0, 0, 0}, tsp[3] = {tS0, 0, 0}, start[3] = {0, 0, 0};
+  int t = 0, stride12 = size, t_spin_mine = 0, spin_rank = 0, region_mine = 0;
+  int ncs[3] = {nc0, 0, 0}, nss[3] = {0, 0, 0}, tsp[3] = {0, 0, 0}, start[3] = {0, 0, 0};
   {
-    int region = tEnd0;                               // start of the slot's region relative to Q_ST
+    int region = 0;                                   // start of the slot's region relative to Q_S12
 #pragma unroll
     for (int sidx = 1; sidx < 3; sidx++) {
       const bool mine = slot == sidx;
@@ -369,111 +388,142 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, const SV& S) {
       const int tnext = __shfl_sync(FULL, ts, nl);
       const int tend = total + shift;
       if (mine) {
-        t = ts; stride = later ? tnext - ts : size;
+        t = ts; stride12 = later ? tnext - ts : size;
         t_spin_mine = tend; spin_rank = __popc(smask & ((1u << lane) - 1u)); region_mine = region;
       }
       ncs[sidx] = __popc(mask); nss[sidx] = __popc(smask); tsp[sidx] = tend; start[sidx] = region;
       region += tend + nss[sidx];
     }
-    if (lane == 0) { W.dbg_p = region; W.dbg_a = tEnd0; }
+    if (lane == 0) { W.dbg_p = Q_S12 + region; W.dbg_a = tEnd0; }
   }
+  // ---- where region 0 goes: a light env keeps it in its stream column; an arm island with contacts (or more joint
+  // rows than the light kernel stages) takes the next slot of its size class's heavy buffer
+  const bool heavy = nc0 > 0 || njr > PGS_MAXJROW_J;
+  const int cls = arm_class_of(tEnd0);
+  int hslot = 0;
+  if (heavy && lane == 0) hslot = atomicAdd(heavy_cnt + 4 * cls, 1);       // heavy_cnt: {bundle-list length, -, work counter, -} per class
+  hslot = __shfl_sync(FULL, hslot, 0);
+  SV R;
+  if (heavy) R = hv_of(hbuf, cls, hslot, N);
+  else { R.b = &S.q(Q_ST); R.stride = 32; }
+  const int info = ncs[1] | (nss[1] << 8) | (slotf[0] << 16) | (slotf[1] << 18);
+  // ---- region 0, fixed part: header, free-body table, arm inverse mass matrix (lane = row), joint rows
+  if (lane == 31) R.q(R0_HQ) = make_float4(__int_as_float(e), __int_as_float(njr | (nc0 << 8) | ((canon ? 1 : 0) << 24)), __int_as_float(info), __int_as_float(tEnd0));
+  if (lane < ND) {
+    float r[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) r[j] = j < ND ? W.Minv[lane][j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) R.q(R0_MINV + 3 * lane + k) = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+  }
+  if (lane >= 24 && lane - 24 < PRB_MAXFREE) {
+    const int b = lane - 24;
+    float4 i0 = make_float4(0.f, 0.f, 0.f, 0.f), i1 = i0;
+    if (b < M.n_free) {
+      i0 = make_float4(W.fIinv[b][0], W.fIinv[b][1], W.fIinv[b][2], W.fIinv[b][3]);
+      i1 = make_float4(W.fIinv[b][4], W.fIinv[b][5], 1.0f / M.free_mass[b], 0.f);
+    }
+    R.q(R0_BODY + 2 * b) = i0; R.q(R0_BODY + 2 * b + 1) = i1;
+    if (heavy) { S.q(Q_ST + R0_BODY + 2 * b) = i0; S.q(Q_ST + R0_BODY + 2 * b + 1) = i1; }    // the free-body kernel reads the stream
+  }
+  {
+    const int pL = jpre & 0xff, pMo = (jpre >> 8) & 0xff, pSl = (jpre >> 16) & 0xff;
+    if (n_lim > 0) R.q(R0_JROW + pL) = jr_lim[0];
+    if (n_lim > 1) R.q(R0_JROW + pL + 1) = jr_lim[1];
+    if (n_mot) R.q(R0_JROW + nL + pMo) = jr_mot;
+    if (n_sl) R.q(R0_JROW + nL + nMo + pSl) = jr_mot;
+    if (n_gear) R.q(R0_JROW + nL + nMo + nSl) = jr_mot;
+  }
+  if (lane == 0) W.n_jrow = njr;
+  // ---- contact rows
   if (lane < nc) {
     const int ca = c.cols & 0xff, cb = (c.cols >> 8) & 0xff;
     v3 n = V3(c.nx, c.ny, c.nz), pb = V3(c.pbx, c.pby, c.pbz), pa = pb + n * c.dist;
     const v3 pP = swapped ? pb : pa, pS = swapped ? pa : pb;
     const float sP = swapped ? -1.0f : 1.0f;
-    float cfm = 0.f, e = erp2;
+    float cfm = 0.f, er = erp2;
     float sa = M.col_stiff[ca], sb = M.col_stiff[cb];
     if (sa >= 0.f || sb >= 0.f) {       // URDF <contact> stiffness / damping on the gripper links
       float ka = sa >= 0.f ? sa : 1e18f, kb = sb >= 0.f ? sb : 1e18f;
       float da = sa >= 0.f ? M.col_damp[ca] : 0.1f, db = sb >= 0.f ? M.col_damp[cb] : 0.1f;
       float kk = 1.0f / (1.0f / ka + 1.0f / kb), dd = da + db;
       float denom = fmaxf(dt * kk + dd, 1.1920929e-7f);
-      cfm = 1.0f / denom; e = dt * kk / denom;
+      cfm = 1.0f / denom; er = dt * kk / denom;
     }
     cfm /= dt;
     const float mu = clampf(M.col_fric[ca] * M.col_fric[cb], -10.f, 10.f);
     v3 t1, t2;
     plane_space(n, t1, t2);
     float cfms = 0.f;
-    float rhs[4] = {0.f, 0.f, 0.f, 0.f}, invDs[4] = {0.f, 0.f, 0.f, 0.f};
-    const int tN = tN0 + offN;
+    float rhs[4] = {0.f, 0.f, 0.f, 0.f}, invDs[4] = {0.f, 0.f, 0.f, 0.f}, jsl[4] = {0.f, 0.f, 0.f, 0.f};
+    float4* rec = s0 ? &R.q(tC0 + off0) : nullptr;           // slot 0 record
+    const int rstride = R.stride;
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
       v3 dir = k == 0 ? n : (k == 1 ? n : (k == 2 ? t1 : t2));
       const bool ang = (k == 1);
       if (k == 1 && !has_spin) continue;      // no torsional row: never visited by the solver
-      const bool xrow = s0 && !cmp0;
-      const int tr = k == 0 ? tN : (k == 1 ? tS0 + offS : tT0 + offT + (k == 3 ? 8 : 0));
-      float4* row = &S.q(Q_ST + tr);
-      float js = 0.f, bs = 0.f;
-      if (xrow && kP != K_ARM) {               // no arm side: zero arm part
-#pragma unroll
-        for (int j = 0; j < 3; j++) { row[j * 32] = make_float4(0.f, 0.f, 0.f, 0.f); row[(4 + j) * 32] = make_float4(0.f, 0.f, 0.f, 0.f); }
-      }
+      const int ridx = k == 0 ? 0 : (k == 1 ? 3 : k - 1);     // arm rows in memory: n, t1, t2, spin
+      float4* rowJ = armP ? rec + (size_t)(CR_BASE_Q + 6 * ridx) * rstride : nullptr;
+      float4* rowB = armP ? rowJ + (size_t)3 * rstride : nullptr;
+      float js = 0.f;
       float rel = 0.f, D = 0.f;
-      D += side_row<ND>(M, W, colP, pP, dir, sP, ang, xrow ? row : nullptr, row + 4 * 32, false, &js, &bs, &rel);
-      if (kS != K_STATIC) D += side_row<ND>(M, W, colS, pS, dir, -sP, ang, xrow ? row : nullptr, row + 4 * 32, true, &js, &bs, &rel);
+      D += side_row<ND>(M, W, colP, pP, dir, sP, ang, rowJ, rowB, rstride, false, &js, &rel);
+      if (kS != K_STATIC) D += side_row<ND>(M, W, colS, pS, dir, -sP, ang, rowJ, rowB, rstride, true, &js, &rel);
       if (k == 0) D += cfm;
       const float invD = D > 1.1920929e-7f ? 1.0f / D : 0.f;
       if (k == 0) {
         float pen = c.dist + M.params[P_LINEAR_SLOP];
         float poserr = 0.f, velerr = -rel;
-        if (pen > 0.f) velerr -= pen / dt; else poserr = -pen * e / dt;
+        if (pen > 0.f) velerr -= pen / dt; else poserr = -pen * er / dt;
         rhs[0] = (poserr + velerr) * invD;
         cfms = cfm * invD;
       } else rhs[k] = -rel * invD;
-      invDs[k] = invD;
-      if (xrow) {                              // arm part written above; slide side as a scalar; free side through the geometry
-        const int sld = kP == K_SLIDE ? M.col_body[colP] - 1 - M.n_free : (kS == K_SLIDE ? M.col_body[colS] - 1 - M.n_free : -1);
-        if (kP == K_SLIDE && kS == K_SLIDE) W.overflow = 1;          // two slide bodies in one contact: not representable
-        const int fb = freeS ? M.col_body[colS] - 1 : 0;
-        const int flags = (k == 0 && freeS ? 1 : 0) | (sld >= 0 ? (4 | (sld << 3)) : 0) | (freeS ? (32 | (fb << 6) | (sP > 0.f ? 128 : 0)) : 0);
-        row[3 * 32] = make_float4(__int_as_float(flags), rhs[k], invD, 0.f);
-        row[7 * 32] = make_float4(k == 0 ? cfms : (k == 1 ? spin : (k == 2 ? mu : 0.f)), __int_as_float(tN), js, bs);
-        if (k == 0 && freeS) {
-          const v3 rS = pS - ld3(W.fpos[fb]);
-          row[8 * 32] = make_float4(n.x, n.y, n.z, 0.f);
-          row[9 * 32] = make_float4(t1.x, t1.y, t1.z, 0.f);
-          row[10 * 32] = make_float4(rS.x, rS.y, rS.z, 0.f);
-          row[11 * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
+      invDs[k] = invD; jsl[k] = js;
     }
-    if (!s0 || cmp0) {                         // compact record (both sides are free bodies or static)
+    if (s0) {
+      // sides by kind: arm (P), slide (P or S), free (P, or S under an arm / slide P; both when P and S are free bodies)
+      const bool slideP = kP == K_SLIDE, slideS = kS == K_SLIDE, freeP = kP == K_FREE, freeS = kS == K_FREE;
+      if (slideP && slideS) W.overflow = 1;                       // two slide bodies in one contact: not representable
+      const int sld = slideP ? M.col_body[colP] - 1 - M.n_free : (slideS ? M.col_body[colS] - 1 - M.n_free : 0);
+      const int fb = freeP ? M.col_body[colP] - 1 : (freeS ? M.col_body[colS] - 1 : 0);
+      const float sgnF = freeP ? sP : -sP;
+      const bool two = freeP && freeS;
+      const int flags = (armP ? CR_ARM : 0) | ((freeP || freeS) ? CR_FREE : 0) | (fb ? CR_FB : 0) | (sgnF < 0.f ? CR_FNEG : 0) |
+                        (two ? CR_TWO : 0) | ((slideP || slideS) ? (CR_SLIDE | (sld << 6)) : 0) | (has_spin ? CR_SPIN : 0) | (size0 << 16);
+      v3 rF = V3(0, 0, 0), rS2 = V3(0, 0, 0);
+      if (freeP) rF = pP - ld3(W.fpos[fb]); else if (freeS) rF = pS - ld3(W.fpos[fb]);
+      if (two) rS2 = pS - ld3(W.fpos[M.col_body[colS] - 1]);
+      rec[0] = make_float4(__int_as_float(flags), rhs[0], invDs[0], cfms);
+      rec[(size_t)1 * rstride] = make_float4(rhs[1], invDs[1], spin, mu);
+      rec[(size_t)2 * rstride] = make_float4(rhs[2], rhs[3], invDs[2], invDs[3]);
+      rec[(size_t)3 * rstride] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rec[(size_t)4 * rstride] = make_float4(n.x, n.y, n.z, rS2.x);
+      rec[(size_t)5 * rstride] = make_float4(t1.x, t1.y, t1.z, rS2.y);
+      rec[(size_t)6 * rstride] = make_float4(rF.x, rF.y, rF.z, rS2.z);
+      rec[(size_t)7 * rstride] = make_float4(jsl[0], jsl[1], jsl[2], jsl[3]);
+    } else {                                   // slots 1, 2: compact record (both sides are free bodies or static)
       const int iP = M.col_body[colP] - 1, iS = kS == K_FREE ? M.col_body[colS] - 1 : 0;
       const v3 rP = pP - ld3(W.fpos[iP]);
-      const int packed = (kS << 2) | (iP << 4) | (iS << 7) | ((swapped ? 1 : 0) << 10) | ((has_spin ? 1 : 0) << 11) | (stride << 12);
-      const float4 r0 = make_float4(__int_as_float(packed), cfms, rhs[0], invDs[0]), r1 = make_float4(n.x, n.y, n.z, 0.f);
-      const float4 r2 = make_float4(rP.x, rP.y, rP.z, mu), r3 = make_float4(t1.x, t1.y, t1.z, 0.f);
-      const float4 r4 = make_float4(rhs[2], rhs[3], invDs[2], invDs[3]), r5 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 r6 = r5;
-      if (kS == K_FREE) { const v3 rS = pS - ld3(W.fpos[iS]); r6 = make_float4(rS.x, rS.y, rS.z, 0.f); }
-      if (!s0) {
-        float4* rec = &S.q(Q_ST + region_mine + t);
-        rec[0] = r0; rec[32] = r1; rec[64] = r2; rec[96] = r3; rec[128] = r4; rec[160] = r5;
-        if (kS == K_FREE) rec[192] = r6;
-        if (has_spin) S.q(Q_ST + region_mine + t_spin_mine + spin_rank) = make_float4(__int_as_float(t), spin, rhs[1], invDs[1]);
-      } else {                                 // slot 0: compact item + pointer items in the spin / friction passes
-        float4* it = &S.q(Q_ST + tN);
-        it[0] = r0; it[32] = r1; it[64] = r2; it[96] = make_float4(__int_as_float(2), 0.f, 0.f, 0.f);
-        it[128] = r3; it[160] = r4; it[192] = r5; it[224] = r6;
-        const float4 ph = make_float4(__int_as_float(3), 0.f, 0.f, 0.f);
-        if (has_spin) { float4* ps = &S.q(Q_ST + tS0 + offS); ps[0] = make_float4(__int_as_float(tN), spin, rhs[1], invDs[1]); ps[96] = ph; }
-        float4* pt_ = &S.q(Q_ST + tT0 + offT);
-        pt_[0] = make_float4(__int_as_float(tN), 0.f, 0.f, 0.f); pt_[96] = ph;
-      }
+      const int packed = (kS << 2) | (iP << 4) | (iS << 7) | ((swapped ? 1 : 0) << 10) | ((has_spin ? 1 : 0) << 11) | (stride12 << 12);
+      float4* r12 = &S.q(Q_S12 + region_mine + t);
+      r12[0] = make_float4(__int_as_float(packed), cfms, rhs[0], invDs[0]);
+      r12[32] = make_float4(n.x, n.y, n.z, 0.f);
+      r12[64] = make_float4(rP.x, rP.y, rP.z, mu);
+      r12[96] = make_float4(t1.x, t1.y, t1.z, 0.f);
+      r12[128] = make_float4(rhs[2], rhs[3], invDs[2], invDs[3]);
+      r12[160] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kS == K_FREE) { const v3 rS = pS - ld3(W.fpos[iS]); r12[192] = make_float4(rS.x, rS.y, rS.z, 0.f); }
+      if (has_spin) S.q(Q_S12 + region_mine + t_spin_mine + spin_rank) = make_float4(__int_as_float(t), spin, rhs[1], invDs[1]);
     }
   }
   __syncwarp();
   if (lane == 0) {
-    S.q(Q_HDR) = make_float4(__int_as_float(njr | (nc0 << 8) | (ns0 << 16)), __int_as_float(tS0), __int_as_float(tT0), __int_as_float(tEnd0));
-    S.q(Q_HDR + 1) = make_float4(__int_as_float(ncs[1] | (nss[1] << 8) | (slotf[0] << 16) | (slotf[1] << 18)), __int_as_float(start[1]),
-                                 __int_as_float(tsp[1]), 0.f);
+    S.q(Q_HDR) = make_float4(__int_as_float(njr | (nc0 << 8) | ((canon ? 1 : 0) << 24) | ((heavy ? cls + 1 : 0) << 25)), 0.f, 0.f, __int_as_float(tEnd0));
+    S.q(Q_HDR + 1) = make_float4(__int_as_float(info), __int_as_float(start[1]), __int_as_float(tsp[1]), 0.f);
     S.q(Q_HDR + 2) = make_float4(__int_as_float(ncs[2] | (nss[2] << 8)), __int_as_float(start[2]), __int_as_float(tsp[2]), 0.f);
     if (nc > W.dbg_c) W.dbg_c = nc;
-    // island of the arm needs the arm-island solver: size class by the q count of region 0
-    W.dbg_u = (nc0 > 0 || njr > PGS_MAXJROW_J) ? (tEnd0 <= 4 * PGS_ROWS_G0 ? 1 : (tEnd0 <= 4 * PGS_ROWS_G1 ? 2 : (tEnd0 <= 4 * PGS_ROWS_G2 ? 3 : 4))) : 0;
+    W.dbg_u = heavy ? cls + 1 : 0;
   }
   if (lane < M.nv) S.w(4 * Q_VSTAR + lane) = W.vs[lane];
 }
@@ -491,7 +541,7 @@ static char g_emu_smem2[8 * sizeof(SetupMemT<SetupCfg>) + 256];
 template <int ND>
 __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
                                                                          float* __restrict__ sbuf, DevOut O, int N, int flags,
-                                                                         int* __restrict__ heavy_list, int* __restrict__ heavy_cnt,
+                                                                         float4* __restrict__ hbuf, int* __restrict__ heavy_cnt,
                                                                          const unsigned char* __restrict__ active) {
   typedef SetupMemT<SetupCfg> WM;
   PRB_SMEM_DECL2;
@@ -517,14 +567,10 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
     phase_crba(M, W, lane);
     phase_minv<ND>(W, lane);
     phase_vstar(M, W, lane);
-    phase_rows_stream<ND>(M, W, lane, S);
+    phase_rows_stream<ND>(M, W, lane, e, N, S, hbuf, heavy_cnt);
     __syncwarp();
     // a dropped contact marks the env; the mark is counted (once per env step) by the launch that observes
     if (lane == 0 && W.overflow) { if (O.ovf_env) O.ovf_env[e] = 1; else if (O.overflow) atomicAdd(O.overflow, 1ull); }
-    if (lane == 0 && W.dbg_u) {                      // order within a list is immaterial: envs are independent
-      const int cls = W.dbg_u - 1;                   // size class of region 0
-      heavy_list[(size_t)cls * N + atomicAdd(heavy_cnt + 4 * cls, 1)] = e;    // heavy_cnt: {length, -, work counter, -} per class
-    }
     if (lane == 0 && O.dbg) { O.dbg[4 * e] = W.dbg_u | (W.dbg_a << 8); O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.n_jrow; }
   }
   if (flags & SETUP_OBSERVE) {
@@ -535,35 +581,220 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
   if (flags & (SETUP_INTEGRATE | SETUP_OBSERVE)) store_state(M, W, st, lane);
 }
 
-// ============================================================================ solver kernels
-//   prb_pgs_joint_kernel   slot 0 of the envs whose arm island has no contacts: joint rows only (32 envs / warp)
-//   prb_pgs_free_kernel    slots 1 and 2 (blockIdx.y): free-body islands, compact records (32 envs / warp)
-//   prb_pgs_arm_kernel     slot 0 of the envs on a "heavy" list (arm island with contacts): joint rows +
-//                          explicit rows; FOUR lanes per env (8 envs / warp), velocities in registers,
-//                          one 2-step quad shuffle reduction per row.  Two size classes, two launches.
+// ============================================================================ solver kernels (one thread per env)
+//   prb_pgs_joint_kernel   slot 0 of the light envs (arm island without contacts): joint rows only, 32 envs / warp
+//   prb_pgs_free_kernel    slots 1 and 2 (blockIdx.y): free-body islands, compact records, 32 envs / warp
+//   prb_pgs_arm_kernel     slot 0 of the heavy envs, one launch per size class: joint rows + contact records,
+//                          ARM_LANES(class) envs / warp, bundle staged by one bulk async copy
 #define PGS_BLOCK 32
-#define PGS_J_DVQ 4      // arm q 0..2, slides q 3
 #define PGS_F_TAILQ 8    // free-body kernel: dv 4 q (body b at 2b, 2b+1) + body table 4 q
-#define PGS_G_EPW (32 >> PGS_G_LW)                      // envs per warp of the arm-island kernel
-#define PGS_SMEM_J ((PGS_STAGE_J + PGS_J_DVQ) * 32 * 16)
+#define PGS_SMEM_J (PGS_STAGE_J * 32 * 16)
 #define PGS_SMEM_F ((PGS_STAGE_F + PGS_F_TAILQ) * 32 * 16)
-#define PGS_G_THREADS 32                                // threads per block of the arm-island kernel
-#define PGS_SMEM_G(rows) ((rows) * PGS_G_THREADS * 16)
+#define PGS_SMEM_ARM(k) (arm_capq(k) * arm_lanes(k) * 16)
 
 #ifdef PRB_EMU
-static float4 g_emu_pgs_smem[(PGS_ROWS_GMAX + 2) * 32 + (PGS_STAGE_J + PGS_STAGE_F + 16) * 32];
+static float4 g_emu_pgs_smem[ARM_BUFQ_MAX * 32 + (PGS_STAGE_J + PGS_STAGE_F + 16) * 32];
 #define PRB_PGS_SMEM_DECL float4* sm = g_emu_pgs_smem
 #else
-#define PRB_PGS_SMEM_DECL extern __shared__ __align__(16) float4 prb_pgs_smem[]; float4* sm = prb_pgs_smem
+#define PRB_PGS_SMEM_DECL extern __shared__ __align__(128) float4 prb_pgs_smem[]; float4* sm = prb_pgs_smem
 #endif
 
-PRB_D float f4comp(const float4& a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : (k == 2 ? a.z : a.w)); }
-PRB_D void f4add(float4& a, int k, float v) { a.x += k == 0 ? v : 0.f; a.y += k == 1 ? v : 0.f; a.z += k == 2 ? v : 0.f; a.w += k == 3 ? v : 0.f; }
+PRB_D float sel3(const float* a, int s) { return s == 0 ? a[0] : (s == 1 ? a[1] : a[2]); }   // register select (constant indices)
 PRB_D float dot4(const float4& a, const float4& b, float s) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s)))); }
-PRB_D void axpy4(float4& y, const float4& b, float a) { y.x = fmaf(b.x, a, y.x); y.y = fmaf(b.y, a, y.y); y.z = fmaf(b.z, a, y.z); y.w = fmaf(b.w, a, y.w); }
 PRB_D float4* stream_col(float* sbuf, int e) { return reinterpret_cast<float4*>(sbuf) + (size_t)(e >> 5) * (SB_Q * 32) + (e & 31); }
 
-// ---- slot 0, arm island without contacts: joint rows only.  sl: this env's column (row t = q t of region 0)
+// velocity change of the arm's island, in registers: arm DoF, slide bodies, free bodies (+ their inverse inertia)
+struct IslandV {
+  float A[12];
+  float sl[PRB_MAXSLIDE];
+  v3 fv[PRB_MAXFREE], fw[PRB_MAXFREE];
+  float I[PRB_MAXFREE][6], invm[PRB_MAXFREE];
+  // register selects (no runtime-indexed arrays: they would live in local memory)
+  PRB_D float arm(int a) const {
+    float r = A[0];
+#pragma unroll
+    for (int k = 1; k < 12; k++) r = a == k ? A[k] : r;
+    return r;
+  }
+  PRB_D float slide(int s) const { return s == 0 ? sl[0] : (s == 1 ? sl[1] : sl[2]); }
+  PRB_D void slide_add(int s, float v) { sl[0] += s == 0 ? v : 0.f; sl[1] += s == 1 ? v : 0.f; sl[2] += s == 2 ? v : 0.f; }
+  PRB_D void arm_axpy(const float4& m0, const float4& m1, const float4& m2, float a) {
+    A[0] = fmaf(m0.x, a, A[0]); A[1] = fmaf(m0.y, a, A[1]); A[2] = fmaf(m0.z, a, A[2]); A[3] = fmaf(m0.w, a, A[3]);
+    A[4] = fmaf(m1.x, a, A[4]); A[5] = fmaf(m1.y, a, A[5]); A[6] = fmaf(m1.z, a, A[6]); A[7] = fmaf(m1.w, a, A[7]);
+    A[8] = fmaf(m2.x, a, A[8]); A[9] = fmaf(m2.y, a, A[9]); A[10] = fmaf(m2.z, a, A[10]); A[11] = fmaf(m2.w, a, A[11]);
+  }
+  PRB_D float arm_dot(const float4& j0, const float4& j1, const float4& j2) const {
+    const float p0 = fmaf(j0.x, A[0], fmaf(j0.y, A[1], fmaf(j0.z, A[2], j0.w * A[3])));
+    const float p1 = fmaf(j1.x, A[4], fmaf(j1.y, A[5], fmaf(j1.z, A[6], j1.w * A[7])));
+    const float p2 = fmaf(j2.x, A[8], fmaf(j2.y, A[9], fmaf(j2.z, A[10], j2.w * A[11])));
+    return (p0 + p1) + p2;
+  }
+  PRB_D v3 vel(int b) const { return b ? fv[PRB_MAXFREE - 1] : fv[0]; }
+  PRB_D v3 ang(int b) const { return b ? fw[PRB_MAXFREE - 1] : fw[0]; }
+  // J . dv of a free-body side: unit force d at lever arm r (or unit torque d), times sgn
+  PRB_D float jdot(int b, float sgn, v3 r, v3 d, bool angular) const {
+    const v3 ww = ang(b);
+    return sgn * (angular ? dot(d, ww) : dot(d, vel(b) + cross(ww, r)));
+  }
+  // dv += B P: P = sum of direction * impulse (linear rows) or the angular impulse (spin row)
+  PRB_D void apply(int b, float sgn, v3 r, v3 P, bool angular) {
+    const v3 Ps = P * sgn;
+    float Ib[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) Ib[k] = b ? I[PRB_MAXFREE - 1][k] : I[0][k];
+    const float im = b ? invm[PRB_MAXFREE - 1] : invm[0];
+    v3 dv = V3(0, 0, 0), dw;
+    if (angular) dw = symmul(Ib, Ps);
+    else { dv = Ps * im; dw = symmul(Ib, cross(r, Ps)); }
+    if (b) { fv[PRB_MAXFREE - 1] = fv[PRB_MAXFREE - 1] + dv; fw[PRB_MAXFREE - 1] = fw[PRB_MAXFREE - 1] + dw; }
+    else { fv[0] = fv[0] + dv; fw[0] = fw[0] + dw; }
+  }
+  PRB_D void clear() {
+#pragma unroll
+    for (int k = 0; k < 12; k++) A[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < PRB_MAXSLIDE; k++) sl[k] = 0.f;
+#pragma unroll
+    for (int b = 0; b < PRB_MAXFREE; b++) { fv[b] = V3(0, 0, 0); fw[b] = V3(0, 0, 0); }
+  }
+};
+
+// ---- joint rows of region 0.  col: this env's column of the staged region (q t at col[t * stride])
+struct JointRows {
+  const float4* col;
+  int stride, njr, nL, t_jlam;
+  bool canon;
+  float ratio;
+  float sminv[PRB_MAXSLIDE];
+  float lm[12], ls[PRB_MAXSLIDE];       // impulses of the canonical motor rows (registers)
+};
+// any row: limits, gear, and every row of an env whose motor set is not the canonical one.  Its impulse lives in the
+// staged region (word j of the area at t_jlam)
+PRB_D bool jrow_generic(JointRows& R, IslandV& V, int j) {
+  const float4 r = R.col[(size_t)(R0_JROW + j) * R.stride];
+  const int pk = __float_as_int(r.x);
+  const int pd = pk & 0xff, a = (pk >> 16) & 15, a2 = (pk >> 20) & 15;
+  const int sidx = pd - DVW_SLIDE(0);                            // slide index when a == 15
+  const float sg = ((pk >> 24) & 1) ? -1.0f : 1.0f;
+  float u = a != 15 ? V.arm(a) : V.slide(sidx);
+  if (a2 != 15) u = fmaf(R.ratio, V.arm(a2), u);
+  u *= sg;
+  float* pl = reinterpret_cast<float*>(const_cast<float4*>(R.col) + (size_t)(R.t_jlam + (j >> 2)) * R.stride) + (j & 3);
+  const float l0 = *pl;
+  const float hi = r.w, lo = ((pk >> 25) & 1) ? -hi : 0.f;
+  const float nl = clampf(l0 + (r.y - u * r.z), lo, hi);
+  const float dl = (nl - l0) * sg;
+  if (dl != 0.f) {
+    *pl = nl;
+    if (a != 15) {
+      const float4* m = R.col + (size_t)(R0_MINV + 3 * a) * R.stride;
+      V.arm_axpy(m[0], m[R.stride], m[2 * R.stride], dl);
+      if (a2 != 15) {
+        const float4* m2 = R.col + (size_t)(R0_MINV + 3 * a2) * R.stride;
+        V.arm_axpy(m2[0], m2[R.stride], m2[2 * R.stride], dl * R.ratio);
+      }
+    } else V.slide_add(sidx, sel3(R.sminv, sidx) * dl);
+  }
+  return dl != 0.f;
+}
+// the motor row of arm DoF D / slide body S_ of a canonical env: compile-time register indices, impulse in a register
+template <int D>
+PRB_D bool jrow_motor(JointRows& R, IslandV& V) {
+  const float4 r = R.col[(size_t)(R0_JROW + R.nL + D) * R.stride];
+  const float4* m = R.col + (size_t)(R0_MINV + 3 * D) * R.stride;
+  const float4 m0 = m[0], m1 = m[R.stride], m2 = m[2 * R.stride];
+  const float l0 = R.lm[D];
+  const float nl = clampf(l0 + (r.y - V.A[D] * r.z), -r.w, r.w);
+  const float dl = nl - l0;
+  R.lm[D] = nl;
+  V.arm_axpy(m0, m1, m2, dl);
+  return dl != 0.f;
+}
+template <int ND, int S_>
+PRB_D bool jrow_slide(JointRows& R, IslandV& V) {
+  const float4 r = R.col[(size_t)(R0_JROW + R.nL + ND + S_) * R.stride];
+  const float l0 = R.ls[S_];
+  const float nl = clampf(l0 + (r.y - V.sl[S_] * r.z), -r.w, r.w);
+  const float dl = nl - l0;
+  R.ls[S_] = nl;
+  V.sl[S_] += R.sminv[S_] * dl;
+  return dl != 0.f;
+}
+template <int ND, int D>
+struct MotorUnroll {
+  static PRB_D bool up(JointRows& R, IslandV& V) { bool c = MotorUnroll<ND, D - 1>::up(R, V); return jrow_motor<D>(R, V) | c; }
+  static PRB_D bool down(JointRows& R, IslandV& V) { bool c = jrow_motor<D>(R, V); return MotorUnroll<ND, D - 1>::down(R, V) | c; }
+};
+template <int ND>
+struct MotorUnroll<ND, -1> {
+  static PRB_D bool up(JointRows&, IslandV&) { return false; }
+  static PRB_D bool down(JointRows&, IslandV&) { return false; }
+};
+// one pass over the joint rows; direction alternates per iteration (btMultiBodyConstraintSolver: odd iterations ascend)
+template <int ND>
+PRB_D bool jrows_pass(JointRows& R, IslandV& V, int n_slide, bool ascending) {
+  bool changed = false;
+  if (!R.canon) {
+#pragma unroll 1
+    for (int ii = 0; ii < R.njr; ii++) changed |= jrow_generic(R, V, ascending ? ii : R.njr - 1 - ii);
+    return changed;
+  }
+  const int tail0 = R.nL + ND + n_slide;                       // rows after the motors (gear)
+  if (ascending) {
+#pragma unroll 1
+    for (int j = 0; j < R.nL; j++) changed |= jrow_generic(R, V, j);
+    changed |= MotorUnroll<ND, ND - 1>::up(R, V);
+    if (n_slide > 0) changed |= jrow_slide<ND, 0>(R, V);
+    if (n_slide > 1) changed |= jrow_slide<ND, 1>(R, V);
+    if (n_slide > 2) changed |= jrow_slide<ND, 2>(R, V);
+#pragma unroll 1
+    for (int j = tail0; j < R.njr; j++) changed |= jrow_generic(R, V, j);
+  } else {
+#pragma unroll 1
+    for (int j = R.njr - 1; j >= tail0; j--) changed |= jrow_generic(R, V, j);
+    if (n_slide > 2) changed |= jrow_slide<ND, 2>(R, V);
+    if (n_slide > 1) changed |= jrow_slide<ND, 1>(R, V);
+    if (n_slide > 0) changed |= jrow_slide<ND, 0>(R, V);
+    changed |= MotorUnroll<ND, ND - 1>::down(R, V);
+#pragma unroll 1
+    for (int j = R.nL - 1; j >= 0; j--) changed |= jrow_generic(R, V, j);
+  }
+  return changed;
+}
+template <int ND>
+PRB_D void jrows_init(JointRows& R, const DevModel& M, const float4* col, int stride, int h1) {
+  R.col = col; R.stride = stride;
+  R.njr = h1 & 0xff; R.canon = (h1 >> 24) & 1;
+  R.nL = R.njr - ND - M.n_slide - (M.gear_a >= 0 ? 1 : 0);     // meaningful when canon
+  R.t_jlam = R0_JROW + R.njr;
+  R.ratio = M.params[P_GEAR_RATIO];
+#pragma unroll
+  for (int s = 0; s < PRB_MAXSLIDE; s++) { R.sminv[s] = s < M.n_slide ? M.slide_minv[s] : 0.f; R.ls[s] = 0.f; }
+#pragma unroll
+  for (int d = 0; d < 12; d++) R.lm[d] = 0.f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < ((R.njr + 3) >> 2); k++) const_cast<float4*>(col)[(size_t)(R.t_jlam + k) * stride] = z4;
+}
+// velocity change -> stream (linear DoF order): arm, slides, and the free bodies this island owns
+PRB_D void island_store(const DevModel& M, const IslandV& V, float* sbuf, int e, int info, bool with_free) {
+  float* gd = reinterpret_cast<float*>(stream_col(sbuf, e) + Q_DV * 32);
+  const int nd = M.nd, nf = M.n_free;
+#pragma unroll
+  for (int i = 0; i < 12; i++) if (i < nd) gd[(i >> 2) * 128 + (i & 3)] = V.A[i];
+#pragma unroll
+  for (int s = 0; s < PRB_MAXSLIDE; s++) if (s < M.n_slide) { const int d = nd + 6 * nf + s; gd[(d >> 2) * 128 + (d & 3)] = V.sl[s]; }
+  if (with_free) {
+#pragma unroll
+    for (int b = 0; b < PRB_MAXFREE; b++)
+      if (b < nf && ((info >> (16 + 2 * b)) & 3) == 0) {
+        const float v6[6] = {V.fv[b].x, V.fv[b].y, V.fv[b].z, V.fw[b].x, V.fw[b].y, V.fw[b].z};
+#pragma unroll
+        for (int k = 0; k < 6; k++) { const int d = nd + 6 * b + k; gd[(d >> 2) * 128 + (d & 3)] = v6[k]; }
+      }
+  }
+}
+
+// ---- slot 0 of the light envs: joint rows only
 template <int ND>
 __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N,
                                                                  const unsigned char* __restrict__ active) {
@@ -573,88 +804,30 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel
   // persistent blocks: a block walks groups of 32 envs (launching one block per group costs more than
   // the solve: each block launch allocates its shared memory)
   for (int e = blockIdx.x * PGS_BLOCK + lane; e < N; e += gridDim.x * PGS_BLOCK) {
-  if (active != nullptr && active[e] == 0) continue;
-  float4* G = stream_col(sbuf, e);
-  const int h0 = __float_as_int(G[Q_HDR * 32].x);
-  const int njr = h0 & 0xff, nc0 = (h0 >> 8) & 0xff;
-  if (nc0 > 0 || njr > PGS_MAXJROW_J) continue;          // on a heavy list: prb_pgs_arm_kernel solves it
-  float4* sl = sm + lane;
-  const float4* Gr = G + Q_ST * 32;
-  float4* dvq = sl + PGS_STAGE_J * 32;                   // arm q 0..2, slides q 3
-  {
-    const int tq = T_JROW + njr;
+    if (active != nullptr && active[e] == 0) continue;
+    float4* G = stream_col(sbuf, e);
+    const int h0 = __float_as_int(G[Q_HDR * 32].x);
+    if ((h0 >> 25) & 7) continue;                          // heavy: prb_pgs_arm_kernel solves it from its class buffer
+    const int njr = h0 & 0xff;
+    float4* col = sm + lane;
+    const float4* Gr = G + Q_ST * 32;
+    {
+      const int tq = R0_JROW + njr;
 #pragma unroll 8
-    for (int q = T_MINV; q < tq; q++) sl[q * 32] = Gr[q * 32];
-  }
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < PGS_J_DVQ; i++) dvq[i * 32] = z4;
-  for (int i = 0; i < ((njr + 3) >> 2); i++) sl[(T_JROW + njr + i) * 32] = z4;
-  const float4* minv = sl + T_MINV * 32;
-  float* jlam = reinterpret_cast<float*>(sl + (T_JROW + njr) * 32);  // word j at jlam[(j >> 2) * 128 + (j & 3)]
-  float* dvw = reinterpret_cast<float*>(dvq);                        // word i at dvw[(i >> 2) * 128 + (i & 3)]
-  const float ratio = M.params[P_GEAR_RATIO];
-  const int iters = M.solver_iters;
-#pragma unroll 1
-  for (int it = 0; it < iters; it++) {
-    // A sweep that changes no impulse leaves the state untouched, so every later sweep repeats it
-    // exactly: stopping there is bit-identical to running all the iterations.
-    bool changed = false;
-    // non-contact rows, sweep direction alternating per iteration
-#pragma unroll 1
-    for (int i = 0; i < njr; i++) {
-      const int j = (it & 1) ? i : njr - 1 - i;
-      const float4 r = sl[(T_JROW + j) * 32];
-      const int pk = __float_as_int(r.x);
-      int pd = pk & 0xff;
-      const int pd2 = (pk >> 8) & 0xff, a = (pk >> 16) & 15, a2 = (pk >> 20) & 15;
-      const int sidx = pd - DVW_SLIDE(0);                            // slide index when a == 15
-      if (a == 15) pd = 12 + sidx;
-      const float sg = ((pk >> 24) & 1) ? -1.0f : 1.0f;
-      // the M^-1 rows are needed only if the impulse changes; issue their loads now anyway
-      float4 m0[3], m1[3];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        m0[k] = z4; m1[k] = z4;
-        if (a != 15) m0[k] = minv[(3 * a + k) * 32];
-        if (a2 != 15) m1[k] = minv[(3 * a2 + k) * 32];
-      }
-      float* pu = &dvw[(pd >> 2) * 128 + (pd & 3)];
-      float u = *pu;
-      if (pd2 != 0xff) u = fmaf(ratio, dvw[(pd2 >> 2) * 128 + (pd2 & 3)], u);
-      u *= sg;
-      float* pl = &jlam[(j >> 2) * 128 + (j & 3)];
-      const float l0 = *pl;
-      const float hi = r.w, lo = ((pk >> 25) & 1) ? -hi : 0.f;
-      const float nl = clampf(l0 + (r.y - u * r.z), lo, hi);
-      const float dl = (nl - l0) * sg;
-      if (dl != 0.f) {
-        changed = true;
-        *pl = nl;
-        if (a != 15) {
-          const float dl2 = dl * ratio;
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            if (4 * k < ND) {
-              float4 y = dvq[k * 32];
-              axpy4(y, m0[k], dl);
-              axpy4(y, m1[k], dl2);
-              dvq[k * 32] = y;
-            }
-          }
-        } else {
-          *pu = fmaf(M.slide_minv[sidx], dl, *pu);
-        }
-      }
+      for (int q = R0_MINV; q < tq; q++) col[q * 32] = Gr[q * 32];
     }
-    if (!changed) break;
-  }
-  float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
-  const int nd = M.nd, o = nd + 6 * M.n_free;
+    IslandV V;
+    V.clear();
+    JointRows R;
+    jrows_init<ND>(R, M, col, 32, h0);
+    const int iters = M.solver_iters;
 #pragma unroll 1
-  for (int i = 0; i < nd; i++) gd[(i >> 2) * 128 + (i & 3)] = dvw[(i >> 2) * 128 + (i & 3)];
-#pragma unroll 1
-  for (int s = 0; s < M.n_slide; s++) gd[((o + s) >> 2) * 128 + ((o + s) & 3)] = dvw[3 * 128 + s];
+    for (int it = 0; it < iters; it++) {
+      // A sweep that changes no impulse leaves the state untouched, so every later sweep repeats it
+      // exactly: stopping there is bit-identical to running all the iterations.
+      if (!jrows_pass<ND>(R, V, M.n_slide, (it & 1) != 0)) break;
+    }
+    island_store(M, V, sbuf, e, 0, false);
   }
 }
 
@@ -705,7 +878,7 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
   for (int b = 0; b < M.n_free; b++) owner = owner || ((info >> (16 + 2 * b)) & 3) == slot;
   if (!owner) continue;                                  // merged into another island
   float4* sl = sm + lane;
-  float4* Gr = G + (Q_ST + start) * 32;
+  float4* Gr = G + (Q_S12 + start) * 32;
   float4* dvq = sl + PGS_STAGE_F * 32;
   float4* body = dvq + 4 * 32;
   {
@@ -716,7 +889,7 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
 #define PGS_PTR(t_) ((t_) < PGS_STAGE_F ? sl + (t_) * 32 : Gr + (t_) * 32)
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 4; i++) { dvq[i * 32] = z4; body[i * 32] = G[(Q_ST + T_BODY + i) * 32]; }
+  for (int i = 0; i < 4; i++) { dvq[i * 32] = z4; body[i * 32] = G[(Q_ST + R0_BODY + i) * 32]; }
   const int iters = M.solver_iters;
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
@@ -836,373 +1009,236 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
   }
 }
 
-// ---- slot 0 of the envs whose arm island has contacts (a heavy list): joint rows + explicit rows.
-// Four lanes per env (quad): lane c of the quad keeps words 4c..4c+3 of the island's velocity change
-// (A: arm, F: free bodies + slides) in registers and owns column c of the env's four shared-memory
-// columns: q number t of region 0 sits in row t >> 2, column t & 3, so a row's J (B) slices are one
-// conflict-free LDS.128 per lane and its header a quad broadcast.  J . dv = 4 FMAs per lane + a 2-step
-// quad shuffle reduction.
-struct QuadMem {
-  float4* base;            // column 0 of this env in shared memory
-  float4* Gr;              // this env's column of region 0 in the stream
-  int cap;                 // staged q count; items that do not end below it are read from the stream in place
-  static constexpr int rs = 32;   // row stride = columns of the block's stage = threads per block
-  PRB_D float4* sp(int t) const { return base + (t >> 2) * rs + (t & 3); }     // always-staged q (fixed part of region 0)
-  PRB_D bool staged(int t) const { return t + 16 <= cap; }                    // item starting at t (items are <= 16 q)
-  PRB_D float4 ldq(int t) const { return t < cap ? *sp(t) : Gr[t * 32]; }     // immutable data (geometry)
+
+// ============================================================================ arm-island solver
+// One thread per env.  Every load of a contact visit sits at a fixed offset from the record start and is issued
+// before the flags are decoded (a record without an arm / slide / free side just reads the next record's bytes
+// or the slack after the region), so a visit is: ~12 independent LDS.128 -> 12-FMA dot + free-body terms ->
+// clamp -> 12-FMA update + one STS of the impulse.  No shuffles, no barriers: the env's records and velocities
+// are private to the thread.
+struct ArmRec {              // pointers of one record (shared memory, or the heavy buffer when read in place)
+  float4* p;
+  int stride;
+  PRB_D float4 ld(int k) const { return p[(size_t)k * stride]; }
+  PRB_D float* lam() const { return reinterpret_cast<float*>(p + (size_t)3 * stride); }
 };
-// an item in shared memory (q k of the item at rp[(k >> 2) * 32 + (k & 3)]) or in the stream (gp[k * 32])
-struct RowS {
-  float4* rp;
-  static constexpr int rs = 32;
-  template <int K0> PRB_D float4 ld(int c) const { return rp[(K0 >> 2) * rs + c]; }
-  template <int K> PRB_D float4* q() const { return rp + (K >> 2) * rs + (K & 3); }
-};
-struct RowG {
-  float4* gp;
-  template <int K0> PRB_D float4 ld(int c) const { return gp[(K0 + c) * 32]; }
-  template <int K> PRB_D float4* q() const { return gp + K * 32; }
-};
-PRB_D float quad_sum(unsigned qmask, float v) {
-  v += __shfl_xor_sync(qmask, v, 1);
-  v += __shfl_xor_sync(qmask, v, 2);
-  return v;
+struct FreeGeom { int fb; float sgn; bool two; v3 n, t1, rF, rS; };
+PRB_D FreeGeom free_geom(int flags, const float4& G0, const float4& G1, const float4& G2) {
+  FreeGeom g;
+  g.fb = (flags & CR_FB) ? 1 : 0; g.sgn = (flags & CR_FNEG) ? -1.0f : 1.0f; g.two = (flags & CR_TWO) != 0;
+  g.n = V3(G0.x, G0.y, G0.z); g.t1 = V3(G1.x, G1.y, G1.z); g.rF = V3(G2.x, G2.y, G2.z); g.rS = V3(G0.w, G1.w, G2.w);
+  return g;
 }
-// velocities of the non-arm bodies of the island, replicated in the four lanes of the quad
-struct QuadFree {
-  v3 v[PRB_MAXFREE], w[PRB_MAXFREE];
-  float4 sl;                                     // slide bodies
-  float I[PRB_MAXFREE][6], invm[PRB_MAXFREE];    // world inverse inertia, 1 / mass
-  PRB_D v3 vel(int b) const { return b ? v[PRB_MAXFREE - 1] : v[0]; }
-  PRB_D v3 ang(int b) const { return b ? w[PRB_MAXFREE - 1] : w[0]; }
-  // J . dv of a free-body side: unit force d at lever arm r (or unit torque d), times sgn
-  PRB_D float jdot(int b, float sgn, v3 r, v3 d, bool angular) const {
-    const v3 ww = ang(b);
-    return sgn * (angular ? dot(d, ww) : dot(d, vel(b) + cross(ww, r)));
+// contact normal: lambda >= 0, soft CFM
+PRB_D bool visit_normal(const ArmRec& r, IslandV& V, const float* sminv, int& size) {
+  const float4 H0 = r.ld(0), L = r.ld(3), G0 = r.ld(4), G1 = r.ld(5), G2 = r.ld(6), SL = r.ld(7);
+  const float4 J0 = r.ld(8), J1 = r.ld(9), J2 = r.ld(10), B0 = r.ld(11), B1 = r.ld(12), B2 = r.ld(13);
+  const int flags = __float_as_int(H0.x);
+  size = flags >> 16;
+  const int sidx = (flags >> 6) & 3;
+  float u = 0.f;
+  if (flags & CR_ARM) u = V.arm_dot(J0, J1, J2);
+  if (flags & CR_SLIDE) u = fmaf(SL.x, V.slide(sidx), u);
+  FreeGeom g = free_geom(flags, G0, G1, G2);
+  if (flags & CR_FREE) {
+    u += V.jdot(g.fb, g.sgn, g.rF, g.n, false);
+    if (g.two) u += V.jdot(1 - g.fb, -g.sgn, g.rS, g.n, false);
   }
-  // dv += B P: P = sum of direction * impulse (linear rows) or the angular impulse (spin row)
-  PRB_D void apply(int b, float sgn, v3 r, v3 P, bool angular) {
-    const v3 Ps = P * sgn;
-    // register selects (no runtime-indexed arrays: they would live in local memory)
-    float Ib[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) Ib[k] = b ? I[PRB_MAXFREE - 1][k] : I[0][k];
-    const float im = b ? invm[PRB_MAXFREE - 1] : invm[0];
-    v3 dv = V3(0, 0, 0), dw;
-    if (angular) dw = symmul(Ib, Ps);
-    else { dv = Ps * im; dw = symmul(Ib, cross(r, Ps)); }
-    if (b) { v[PRB_MAXFREE - 1] = v[PRB_MAXFREE - 1] + dv; w[PRB_MAXFREE - 1] = w[PRB_MAXFREE - 1] + dw; }
-    else { v[0] = v[0] + dv; w[0] = w[0] + dw; }
-  }
-};
-PRB_D float* quad_lam0(const QuadMem& m, int tN) {        // normal impulse of the contact whose normal item is at tN
-  float4* h = m.staged(tN) ? m.sp(tN + 3) : m.Gr + (tN + 3) * 32;
-  const int type = __float_as_int(h->x) & 3;
-  if (type == 2) { float4* q1 = m.staged(tN) ? m.sp(tN + 1) : m.Gr + (tN + 1) * 32; return reinterpret_cast<float*>(q1) + 3; }
-  return reinterpret_cast<float*>(h) + 3;
-}
-// one explicit row; KIND 0: contact normal (lambda >= 0, soft CFM), 1: spin (|lambda| <= coefficient * normal impulse)
-template <int KIND, class Row>
-PRB_D bool quad_xrow(const Row& r, const QuadMem& m, int c, unsigned qmask, float4& A, QuadFree& Fr, float tot) {
-  const float4 H1 = *r.template q<3>(), H2 = *r.template q<7>();
-  const int flags = __float_as_int(H1.x);
-  const float4 J = r.template ld<0>(c), B = r.template ld<4>(c);
-  float u = quad_sum(qmask, c < 3 ? dot4(J, A, 0.f) : 0.f);
-  const int sidx = (flags >> 3) & 3, fb = (flags >> 6) & 1;
-  const float fs = (flags & 128) ? -1.0f : 1.0f;
-  v3 n = V3(0, 0, 0), rr = n;
-  if (flags & 4) u = fmaf(H2.z, f4comp(Fr.sl, sidx), u);
-  if (flags & 32) {
-    const int tg = (KIND == 0 ? 0 : __float_as_int(H2.y)) + 8;      // geometry of the contact: after its normal row
-    float4 g0, g2;
-    if (KIND == 0) { g0 = *r.template q<8>(); g2 = *r.template q<10>(); } else { g0 = m.ldq(tg); g2 = m.ldq(tg + 2); }
-    n = V3(g0.x, g0.y, g0.z); rr = V3(g2.x, g2.y, g2.z);
-    u += Fr.jdot(fb, fs, rr, n, KIND == 1);
-  }
-  const float l0 = H1.w;
-  float nl;
-  if (KIND == 0) nl = fmaxf(l0 + (H1.y - l0 * H2.x - u * H1.z), 0.f);
-  else { const float lim = H2.x * tot; nl = clampf(l0 + (H1.y - u * H1.z), -lim, lim); }
+  const float l0 = L.x;
+  const float nl = fmaxf(l0 + (H0.y - l0 * H0.w - u * H0.z), 0.f);
   const float dl = nl - l0;
-  __syncwarp(qmask);                                     // every lane of the quad has read lambda
   if (dl != 0.f) {
-    if (c == 3) reinterpret_cast<float*>(r.template q<3>())[3] = nl;
-    if (c < 3) axpy4(A, B, dl);
-    if (flags & 4) f4add(Fr.sl, sidx, H2.w * dl);
-    if (flags & 32) Fr.apply(fb, fs, rr, n * dl, KIND == 1);
+    r.lam()[0] = nl;
+    if (flags & CR_ARM) V.arm_axpy(B0, B1, B2, dl);
+    if (flags & CR_SLIDE) V.slide_add(sidx, (SL.x * sel3(sminv, sidx)) * dl);
+    if (flags & CR_FREE) {
+      V.apply(g.fb, g.sgn, g.rF, g.n * dl, false);
+      if (g.two) V.apply(1 - g.fb, -g.sgn, g.rS, g.n * dl, false);
+    }
   }
-  __syncwarp(qmask);                                     // the new impulse is visible to the quad
   return dl != 0.f;
 }
-// lateral friction of an explicit contact: the two rows are solved together (implicit cone)
-template <class Row>
-PRB_D bool quad_xfriction(const Row& r, const QuadMem& m, int c, unsigned qmask, float4& A, QuadFree& Fr) {
-  const float4 H1 = *r.template q<3>(), H2 = *r.template q<7>(), G1 = *r.template q<11>(), G2 = *r.template q<15>();
-  const int flags = __float_as_int(H1.x);
-  const float4 J1 = r.template ld<0>(c), B1 = r.template ld<4>(c), J2 = r.template ld<8>(c), B2 = r.template ld<12>(c);
-  const int tN = __float_as_int(H2.y);
-  const float tot = *quad_lam0(m, tN);
-  float ua = quad_sum(qmask, c < 3 ? dot4(J1, A, 0.f) : 0.f), ub = quad_sum(qmask, c < 3 ? dot4(J2, A, 0.f) : 0.f);
-  const int sidx = (flags >> 3) & 3, fb = (flags >> 6) & 1;
-  const float fs = (flags & 128) ? -1.0f : 1.0f;
-  v3 t1 = V3(0, 0, 0), t2 = t1, rr = t1;
-  if (flags & 4) { const float vs = f4comp(Fr.sl, sidx); ua = fmaf(H2.z, vs, ua); ub = fmaf(G2.z, vs, ub); }
-  if (flags & 32) {
-    const float4 g0 = m.ldq(tN + 8), g1 = m.ldq(tN + 9), g2 = m.ldq(tN + 10);
-    const v3 n = V3(g0.x, g0.y, g0.z);
-    t1 = V3(g1.x, g1.y, g1.z); t2 = cross(n, t1); rr = V3(g2.x, g2.y, g2.z);
-    ua += Fr.jdot(fb, fs, rr, t1, false); ub += Fr.jdot(fb, fs, rr, t2, false);
+// spinning friction: |lambda| <= coefficient * normal impulse (Bullet skips the row while the normal impulse is 0)
+PRB_D bool visit_spin(const ArmRec& r, IslandV& V, const float* sminv, int& size) {
+  const float4 H0 = r.ld(0), H1 = r.ld(1), L = r.ld(3), G0 = r.ld(4), G1 = r.ld(5), G2 = r.ld(6), SL = r.ld(7);
+  const float4 J0 = r.ld(26), J1 = r.ld(27), J2 = r.ld(28), B0 = r.ld(29), B1 = r.ld(30), B2 = r.ld(31);
+  const int flags = __float_as_int(H0.x);
+  size = flags >> 16;
+  const float tot = L.x;
+  if (!(flags & CR_SPIN) || !(tot > 0.f)) return false;
+  const int sidx = (flags >> 6) & 3;
+  float u = 0.f;
+  if (flags & CR_ARM) u = V.arm_dot(J0, J1, J2);
+  if (flags & CR_SLIDE) u = fmaf(SL.y, V.slide(sidx), u);
+  FreeGeom g = free_geom(flags, G0, G1, G2);
+  if (flags & CR_FREE) {
+    u += V.jdot(g.fb, g.sgn, g.rF, g.n, true);
+    if (g.two) u += V.jdot(1 - g.fb, -g.sgn, g.rS, g.n, true);
   }
-  const float lim = H2.x * tot;
-  const float la = H1.w, lb = G1.w;
-  const float sumA = la + (H1.y - ua * H1.z);
-  const float sumB = lb + (G1.y - ub * G1.z);
+  const float lim = H1.z * tot;
+  const float l0 = L.y;
+  const float nl = clampf(l0 + (H1.x - u * H1.y), -lim, lim);
+  const float dl = nl - l0;
+  if (dl != 0.f) {
+    r.lam()[1] = nl;
+    if (flags & CR_ARM) V.arm_axpy(B0, B1, B2, dl);
+    if (flags & CR_SLIDE) V.slide_add(sidx, (SL.y * sel3(sminv, sidx)) * dl);
+    if (flags & CR_FREE) {
+      V.apply(g.fb, g.sgn, g.rF, g.n * dl, true);
+      if (g.two) V.apply(1 - g.fb, -g.sgn, g.rS, g.n * dl, true);
+    }
+  }
+  return dl != 0.f;
+}
+// lateral friction: the two rows of a contact are solved together (implicit cone)
+PRB_D bool visit_friction(const ArmRec& r, IslandV& V, const float* sminv, int& size) {
+  const float4 H0 = r.ld(0), H1 = r.ld(1), H2 = r.ld(2), L = r.ld(3), G0 = r.ld(4), G1 = r.ld(5), G2 = r.ld(6), SL = r.ld(7);
+  const float4 Ja0 = r.ld(14), Ja1 = r.ld(15), Ja2 = r.ld(16), Ba0 = r.ld(17), Ba1 = r.ld(18), Ba2 = r.ld(19);
+  const float4 Jb0 = r.ld(20), Jb1 = r.ld(21), Jb2 = r.ld(22), Bb0 = r.ld(23), Bb1 = r.ld(24), Bb2 = r.ld(25);
+  const int flags = __float_as_int(H0.x);
+  size = flags >> 16;
+  const int sidx = (flags >> 6) & 3;
+  float ua = 0.f, ub = 0.f;
+  if (flags & CR_ARM) { ua = V.arm_dot(Ja0, Ja1, Ja2); ub = V.arm_dot(Jb0, Jb1, Jb2); }
+  if (flags & CR_SLIDE) { const float vs = V.slide(sidx); ua = fmaf(SL.z, vs, ua); ub = fmaf(SL.w, vs, ub); }
+  FreeGeom g = free_geom(flags, G0, G1, G2);
+  const v3 t2 = cross(g.n, g.t1);
+  if (flags & CR_FREE) {
+    ua += V.jdot(g.fb, g.sgn, g.rF, g.t1, false); ub += V.jdot(g.fb, g.sgn, g.rF, t2, false);
+    if (g.two) { ua += V.jdot(1 - g.fb, -g.sgn, g.rS, g.t1, false); ub += V.jdot(1 - g.fb, -g.sgn, g.rS, t2, false); }
+  }
+  const float lim = H1.w * L.x;
+  const float la = L.z, lb = L.w;
+  const float sumA = la + (H2.x - ua * H2.z);
+  const float sumB = lb + (H2.y - ub * H2.w);
   float na = sumA, nb = sumB;
   if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
+    // |lim sin(atan2(A,B))| and |lim cos(atan2(A,B))| as |lim A| / r and |lim B| / r
     const float ss = sumA * sumA + sumB * sumB;
     const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
     const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
     na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
   }
   const float d1 = na - la, d2 = nb - lb;
-  __syncwarp(qmask);
   if (d1 != 0.f || d2 != 0.f) {
-    if (c == 3) { reinterpret_cast<float*>(r.template q<3>())[3] = na; reinterpret_cast<float*>(r.template q<11>())[3] = nb; }
-    if (c < 3) { axpy4(A, B1, d1); axpy4(A, B2, d2); }
-    if (flags & 4) f4add(Fr.sl, sidx, H2.w * d1 + G2.w * d2);
-    if (flags & 32) Fr.apply(fb, fs, rr, t1 * d1 + t2 * d2, false);
+    r.lam()[2] = na; r.lam()[3] = nb;
+    if (flags & CR_ARM) { V.arm_axpy(Ba0, Ba1, Ba2, d1); V.arm_axpy(Bb0, Bb1, Bb2, d2); }
+    if (flags & CR_SLIDE) { const float mi = sel3(sminv, sidx); V.slide_add(sidx, (SL.z * mi) * d1 + (SL.w * mi) * d2); }
+    if (flags & CR_FREE) {
+      const v3 Pv = g.t1 * d1 + t2 * d2;
+      V.apply(g.fb, g.sgn, g.rF, Pv, false);
+      if (g.two) V.apply(1 - g.fb, -g.sgn, g.rS, Pv, false);
+    }
   }
-  __syncwarp(qmask);
   return d1 != 0.f || d2 != 0.f;
 }
-// a compact record (both sides free body / static) inside the arm island: the free-body solver's arithmetic
-// on the replicated velocities.  PASS 0 normal, 1 spin (h: its pointer item), 2 friction
-template <int PASS, class Row>
-PRB_D bool quad_compact(const Row& r, float4 h, int c, unsigned qmask, QuadFree& Fr) {
-  bool changed = false;
-  const float4 q0 = *r.template q<0>(), q1 = *r.template q<1>(), q2 = *r.template q<2>();
-  const int pk = __float_as_int(q0.x);
-  const int iP = (pk >> 4) & 7, iS = (pk >> 7) & 7;
-  const float sP = ((pk >> 10) & 1) ? -1.0f : 1.0f;
-  const bool two = ((pk >> 2) & 3) == K_FREE;
-  const v3 n = V3(q1.x, q1.y, q1.z), rP = V3(q2.x, q2.y, q2.z);
-  v3 rS = V3(0, 0, 0);
-  if (two) { const float4 g = *r.template q<7>(); rS = V3(g.x, g.y, g.z); }
-  if (PASS == 0) {
-    float u = Fr.jdot(iP, sP, rP, n, false);
-    if (two) u += Fr.jdot(iS, -sP, rS, n, false);
-    const float l0 = q1.w;
-    const float nl = fmaxf(l0 + (q0.z - l0 * q0.y - u * q0.w), 0.f);
-    const float dl = nl - l0;
-    __syncwarp(qmask);
-    changed = dl != 0.f;
-    if (dl != 0.f) {
-      if (c == 3) reinterpret_cast<float*>(r.template q<1>())[3] = nl;
-      Fr.apply(iP, sP, rP, n * dl, false);
-      if (two) Fr.apply(iS, -sP, rS, n * dl, false);
-    }
-  } else if (PASS == 1) {
-    const float tot = q1.w;
-    if (tot > 0.f) {                                   // Bullet skips the row while the normal impulse is 0
-      float u = Fr.jdot(iP, sP, rP, n, true);
-      if (two) u += Fr.jdot(iS, -sP, rS, n, true);
-      const float lim = h.y * tot;
-      float* pl = reinterpret_cast<float*>(r.template q<4>()) + 3;
-      const float l0 = *pl;
-      const float nl = clampf(l0 + (h.z - u * h.w), -lim, lim);
-      const float dl = nl - l0;
-      __syncwarp(qmask);
-      changed = dl != 0.f;
-      if (dl != 0.f) {
-        if (c == 3) *pl = nl;
-        Fr.apply(iP, sP, rP, n * dl, true);
-        if (two) Fr.apply(iS, -sP, rS, n * dl, true);
-      }
-    }
-  } else {
-    const float4 q3 = *r.template q<4>(), q4 = *r.template q<5>(), q5 = *r.template q<6>();
-    const v3 t1 = V3(q3.x, q3.y, q3.z), t2 = cross(n, t1);
-    float ua = Fr.jdot(iP, sP, rP, t1, false), ub = Fr.jdot(iP, sP, rP, t2, false);
-    if (two) { ua += Fr.jdot(iS, -sP, rS, t1, false); ub += Fr.jdot(iS, -sP, rS, t2, false); }
-    const float lim = q2.w * q1.w;
-    const float la = q5.x, lb = q5.y;
-    const float sumA = la + (q4.x - ua * q4.z);
-    const float sumB = lb + (q4.y - ub * q4.w);
-    float na = sumA, nb = sumB;
-    if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
-      const float ss = sumA * sumA + sumB * sumB;
-      const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
-      const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
-      na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
-    }
-    const float d1 = na - la, d2 = nb - lb;
-    __syncwarp(qmask);
-    changed = d1 != 0.f || d2 != 0.f;
-    if (d1 != 0.f || d2 != 0.f) {
-      if (c == 3) *r.template q<6>() = make_float4(na, nb, 0.f, 0.f);
-      const v3 Pv = t1 * d1 + t2 * d2;
-      Fr.apply(iP, sP, rP, Pv, false);
-      if (two) Fr.apply(iS, -sP, rS, Pv, false);
-    }
-  }
-  __syncwarp(qmask);
-  return changed;
-}
 
-template <int ND>
-__global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf,
-                                                                const int* __restrict__ heavy_list, int* __restrict__ heavy_cnt, int rows) {
+#ifndef PRB_EMU
+// 1-D bulk async copy global -> shared, completion on an mbarrier (the TMA engine of sm_90+/sm_100a)
+PRB_D void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+PRB_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+PRB_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+PRB_D void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+PRB_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
+// lanes: envs per block (<= 32, the other threads of the warp idle); capq: staged q per env; bufq: q reserved per env in the
+// class buffer (> capq only for the last class, whose islands may be read in place beyond the stage)
+template <int ND, bool INPLACE>
+__global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, float4* __restrict__ hcls,
+                                                                int* __restrict__ heavy_cnt, int lanes, int capq, int bufq) {
   PRB_PGS_SMEM_DECL;
-  // 32 threads = 8 envs per block.  (Smaller blocks were measured: 16 threads equal, 8 and 4 slower — the
-  // kernel is bound by the instruction count per row visit, which a warp amortises over its converged quads.)
-  const int lane = threadIdx.x, c = lane & 3, qb = lane & ~3;
-  const unsigned qmask = 0xfu << qb;
-  const int cnt = *heavy_cnt;
+  const int lane = threadIdx.x;
   const DevModel& M = *Mp;
-  // persistent blocks, dynamic scheduling: every quad (the quads of a warp are independent) draws the
-  // next env of the list from a device counter (heavy_cnt[2]), so long islands do not queue behind each other
+  const int cnt = heavy_cnt[0];
+  const int nb = (cnt + lanes - 1) / lanes;
+#ifndef PRB_EMU
+  __shared__ __align__(8) unsigned long long mbar;
+  if (lane == 0) mbar_init(&mbar, 1);
+  __syncwarp();
+  unsigned parity = 0;
+#endif
+  float sminv[PRB_MAXSLIDE];
+#pragma unroll
+  for (int s = 0; s < PRB_MAXSLIDE; s++) sminv[s] = s < M.n_slide ? M.slide_minv[s] : 0.f;
+  // persistent blocks, dynamic scheduling: the block draws the next bundle of the class from a device counter
   for (;;) {
-  int i = 0;
-  if (c == 0) i = atomicAdd(heavy_cnt + 2, 1);
-  i = __shfl_sync(qmask, i, qb);
-  if (i >= cnt) break;
-  const int e = heavy_list[i];
-  float4* G = stream_col(sbuf, e);
-  const float4 hdr = G[Q_HDR * 32];
-  const int h0 = __float_as_int(hdr.x), info = __float_as_int(G[(Q_HDR + 1) * 32].x);
-  const int njr = h0 & 0xff, nc = (h0 >> 8) & 0xff, ns = (h0 >> 16) & 0xff;
-  const int tS0 = __float_as_int(hdr.y), tT0 = __float_as_int(hdr.z), tEnd = __float_as_int(hdr.w);
-  const int tN0 = (T_JROW + njr + ((njr + 3) >> 2) + 3) & ~3;
-  QuadMem m;
-  m.base = sm + qb; m.Gr = G + Q_ST * 32; m.cap = rows << 2;
-  {
-    const int tq = min(tEnd, m.cap);
-#pragma unroll 4
-    for (int q = c; q < tq; q += 4) *m.sp(q) = m.Gr[q * 32];
-  }
-  __syncwarp(qmask);
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (c == 0) for (int k = 0; k < ((njr + 3) >> 2); k++) *m.sp(T_JROW + njr + k) = z4;
-  __syncwarp(qmask);
-  float4 A = z4;
-  QuadFree Fr;
-  Fr.sl = z4;
-#pragma unroll
-  for (int b = 0; b < PRB_MAXFREE; b++) {
-    Fr.v[b] = V3(0, 0, 0); Fr.w[b] = V3(0, 0, 0);
-    const float4 i0 = *m.sp(T_BODY + 2 * b), i1 = *m.sp(T_BODY + 2 * b + 1);
-    Fr.I[b][0] = i0.x; Fr.I[b][1] = i0.y; Fr.I[b][2] = i0.z; Fr.I[b][3] = i0.w; Fr.I[b][4] = i1.x; Fr.I[b][5] = i1.y;
-    Fr.invm[b] = i1.z;
-  }
-  const float ratio = M.params[P_GEAR_RATIO];
-  const int iters = M.solver_iters;
-  const int t_jlam = T_JROW + njr;
-#pragma unroll 1
-  for (int it = 0; it < iters; it++) {
-    bool changed = false;                                  // fixed point reached: later sweeps are exact repeats
-    // ---- non-contact rows, sweep direction alternating per iteration
-#pragma unroll 1
-    for (int ii = 0; ii < njr; ii++) {
-      const int j = (it & 1) ? ii : njr - 1 - ii;
-      const float4 r = *m.sp(T_JROW + j);
-      const int pk = __float_as_int(r.x);
-      const int pd = pk & 0xff, a = (pk >> 16) & 15, a2 = (pk >> 20) & 15;
-      const int sidx = pd - DVW_SLIDE(0);                            // slide index when a == 15
-      const float sg = ((pk >> 24) & 1) ? -1.0f : 1.0f;
-      float4 m0 = z4, m1 = z4;                                       // this lane's slice of the M^-1 rows
-      if (a != 15 && c < 3) m0 = *m.sp(T_MINV + 3 * a + c);
-      if (a2 != 15 && c < 3) m1 = *m.sp(T_MINV + 3 * a2 + c);
-      // u = J . dv: J = e_a (+ ratio e_a2): broadcast of the owning lane's word; slide rows are replicated
-      float u = __shfl_sync(qmask, f4comp(A, a & 3), qb + ((a >> 2) & 3));
-      if (a2 != 15) u = fmaf(ratio, __shfl_sync(qmask, f4comp(A, a2 & 3), qb + (a2 >> 2)), u);
-      if (a == 15) u = f4comp(Fr.sl, sidx);
-      u *= sg;
-      float* pl = reinterpret_cast<float*>(m.sp(t_jlam + (j >> 2))) + (j & 3);
-      const float l0 = *pl;
-      const float hi = r.w, lo = ((pk >> 25) & 1) ? -hi : 0.f;
-      const float nl = clampf(l0 + (r.y - u * r.z), lo, hi);
-      const float dl = (nl - l0) * sg;
-      __syncwarp(qmask);                                             // every lane of the quad has read l0
-      if (dl != 0.f) {
-        changed = true;
-        if (c == 0) *pl = nl;
-        if (a != 15) { axpy4(A, m0, dl); axpy4(A, m1, dl * ratio); }
-        else f4add(Fr.sl, sidx, M.slide_minv[sidx] * dl);
-      }
-      __syncwarp(qmask);                                             // the new impulse is visible to the quad
+    int b = 0;
+    if (lane == 0) b = atomicAdd(heavy_cnt + 2, 1);
+    b = __shfl_sync(FULL, b, 0);
+    if (b >= nb) break;
+    float4* Gb = hcls + (size_t)b * ((size_t)bufq * lanes);
+    // ---- stage the bundle: capq x lanes float4, contiguous in the class buffer
+#ifndef PRB_EMU
+    if (lane == 0) {
+      fence_async_smem();                                  // the previous bundle's impulse stores precede the async writes
+      const unsigned bytes = (unsigned)(capq * lanes * 16);
+      mbar_expect_tx(&mbar, bytes);
+      bulk_g2s(sm, Gb, bytes, &mbar);
     }
-    // ---- contact normals
-    {
-      int t = tN0;
-#pragma unroll 1
-      for (int k = 0; k < nc; k++) {
-        const bool st = m.staged(t);
-        const int type = __float_as_int((st ? m.sp(t + 3) : m.Gr + (t + 3) * 32)->x) & 3;
-        if (type == 2) changed |= st ? quad_compact<0>(RowS{m.sp(t)}, z4, c, qmask, Fr) : quad_compact<0>(RowG{m.Gr + t * 32}, z4, c, qmask, Fr);
-        else changed |= st ? quad_xrow<0>(RowS{m.sp(t)}, m, c, qmask, A, Fr, 0.f) : quad_xrow<0>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, 0.f);
-        t += type == 1 ? 12 : 8;
-      }
-    }
-    // ---- spinning friction (Bullet skips the row while the normal impulse is 0)
-    {
-      int t = tS0;
-#pragma unroll 1
-      for (int k = 0; k < ns; k++) {
-        const bool st = m.staged(t);
-        const int type = __float_as_int((st ? m.sp(t + 3) : m.Gr + (t + 3) * 32)->x) & 3;
-        if (type == 3) {
-          const float4 h = *(st ? m.sp(t) : m.Gr + t * 32);
-          const int tr = __float_as_int(h.x);
-          changed |= m.staged(tr) ? quad_compact<1>(RowS{m.sp(tr)}, h, c, qmask, Fr) : quad_compact<1>(RowG{m.Gr + tr * 32}, h, c, qmask, Fr);
-          t += 4;
-        } else {
-          const float4 H2 = *(st ? m.sp(t + 7) : m.Gr + (t + 7) * 32);
-          const float tot = *quad_lam0(m, __float_as_int(H2.y));     // normal impulse of the contact
-          if (tot > 0.f) {
-            changed |= st ? quad_xrow<1>(RowS{m.sp(t)}, m, c, qmask, A, Fr, tot) : quad_xrow<1>(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr, tot);
-          }
-          t += 8;
-        }
-      }
-    }
-    // ---- lateral friction
-    {
-      int t = tT0;
-#pragma unroll 1
-      for (int k = 0; k < nc; k++) {
-        const bool st = m.staged(t);
-        const int type = __float_as_int((st ? m.sp(t + 3) : m.Gr + (t + 3) * 32)->x) & 3;
-        if (type == 3) {
-          const int tr = __float_as_int((st ? m.sp(t) : m.Gr + t * 32)->x);
-          changed |= m.staged(tr) ? quad_compact<2>(RowS{m.sp(tr)}, z4, c, qmask, Fr) : quad_compact<2>(RowG{m.Gr + tr * 32}, z4, c, qmask, Fr);
-          t += 4;
-        } else {
-          changed |= st ? quad_xfriction(RowS{m.sp(t)}, m, c, qmask, A, Fr) : quad_xfriction(RowG{m.Gr + t * 32}, m, c, qmask, A, Fr);
-          t += 16;
-        }
-      }
-    }
-    if (!changed) break;
-  }
-  // ---- velocity change -> stream (linear DoF order): arm, slides, and the free bodies this island owns
-  float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
-  const int nd = M.nd, nf = M.n_free;
-  const float a4[4] = {A.x, A.y, A.z, A.w};
+    mbar_wait(&mbar, parity);
+    parity ^= 1;
+#else
+    for (int q = lane; q < capq * lanes; q += 32) sm[q] = Gb[q];
+    __syncwarp();
+#endif
+    const int i = b * lanes + lane;
+    if (lane < lanes && i < cnt) {
+      float4* col = sm + lane;
+      float4* gcol = Gb + lane;
+      const float4 hq = col[R0_HQ * lanes];
+      const int e = __float_as_int(hq.x), h1 = __float_as_int(hq.y), info = __float_as_int(hq.z);
+      const int nc = (h1 >> 8) & 0xff;
+      IslandV V;
+      V.clear();
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int wa = 4 * c + k;                    // arm DoF of this lane's word k
-    if (c < 3 && wa < nd) gd[(wa >> 2) * 128 + (wa & 3)] = a4[k];
-  }
-  if (c == 3) {
-    for (int s_ = 0; s_ < M.n_slide; s_++) { const int d = nd + 6 * nf + s_; gd[(d >> 2) * 128 + (d & 3)] = f4comp(Fr.sl, s_); }
-#pragma unroll
-    for (int b = 0; b < PRB_MAXFREE; b++)
-      if (b < nf && ((info >> (16 + 2 * b)) & 3) == 0) {
-        const float v6[6] = {Fr.v[b].x, Fr.v[b].y, Fr.v[b].z, Fr.w[b].x, Fr.w[b].y, Fr.w[b].z};
-#pragma unroll
-        for (int k = 0; k < 6; k++) { const int d = nd + 6 * b + k; gd[(d >> 2) * 128 + (d & 3)] = v6[k]; }
+      for (int fb = 0; fb < PRB_MAXFREE; fb++) {
+        const float4 i0 = col[(R0_BODY + 2 * fb) * lanes], i1 = col[(R0_BODY + 2 * fb + 1) * lanes];
+        V.I[fb][0] = i0.x; V.I[fb][1] = i0.y; V.I[fb][2] = i0.z; V.I[fb][3] = i0.w; V.I[fb][4] = i1.x; V.I[fb][5] = i1.y;
+        V.invm[fb] = i1.z;
       }
-  }
-  __syncwarp(qmask);                                     // the quad's columns are re-staged by the next env
+      JointRows R;
+      jrows_init<ND>(R, M, col, lanes, h1);
+      const int tC0 = R.t_jlam + ((R.njr + 3) >> 2);
+      const int iters = M.solver_iters;
+#define ARM_REC(t_) ArmRec{(INPLACE && (t_) + CR_MAX_Q > capq) ? gcol + (size_t)(t_) * lanes : col + (size_t)(t_) * lanes, lanes}
+#pragma unroll 1
+      for (int it = 0; it < iters; it++) {
+        // fixed point reached (a sweep changed no impulse): later sweeps are exact repeats
+        bool changed = jrows_pass<ND>(R, V, M.n_slide, (it & 1) != 0);
+        int t = tC0, size;
+#pragma unroll 1
+        for (int k = 0; k < nc; k++) { changed |= visit_normal(ARM_REC(t), V, sminv, size); t += size; }
+        t = tC0;
+#pragma unroll 1
+        for (int k = 0; k < nc; k++) { changed |= visit_spin(ARM_REC(t), V, sminv, size); t += size; }
+        t = tC0;
+#pragma unroll 1
+        for (int k = 0; k < nc; k++) { changed |= visit_friction(ARM_REC(t), V, sminv, size); t += size; }
+        if (!changed) break;
+      }
+#undef ARM_REC
+      island_store(M, V, sbuf, e, info, true);
+    }
+    __syncwarp();                                          // the stage is re-filled by the next bundle
   }
 }

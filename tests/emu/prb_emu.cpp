@@ -7,6 +7,8 @@ static DevModel g_M;
 static std::string g_err;
 
 static std::vector<float> g_sbuf;
+static std::vector<float4> g_hbuf;
+static long long g_class_count[ARM_NCLASS] = {0};     // envs solved per arm-island class since the last query
 static int g_fused = 0;     // 1: run the fused warp-per-env kernel instead of the split pipeline
 template <int ND>
 static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe, const unsigned char* active = nullptr) {
@@ -16,8 +18,8 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe, co
     return;
   }
   g_sbuf.assign(sbuf_bytes(N) / sizeof(float), 0.f);
-  std::vector<int> heavy(PGS_NCLASS * N);
-  int heavy_cnt[4 * PGS_NCLASS] = {0};
+  g_hbuf.assign(hbuf_bytes(N) / sizeof(float4), make_float4(0.f, 0.f, 0.f, 0.f));
+  int heavy_cnt[4 * ARM_NCLASS] = {0};
   emu_dim3 gs, bs, gp, bp;
   bs.x = 32 * SetupCfg::WPB; gs.x = (N + SetupCfg::WPB - 1) / SetupCfg::WPB;
   bp.x = PGS_BLOCK; gp.x = (N + PGS_BLOCK - 1) / PGS_BLOCK;
@@ -25,16 +27,22 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe, co
     int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
     if (flags == 0) break;
     memset(heavy_cnt, 0, sizeof(heavy_cnt));
-    emu::launch(gs, bs, [&]() { prb_setup_kernel<ND>(&g_M, state, g_sbuf.data(), O, N, flags, heavy.data(), heavy_cnt, active); });
+    emu::launch(gs, bs, [&]() { prb_setup_kernel<ND>(&g_M, state, g_sbuf.data(), O, N, flags, g_hbuf.data(), heavy_cnt, active); });
     if (i < nsub) {
       emu::launch(gp, bp, [&]() { prb_pgs_joint_kernel<ND>(&g_M, g_sbuf.data(), N, active); });
       for (int y = 0; y < g_M.n_free; y++) {
         emu_dim3 gy = gp;
         emu::launch_y(gy, bp, y, [&]() { prb_pgs_free_kernel(&g_M, g_sbuf.data(), N, active); });
       }
-      emu_dim3 gh, bq; gh.x = (N + 7) / 8; bq.x = PGS_G_THREADS;
-      for (int k = 0; k < PGS_NCLASS; k++)
-        emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND>(&g_M, g_sbuf.data(), heavy.data() + (size_t)k * N, heavy_cnt + 4 * k, pgs_class_rows(k)); });
+      for (int k = 0; k < ARM_NCLASS; k++) {
+        g_class_count[k] += heavy_cnt[4 * k];
+        emu_dim3 gh, bq; gh.x = 2; bq.x = 32;             // two persistent blocks share the class's work counter
+        float4* hc = g_hbuf.data() + arm_class_base(k, N);
+        if (k == ARM_NCLASS - 1)
+          emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND, true>(&g_M, g_sbuf.data(), hc, heavy_cnt + 4 * k, arm_lanes(k), arm_capq(k), arm_bufq(k)); });
+        else
+          emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND, false>(&g_M, g_sbuf.data(), hc, heavy_cnt + 4 * k, arm_lanes(k), arm_capq(k), arm_bufq(k)); });
+      }
     }
   }
 }
@@ -84,6 +92,9 @@ void emu_ik(float* state, const float* action, float* target, int N) {
 void emu_set_fused(int f) { g_fused = f; }
 float* emu_sbuf() { return g_sbuf.data(); }
 int emu_sbuf_q() { return SB_Q; }
+void emu_class_counts(long long* out, int clear) { for (int k = 0; k < ARM_NCLASS; k++) { out[k] = g_class_count[k]; if (clear) g_class_count[k] = 0; } }
+int emu_arm_nclass() { return ARM_NCLASS; }
+int emu_arm_capq(int k) { return arm_capq(k); }
 unsigned long long emu_overflow() { return g_overflow; }
 void emu_substeps(float* state, int N, int nsub) { DevOut O; memset(&O, 0, sizeof(O)); O.overflow = &g_overflow; O.dbg = nullptr; O.ovf_env = nullptr; run_step(state, O, N, nsub, 0); }
 void emu_step(float* state, const float* action, DevOut* O, int N) {

@@ -77,7 +77,7 @@ def _stream_headers(env=0):
     sbq = L.emu_sbuf_q()
     buf = np.ctypeslib.as_array(L.emu_sbuf(), shape=(sbq, 32, 4))
     h = [buf[i, env].view(np.int32).copy() for i in range(3)]
-    return {'njr': int(h[0][0] & 0xff), 'nc0': int((h[0][0] >> 8) & 0xff), 'ns0': int((h[0][0] >> 16) & 0xff),
+    return {'njr': int(h[0][0] & 0xff), 'nc0': int((h[0][0] >> 8) & 0xff), 'canon': int((h[0][0] >> 24) & 1), 'cls': int((h[0][0] >> 25) & 7),
             'nc1': int(h[1][0] & 0xff), 'nc2': int(h[2][0] & 0xff),
             'slot_free0': int((h[1][0] >> 16) & 3), 'slot_free1': int((h[1][0] >> 18) & 3)}
 
@@ -86,7 +86,7 @@ def test_emu_grasp_sequence_islands_and_arm_solver():
     """Scripted reach-close-lift of the block, every env step started from the oracle's state.  While the
     gripper is away the block and the drawer are their own constraint islands (slots 1, 2: free-body
     solver) and the arm island has joint rows only; once the fingers touch the block its island merges
-    into slot 0 and is solved by the four-lanes-per-env arm-island kernel.  Both paths must match the
+    into slot 0 and is solved by the arm-island kernel from its size class's heavy buffer.  Both paths must match the
     fp64 oracle to the one-step pose tolerance."""
     m = load_model('UR5PlayAbsRPY1Obj-v0')
     sim, o = EmuSim(m, 1, seed=3), Oracle(m, seed=3)
@@ -106,6 +106,7 @@ def test_emu_grasp_sequence_islands_and_arm_solver():
         if h['slot_free0'] == 0:
             merged += 1
             assert h['nc0'] > 0 and h['nc1'] == 0                # block contacts moved to the arm island
+            assert h['cls'] >= 1 and h['canon'] == 1             # heavy: solved from a class buffer; all 12 + 3 motors present
         else:
             separate += 1
             assert h['slot_free0'] == 1 and h['nc1'] >= 1
@@ -149,11 +150,11 @@ def test_emu_action_decoders_match_oracle(env_id):
 
 
 def test_emu_records_read_in_place_when_stage_is_small():
-    """Capacity only costs speed, never contacts: with tiny solver stages (arm-island classes of 112-160 q, free-body
-    stage of 16 q) most records are read from the stream in place; the grasp sequence must give the SAME states as
-    the normal build, bit for bit."""
+    """Capacity only costs speed, never contacts: with tiny solver stages (arm-island classes of 104-120 q, free-body
+    stage of 16 q) every grasp lands in the last class and most of its records are read from the class buffer in
+    place; the grasp sequence must give the SAME states as the normal build, bit for bit."""
     from emu_lib import lib_variant
-    small = lib_variant('smallstage', ['PGS_ROWS_G0=28', 'PGS_ROWS_G1=32', 'PGS_ROWS_G2=36', 'PGS_ROWS_G3=40', 'PGS_STAGE_F=16'])
+    small = lib_variant('smallstage', ['ARM_CAPQ0=104', 'ARM_CAPQ1=108', 'ARM_CAPQ2=112', 'ARM_CAPQ3=116', 'ARM_CAPQ4=120', 'PGS_STAGE_F=16'])
     m = load_model('UR5PlayAbsRPY1Obj-v0')
     a_sim, b_sim, o = EmuSim(m, 1, seed=3), EmuSim(m, 1, seed=3, library=small), Oracle(m, seed=3)
     o.reset()
@@ -218,3 +219,30 @@ def test_emu_every_key_matches_oracle(env_id):
                            st, a, Oracle)
         assert res['bad_pose'] == res['bad_vel'] == res['bad_flags'] == res['bad_reward'] == res['stiff'] == 0, res
         assert res['worst_pose'] < 2e-5 and res['worst_vel'] < 0.1, res
+
+
+def test_emu_solver_regression_bit_identical():
+    """48 heavy states sampled on the B200 from the scripted bench workload (arm islands of 150-770 stream q: every size
+    class of the arm-island solver), stepped once.  The fixture (tools/make_solver_golden.py) holds the states the ROUND-1
+    solver produced (four lanes per env, quad-shuffle reductions); the thread-per-env solver that replaced it keeps the
+    arithmetic of every row visit, so the results must be the same bits — and match the oracle by the all-key rule."""
+    import os
+    from helpers import compare_step, oracle_step_from, OBS_KEYS
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'heavy_step_r1.npz'))
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    n = len(g['state'])
+    sim = EmuSim(m, n, seed=1)
+    sd = Oracle(m).state_dim
+    sim.state[:, :sd] = g['state']
+    import ctypes
+    cc = (ctypes.c_longlong * 8)()
+    sim.L.emu_class_counts(cc, 1)
+    de = sim.step(g['action'])
+    sim.L.emu_class_counts(cc, 1)
+    assert all(c > 0 for c in list(cc)[:5]), list(cc)[:5]          # every size class (incl. read-in-place) solved something
+    assert np.array_equal(sim.state[:, :sd], g['state_after'])
+    assert np.array_equal(de['obs_quat'], g['obs_quat']) and np.array_equal(de['reward'], g['reward'])
+    outs = [oracle_step_from(m, g['state'][i], g['action'][i], Oracle)[0] for i in range(n)]
+    res = compare_step(m, {k: de[k] for k in OBS_KEYS}, de['reward'][:, 0], {'is_success': de['is_success'][:, 0]}, outs,
+                       g['state'], g['action'], Oracle)
+    assert res['bad_pose'] <= 2 and res['bad_reward'] <= 1, res       # these are the stiffest 0.1 % of the workload

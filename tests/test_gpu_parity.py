@@ -257,9 +257,9 @@ def test_parity_at_baseline_size(env_id, N):
     cls, region = use[:, 0] & 0x7f, use[:, 0] >> 8
     rng = np.random.default_rng(9)
     pick = []
-    for c in (4, 3, 2, 1):
+    for c in (5, 4, 3, 2, 1):
         idx = np.nonzero(cls == c)[0]
-        idx = idx[np.argsort(-region[idx], kind='stable')][:48]
+        idx = idx[np.argsort(-region[idx], kind='stable')][:40]
         pick += list(idx)
     if play and N >= 8192:
         assert len(set(cls[pick])) >= 3, np.bincount(cls)            # the sample really spans the solver's size classes
@@ -322,21 +322,3 @@ def test_action_decoder_variants(env_id):
         total_bad += res['bad_pose'] + res['bad_vel'] + res['bad_flags'] + res['bad_reward']
     assert total_bad <= 2, total_bad
     env.close()
-
-
-def test_batched_stepping_bit_identical(monkeypatch):
-    """PRB_BATCHES=2 steps the envs as two pipelined stream chains; envs are independent, so the results must be
-    bit-identical to the single-chain default."""
-    n = 96
-    act = random_actions(np.random.default_rng(8), n, 'UR5PlayAbsRPY1Obj-v0')
-    outs = []
-    for nb in ('1', '2'):
-        monkeypatch.setenv('PRB_BATCHES', nb)
-        env = _mk('UR5PlayAbsRPY1Obj-v0', n, seed=4)
-        env.reset()
-        for _ in range(3):
-            obs, r, _, info = env.step(act)
-        outs.append((obs['obs_quat'].copy(), r.copy(), info['target_poses'].copy(), env.get_state()))
-        env.close()
-    for a, b in zip(outs[0], outs[1]):
-        assert np.array_equal(a, b)
