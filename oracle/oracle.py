@@ -100,6 +100,16 @@ class Oracle:
     def substeps(self, n):
         self.L.orc_substeps(self.mp, _p(self.state), ctypes.c_int(n))
 
+    def last_rows(self):
+        """Rows of the most recent substep: J [R, nv], B = M^-1 J^T [R, nv], scalars [R, 8] =
+        {rhs, cfm, invD, lo, hi, lambda, mu, normal_row}, number of contacts."""
+        self.L.orc_nv.restype = ctypes.c_int
+        nv, R = self.L.orc_nv(self.mp), self.L.orc_last_rows()
+        J, B, sc = np.zeros((R, nv), self.dtype), np.zeros((R, nv), self.dtype), np.zeros((R, 8), self.dtype)
+        for i in range(R):
+            self.L.orc_last_row(self.mp, ctypes.c_int(i), _p(J[i]), _p(B[i]), _p(sc[i]))
+        return J, B, sc, self.L.orc_last_contacts()
+
     def ik(self, q, pos, quat, iters):
         q = _d(q); pos = _d(pos); quat = _d(quat)
         out = np.zeros(self.model['nd'])

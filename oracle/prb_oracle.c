@@ -434,7 +434,9 @@ static void line_closest(v3 pa, v3 ua, v3 pb, v3 ub, real* alpha, real* beta) {
   else { d = 1.0 / d; *alpha = (q1 + uaub * q2) * d; *beta = (uaub * q1 + q2) * d; }
 }
 int orc_box_box_impl(v3 p1, const m3* R1, v3 side1h, v3 p2, const m3* R2, v3 side2h, CPoint* out) {
-  const real fudge = 1.05;
+  /* TIE: a later axis replaces the current best only if it separates by 1 um more (structural ties of resting boxes are
+   * otherwise decided by rounding, differently in fp32 and fp64: see the kernels' box_box) */
+  const real fudge = 1.05, TIE = 1e-6;
   real A[3] = {side1h.x, side1h.y, side1h.z}, B[3] = {side2h.x, side2h.y, side2h.z};
   v3 p = vsub(p2, p1);
   v3 pp = mtmulv(R1, p);
@@ -445,7 +447,7 @@ int orc_box_box_impl(v3 p1, const m3* R1, v3 side1h, v3 p2, const m3* R2, v3 sid
   real ppv[3] = {pp.x, pp.y, pp.z};
 #define TST(expr1, expr2, Rmat, col, cc) \
   s2 = fabs(expr1) - (expr2); if (s2 > 0) return 0; \
-  if (s2 > s) { s = s2; normalRm = Rmat; normalRcol = col; invert_normal = ((expr1) < 0); code = (cc); }
+  if (s2 > s + TIE) { s = s2; normalRm = Rmat; normalRcol = col; invert_normal = ((expr1) < 0); code = (cc); }
   TST(ppv[0], (A[0] + B[0] * Q[0][0] + B[1] * Q[0][1] + B[2] * Q[0][2]), R1, 0, 1);
   TST(ppv[1], (A[1] + B[0] * Q[1][0] + B[1] * Q[1][1] + B[2] * Q[1][2]), R1, 1, 2);
   TST(ppv[2], (A[2] + B[0] * Q[2][0] + B[1] * Q[2][1] + B[2] * Q[2][2]), R1, 2, 3);
@@ -459,7 +461,7 @@ int orc_box_box_impl(v3 p1, const m3* R1, v3 side1h, v3 p2, const m3* R2, v3 sid
   s2 = fabs(expr1) - (expr2); if (s2 > 2.220446049250313e-16) return 0; \
   l = sqrt((n1) * (n1) + (n2) * (n2) + (n3) * (n3)); \
   if (l > 2.220446049250313e-16) { s2 /= l; \
-    if (s2 * fudge > s) { s = s2; normalRm = 0; normalC = V((n1) / l, (n2) / l, (n3) / l); invert_normal = ((expr1) < 0); code = (cc); } }
+    if (s2 * fudge > s + TIE) { s = s2; normalRm = 0; normalC = V((n1) / l, (n2) / l, (n3) / l); invert_normal = ((expr1) < 0); code = (cc); } }
   TST(ppv[2] * Rm[1][0] - ppv[1] * Rm[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + B[1] * Q[0][2] + B[2] * Q[0][1]), 0, -Rm[2][0], Rm[1][0], 7);
   TST(ppv[2] * Rm[1][1] - ppv[1] * Rm[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + B[0] * Q[0][2] + B[2] * Q[0][0]), 0, -Rm[2][1], Rm[1][1], 8);
   TST(ppv[2] * Rm[1][2] - ppv[1] * Rm[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + B[0] * Q[0][1] + B[1] * Q[0][0]), 0, -Rm[2][2], Rm[1][2], 9);
@@ -601,17 +603,17 @@ typedef struct { int ca, cb; v3 pa, pb, n; real dist; } Contact;
 static int reduce_manifold(const Contact* c, int n, int* keep) {
   if (n <= 4) { for (int i = 0; i < n; i++) keep[i] = i; return n; }
   int i0 = 0;
-  for (int i = 1; i < n; i++) if (c[i].dist < c[i0].dist) i0 = i;
+  for (int i = 1; i < n; i++) if (c[i].dist < c[i0].dist - 1e-7) i0 = i;   /* ties: the first candidate wins (same rule as the kernels) */
   int i1 = -1; real best = -1;
-  for (int i = 0; i < n; i++) if (i != i0) { v3 d = vsub(c[i].pb, c[i0].pb); real v = vdot(d, d); if (v > best) { best = v; i1 = i; } }
+  for (int i = 0; i < n; i++) if (i != i0) { v3 d = vsub(c[i].pb, c[i0].pb); real v = vdot(d, d); if (v > best * 1.0001 + 1e-12) { best = v; i1 = i; } }
   int i2 = -1; best = -1;
   v3 e01 = vsub(c[i1].pb, c[i0].pb);
-  for (int i = 0; i < n; i++) if (i != i0 && i != i1) { v3 x = vcross(vsub(c[i].pb, c[i0].pb), e01); real v = vdot(x, x); if (v > best) { best = v; i2 = i; } }
+  for (int i = 0; i < n; i++) if (i != i0 && i != i1) { v3 x = vcross(vsub(c[i].pb, c[i0].pb), e01); real v = vdot(x, x); if (v > best * 1.0001 + 1e-16) { best = v; i2 = i; } }
   int i3 = -1; best = -1;
   for (int i = 0; i < n; i++) if (i != i0 && i != i1 && i != i2) {
     v3 a = vsub(c[i].pb, c[i0].pb), b = vsub(c[i].pb, c[i1].pb), d = vsub(c[i].pb, c[i2].pb);
     real v = vnorm(vcross(a, b)) + vnorm(vcross(b, d)) + vnorm(vcross(d, a));
-    if (v > best) { best = v; i3 = i; }
+    if (v > best * 1.0001 + 1e-10) { best = v; i3 = i; }
   }
   int sel[4] = {i0, i1, i2, i3}, m = 0;
   for (int i = 0; i < n; i++) if (i == sel[0] || i == sel[1] || i == sel[2] || i == sel[3]) keep[m++] = i;
@@ -881,8 +883,11 @@ static void resolve_cone(Row* ra, Row* rb, real* dv, int nv) { /* btMultiBodyCon
 /* diagnostics of the last substep (tests) */
 static int g_last_contacts = 0, g_last_rows = 0;
 static int g_last_pairs[MAXCONTACT][2];
+static real g_last_cdata[MAXCONTACT][10];   /* pa, pb, n, dist */
 void orc_last_contact_pairs(int* out) { for (int i = 0; i < g_last_contacts; i++) { out[2 * i] = g_last_pairs[i][0]; out[2 * i + 1] = g_last_pairs[i][1]; } }
 int orc_last_contacts(void) { return g_last_contacts; }
+/* contacts of the last substep: {pa, pb, n, dist} each (tests) */
+void orc_last_contact_data(real* out) { for (int i = 0; i < g_last_contacts; i++) for (int k = 0; k < 10; k++) out[10 * i + k] = g_last_cdata[i][k]; }
 int orc_last_rows(void) { return g_last_rows; }
 
 /* One stepSimulation() (environments.py:490,535): btMultiBodyDynamicsWorld::
@@ -1031,7 +1036,12 @@ static void substep(const prb_model* M, State* S) {
     }
   }
   g_last_contacts = nc; g_last_rows = nr;
-  for (int k = 0; k < nc; k++) { g_last_pairs[k][0] = C[k].ca; g_last_pairs[k][1] = C[k].cb; }
+  for (int k = 0; k < nc; k++) {
+    g_last_pairs[k][0] = C[k].ca; g_last_pairs[k][1] = C[k].cb;
+    real* o = g_last_cdata[k];
+    o[0] = C[k].pa.x; o[1] = C[k].pa.y; o[2] = C[k].pa.z; o[3] = C[k].pb.x; o[4] = C[k].pb.y; o[5] = C[k].pb.z;
+    o[6] = C[k].n.x; o[7] = C[k].n.y; o[8] = C[k].n.z; o[9] = C[k].dist;
+  }
   /* ---- PGS, btMultiBodyConstraintSolver::solveSingleIteration order */
   real dv[MAXV]; for (int i = 0; i < nv; i++) dv[i] = 0;
   for (int it = 0; it < M->solver_iters; it++) {
@@ -1073,6 +1083,16 @@ static void substep(const prb_model* M, State* S) {
     S->sqd[s] = X.v[o]; S->sq[s] += dt * S->sqd[s];
   }
 }
+/* Rows of the most recent substep, for the independent LCP check (tests/test_cpu_oracle_independent.py):
+ * J and B = M^-1 J^T (nv each) and {rhs, cfm, invD, lo, hi, lambda, mu, normal_row} of row i. */
+void orc_last_row(const prb_model* M, int i, real* J, real* B, real* sc) {
+  const Row* r = &g_rows[i];
+  int nv = nv_total(M);
+  for (int k = 0; k < nv; k++) { J[k] = r->J[k]; B[k] = r->B[k]; }
+  sc[0] = r->rhs; sc[1] = r->cfm; sc[2] = r->invD; sc[3] = r->lo; sc[4] = r->hi; sc[5] = r->lambda; sc[6] = r->mu; sc[7] = (real)r->normal_row;
+}
+int orc_nv(const prb_model* M) { return nv_total(M); }
+
 void orc_substeps(const prb_model* M, real* state, int n) {
   State S; state_unpack(M, state, &S);
   for (int i = 0; i < n; i++) substep(M, &S);

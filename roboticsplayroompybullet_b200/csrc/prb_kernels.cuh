@@ -662,7 +662,11 @@ PRB_DN void cull_points(int n, const float p[], int m, int i0, int iret[]) {
 // box-box: separating-axis search + face clipping / edge-edge closest points; normal from box 2
 // (B) to box 1 (A), points on B, depth >= 0; at most 4 points.
 PRB_DN int box_box(v3 p1, const m3& R1, v3 h1, v3 p2, const m3& R2, v3 h2, CPoint* out) {
-  const float fudge = 1.05f, EPS = 1.1920929e-7f;
+  // TIE: a later axis replaces the current best only if it separates by 1 um more.  Resting boxes tie structurally (the
+  // table's top face and the block's bottom face are the same axis); with Bullet's plain `>` the winner - and with it the
+  // ORDER of the clipped points, which a 50-sweep Gauss-Seidel is sensitive to - is decided by the last rounding error,
+  // differently in fp32 and fp64.  The oracle applies the same rule.
+  const float fudge = 1.05f, EPS = 1.1920929e-7f, TIE = 1e-6f;
   float A[3] = {h1.x, h1.y, h1.z}, B[3] = {h2.x, h2.y, h2.z};
   v3 p = p2 - p1, ppv3 = tmul(R1, p);
   float pp[3] = {ppv3.x, ppv3.y, ppv3.z};
@@ -672,7 +676,7 @@ PRB_DN int box_box(v3 p1, const m3& R1, v3 h1, v3 p2, const m3& R2, v3 h2, CPoin
   int invert = 0, code = 0, nrm_box = 0, nrm_col = 0;
   v3 normalC = V3(0, 0, 0);
 #define PRB_TST(e1, e2, bx, cl, cc) { float E1 = (e1); s2 = fabsf(E1) - (e2); if (s2 > 0) return 0; \
-    if (s2 > s) { s = s2; nrm_box = bx; nrm_col = cl; invert = (E1 < 0); code = (cc); } }
+    if (s2 > s + TIE) { s = s2; nrm_box = bx; nrm_col = cl; invert = (E1 < 0); code = (cc); } }
   PRB_TST(pp[0], (A[0] + B[0] * Q[0][0] + B[1] * Q[0][1] + B[2] * Q[0][2]), 1, 0, 1);
   PRB_TST(pp[1], (A[1] + B[0] * Q[1][0] + B[1] * Q[1][1] + B[2] * Q[1][2]), 1, 1, 2);
   PRB_TST(pp[2], (A[2] + B[0] * Q[2][0] + B[1] * Q[2][1] + B[2] * Q[2][2]), 1, 2, 3);
@@ -683,7 +687,7 @@ PRB_DN int box_box(v3 p1, const m3& R1, v3 h1, v3 p2, const m3& R2, v3 h2, CPoin
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Q[i][j] += 1.0e-5f;
 #define PRB_TST(e1, e2, n1, n2, n3, cc) { float E1 = (e1); s2 = fabsf(E1) - (e2); if (s2 > EPS) return 0; \
     l = sqrtf((n1) * (n1) + (n2) * (n2) + (n3) * (n3)); \
-    if (l > EPS) { s2 /= l; if (s2 * fudge > s) { s = s2; nrm_box = 0; normalC = V3((n1) / l, (n2) / l, (n3) / l); invert = (E1 < 0); code = (cc); } } }
+    if (l > EPS) { s2 /= l; if (s2 * fudge > s + TIE) { s = s2; nrm_box = 0; normalC = V3((n1) / l, (n2) / l, (n3) / l); invert = (E1 < 0); code = (cc); } } }
   PRB_TST(pp[2] * Rm[1][0] - pp[1] * Rm[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + B[1] * Q[0][2] + B[2] * Q[0][1]), 0, -Rm[2][0], Rm[1][0], 7);
   PRB_TST(pp[2] * Rm[1][1] - pp[1] * Rm[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + B[0] * Q[0][2] + B[2] * Q[0][0]), 0, -Rm[2][1], Rm[1][1], 8);
   PRB_TST(pp[2] * Rm[1][2] - pp[1] * Rm[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + B[0] * Q[0][1] + B[1] * Q[0][0]), 0, -Rm[2][2], Rm[1][2], 9);
@@ -835,19 +839,19 @@ PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
     if (nn <= 4) { m = nn; for (int i = 0; i < nn; i++) keep[i] = b0 + i; }
     else {
       int i0 = 0;
-      for (int i = 1; i < nn; i++) if (c[i].dist < c[i0].dist) i0 = i;
+      for (int i = 1; i < nn; i++) if (c[i].dist < c[i0].dist - 1e-7f) i0 = i;     // ties (equal depths to 0.1 um): the first candidate wins
       v3 p0 = V3(c[i0].pbx, c[i0].pby, c[i0].pbz);
       int i1 = -1; float best = -1.f;
-      for (int i = 0; i < nn; i++) if (i != i0) { v3 d = V3(c[i].pbx, c[i].pby, c[i].pbz) - p0; float v = dot(d, d); if (v > best) { best = v; i1 = i; } }
+      for (int i = 0; i < nn; i++) if (i != i0) { v3 d = V3(c[i].pbx, c[i].pby, c[i].pbz) - p0; float v = dot(d, d); if (v > best * 1.0001f + 1e-12f) { best = v; i1 = i; } }
       v3 p1 = V3(c[i1].pbx, c[i1].pby, c[i1].pbz), e01 = p1 - p0;
       int i2 = -1; best = -1.f;
-      for (int i = 0; i < nn; i++) if (i != i0 && i != i1) { v3 x = cross(V3(c[i].pbx, c[i].pby, c[i].pbz) - p0, e01); float v = dot(x, x); if (v > best) { best = v; i2 = i; } }
+      for (int i = 0; i < nn; i++) if (i != i0 && i != i1) { v3 x = cross(V3(c[i].pbx, c[i].pby, c[i].pbz) - p0, e01); float v = dot(x, x); if (v > best * 1.0001f + 1e-16f) { best = v; i2 = i; } }
       v3 p2 = V3(c[i2].pbx, c[i2].pby, c[i2].pbz);
       int i3 = -1; best = -1.f;
       for (int i = 0; i < nn; i++) if (i != i0 && i != i1 && i != i2) {
         v3 pi = V3(c[i].pbx, c[i].pby, c[i].pbz), a = pi - p0, b = pi - p1, d = pi - p2;
         float v = norm(cross(a, b)) + norm(cross(b, d)) + norm(cross(d, a));
-        if (v > best) { best = v; i3 = i; }
+        if (v > best * 1.0001f + 1e-10f) { best = v; i3 = i; }
       }
       for (int i = 0; i < nn; i++) if (i == i0 || i == i1 || i == i2 || i == i3) keep[m++] = b0 + i;
     }

@@ -98,14 +98,15 @@
 // ARM_CAPQ(4) q and reads the records beyond that in place.  The heavy buffer of a class is an array of bundles of
 // ARM_LANES(k) envs, lane-interleaved like the stage: a block stages its bundle with ONE bulk copy.
 #define ARM_NCLASS 5
+#define ARM_BUFQ_MAX (R0_LIGHT_END + SB_MAXCONTACT * CR_MAX_Q + CR_MAX_Q + 4)
 #ifndef ARM_CAPQ0         // (overridable: the CPU tests build a variant with tiny stages to exercise the read-in-place path)
 #define ARM_CAPQ0 136
 #define ARM_CAPQ1 220
 #define ARM_CAPQ2 288
 #define ARM_CAPQ3 440
-#define ARM_CAPQ4 880
+#define ARM_CAPQ4 ARM_BUFQ_MAX    // the largest islands are staged whole too (4 envs per block); smaller test builds read in place
 #endif
-#define ARM_BUFQ_MAX (R0_LIGHT_END + SB_MAXCONTACT * CR_MAX_Q + CR_MAX_Q + 4)
+
 PRB_HD int arm_lanes(int k) { return k == 0 ? 32 : (k <= 2 ? 16 : (k == 3 ? 8 : 4)); }
 PRB_HD int arm_capq(int k) { return k == 0 ? ARM_CAPQ0 : (k == 1 ? ARM_CAPQ1 : (k == 2 ? ARM_CAPQ2 : (k == 3 ? ARM_CAPQ3 : ARM_CAPQ4))); }
 PRB_HD int arm_bufq(int k) { return k == ARM_NCLASS - 1 ? ARM_BUFQ_MAX : arm_capq(k); }
@@ -152,8 +153,23 @@ struct SetupCfg {
   static constexpr int MAXCONTACT = SB_MAXCONTACT;
   static constexpr int MAXOVL = 32;
   static constexpr int MAXCAND = 128;
-  static constexpr int WPB = 4;
+#ifndef PRB_SETUP_WPB
+#define PRB_SETUP_WPB 8       // measured r2c at 65536 envs: 4 warps 35.6 ms of setup per env step, 8 warps 29.9 ms, 16 warps 31.2 ms
+#endif
+  static constexpr int WPB = PRB_SETUP_WPB;     // warps (envs) per thread block
 };
+// PRB_SETUP_SYNC: the warps of a block are re-aligned with a block barrier between the phases of the setup kernel.  Its
+// code (~15k SASS instructions, executed once per warp) is far larger than the instruction caches; warps drifting apart
+// each stream it on their own (r2b: 3.4 stall cycles per issue waiting for instructions).  Measured r2c: no gain over
+// simply running 8 warps per block (29.7 vs 29.9 ms), so off by default.
+#ifndef PRB_SETUP_SYNC
+#define PRB_SETUP_SYNC 0
+#endif
+#if PRB_SETUP_SYNC && !defined(PRB_EMU)
+#define SETUP_ALIGN() __syncthreads()
+#else
+#define SETUP_ALIGN() ((void)0)
+#endif
 
 // shared memory of one env in the setup kernel: state + the substep's kinematics / collision scratch
 template <class CFG>
@@ -547,32 +563,42 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
   PRB_SMEM_DECL2;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int e = blockIdx.x * SetupCfg::WPB + wib;
-  if (e >= N) return;
-  if (active != nullptr && active[e] == 0) return;       // masked stepping (reset: only the envs being reset settle)
+  // masked stepping (reset: only the envs being reset settle); an idle warp still takes part in the block barriers
+  const bool on = e < N && (active == nullptr || active[e] != 0);
+#if !PRB_SETUP_SYNC
+  if (!on) return;
+#endif
   const DevModel& M = *Mp;
   WM& W = wm[wib];
-  float* st = state + (size_t)e * M.state_stride;
-  const SV S = sv_of(sbuf, e);
-  load_state(M, W, st, lane);
-  if (lane == 0) { W.overflow = 0; W.dbg_a = 0; W.dbg_c = 0; W.dbg_p = 0; W.dbg_u = 0; }
-  __syncwarp();
-  if (flags & SETUP_INTEGRATE) {
-    float vstar = 0.f, dv = 0.f;
-    if (lane < M.nv) { vstar = S.w(4 * Q_VSTAR + lane); dv = S.w(4 * Q_DV + lane); }
-    phase_integrate(M, W, lane, vstar, dv);
+  float* st = state + (size_t)(on ? e : 0) * M.state_stride;
+  const SV S = sv_of(sbuf, on ? e : 0);
+  if (on) {
+    load_state(M, W, st, lane);
+    if (lane == 0) { W.overflow = 0; W.dbg_a = 0; W.dbg_c = 0; W.dbg_p = 0; W.dbg_u = 0; }
+    __syncwarp();
+    if (flags & SETUP_INTEGRATE) {
+      float vstar = 0.f, dv = 0.f;
+      if (lane < M.nv) { vstar = S.w(4 * Q_VSTAR + lane); dv = S.w(4 * Q_DV + lane); }
+      phase_integrate(M, W, lane, vstar, dv);
+    }
   }
   if (flags & SETUP_BUILD) {
-    phase_fk(M, W, lane, true);
-    phase_collide(M, W, lane);
-    phase_crba(M, W, lane);
-    phase_minv<ND>(W, lane);
-    phase_vstar(M, W, lane);
-    phase_rows_stream<ND>(M, W, lane, e, N, S, hbuf, heavy_cnt);
-    __syncwarp();
-    // a dropped contact marks the env; the mark is counted (once per env step) by the launch that observes
-    if (lane == 0 && W.overflow) { if (O.ovf_env) O.ovf_env[e] = 1; else if (O.overflow) atomicAdd(O.overflow, 1ull); }
-    if (lane == 0 && O.dbg) { O.dbg[4 * e] = W.dbg_u | (W.dbg_a << 8); O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.n_jrow; }
+    SETUP_ALIGN();
+    if (on) phase_fk(M, W, lane, true);
+    SETUP_ALIGN();
+    if (on) phase_collide(M, W, lane);
+    SETUP_ALIGN();
+    if (on) { phase_crba(M, W, lane); phase_minv<ND>(W, lane); phase_vstar(M, W, lane); }
+    SETUP_ALIGN();
+    if (on) {
+      phase_rows_stream<ND>(M, W, lane, e, N, S, hbuf, heavy_cnt);
+      __syncwarp();
+      // a dropped contact marks the env; the mark is counted (once per env step) by the launch that observes
+      if (lane == 0 && W.overflow) { if (O.ovf_env) O.ovf_env[e] = 1; else if (O.overflow) atomicAdd(O.overflow, 1ull); }
+      if (lane == 0 && O.dbg) { O.dbg[4 * e] = W.dbg_u | (W.dbg_a << 8); O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.n_jrow; }
+    }
   }
+  if (!on) return;
   if (flags & SETUP_OBSERVE) {
     phase_observe(M, W, lane, O, (size_t)e, true);
     if (lane == 0 && O.ovf_env && O.ovf_env[e]) { O.ovf_env[e] = 0; if (O.overflow) atomicAdd(O.overflow, 1ull); }
@@ -762,9 +788,9 @@ PRB_D bool jrows_pass(JointRows& R, IslandV& V, int n_slide, bool ascending) {
   return changed;
 }
 template <int ND>
-PRB_D void jrows_init(JointRows& R, const DevModel& M, const float4* col, int stride, int h1) {
+PRB_D void jrows_init(JointRows& R, const DevModel& M, const float4* col, int stride, int h1, bool valid) {
   R.col = col; R.stride = stride;
-  R.njr = h1 & 0xff; R.canon = (h1 >> 24) & 1;
+  R.njr = valid ? (h1 & 0xff) : 0; R.canon = (h1 >> 24) & 1;
   R.nL = R.njr - ND - M.n_slide - (M.gear_a >= 0 ? 1 : 0);     // meaningful when canon
   R.t_jlam = R0_JROW + R.njr;
   R.ratio = M.params[P_GEAR_RATIO];
@@ -773,7 +799,7 @@ PRB_D void jrows_init(JointRows& R, const DevModel& M, const float4* col, int st
 #pragma unroll
   for (int d = 0; d < 12; d++) R.lm[d] = 0.f;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = 0; k < ((R.njr + 3) >> 2); k++) const_cast<float4*>(col)[(size_t)(R.t_jlam + k) * stride] = z4;
+  if (valid) for (int k = 0; k < ((R.njr + 3) >> 2); k++) const_cast<float4*>(col)[(size_t)(R.t_jlam + k) * stride] = z4;
 }
 // velocity change -> stream (linear DoF order): arm, slides, and the free bodies this island owns
 PRB_D void island_store(const DevModel& M, const IslandV& V, float* sbuf, int e, int info, bool with_free) {
@@ -802,13 +828,16 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel
   const int lane = threadIdx.x;
   const DevModel& M = *Mp;
   // persistent blocks: a block walks groups of 32 envs (launching one block per group costs more than
-  // the solve: each block launch allocates its shared memory)
-  for (int e = blockIdx.x * PGS_BLOCK + lane; e < N; e += gridDim.x * PGS_BLOCK) {
-    if (active != nullptr && active[e] == 0) continue;
-    float4* G = stream_col(sbuf, e);
-    const int h0 = __float_as_int(G[Q_HDR * 32].x);
-    if ((h0 >> 25) & 7) continue;                          // heavy: prb_pgs_arm_kernel solves it from its class buffer
-    const int njr = h0 & 0xff;
+  // the solve: each block launch allocates its shared memory); warp-uniform control flow, per-lane predicates
+  const int ngroups = (N + PGS_BLOCK - 1) / PGS_BLOCK;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int e = g * PGS_BLOCK + lane;
+    bool valid = e < N && (active == nullptr || active[e] != 0);
+    float4* G = stream_col(sbuf, valid ? e : 0);
+    const int h0 = valid ? __float_as_int(G[Q_HDR * 32].x) : 0;
+    if ((h0 >> 25) & 7) valid = false;                     // heavy: prb_pgs_arm_kernel solves it from its class buffer
+    if (!__any_sync(FULL, valid)) continue;
+    const int njr = valid ? (h0 & 0xff) : 0;
     float4* col = sm + lane;
     const float4* Gr = G + Q_ST * 32;
     {
@@ -819,15 +848,21 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel
     IslandV V;
     V.clear();
     JointRows R;
-    jrows_init<ND>(R, M, col, 32, h0);
+    jrows_init<ND>(R, M, col, 32, h0, valid);
     const int iters = M.solver_iters;
+    bool live = valid;
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
       // A sweep that changes no impulse leaves the state untouched, so every later sweep repeats it
-      // exactly: stopping there is bit-identical to running all the iterations.
-      if (!jrows_pass<ND>(R, V, M.n_slide, (it & 1) != 0)) break;
+      // exactly: retiring the lane there is bit-identical to running all the iterations.
+      bool changed = false;
+      if (live) changed = jrows_pass<ND>(R, V, M.n_slide, (it & 1) != 0);
+      __syncwarp();
+      live = live && changed;
+      if (!__any_sync(FULL, live)) break;
     }
-    island_store(M, V, sbuf, e, 0, false);
+    if (valid) island_store(M, V, sbuf, e, 0, false);
+    __syncwarp();
   }
 }
 
@@ -1201,44 +1236,62 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
     for (int q = lane; q < capq * lanes; q += 32) sm[q] = Gb[q];
     __syncwarp();
 #endif
+    // Control flow is kept WARP-UNIFORM (loop bounds = the bundle's maxima, per-lane predicates inside): lanes that
+    // drift apart in data-dependent loops would each fetch and issue the same code on their own (measured in r2b:
+    // 4.7 of 16 lanes active per instruction, 2-3 x the warp instructions).
     const int i = b * lanes + lane;
-    if (lane < lanes && i < cnt) {
-      float4* col = sm + lane;
-      float4* gcol = Gb + lane;
-      const float4 hq = col[R0_HQ * lanes];
-      const int e = __float_as_int(hq.x), h1 = __float_as_int(hq.y), info = __float_as_int(hq.z);
-      const int nc = (h1 >> 8) & 0xff;
-      IslandV V;
-      V.clear();
+    const bool valid = lane < lanes && i < cnt;
+    float4* col = sm + (valid ? lane : 0);
+    float4* gcol = Gb + (valid ? lane : 0);
+    const float4 hq = col[R0_HQ * lanes];
+    const int e = __float_as_int(hq.x), h1 = valid ? __float_as_int(hq.y) : 0, info = __float_as_int(hq.z);
+    const int nc = (h1 >> 8) & 0xff;
+    int ncmax = nc;
 #pragma unroll
-      for (int fb = 0; fb < PRB_MAXFREE; fb++) {
-        const float4 i0 = col[(R0_BODY + 2 * fb) * lanes], i1 = col[(R0_BODY + 2 * fb + 1) * lanes];
-        V.I[fb][0] = i0.x; V.I[fb][1] = i0.y; V.I[fb][2] = i0.z; V.I[fb][3] = i0.w; V.I[fb][4] = i1.x; V.I[fb][5] = i1.y;
-        V.invm[fb] = i1.z;
-      }
-      JointRows R;
-      jrows_init<ND>(R, M, col, lanes, h1);
-      const int tC0 = R.t_jlam + ((R.njr + 3) >> 2);
-      const int iters = M.solver_iters;
+    for (int o = 16; o > 0; o >>= 1) ncmax = max(ncmax, __shfl_xor_sync(FULL, ncmax, o));
+    IslandV V;
+    V.clear();
+#pragma unroll
+    for (int fb = 0; fb < PRB_MAXFREE; fb++) {
+      const float4 i0 = col[(R0_BODY + 2 * fb) * lanes], i1 = col[(R0_BODY + 2 * fb + 1) * lanes];
+      V.I[fb][0] = i0.x; V.I[fb][1] = i0.y; V.I[fb][2] = i0.z; V.I[fb][3] = i0.w; V.I[fb][4] = i1.x; V.I[fb][5] = i1.y;
+      V.invm[fb] = i1.z;
+    }
+    JointRows R;
+    jrows_init<ND>(R, M, col, lanes, h1, valid);
+    const int tC0 = R.t_jlam + ((R.njr + 3) >> 2);
+    const int iters = M.solver_iters;
+    bool live = valid;
 #define ARM_REC(t_) ArmRec{(INPLACE && (t_) + CR_MAX_Q > capq) ? gcol + (size_t)(t_) * lanes : col + (size_t)(t_) * lanes, lanes}
 #pragma unroll 1
-      for (int it = 0; it < iters; it++) {
-        // fixed point reached (a sweep changed no impulse): later sweeps are exact repeats
-        bool changed = jrows_pass<ND>(R, V, M.n_slide, (it & 1) != 0);
-        int t = tC0, size;
+    for (int it = 0; it < iters; it++) {
+      bool changed = false;
+      if (live) changed = jrows_pass<ND>(R, V, M.n_slide, (it & 1) != 0);
+      __syncwarp();
+      int t = tC0, size;
 #pragma unroll 1
-        for (int k = 0; k < nc; k++) { changed |= visit_normal(ARM_REC(t), V, sminv, size); t += size; }
-        t = tC0;
-#pragma unroll 1
-        for (int k = 0; k < nc; k++) { changed |= visit_spin(ARM_REC(t), V, sminv, size); t += size; }
-        t = tC0;
-#pragma unroll 1
-        for (int k = 0; k < nc; k++) { changed |= visit_friction(ARM_REC(t), V, sminv, size); t += size; }
-        if (!changed) break;
+      for (int k = 0; k < ncmax; k++) {
+        if (live && k < nc) { changed |= visit_normal(ARM_REC(t), V, sminv, size); t += size; }
+        __syncwarp();
       }
-#undef ARM_REC
-      island_store(M, V, sbuf, e, info, true);
+      t = tC0;
+#pragma unroll 1
+      for (int k = 0; k < ncmax; k++) {
+        if (live && k < nc) { changed |= visit_spin(ARM_REC(t), V, sminv, size); t += size; }
+        __syncwarp();
+      }
+      t = tC0;
+#pragma unroll 1
+      for (int k = 0; k < ncmax; k++) {
+        if (live && k < nc) { changed |= visit_friction(ARM_REC(t), V, sminv, size); t += size; }
+        __syncwarp();
+      }
+      // fixed point reached (a sweep changed no impulse): later sweeps are exact repeats, the lane retires
+      live = live && changed;
+      if (!__any_sync(FULL, live)) break;
     }
+#undef ARM_REC
+    if (valid) island_store(M, V, sbuf, e, info, true);
     __syncwarp();                                          // the stage is re-filled by the next bundle
   }
 }

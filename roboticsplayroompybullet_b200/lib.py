@@ -7,7 +7,8 @@ import os
 from .model import PrbModelStruct
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libprb_b200.so')
+# PRB_LIB selects another build of the same sources (A/B experiments with compile-time knobs, tools/build_variants.sh)
+LIB_PATH = os.environ.get('PRB_LIB') or os.path.join(_HERE, 'libprb_b200.so')
 _LIB = None
 
 

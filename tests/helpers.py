@@ -111,13 +111,13 @@ def key_errors(model, got, ref):
     return {'pose': pose, 'ang': ang, 'vel': vel, 'flags': flags}
 
 
-def ulp_spread(model, state_row, action, Oracle, ref, rng, n_pert=6):
-    """Worst pose-group deviation of the oracle's own fp64 step when every non-zero entry of its (fp32) input state
-    moves by one ulp in a random direction (goal / bookkeeping entries untouched)."""
+def ulp_spread(model, state_row, action, Oracle, ref, rng, n_pert=8):
+    """Worst pose-group and velocity-group deviation of the oracle's own fp64 step when every non-zero entry of its (fp32)
+    input state moves by one ulp in a random direction (goal / bookkeeping entries untouched)."""
     x = np.asarray(state_row, np.float32)
     G = int(model['goal_dim'])
     tail = G + 10
-    worst = 0.0
+    worst = {'pose': 0.0, 'vel': 0.0}
     for _ in range(n_pert):
         sgn = np.sign(rng.standard_normal(len(x))).astype(np.float32)
         y = np.nextafter(x, x + sgn * np.float32(1e9)).astype(np.float32)
@@ -126,14 +126,16 @@ def ulp_spread(model, state_row, action, Oracle, ref, rng, n_pert=6):
         o = Oracle(model)
         o.state[:] = y.astype(np.float64)
         d = o.step(np.asarray(action, np.float64))
-        worst = max(worst, key_errors(model, d, ref)['pose'])
+        e = key_errors(model, d, ref)
+        worst['pose'] = max(worst['pose'], e['pose'], e['ang'] * POS_TOL / ANG_TOL)
+        worst['vel'] = max(worst['vel'], e['vel'])
     return worst
 
 
 def compare_step(model, obs, r, info, oracle_outs, states=None, actions=None, Oracle=None, rng=None):
     """Compares every key of a batched step with the per-env oracle results.  Returns a dict:
-    n, bad_pose (envs beyond the pose tolerance and not explained by conditioning), stiff (envs beyond the pose tolerance
-    but within COND_K x their ulp spread), bad_vel, bad_flags, bad_reward, worst_pose, worst_unexplained."""
+    n, bad_pose (envs beyond the pose tolerance and not explained by conditioning), stiff (envs beyond a tolerance
+    but within COND_K x their ulp spread), bad_vel, bad_flags, bad_reward, worst_pose, worst_unexplained, worst_vel."""
     n = len(oracle_outs)
     out = {'n': n, 'bad_pose': 0, 'stiff': 0, 'bad_vel': 0, 'bad_flags': 0, 'bad_reward': 0, 'worst_pose': 0.0,
            'worst_unexplained': 0.0, 'worst_vel': 0.0}
@@ -142,26 +144,30 @@ def compare_step(model, obs, r, info, oracle_outs, states=None, actions=None, Or
         ref = oracle_outs[i]
         got = {k: np.asarray(obs[k][i]) for k in OBS_KEYS}
         e = key_errors(model, got, ref)
-        out['worst_pose'] = max(out['worst_pose'], e['pose'])
+        pose = max(e['pose'], e['ang'] * POS_TOL / ANG_TOL)          # angles on the pose scale
+        out['worst_pose'] = max(out['worst_pose'], pose)
         out['worst_vel'] = max(out['worst_vel'], e['vel'])
-        over = e['pose'] > POS_TOL or e['ang'] > ANG_TOL
-        explained = False
-        if (over or e['vel'] > 1.0) and states is not None:
+        rr = float(ref['reward'][0])
+        rew_bad = not (r[i] == rr or abs(r[i] - rr) < 1e-4) or int(info['is_success'][i]) != int(ref['is_success'][0])
+        over_pose, over_vel = pose > POS_TOL, e['vel'] > 1.0
+        ex_pose = ex_vel = False
+        if (over_pose or over_vel or e['flags'] or rew_bad) and states is not None:
             sp = ulp_spread(model, states[i], actions[i], Oracle, ref, rng)
-            explained = e['pose'] <= COND_K * sp and sp > POS_TOL / COND_K
-        if over:
-            if explained:
+            ex_pose = pose <= COND_K * sp['pose'] and sp['pose'] > POS_TOL / COND_K
+            ex_vel = e['vel'] <= COND_K * sp['vel'] and sp['vel'] > 1.0 / COND_K
+        if over_pose:
+            if ex_pose:
                 out['stiff'] += 1
             else:
                 out['bad_pose'] += 1
-                out['worst_unexplained'] = max(out['worst_unexplained'], e['pose'])
-        if e['vel'] > 1.0 and not explained:
-            out['bad_vel'] += 1
-        if e['flags'] and not explained:
+                out['worst_unexplained'] = max(out['worst_unexplained'], pose)
+        if over_vel:
+            if ex_vel or ex_pose:
+                out['stiff'] += 0 if over_pose else 1
+            else:
+                out['bad_vel'] += 1
+        if e['flags'] and not (ex_pose or ex_vel):
             out['bad_flags'] += 1
-        rr = float(ref['reward'][0])
-        if not (r[i] == rr or abs(r[i] - rr) < 1e-4) and not explained:
-            out['bad_reward'] += 1
-        if int(info['is_success'][i]) != int(ref['is_success'][0]) and not explained:
+        if rew_bad and not (ex_pose or ex_vel):
             out['bad_reward'] += 1
     return out

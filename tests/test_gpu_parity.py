@@ -10,6 +10,15 @@ pytestmark = pytest.mark.gpu
 ENVS = ['UR5Reach-v0', 'UR5PlayAbsRPY1Obj-v0', 'pandaPick-v0']
 
 
+def _record(name, res):
+    """Append the measured parity statistics of a test to gpurun_out/parity_stats.jsonl (kept under profiles/)."""
+    import json, os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(d):
+        with open(os.path.join(d, 'parity_stats.jsonl'), 'a') as f:
+            f.write(json.dumps(dict(test=name, **{k: (float(v) if isinstance(v, (float, np.floating)) else int(v)) for k, v in res.items()})) + '\n')
+
+
 def _mk(env_id, n, seed=5):
     from roboticsplayroompybullet_b200.envs import make
     return make(env_id, num_envs=n, seed=seed)
@@ -83,6 +92,7 @@ def test_step_parity_identical_states(env_id):
         assert np.quantile(terr, 0.9) < 2e-5 and terr.max() < 2e-3, (np.quantile(terr, 0.9), terr.max())
     # a contact that appears one substep earlier or later in fp32 than in fp64 is the one legitimate source of
     # unexplained outliers: <= 2 % of the env steps
+    _record('step_parity_identical_states[%s]' % env_id, dict(tot, n=4 * n))
     lim = max(1, int(0.02 * 4 * n))
     assert tot['bad_pose'] <= lim and tot['bad_vel'] <= lim and tot['bad_flags'] <= lim and tot['bad_reward'] <= lim, tot
     env.close()
@@ -217,6 +227,7 @@ def test_step_parity_scripted_steady_state():
         for k in tot:
             tot[k] += res[k]
     assert merged >= 6, merged                                      # the heavy path was exercised
+    _record('step_parity_scripted_steady_state', dict(tot, n=3 * n, heavy=merged))
     lim = int(0.02 * 3 * n)
     assert tot['bad_pose'] <= lim and tot['bad_vel'] <= lim and tot['bad_flags'] <= lim and tot['bad_reward'] <= lim, tot
     env.close()
@@ -272,6 +283,7 @@ def test_parity_at_baseline_size(env_id, N):
     outs = [oracle_step_from(m, st[i], acts[pre][i], Oracle)[0] for i in pick]
     sub_obs = {k: obs[k][pick] for k in OBS_KEYS}
     res = compare_step(m, sub_obs, r[pick], {'is_success': info['is_success'][pick]}, outs, st[pick], acts[pre][pick], Oracle)
+    _record('parity_at_baseline_size[%s-%d]' % (env_id, N), dict(res, heavy_in_sample=int((cls[pick] > 0).sum())))
     lim = max(2, int(0.02 * 256))
     assert res['bad_pose'] <= lim and res['bad_vel'] <= lim and res['bad_flags'] <= lim and res['bad_reward'] <= lim, res
     # (2) the same envs in a small handle

@@ -1,6 +1,8 @@
 """Regression fixture for the solver kernels: heavy (arm island in contact) states sampled on the GPU from the scripted
 bench workload (tools/exp_usage.py -> gpurun_out/heavy_sample.npz), stepped once by the kernels of the checkout this
-script runs in, under the CPU SIMT emulator.  Written once from the round-1 tree (four-lanes-per-env arm-island solver);
+script runs in, under the CPU SIMT emulator.  Written from the round-1 tree (four-lanes-per-env arm-island solver) with
+round 2's tie rule of the collision code patched in (box_box TIE, manifold-reduction ties: prb_kernels.cuh), so that both
+solvers see the same contacts;
 tests/test_cpu_emu_parity.py::test_emu_solver_regression_bit_identical then holds every later solver to those bits.
 
     python tools/make_solver_golden.py <repo root> <heavy_sample.npz> <out.npz>

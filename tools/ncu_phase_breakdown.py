@@ -1,30 +1,29 @@
 #!/usr/bin/env python
-"""Phase breakdown of the fused step kernel from an ncu source-page export.
+"""Phase breakdown of a kernel from an ncu source-page export.
 
-    ncu -i gpurun_out/prof.ncu-rep --page source --csv --print-source cuda,sass > src.csv
-    python tools/ncu_phase_breakdown.py src.csv [kernel-name-substring]
+    ncu -i gpurun_out/prof.ncu-rep --page source --csv --print-source cuda,sass --kernel-id ::regex:NAME:1 > src.csv
+    python tools/ncu_phase_breakdown.py src.csv
 
-Every SASS instruction row carries executed-instruction and stall-sample counts.  Rows are attributed
-to the device function (phase_*, box_box, ...) whose source lines produced them; instructions that
-come from the small inlined helpers of prb_device.h are attributed to the phase of the nearest
-preceding instruction (by address) that maps to prb_kernels.cuh.
+Every SASS instruction row carries executed-instruction and stall-sample counts.  Rows are attributed to the device
+function (phase_*, box_box, side_row, ...) whose source lines produced them; instructions that come from the small
+inlined helpers of prb_device.h are attributed to the function of the nearest preceding instruction (by address) that
+maps to prb_kernels.cuh / prb_stream.cuh / prb_reset.cuh.
 """
 import csv
+import os
 import re
 import sys
 from collections import defaultdict
 
-KERNELS = 'roboticsplayroompybullet_b200/csrc/prb_kernels.cuh'
+CSRC = os.environ.get('PRB_CSRC') or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'roboticsplayroompybullet_b200', 'csrc')
+FILES = ['prb_kernels.cuh', 'prb_stream.cuh', 'prb_reset.cuh']
 
 
 def function_spans(path):
-    """[(first_line, name)] of the top-level device functions of prb_kernels.cuh."""
     spans = []
-    pat = re.compile(r'^(?:PRB_DN?|__global__|static|template)?.*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(')
-    lines = open(path).read().split('\n')
-    for i, l in enumerate(lines, 1):
-        if l.startswith(('PRB_D ', 'PRB_DN ', '__global__')):
-            m = re.search(r'\b([A-Za-z_][A-Za-z0-9_]*)\s*\(', l.split(')', 1)[0] if l.startswith('__global__') else l)
+    for i, l in enumerate(open(path).read().split('\n'), 1):
+        if l.startswith(('PRB_D ', 'PRB_DN ', '__global__', 'static PRB_D')) or re.match(r'^\s*(static )?PRB_D ', l):
+            m = re.search(r'\b([A-Za-z_][A-Za-z0-9_]*)\s*\(', l)
             if l.startswith('__global__'):
                 m = re.search(r'\b(prb_[a-z_]+kernel)\b', l) or m
             if m:
@@ -33,77 +32,62 @@ def function_spans(path):
 
 
 def main():
-    src = sys.argv[1]
-    want = sys.argv[2] if len(sys.argv) > 2 else ''
-    spans = function_spans(KERNELS)
+    spans = {f: function_spans(os.path.join(CSRC, f)) for f in FILES}
 
-    def func_of(line):
+    def func_of(f, line):
         name = '?'
-        for first, n in spans:
+        for first, n in spans[f]:
             if first <= line:
                 name = n
             else:
                 break
         return name
 
-    sections, cur = [], None
-    fpath = None
-    for row in csv.reader(open(src, newline='')):
+    rows, hdr, fpath, line = [], None, None, None
+    for row in csv.reader(open(sys.argv[1], newline='')):
         if not row:
             continue
         if row[0] == 'File Path':
-            fpath = row[1]
+            fpath = os.path.basename(row[1])
             continue
-        if row[0] == 'Function Name':
-            cur = {'kernel': row[1], 'file': fpath, 'rows': [], 'hdr': None}
-            sections.append(cur)
+        if row[0] in ('Function Name', 'Kernel Name'):
             continue
         if row[0] == 'Line No':
-            cur['hdr'] = row
+            hdr = row
             continue
-        if cur is not None and cur['hdr'] is not None:
-            cur['rows'].append(row)
-    # instruction rows: (addr, file, line, inst, samples)
-    by_kernel = defaultdict(list)
-    for s in sections:
-        h = s['hdr']
-        ia, ii, isamp = h.index('Address'), h.index('Instructions Executed'), h.index('# Samples')
-        line = None
-        for r in s['rows']:
-            if r[0] != '':
-                try:
-                    line = int(r[0])
-                except ValueError:
-                    line = None
-                continue
-            if len(r) <= ii or not r[ia].startswith('0x'):
-                continue
+        if hdr is None:
+            continue
+        if row[0] != '':
             try:
-                by_kernel[s['kernel']].append((int(r[ia], 16), s['file'], line, int(r[ii]), int(r[isamp])))
+                line = int(row[0])
             except ValueError:
-                pass
-    for k, rows in by_kernel.items():
-        if want and want not in k:
+                line = None
             continue
-        rows.sort()
-        seen, uniq = set(), []
-        for r in rows:
-            if r[0] in seen:
-                continue
+        ia, ii, isamp, it = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('# Samples'), hdr.index('Thread Instructions Executed')
+        if len(row) <= ii or not row[ia].startswith('0x'):
+            continue
+        try:
+            rows.append((int(row[ia], 16), fpath, line, int(row[ii]), int(row[isamp]), int(row[it])))
+        except ValueError:
+            pass
+    rows.sort()
+    seen, uniq = set(), []
+    for r in rows:
+        if r[0] not in seen:
             seen.add(r[0])
             uniq.append(r)
-        phase_inst, phase_samp = defaultdict(int), defaultdict(int)
-        cur_phase = 'prologue'
-        for addr, f, line, inst, samp in uniq:
-            if f and f.endswith('prb_kernels.cuh') and line:
-                cur_phase = func_of(line)
-            phase_inst[cur_phase] += inst
-            phase_samp[cur_phase] += samp
-        ti, ts = sum(phase_inst.values()) or 1, sum(phase_samp.values()) or 1
-        print('==', k[:110])
-        print('   %d SASS instructions, %.3e warp-instructions executed, %d samples' % (len(uniq), ti, ts))
-        for p in sorted(phase_inst, key=lambda p: -phase_samp[p]):
-            print('   %-22s inst %6.2f%%   samples %6.2f%%' % (p, 100.0 * phase_inst[p] / ti, 100.0 * phase_samp[p] / ts))
+    inst, samp, thr = defaultdict(int), defaultdict(int), defaultdict(int)
+    cur = 'prologue'
+    for addr, f, ln, ni, ns, nt in uniq:
+        if f in spans and ln:
+            cur = func_of(f, ln)
+        inst[cur] += ni
+        samp[cur] += ns
+        thr[cur] += nt
+    ti, ts = sum(inst.values()) or 1, sum(samp.values()) or 1
+    print('%d SASS instructions, %.3e warp instructions executed, %d samples' % (len(uniq), ti, ts))
+    for p in sorted(inst, key=lambda p: -samp[p]):
+        print('   %-26s inst %6.2f%%   samples %6.2f%%   active lanes %.1f' % (p, 100.0 * inst[p] / ti, 100.0 * samp[p] / ts, thr[p] / max(inst[p], 1)))
 
 
 if __name__ == '__main__':
