@@ -34,17 +34,21 @@ BYTES_PER_ENV_STEP = {'UR5Reach-v0': 416, 'pandaPick-v0': 560, 'UR5PlayAbsRPY1Ob
 METRIC = 'UR5PlayAbsRPY1Obj-v0 env-steps/s'
 
 
-# Interaction regions of the playroom scene (scenes.py:46-426), arm base frame.  Round 1: the block
-# sub-tasks make real contact (reach, grasp, lift, carry); the drawer / door / button / dial sub-tasks
-# trace their gestures a few centimetres clear of the furniture (handle geometry is not scripted yet).
-_ANCHORS = {'drawer': (-0.10, 0.06, 0.08), 'door': (0.05, 0.32, 0.10), 'button': (-0.20, 0.33, 0.12), 'dial': (0.20, 0.10, 0.07)}
+# Interaction regions of the playroom scene (scenes.py:46-426; world frame of the compiled model).  The block sub-tasks
+# grasp, lift and carry; the drawer sub-task drops the closed fingers into the slot behind the drawer's front plate, pulls
+# it out against its stoppers (-y) and pushes it back; the door sub-task presses the closed fingers against the vertical
+# bar of the door's ring handle, slides the door +x and back.  Button and dial gestures are traced next to the parts (the
+# button sits under the cabinet shelf and the dial under the table edge: a top-down gripper cannot reach them).
+_ANCHORS = {'drawer': (-0.131, -0.167, -0.055), 'door': (0.0, 0.322, 0.10), 'button': (-0.20, 0.33, 0.12), 'dial': (0.20, 0.10, 0.07)}
 # sub-task scripts: waypoints (dx, dy, dz relative to the anchor, yaw, gripper, dwell steps)
 _SCRIPTS = [
     ('block', [(0, 0, 0.15, 0, -1, 0), (0, 0, 0.03, 0, -1, 4)]),                                             # reach block
     ('block', [(0, 0, 0.15, 0, -1, 0), (0, 0, -0.01, 0, -1, 2), (0, 0, -0.01, 0, 1, 10), (0, 0, 0.2, 0, 1, 6),
                (0.05, 0.05, 0.2, 0, 1, 2), (0.05, 0.05, 0.03, 0, -1, 4)]),                                    # grasp, lift, carry, release
-    ('drawer', [(0, 0, 0.06, 0, -1, 0), (0, 0, 0.0, 0, 1, 6), (0, -0.08, 0.0, 0, 1, 4)]),                        # drawer pull gesture (-y)
-    ('door', [(-0.08, 0, 0.0, 0, -1, 0), (0.08, 0.0, 0.0, 0, -1, 4)]),                                          # door slide gesture (+x)
+    ('drawer', [(0, 0, 0.12, 0, 1, 0), (0, 0, 0, 0, 1, 1), (0, -0.09, 0, 0, 1, 1), (0, 0.03, 0, 0, 1, 1),
+                (0, 0, 0.12, 0, 1, 0)]),                                                                       # drawer: pull out, push back
+    ('door', [(-0.07, 0, 0.10, 0, 1, 0), (-0.07, 0, 0, 0, 1, 1), (0.09, 0, 0, 0, 1, 2), (0.09, -0.08, 0, 0, 1, 0),
+              (0.20, -0.08, 0, 0, 1, 0), (0.20, 0, 0, 0, 1, 0), (0.03, 0, 0, 0, 1, 2), (0.10, -0.08, 0.05, 0, 1, 0)]),   # door: slide +x, slide back
     ('button', [(0, 0, 0.06, 0, 1, 0), (0, 0, 0.0, 0, 1, 6), (0, 0, 0.06, 0, 1, 2)]),                           # button press gesture
     ('dial', [(0, 0, 0.06, 0, -1, 0), (0, 0, 0.0, 0, 1, 6), (0, 0, 0.0, 1.0, 1, 4)]),                           # dial turn gesture
 ]
@@ -142,7 +146,7 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
 def _cpu_worker(args):
-    env_id, seed, wid, budget_s, warm = args
+    env_id, seed, wid, budget_s, preroll = args
     try:
         os.sched_setaffinity(0, {wid % os.cpu_count()})
     except Exception:
@@ -155,28 +159,29 @@ def _cpu_worker(args):
     blk = d0['achieved_goal'][None, :3] if env_id == ENV_ID else None
     ee = d0['obs_quat'][None, :3]
     acts = synth_actions(np.random.default_rng(seed + wid), 1, 4096, env_id, block_xyz=blk, ee_xyz=ee)[:, 0, :]
-    # the same scripted stream as the GPU arm; the CPU sample starts inside the contact phases too
-    # (the pre-roll is skipped through by stepping, untimed, every 4th action: cheap approach to the objects)
-    for i in range(warm):
-        o.step(acts[min(4 * i, 95)])
+    # the same scripted stream and the same untimed pre-roll as the GPU arm: the timed sample starts in the steady state
+    # of scripted play (sub-tasks in their contact phases), not in the approach from the rest pose
+    for i in range(preroll):
+        o.step(acts[i])
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s:
-        o.step(acts[(96 + n) % len(acts)])
+        o.step(acts[(preroll + n) % len(acts)])
         n += 1
     return n, time.perf_counter() - t0
 
 
-def cpu_baseline(env_id, seed, budget_s=12.0, warm=24):
+def cpu_baseline(env_id, seed, budget_s=12.0, preroll=96):
     """Oracle (kind 'port') on every host core, one process per core, bounded to ~budget_s."""
     cores = os.cpu_count() or 1
     ctx = mp.get_context('fork')
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(env_id, seed, w, budget_s, warm) for w in range(cores)])
+        res = pool.map(_cpu_worker, [(env_id, seed, w, budget_s, preroll) for w in range(cores)])
     steps = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
     return {'value': steps / wall, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d procs x ~%.0fs of %s steps (reset + %d warm-up untimed), %d env-steps total; '
-                      'PyBullet itself is not installable here (DESIGN.md)' % (cores, budget_s, env_id, warm, steps)}
+            'sample': '%d procs x ~%.0fs of %s steps (reset + the same %d-step scripted pre-roll as the GPU arm, untimed), '
+                      '%d env-steps total; PyBullet itself is not installable here or on the GPU box '
+                      '(profiles/r2_pybullet_probe.log)' % (cores, budget_s, env_id, preroll, steps)}
 
 
 def run_reference(args):
@@ -187,7 +192,7 @@ def run_reference(args):
     per = []
     # each "step" = one bounded sample: ~ (budget / steps) seconds of oracle stepping on all cores
     total_budget = min(150.0, max(10.0, 3.0 * (args.steps + args.warmup)))
-    b = cpu_baseline(args.env, args.seed, budget_s=total_budget, warm=24)
+    b = cpu_baseline(args.env, args.seed, budget_s=total_budget, preroll=args.preroll)
     v = b['value']
     line = {'impl': 'reference', 'metric': METRIC if args.env == ENV_ID else args.env + ' env-steps/s',
             'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -216,6 +221,9 @@ def run_gpu(args):
         dist.init_process_group('nccl', device_id=dev)
     from roboticsplayroompybullet_b200.envs import make
     N = args.envs_per_gpu
+    if args.scaling == 'strong':                      # BASELINE config 5 as written: a fixed total sharded over the ranks
+        assert args.total_envs % world == 0
+        N = args.total_envs // world
     K, W = args.steps, args.warmup
     env = make(args.env, num_envs=N, device=local, seed=args.seed, env_offset=rank * N)
     P = args.preroll
@@ -330,10 +338,10 @@ def run_gpu(args):
         info_k = env.kernel_info()
         line = {'metric': METRIC if args.env == ENV_ID else args.env + ' env-steps/s', 'value': value,
                 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
-                'ms_per_step': 1000.0 * dev_s / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'ms_per_step': 1000.0 * dev_s / K, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': '%s, %d envs per GPU (%d total), sharded by env index; scripted teleop-shaped synthetic '
-                                       'sub-task trajectories (reach / grasp+lift / drawer / door / button / dial), goal '
+                                       'sub-task trajectories (reach / grasp+lift+carry / drawer pull+push / door slide / button / dial), goal '
                                        'relabelling every %d steps, %d untimed pre-roll steps; L2 flushed (256 MB fill) '
                                        'between timed steps' % (args.env, N, N * world, RELABEL_EVERY, P),
                            'envs_per_gpu': N, 'substeps_per_step': 12, 'solver_iterations': 50, 'seed': args.seed,
@@ -362,7 +370,7 @@ def run_gpu(args):
                           'note': 'env-steps/s of a whole episode: episode_steps steps + one full-batch reset'},
                 'wall_s_timed_region': t_wall}
         if not args.no_cpu_baseline and world == 1:
-            line['cpu_baseline'] = cpu_baseline(args.env, args.seed, budget_s=args.cpu_seconds)
+            line['cpu_baseline'] = cpu_baseline(args.env, args.seed, budget_s=args.cpu_seconds, preroll=args.preroll)
         elif not args.no_cpu_baseline:
             line['cpu_baseline'] = None
         print(json.dumps(line), flush=True)
@@ -379,6 +387,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--env', default=ENV_ID)
     ap.add_argument('--envs-per-gpu', type=int, default=65536)
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --envs-per-gpu envs on every GPU; strong: --total-envs sharded over the GPUs (BASELINE config 5 as written)')
+    ap.add_argument('--total-envs', type=int, default=65536)
     ap.add_argument('--seed', type=int, default=1234)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')

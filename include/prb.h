@@ -79,6 +79,14 @@ int prb_destroy(prb_handle* h);
 int prb_reset(prb_handle* h, const uint8_t* mask_dev, void* stream);
 int prb_reset_rounds(prb_handle* h);
 
+/* playEnv.reset(o) (environments.py:173-187, 541-556, 582-596): re-seat the masked envs FROM AN OBSERVATION — trajectory
+ * replay.  obs_dev is [N, obs_dim] in the obs_quat layout: the object pose is taken from it (no settle steps), the arm
+ * goes from its rest pose through one IK call to the observed end-effector pose, a new goal is drawn (again while already
+ * satisfied).  Two documented differences from the reference: the object is read at its real offset in the layout (the
+ * reference's hard-coded 11 / 10 indexing is wrong for the 19-D play layout), and with restore_env != 0 the drawer, door,
+ * button and dial are restored from the observation too (the reference leaves them at their defaults).  Asynchronous. */
+int prb_reset_to(prb_handle* h, const float* obs_dev, const uint8_t* mask_dev, int32_t restore_env, void* stream);
+
 /* playEnv.reset_goal_pos(goal) (environments.py:190-191, 492-501): goal_dev is [N, goal_dim]. */
 int prb_set_goal(prb_handle* h, const float* goal_dev, const uint8_t* mask_dev, void* stream);
 

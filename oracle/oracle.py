@@ -86,6 +86,13 @@ class Oracle:
         self.L.orc_reset(self.mp, _p(self.state), ctypes.c_uint64(self.seed), ctypes.c_uint32(self.env_id), _p(out))
         return self.split_out(out)
 
+    def reset_to(self, obs, restore_env=True):
+        out = np.zeros(self.out_dim, self.dtype)
+        o = np.ascontiguousarray(np.asarray(obs, dtype=self.dtype))
+        self.L.orc_reset_to(self.mp, _p(self.state), _p(o), ctypes.c_int(1 if restore_env else 0), ctypes.c_uint64(self.seed),
+                            ctypes.c_uint32(self.env_id), _p(out))
+        return self.split_out(out)
+
     def step(self, action):
         out = np.zeros(self.out_dim, self.dtype)
         a = np.ascontiguousarray(np.asarray(action, dtype=self.dtype))

@@ -1369,3 +1369,57 @@ void orc_reset(const prb_model* M, real* state, uint64_t seed, uint32_t env_id, 
   state_pack(M, &S, state);
   out_pack(M, &O, out);
 }
+
+/* playEnv.reset(o) (environments.py:173-187 with o given): objects re-seated from the observation without settle steps
+ * (:541-556), arm from the rest pose through one IK call to the observed end-effector pose (:582-596), new goal (:492-516),
+ * again while the state already satisfies it.  Deviations kept identical to the kernels: the object is read
+ * at its real offset in the obs_quat layout (the reference's 11 / 10 indexing is wrong for the 19-D play layout), and
+ * restore_env also restores drawer y / door / button / dial from the observation (the reference leaves them at defaults). */
+void orc_reset_to(const prb_model* M, real* state, const real* obs, int restore_env, uint64_t seed, uint32_t env_id, real* out) {
+  State S; state_unpack(M, state, &S);
+  Out O; memset(&O, 0, sizeof(O));
+  const int rv = M->return_velocity, uo = M->use_orientation;
+  const int o_obj = 3 + (rv ? 3 : 0) + (uo ? 4 : 0) + 1;
+  if (M->play) {
+    for (int k = 0; k < 3; k++) { S.fpos[1][k] = M->free_pos0[3 + k]; S.fvel[1][k] = 0; S.fang[1][k] = 0; }
+    for (int k = 0; k < 4; k++) S.fquat[1][k] = M->free_quat0[4 + k];
+    for (int s = 0; s < M->n_slide; s++) { S.sq[s] = 0; S.sqd[s] = 0; }
+  }
+  if (M->n_free > 0) {
+    for (int k = 0; k < 3; k++) { S.fpos[0][k] = obs[o_obj + k]; S.fvel[0][k] = 0; S.fang[0][k] = 0; }
+    if (uo) for (int k = 0; k < 4; k++) S.fquat[0][k] = obs[o_obj + 3 + k];
+    else { S.fquat[0][0] = 0; S.fquat[0][1] = 0; S.fquat[0][2] = 0; S.fquat[0][3] = 1; }
+  }
+  if (M->play && restore_env) {
+    const int o_env = o_obj + 7;
+    S.fpos[1][1] = obs[o_env];
+    S.sq[0] = obs[o_env + 1]; S.sq[1] = obs[o_env + 2]; S.sq[2] = obs[o_env + 3] * 2.2;
+  }
+  real tp[3] = {obs[0], obs[1], obs[2]}, tq[4];
+  for (int k = 0; k < 4; k++) tq[k] = uo ? obs[(rv ? 6 : 3) + k] : (real)M->default_orn[k];
+  for (int i = 0; i < M->n_ik; i++) { S.q[i] = M->arm_rest[i]; S.qd[i] = 0; }
+  if (M->arm_kind == 1) { S.q[M->n_ik] = 0; S.qd[M->n_ik] = 0; }
+  real jp[MAXD];
+  orc_ik(M, S.q, tp, tq, M->ik_reset_iters, jp);
+  for (int i = 0; i < 6; i++) { S.q[i] = jp[i]; S.qd[i] = 0; }
+  real r = 0;
+  int guard = 0;
+  while (r > -1 && guard++ < 16) {
+    uint32_t attempt = (uint32_t)S.reset_count;
+    S.reset_count += 1;
+    real u[4];
+    rng4(seed, env_id, attempt, 5, u);
+    if (!M->play) for (int k = 0; k < 3; k++) S.goal[k] = M->goal_lo[k] + (M->goal_hi[k] - M->goal_lo[k]) * u[k];
+    else {
+      calc_state(M, &S, &O);
+      int idx = (int)(u[0] * M->goal_dim); if (idx >= M->goal_dim) idx = M->goal_dim - 1;
+      for (int k = 0; k < M->goal_dim; k++) S.goal[k] = O.achieved_goal[k];
+      S.goal[idx] = f32(S.goal[idx] + u[1]);
+    }
+    calc_state(M, &S, &O);
+    r = O.reward;
+  }
+  state_pack(M, &S, state);
+  out_pack(M, &O, out);
+}
+

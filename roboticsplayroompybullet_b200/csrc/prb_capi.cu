@@ -141,6 +141,7 @@ static int setup_kernels(prb_handle* h) {
   CK(h, cudaFuncSetAttribute(prb_setup_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
   CK(h, cudaFuncSetAttribute(prb_step_kernel<ND, CfgL>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_fused));
   CK(h, cudaFuncSetAttribute(prb_reset_finish_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+  CK(h, cudaFuncSetAttribute(prb_reset_to_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
   cudaFuncAttributes fa;
   CK(h, cudaFuncGetAttributes(&fa, prb_setup_kernel<ND>));
   h->regs = fa.numRegs;
@@ -370,6 +371,18 @@ int prb_reset(prb_handle* h, const uint8_t* mask_dev, void* stream) {
 }
 
 int prb_reset_rounds(prb_handle* h) { return h ? h->reset_rounds : -1; }
+
+int prb_reset_to(prb_handle* h, const float* obs_dev, const uint8_t* mask_dev, int32_t restore_env, void* stream) {
+  if (!h || !obs_dev) return PRB_ERR_INVALID;
+  DevGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 g((h->N + SetupCfg::WPB - 1) / SetupCfg::WPB), b(32 * SetupCfg::WPB);
+  if (h->hm.nd == 12) prb_reset_to_kernel<12><<<g, b, h->smem, s>>>(h->dm, h->state, h->O, obs_dev, mask_dev, h->N, h->seed, h->env_offset, restore_env);
+  else prb_reset_to_kernel<9><<<g, b, h->smem, s>>>(h->dm, h->state, h->O, obs_dev, mask_dev, h->N, h->seed, h->env_offset, restore_env);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  return PRB_OK;
+}
 
 __global__ void prb_set_goal_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state, const float* __restrict__ goal,
                                     const unsigned char* __restrict__ mask, int N) {

@@ -126,3 +126,80 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_reset_finish_kernel(co
     else pending[e] = 0;
   }
 }
+
+// playEnv.reset(o) (environments.py:173-187 with an observation): objects re-seated from obs_quat without settle steps
+// (:541-556), the arm from the rest pose through one IK call to the observed end-effector pose (:582-596), a new goal
+// (:492-516), again while the state already satisfies it (only the goal draw changes between attempts).  The object is
+// read at its real offset in the obs_quat layout (the reference's 11 / 10 indexing is wrong for the 19-D play layout);
+// restore_env also restores drawer y / door / button / dial (the reference leaves them at their defaults): INTEGRATION.md.
+template <int ND>
+__global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_reset_to_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state, DevOut O,
+                                                                            const float* __restrict__ obs, const unsigned char* __restrict__ mask,
+                                                                            int N, unsigned long long seed, unsigned env_offset, int restore_env) {
+  typedef SetupMemT<SetupCfg> WM;
+  PRB_SMEM_DECL2;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * SetupCfg::WPB + wib;
+  if (e >= N) return;
+  if (mask != nullptr && mask[e] == 0) return;
+  const DevModel& M = *Mp;
+  WM& W = wm[wib];
+  float* st = state + (size_t)e * M.state_stride;
+  load_state(M, W, st, lane);
+  const float* ob = obs + (size_t)e * M.obs_dim;
+  const int rv = M.return_velocity, uo = M.use_orientation;
+  const int o_obj = 3 + (rv ? 3 : 0) + (uo ? 4 : 0) + 1;
+  if (lane == 0) {
+    if (M.play) {
+      for (int k = 0; k < 3; k++) { W.fpos[1][k] = M.free_pos0[1][k]; W.fvel[1][k] = 0.f; W.fang[1][k] = 0.f; }
+      for (int k = 0; k < 4; k++) W.fquat[1][k] = M.free_quat0[1][k];
+      for (int s = 0; s < M.n_slide; s++) { W.sq[s] = 0.f; W.sqd[s] = 0.f; }
+    }
+    if (M.n_free > 0) {
+      for (int k = 0; k < 3; k++) { W.fpos[0][k] = ob[o_obj + k]; W.fvel[0][k] = 0.f; W.fang[0][k] = 0.f; }
+      if (uo) for (int k = 0; k < 4; k++) W.fquat[0][k] = ob[o_obj + 3 + k];
+      else { W.fquat[0][0] = 0.f; W.fquat[0][1] = 0.f; W.fquat[0][2] = 0.f; W.fquat[0][3] = 1.f; }
+    }
+    if (M.play && restore_env) {
+      const int o_env = o_obj + 7;
+      W.fpos[1][1] = ob[o_env];
+      W.sq[0] = ob[o_env + 1]; W.sq[1] = ob[o_env + 2]; W.sq[2] = ob[o_env + 3] * 2.2f;
+    }
+    float tp[3] = {ob[0], ob[1], ob[2]}, tq[4];
+    for (int k = 0; k < 4; k++) tq[k] = uo ? ob[(rv ? 6 : 3) + k] : M.default_orn[k];
+    float qq[7];
+    for (int i = 0; i < M.n_ik; i++) { qq[i] = M.rest[i]; W.q[i] = M.rest[i]; W.qd[i] = 0.f; }
+    if (M.arm_kind == 1) { W.q[M.n_ik] = 0.f; W.qd[M.n_ik] = 0.f; }
+    if (M.n_ik == 6) ik_world<6>(M, qq, tp, tq, 1, M.ik_reset_iters);
+    else ik_world<7>(M, qq, tp, tq, 1, M.ik_reset_iters);
+    for (int i = 0; i < 6; i++) { W.q[i] = qq[i]; W.qd[i] = 0.f; }
+  }
+  __syncwarp();
+  float r = 0.f;
+  for (int guard = 0; guard < RESET_MAX_ATTEMPTS && r > -1.f; guard++) {
+    const uint32_t attempt = (uint32_t)W.reset_count;
+    __syncwarp();
+    if (lane == 0) W.reset_count += 1.0f;
+    float u[4];
+    rng4(seed, env_offset + (uint32_t)e, attempt, 5u, u);
+    if (!M.play) {
+      if (lane < 3) W.goal[lane] = M.goal_lo[lane] + (M.goal_hi[lane] - M.goal_lo[lane]) * u[lane];
+      __syncwarp();
+    } else {
+      phase_observe(M, W, lane, O, (size_t)e, true);
+      __syncwarp();
+      int idx = (int)(u[0] * M.goal_dim);
+      if (idx >= M.goal_dim) idx = M.goal_dim - 1;
+      if (lane < M.goal_dim) {
+        float g = O.achieved_goal[(size_t)e * M.goal_dim + lane];
+        if (lane == idx) g = g + u[1];
+        W.goal[lane] = g;
+      }
+      __syncwarp();
+    }
+    r = phase_observe(M, W, lane, O, (size_t)e, true);
+    __syncwarp();
+  }
+  store_state(M, W, st, lane);
+}
+

@@ -451,6 +451,9 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, int e, int N, c
     if (n_gear) R.q(R0_JROW + nL + nMo + nSl) = jr_mot;
   }
   if (lane == 0) W.n_jrow = njr;
+  // the solver's fixed-offset loads look up to CR_MAX_Q - CR_BASE_Q q past the last record: keep that finite (zeros), so that
+  // its unconditional arm-side arithmetic never meets stale NaNs of an env that used this slot before
+  if (heavy && lane < CR_MAX_Q - CR_BASE_Q) R.q(tEnd0 + lane) = make_float4(0.f, 0.f, 0.f, 0.f);
   // ---- contact rows
   if (lane < nc) {
     const int ca = c.cols & 0xff, cb = (c.cols >> 8) & 0xff;
@@ -613,9 +616,8 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
 //   prb_pgs_arm_kernel     slot 0 of the heavy envs, one launch per size class: joint rows + contact records,
 //                          ARM_LANES(class) envs / warp, bundle staged by one bulk async copy
 #define PGS_BLOCK 32
-#define PGS_F_TAILQ 8    // free-body kernel: dv 4 q (body b at 2b, 2b+1) + body table 4 q
 #define PGS_SMEM_J (PGS_STAGE_J * 32 * 16)
-#define PGS_SMEM_F ((PGS_STAGE_F + PGS_F_TAILQ) * 32 * 16)
+#define PGS_SMEM_F (PGS_STAGE_F * 32 * 16)
 #define PGS_SMEM_ARM(k) (arm_capq(k) * arm_lanes(k) * 16)
 
 #ifdef PRB_EMU
@@ -723,6 +725,23 @@ PRB_D bool jrow_generic(JointRows& R, IslandV& V, int j) {
   }
   return dl != 0.f;
 }
+// a joint-limit row of an arm DoF (the rows before the motors of a canonical env): one-sided, single DoF
+PRB_D bool jrow_limit(JointRows& R, IslandV& V, int j) {
+  const float4 r = R.col[(size_t)(R0_JROW + j) * R.stride];
+  const int pk = __float_as_int(r.x);
+  const int a = (pk >> 16) & 15;
+  const float sg = ((pk >> 24) & 1) ? -1.0f : 1.0f;
+  const float4* m = R.col + (size_t)(R0_MINV + 3 * a) * R.stride;
+  const float4 m0 = m[0], m1 = m[R.stride], m2 = m[2 * R.stride];
+  float* pl = reinterpret_cast<float*>(const_cast<float4*>(R.col) + (size_t)(R.t_jlam + (j >> 2)) * R.stride) + (j & 3);
+  const float l0 = *pl;
+  const float u = V.arm(a) * sg;
+  const float nl = clampf(l0 + (r.y - u * r.z), 0.f, r.w);
+  const float dl = (nl - l0) * sg;
+  *pl = nl;
+  V.arm_axpy(m0, m1, m2, dl);
+  return dl != 0.f;
+}
 // the motor row of arm DoF D / slide body S_ of a canonical env: compile-time register indices, impulse in a register
 template <int D>
 PRB_D bool jrow_motor(JointRows& R, IslandV& V) {
@@ -768,7 +787,7 @@ PRB_D bool jrows_pass(JointRows& R, IslandV& V, int n_slide, bool ascending) {
   const int tail0 = R.nL + ND + n_slide;                       // rows after the motors (gear)
   if (ascending) {
 #pragma unroll 1
-    for (int j = 0; j < R.nL; j++) changed |= jrow_generic(R, V, j);
+    for (int j = 0; j < R.nL; j++) changed |= jrow_limit(R, V, j);
     changed |= MotorUnroll<ND, ND - 1>::up(R, V);
     if (n_slide > 0) changed |= jrow_slide<ND, 0>(R, V);
     if (n_slide > 1) changed |= jrow_slide<ND, 1>(R, V);
@@ -783,7 +802,7 @@ PRB_D bool jrows_pass(JointRows& R, IslandV& V, int n_slide, bool ascending) {
     if (n_slide > 0) changed |= jrow_slide<ND, 0>(R, V);
     changed |= MotorUnroll<ND, ND - 1>::down(R, V);
 #pragma unroll 1
-    for (int j = R.nL - 1; j >= 0; j--) changed |= jrow_generic(R, V, j);
+    for (int j = R.nL - 1; j >= 0; j--) changed |= jrow_limit(R, V, j);
   }
   return changed;
 }
@@ -866,34 +885,20 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel
   }
 }
 
-// ---- slots 1 and 2 (blockIdx.y + 1): islands of free bodies against static geometry / each other.
-// dv of free body b at dvq q 2b, 2b+1 (6 words used)
-struct FSide { int idx; float sgn; v3 r; };
-struct FVel { v3 v, w, pv; };
-PRB_D void fside_load(const FSide& s, const float4* dvq, FVel& V) {
-  const float4 x = dvq[(2 * s.idx) * 32], y = dvq[(2 * s.idx + 1) * 32];
-  V.v = V3(x.x, x.y, x.z); V.w = V3(x.w, y.x, y.y);
-  V.pv = V.v + cross(V.w, s.r);
-}
-// dv += B P: P = sum of direction * impulse (linear rows) or the angular impulse (spin row)
-PRB_D void fside_apply(const FSide& s, const FVel& V, float4* dvq, const float4* body, v3 P, bool ang) {
-  const float4 i0 = body[(2 * s.idx) * 32], i1 = body[(2 * s.idx + 1) * 32];
-  const float I[6] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y};
-  const v3 Ps = P * s.sgn;
-  v3 v = V.v, w = V.w;
-  if (ang) w = w + symmul(I, Ps);
-  else { v = v + Ps * i1.z; w = w + symmul(I, cross(s.r, Ps)); }
-  dvq[(2 * s.idx) * 32] = make_float4(v.x, v.y, v.z, w.x);
-  dvq[(2 * s.idx + 1) * 32] = make_float4(w.y, w.z, 0.f, 0.f);
-}
-PRB_D bool fsides_of(int pk, const float4* rec, const float4& q2, FSide& P, FSide& Sd) {
-  P.idx = (pk >> 4) & 7; Sd.idx = (pk >> 7) & 7;
-  P.sgn = ((pk >> 10) & 1) ? -1.0f : 1.0f; Sd.sgn = -P.sgn;
-  P.r = V3(q2.x, q2.y, q2.z);
-  Sd.r = V3(0, 0, 0);
-  const bool two = ((pk >> 2) & 3) == K_FREE;
-  if (two) { const float4 g = rec[CT_BASE_Q * 32]; Sd.r = V3(g.x, g.y, g.z); }
-  return two;
+// ---- slots 1 and 2 (blockIdx.y + 1): islands of free bodies against static geometry / each other.  One thread per
+// env, the bodies' velocity change in registers (IslandV's free-body part), compact records in the stage (records past
+// PGS_STAGE_F are read from the stream in place), warp-uniform loops.
+struct FreeRec {
+  int iP, iS; float sP; bool two; v3 n, rP, rS;
+};
+PRB_D FreeRec free_rec(int pk, const float4& q1, const float4& q2, const float4* rec) {
+  FreeRec f;
+  f.iP = (pk >> 4) & 7; f.iS = (pk >> 7) & 7;
+  f.sP = ((pk >> 10) & 1) ? -1.0f : 1.0f;
+  f.two = ((pk >> 2) & 3) == K_FREE;
+  f.n = V3(q1.x, q1.y, q1.z); f.rP = V3(q2.x, q2.y, q2.z); f.rS = V3(0, 0, 0);
+  if (f.two) { const float4 g = rec[CT_BASE_Q * 32]; f.rS = V3(g.x, g.y, g.z); }
+  return f;
 }
 
 __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N,
@@ -902,148 +907,149 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
   const int lane = threadIdx.x;
   const int slot = blockIdx.y + 1;
   const DevModel& M = *Mp;
-  for (int e = blockIdx.x * PGS_BLOCK + lane; e < N; e += gridDim.x * PGS_BLOCK) {     // persistent blocks
-  if (active != nullptr && active[e] == 0) continue;
-  float4* G = stream_col(sbuf, e);
-  const float4 h1 = G[(Q_HDR + 1) * 32], hs = G[(Q_HDR + slot) * 32];
-  const int info = __float_as_int(h1.x);
-  const int cnt = __float_as_int(hs.x);
-  const int nc = cnt & 0xff, ns = (cnt >> 8) & 0xff, start = __float_as_int(hs.y), t_spin = __float_as_int(hs.z);
-  bool owner = false;
-  for (int b = 0; b < M.n_free; b++) owner = owner || ((info >> (16 + 2 * b)) & 3) == slot;
-  if (!owner) continue;                                  // merged into another island
-  float4* sl = sm + lane;
-  float4* Gr = G + (Q_S12 + start) * 32;
-  float4* dvq = sl + PGS_STAGE_F * 32;
-  float4* body = dvq + 4 * 32;
-  {
-    const int tq = min(t_spin + ns, PGS_STAGE_F);
+  const int ngroups = (N + PGS_BLOCK - 1) / PGS_BLOCK;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {     // persistent blocks, warp-uniform control flow
+    const int e = g * PGS_BLOCK + lane;
+    bool valid = e < N && (active == nullptr || active[e] != 0);
+    float4* G = stream_col(sbuf, valid ? e : 0);
+    const float4 h1 = G[(Q_HDR + 1) * 32], hs = G[(Q_HDR + slot) * 32];
+    const int info = __float_as_int(h1.x);
+    const int cnt = __float_as_int(hs.x);
+    const int start = __float_as_int(hs.y), t_spin = __float_as_int(hs.z);
+    bool owner = false;
+    for (int b = 0; b < M.n_free; b++) owner = owner || ((info >> (16 + 2 * b)) & 3) == slot;
+    valid = valid && owner;                                // not owner: merged into another island
+    if (!__any_sync(FULL, valid)) continue;
+    const int nc = valid ? (cnt & 0xff) : 0, ns = valid ? ((cnt >> 8) & 0xff) : 0;
+    int ncmax = nc, nsmax = ns;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ncmax = max(ncmax, __shfl_xor_sync(FULL, ncmax, o)); nsmax = max(nsmax, __shfl_xor_sync(FULL, nsmax, o)); }
+    float4* sl = sm + lane;
+    float4* Gr = G + (Q_S12 + start) * 32;
+    if (valid) {
+      const int tq = min(t_spin + ns, PGS_STAGE_F);
 #pragma unroll 8
-    for (int q = 0; q < tq; q++) sl[q * 32] = Gr[q * 32];
-  }
+      for (int q = 0; q < tq; q++) sl[q * 32] = Gr[q * 32];
+    }
 #define PGS_PTR(t_) ((t_) < PGS_STAGE_F ? sl + (t_) * 32 : Gr + (t_) * 32)
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    IslandV V;
+    V.clear();
 #pragma unroll
-  for (int i = 0; i < 4; i++) { dvq[i * 32] = z4; body[i * 32] = G[(Q_ST + R0_BODY + i) * 32]; }
-  const int iters = M.solver_iters;
+    for (int fb = 0; fb < PRB_MAXFREE; fb++) {
+      const float4 i0 = G[(Q_ST + R0_BODY + 2 * fb) * 32], i1 = G[(Q_ST + R0_BODY + 2 * fb + 1) * 32];
+      V.I[fb][0] = i0.x; V.I[fb][1] = i0.y; V.I[fb][2] = i0.z; V.I[fb][3] = i0.w; V.I[fb][4] = i1.x; V.I[fb][5] = i1.y;
+      V.invm[fb] = i1.z;
+    }
+    const int iters = M.solver_iters;
+    bool live = valid;
 #pragma unroll 1
-  for (int it = 0; it < iters; it++) {
-    bool changed = false;                                  // fixed point reached: later sweeps are exact repeats
-    // ---- contact normals
-    {
+    for (int it = 0; it < iters; it++) {
+      bool changed = false;
+      // ---- contact normals
       int t = 0;
-      float4* rec = PGS_PTR(t);
-      float4 q0 = rec[0], q1 = rec[32], q2 = rec[64];
 #pragma unroll 1
-      for (int c = 0; c < nc; c++) {
-        const int pk = __float_as_int(q0.x);
-        const int tn = t + ((pk >> 12) & 255);
-        float4* recn = PGS_PTR(tn);
-        const float4 n0 = recn[0], n1 = recn[32], n2 = recn[64];     // next record (readable slack after the last)
-        FSide P, Sd;
-        const bool two = fsides_of(pk, rec, q2, P, Sd);
-        const v3 n = V3(q1.x, q1.y, q1.z);
-        FVel VP, VS;
-        fside_load(P, dvq, VP);
-        float u = P.sgn * dot(n, VP.pv);
-        if (two) { fside_load(Sd, dvq, VS); u += Sd.sgn * dot(n, VS.pv); }
-        const float l0 = q1.w;
-        const float nl = fmaxf(l0 + (q0.z - l0 * q0.y - u * q0.w), 0.f);
-        const float dl = nl - l0;
-        if (dl != 0.f) {
-          changed = true;
-          reinterpret_cast<float*>(rec + 32)[3] = nl;
-          fside_apply(P, VP, dvq, body, n * dl, false);
-          if (two) fside_apply(Sd, VS, dvq, body, n * dl, false);
+      for (int c = 0; c < ncmax; c++) {
+        if (live && c < nc) {
+          float4* rec = PGS_PTR(t);
+          const float4 q0 = rec[0], q1 = rec[32], q2 = rec[64];
+          const int pk = __float_as_int(q0.x);
+          const FreeRec f = free_rec(pk, q1, q2, rec);
+          float u = V.jdot(f.iP, f.sP, f.rP, f.n, false);
+          if (f.two) u += V.jdot(f.iS, -f.sP, f.rS, f.n, false);
+          const float l0 = q1.w;
+          const float nl = fmaxf(l0 + (q0.z - l0 * q0.y - u * q0.w), 0.f);
+          const float dl = nl - l0;
+          if (dl != 0.f) {
+            changed = true;
+            reinterpret_cast<float*>(rec + 32)[3] = nl;
+            V.apply(f.iP, f.sP, f.rP, f.n * dl, false);
+            if (f.two) V.apply(f.iS, -f.sP, f.rS, f.n * dl, false);
+          }
+          t += (pk >> 12) & 255;
         }
-        t = tn; rec = recn; q0 = n0; q1 = n1; q2 = n2;
+        __syncwarp();
       }
-    }
-    // ---- spinning friction (Bullet skips the row while the normal impulse is 0)
+      // ---- spinning friction (Bullet skips the row while the normal impulse is 0)
 #pragma unroll 1
-    for (int i = 0; i < ns; i++) {
-      const float4 h = *PGS_PTR(t_spin + i);
-      float4* rec = PGS_PTR(__float_as_int(h.x));
-      const float4 q0 = rec[0], q1 = rec[32], q2 = rec[64];
-      const float tot = q1.w;
-      if (!(tot > 0.f)) continue;
-      FSide P, Sd;
-      const bool two = fsides_of(__float_as_int(q0.x), rec, q2, P, Sd);
-      const v3 n = V3(q1.x, q1.y, q1.z);
-      FVel VP, VS;
-      fside_load(P, dvq, VP);
-      float u = P.sgn * dot(n, VP.w);
-      if (two) { fside_load(Sd, dvq, VS); u += Sd.sgn * dot(n, VS.w); }
-      const float lim = h.y * tot;
-      float* pl = reinterpret_cast<float*>(rec + 96) + 3;
-      const float l0 = *pl;
-      const float nl = clampf(l0 + (h.z - u * h.w), -lim, lim);
-      const float dl = nl - l0;
-      if (dl != 0.f) {
-        changed = true;
-        *pl = nl;
-        fside_apply(P, VP, dvq, body, n * dl, true);
-        if (two) fside_apply(Sd, VS, dvq, body, n * dl, true);
+      for (int i = 0; i < nsmax; i++) {
+        if (live && i < ns) {
+          const float4 h = *PGS_PTR(t_spin + i);
+          float4* rec = PGS_PTR(__float_as_int(h.x));
+          const float4 q0 = rec[0], q1 = rec[32], q2 = rec[64];
+          const float tot = q1.w;
+          if (tot > 0.f) {
+            const FreeRec f = free_rec(__float_as_int(q0.x), q1, q2, rec);
+            float u = V.jdot(f.iP, f.sP, f.rP, f.n, true);
+            if (f.two) u += V.jdot(f.iS, -f.sP, f.rS, f.n, true);
+            const float lim = h.y * tot;
+            float* pl = reinterpret_cast<float*>(rec + 96) + 3;
+            const float l0 = *pl;
+            const float nl = clampf(l0 + (h.z - u * h.w), -lim, lim);
+            const float dl = nl - l0;
+            if (dl != 0.f) {
+              changed = true;
+              *pl = nl;
+              V.apply(f.iP, f.sP, f.rP, f.n * dl, true);
+              if (f.two) V.apply(f.iS, -f.sP, f.rS, f.n * dl, true);
+            }
+          }
+        }
+        __syncwarp();
       }
-    }
-    // ---- lateral friction: the two rows of a contact are solved together (implicit cone)
-    {
-      int t = 0;
-      float4* rec = PGS_PTR(t);
-      float4 q0 = rec[0], q1 = rec[32], q2 = rec[64], q3 = rec[96], q4 = rec[128], q5 = rec[160];
+      // ---- lateral friction: the two rows of a contact are solved together (implicit cone)
+      t = 0;
 #pragma unroll 1
-      for (int c = 0; c < nc; c++) {
-        const int pk = __float_as_int(q0.x);
-        const int tn = t + ((pk >> 12) & 255);
-        float4* recn = PGS_PTR(tn);
-        const float4 n0 = recn[0], n1 = recn[32], n2 = recn[64], n3 = recn[96], n4 = recn[128], n5 = recn[160];
-        FSide P, Sd;
-        const bool two = fsides_of(pk, rec, q2, P, Sd);
-        const v3 n = V3(q1.x, q1.y, q1.z), t1 = V3(q3.x, q3.y, q3.z), t2 = cross(n, t1);
-        FVel VP, VS;
-        fside_load(P, dvq, VP);
-        float ua = P.sgn * dot(t1, VP.pv), ub = P.sgn * dot(t2, VP.pv);
-        if (two) {
-          fside_load(Sd, dvq, VS);
-          ua += Sd.sgn * dot(t1, VS.pv); ub += Sd.sgn * dot(t2, VS.pv);
+      for (int c = 0; c < ncmax; c++) {
+        if (live && c < nc) {
+          float4* rec = PGS_PTR(t);
+          const float4 q0 = rec[0], q1 = rec[32], q2 = rec[64], q3 = rec[96], q4 = rec[128], q5 = rec[160];
+          const int pk = __float_as_int(q0.x);
+          const FreeRec f = free_rec(pk, q1, q2, rec);
+          const v3 t1 = V3(q3.x, q3.y, q3.z), t2 = cross(f.n, t1);
+          float ua = V.jdot(f.iP, f.sP, f.rP, t1, false), ub = V.jdot(f.iP, f.sP, f.rP, t2, false);
+          if (f.two) { ua += V.jdot(f.iS, -f.sP, f.rS, t1, false); ub += V.jdot(f.iS, -f.sP, f.rS, t2, false); }
+          const float lim = q2.w * q1.w;
+          const float la = q5.x, lb = q5.y;
+          const float sumA = la + (q4.x - ua * q4.z);
+          const float sumB = lb + (q4.y - ub * q4.w);
+          float na = sumA, nb = sumB;
+          if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
+            const float ss = sumA * sumA + sumB * sumB;
+            const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+            const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
+            na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
+          }
+          const float d1 = na - la, d2 = nb - lb;
+          if (d1 != 0.f || d2 != 0.f) {
+            changed = true;
+            rec[160] = make_float4(na, nb, 0.f, 0.f);
+            const v3 Pv = t1 * d1 + t2 * d2;
+            V.apply(f.iP, f.sP, f.rP, Pv, false);
+            if (f.two) V.apply(f.iS, -f.sP, f.rS, Pv, false);
+          }
+          t += (pk >> 12) & 255;
         }
-        const float lim = q2.w * q1.w;
-        const float la = q5.x, lb = q5.y;
-        const float sumA = la + (q4.x - ua * q4.z);
-        const float sumB = lb + (q4.y - ub * q4.w);
-        float na = sumA, nb = sumB;
-        if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
-          const float ss = sumA * sumA + sumB * sumB;
-          const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
-          const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
-          na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
-        }
-        const float d1 = na - la, d2 = nb - lb;
-        if (d1 != 0.f || d2 != 0.f) {
-          changed = true;
-          rec[160] = make_float4(na, nb, 0.f, 0.f);
-          const v3 Pv = t1 * d1 + t2 * d2;
-          fside_apply(P, VP, dvq, body, Pv, false);
-          if (two) fside_apply(Sd, VS, dvq, body, Pv, false);
-        }
-        t = tn; rec = recn; q0 = n0; q1 = n1; q2 = n2; q3 = n3; q4 = n4; q5 = n5;
+        __syncwarp();
       }
+      // fixed point reached (a sweep changed no impulse): later sweeps are exact repeats, the lane retires
+      live = live && changed;
+      if (!__any_sync(FULL, live)) break;
     }
-    if (!changed) break;
-  }
 #undef PGS_PTR
-  float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
-  for (int b = 0; b < M.n_free; b++)
-    if (((info >> (16 + 2 * b)) & 3) == slot) {
-      const float4 x = dvq[(2 * b) * 32], y = dvq[(2 * b + 1) * 32];
-      const float v[6] = {x.x, x.y, x.z, x.w, y.x, y.y};
-      const int o = M.nd + 6 * b;
+    if (valid) {
+      float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
 #pragma unroll
-      for (int k = 0; k < 6; k++) gd[((o + k) >> 2) * 128 + ((o + k) & 3)] = v[k];
+      for (int b = 0; b < PRB_MAXFREE; b++)
+        if (b < M.n_free && ((info >> (16 + 2 * b)) & 3) == slot) {
+          const float v6[6] = {V.fv[b].x, V.fv[b].y, V.fv[b].z, V.fw[b].x, V.fw[b].y, V.fw[b].z};
+          const int o = M.nd + 6 * b;
+#pragma unroll
+          for (int k = 0; k < 6; k++) gd[((o + k) >> 2) * 128 + ((o + k) & 3)] = v6[k];
+        }
     }
+    __syncwarp();
   }
 }
-
 
 // ============================================================================ arm-island solver
 // One thread per env.  Every load of a contact visit sits at a fixed offset from the record start and is issued
@@ -1071,8 +1077,10 @@ PRB_D bool visit_normal(const ArmRec& r, IslandV& V, const float* sminv, int& si
   const int flags = __float_as_int(H0.x);
   size = flags >> 16;
   const int sidx = (flags >> 6) & 3;
-  float u = 0.f;
-  if (flags & CR_ARM) u = V.arm_dot(J0, J1, J2);
+  // the arm side is computed unconditionally and masked (a record without one reads finite bytes of its neighbour):
+  // straight-line code schedules better than a branch per side in this latency-bound loop
+  const bool arm = (flags & CR_ARM) != 0;
+  float u = arm ? V.arm_dot(J0, J1, J2) : 0.f;
   if (flags & CR_SLIDE) u = fmaf(SL.x, V.slide(sidx), u);
   FreeGeom g = free_geom(flags, G0, G1, G2);
   if (flags & CR_FREE) {
@@ -1082,9 +1090,9 @@ PRB_D bool visit_normal(const ArmRec& r, IslandV& V, const float* sminv, int& si
   const float l0 = L.x;
   const float nl = fmaxf(l0 + (H0.y - l0 * H0.w - u * H0.z), 0.f);
   const float dl = nl - l0;
+  r.lam()[0] = nl;
+  V.arm_axpy(B0, B1, B2, arm ? dl : 0.f);
   if (dl != 0.f) {
-    r.lam()[0] = nl;
-    if (flags & CR_ARM) V.arm_axpy(B0, B1, B2, dl);
     if (flags & CR_SLIDE) V.slide_add(sidx, (SL.x * sel3(sminv, sidx)) * dl);
     if (flags & CR_FREE) {
       V.apply(g.fb, g.sgn, g.rF, g.n * dl, false);
@@ -1102,8 +1110,8 @@ PRB_D bool visit_spin(const ArmRec& r, IslandV& V, const float* sminv, int& size
   const float tot = L.x;
   if (!(flags & CR_SPIN) || !(tot > 0.f)) return false;
   const int sidx = (flags >> 6) & 3;
-  float u = 0.f;
-  if (flags & CR_ARM) u = V.arm_dot(J0, J1, J2);
+  const bool arm = (flags & CR_ARM) != 0;
+  float u = arm ? V.arm_dot(J0, J1, J2) : 0.f;
   if (flags & CR_SLIDE) u = fmaf(SL.y, V.slide(sidx), u);
   FreeGeom g = free_geom(flags, G0, G1, G2);
   if (flags & CR_FREE) {
@@ -1114,9 +1122,9 @@ PRB_D bool visit_spin(const ArmRec& r, IslandV& V, const float* sminv, int& size
   const float l0 = L.y;
   const float nl = clampf(l0 + (H1.x - u * H1.y), -lim, lim);
   const float dl = nl - l0;
+  r.lam()[1] = nl;
+  V.arm_axpy(B0, B1, B2, arm ? dl : 0.f);
   if (dl != 0.f) {
-    r.lam()[1] = nl;
-    if (flags & CR_ARM) V.arm_axpy(B0, B1, B2, dl);
     if (flags & CR_SLIDE) V.slide_add(sidx, (SL.y * sel3(sminv, sidx)) * dl);
     if (flags & CR_FREE) {
       V.apply(g.fb, g.sgn, g.rF, g.n * dl, true);
@@ -1133,8 +1141,8 @@ PRB_D bool visit_friction(const ArmRec& r, IslandV& V, const float* sminv, int& 
   const int flags = __float_as_int(H0.x);
   size = flags >> 16;
   const int sidx = (flags >> 6) & 3;
-  float ua = 0.f, ub = 0.f;
-  if (flags & CR_ARM) { ua = V.arm_dot(Ja0, Ja1, Ja2); ub = V.arm_dot(Jb0, Jb1, Jb2); }
+  const bool arm = (flags & CR_ARM) != 0;
+  float ua = arm ? V.arm_dot(Ja0, Ja1, Ja2) : 0.f, ub = arm ? V.arm_dot(Jb0, Jb1, Jb2) : 0.f;
   if (flags & CR_SLIDE) { const float vs = V.slide(sidx); ua = fmaf(SL.z, vs, ua); ub = fmaf(SL.w, vs, ub); }
   FreeGeom g = free_geom(flags, G0, G1, G2);
   const v3 t2 = cross(g.n, g.t1);
@@ -1155,9 +1163,10 @@ PRB_D bool visit_friction(const ArmRec& r, IslandV& V, const float* sminv, int& 
     na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
   }
   const float d1 = na - la, d2 = nb - lb;
+  r.lam()[2] = na; r.lam()[3] = nb;
+  V.arm_axpy(Ba0, Ba1, Ba2, arm ? d1 : 0.f);
+  V.arm_axpy(Bb0, Bb1, Bb2, arm ? d2 : 0.f);
   if (d1 != 0.f || d2 != 0.f) {
-    r.lam()[2] = na; r.lam()[3] = nb;
-    if (flags & CR_ARM) { V.arm_axpy(Ba0, Ba1, Ba2, d1); V.arm_axpy(Bb0, Bb1, Bb2, d2); }
     if (flags & CR_SLIDE) { const float mi = sel3(sminv, sidx); V.slide_add(sidx, (SL.z * mi) * d1 + (SL.w * mi) * d2); }
     if (flags & CR_FREE) {
       const v3 Pv = g.t1 * d1 + t2 * d2;

@@ -120,12 +120,20 @@ class VecPlayEnv:
             pass
 
     # ------------------------------------------------------------------ device-resident API
-    def reset_device(self, mask=None):
+    def reset_device(self, mask=None, o=None, restore_env=True):
+        """reset() of the masked envs (all when mask is None).  With `o` ([N, obs_dim] float32 CUDA tensor in the obs_quat
+        layout) the envs are re-seated from that observation instead of sampled: playEnv.reset(o), trajectory replay."""
         mp = None
         if mask is not None:
             self._mask = mask.to(self.device, self.torch.uint8).contiguous()
             mp = ctypes.c_void_p(self._mask.data_ptr())
-        _lib.check(self.L, self._h, self.L.prb_reset(self._h, mp, self._stream()))
+        if o is not None:
+            ob = o.to(self.device, self.torch.float32).contiguous()
+            assert ob.shape == (self.num_envs, self.dims['obs_quat']), 'o must be [num_envs, %d] (obs_quat layout)' % self.dims['obs_quat']
+            self._o_keep = ob
+            _lib.check(self.L, self._h, self.L.prb_reset_to(self._h, ctypes.c_void_p(ob.data_ptr()), mp, 1 if restore_env else 0, self._stream()))
+        else:
+            _lib.check(self.L, self._h, self.L.prb_reset(self._h, mp, self._stream()))
         return self._obs_dev()
 
     def step_device(self, action):
@@ -142,11 +150,16 @@ class VecPlayEnv:
         return self._obs_dev()
 
     # ------------------------------------------------------------------ reference-style (numpy) API
-    def reset(self, mask=None):
+    def reset(self, o=None, mask=None, restore_env=True):
+        """playEnv.reset(o=None) (environments.py:173-187) for every env, or for the envs of `mask`.  `o`: [N, obs_dim]
+        obs_quat rows to re-seat the envs from (trajectory replay) instead of sampling."""
         mt = None
         if mask is not None:
             mt = self.torch.as_tensor(np.asarray(mask, np.uint8))
-        self.reset_device(mt)
+        ot = None
+        if o is not None:
+            ot = self.torch.as_tensor(np.ascontiguousarray(np.asarray(o, np.float32)).reshape(self.num_envs, -1))
+        self.reset_device(mt, ot, restore_env)
         self.torch.cuda.current_stream(self.device).synchronize()
         self._pull()
         return self._obs_host()

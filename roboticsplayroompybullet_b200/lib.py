@@ -29,7 +29,7 @@ class PrbBuffers(ctypes.Structure):
 
 
 # every symbol include/prb.h declares (a CPU test checks the built library exports them all)
-SYMBOLS = ['prb_create', 'prb_destroy', 'prb_reset', 'prb_reset_rounds', 'prb_set_goal', 'prb_step', 'prb_observe', 'prb_substeps',
+SYMBOLS = ['prb_create', 'prb_destroy', 'prb_reset', 'prb_reset_rounds', 'prb_reset_to', 'prb_set_goal', 'prb_step', 'prb_observe', 'prb_substeps',
            'prb_get_buffers', 'prb_compute_reward', 'prb_get_state', 'prb_set_state', 'prb_step_host',
            'prb_enable_kernel_timing', 'prb_last_kernel_ms', 'prb_last_tier_ms', 'prb_launch_count', 'prb_overflow_count', 'prb_debug_usage', 'prb_kernel_info', 'prb_last_error', 'prb_version']
 
@@ -51,6 +51,7 @@ def load():
     L.prb_destroy.argtypes = [vp]
     L.prb_reset.argtypes = [vp, vp, vp]
     L.prb_reset_rounds.argtypes = [vp]
+    L.prb_reset_to.argtypes = [vp, vp, vp, i32, vp]
     L.prb_set_goal.argtypes = [vp, vp, vp, vp]
     L.prb_step.argtypes = [vp, vp, vp]
     L.prb_observe.argtypes = [vp, vp]

@@ -119,6 +119,13 @@ void emu_reset(float* state, DevOut* O, const unsigned char* mask, int N, unsign
   if (g_M.nd == 12) emu_reset_nd<12>(state, o, mask, N, seed, env_offset);
   else emu_reset_nd<9>(state, o, mask, N, seed, env_offset);
 }
+void emu_reset_to(float* state, DevOut* O, const float* obs, const unsigned char* mask, int N, unsigned long long seed, unsigned env_offset, int restore_env) {
+  DevOut o = *O;
+  o.overflow = &g_overflow; o.dbg = nullptr; o.ovf_env = nullptr;
+  emu_dim3 g, b; b.x = 32 * SetupCfg::WPB; g.x = (N + SetupCfg::WPB - 1) / SetupCfg::WPB;
+  if (g_M.nd == 12) emu::launch(g, b, [&]() { prb_reset_to_kernel<12>(&g_M, state, o, obs, mask, N, seed, env_offset, restore_env); });
+  else emu::launch(g, b, [&]() { prb_reset_to_kernel<9>(&g_M, state, o, obs, mask, N, seed, env_offset, restore_env); });
+}
 void emu_reward(const float* ag, const float* dg, long long B, float* out) {
   emu_dim3 g, b; b.x = 128; g.x = (unsigned)((B + 127) / 128);
   emu::launch(g, b, [&]() { prb_reward_kernel(&g_M, ag, dg, B, out); });

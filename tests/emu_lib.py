@@ -98,6 +98,17 @@ class EmuSim:
                          ctypes.c_uint64(self.seed), ctypes.c_uint32(self.env_offset))
         return {k: v.copy() for k, v in self.out.items()}
 
+    def reset_to(self, obs, mask=None, restore_env=True):
+        self._sel()
+        mp = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+            mp = mask.ctypes.data_as(ctypes.c_void_p)
+        ob = np.ascontiguousarray(obs, np.float32).reshape(self.N, -1)
+        self.L.emu_reset_to(self.state.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self.O), ob.ctypes.data_as(ctypes.c_void_p), mp,
+                            self.N, ctypes.c_uint64(self.seed), ctypes.c_uint32(self.env_offset), 1 if restore_env else 0)
+        return {k: v.copy() for k, v in self.out.items()}
+
     def ik(self, action):
         self._sel()
         from roboticsplayroompybullet_b200.model import action_dim

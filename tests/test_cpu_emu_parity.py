@@ -246,3 +246,46 @@ def test_emu_solver_regression_bit_identical():
     res = compare_step(m, {k: de[k] for k in OBS_KEYS}, de['reward'][:, 0], {'is_success': de['is_success'][:, 0]}, outs,
                        g['state'], g['action'], Oracle)
     assert res['bad_pose'] <= 2 and res['bad_reward'] <= 1, res       # these are the stiffest 0.1 % of the workload
+
+
+@pytest.mark.parametrize('env_id', ['UR5PlayAbsRPY1Obj-v0', 'pandaPick-v0', 'UR5Reach-v0'])
+def test_emu_reset_from_observation(env_id):
+    """playEnv.reset(o) (environments.py:173-187, 541-556, 582-596): re-seating from an observation of a rollout puts the
+    object and the end effector back where the observation says (trajectory replay), with the oracle's reset_to as the
+    reference; in the play env the drawer / door / button / dial are restored as well (restore_env, a documented
+    extension) or left at their defaults like the reference does."""
+    m = load_model(env_id)
+    sim, o = EmuSim(m, 2, seed=9), Oracle(m, seed=9, env_id=0)
+    o.reset()
+    rng = np.random.default_rng(1)
+    play = env_id.startswith('UR5Play')
+    blk = o.state[60:63].copy() if play else None
+    for k in range(6):                                    # a short rollout; in the play env push the door a little
+        a = np.concatenate([rng.uniform(-0.1, 0.1, 3) + (np.array([0.0, 0.3, 0.12]) if play else 0), rng.uniform(-0.2, 0.2, 3), [1.0]])
+        d = o.step(a)
+    if play:
+        o.state[86] = 0.05; o.state[88] = 0.02; o.state[90] = 0.7   # door, button, dial away from their defaults
+        o.state[74] = -0.04                                          # drawer pulled
+        d = o.calc_state()
+    obs = d['obs_quat'].astype(np.float32)
+    o2 = Oracle(m, seed=9, env_id=0)
+    o2.state[:] = o.state
+    sim.state[0, :o.state_dim] = o.state.astype(np.float32)
+    sim.state[1, :o.state_dim] = o.state.astype(np.float32)
+    before1 = sim.state[1].copy()
+    de = sim.reset_to(np.stack([obs, obs]), mask=np.array([1, 0], np.uint8))
+    do = o2.reset_to(obs)
+    assert np.array_equal(sim.state[1], before1)                                     # masked out: untouched
+    assert np.abs(de['obs_quat'][0] - do['obs_quat']).max() < 2e-5
+    assert np.abs(de['desired_goal'][0] - do['desired_goal']).max() < 2e-5
+    assert sim.state[0, o.state_dim - 1] == o2.state[-1]                             # same number of goal draws
+    # replay property: object pose exactly as observed, end effector at the observed pose up to the IK tolerance
+    od = m['obs_dim']
+    o_obj = {7: None, 13: 7, 19: 8}[od]
+    if o_obj is not None:
+        assert np.abs(de['obs_quat'][0][o_obj:o_obj + 3] - obs[o_obj:o_obj + 3]).max() < 1e-6
+    assert np.abs(de['obs_quat'][0][:3] - obs[:3]).max() < 2.5e-2             # one 20-iteration IK call from the rest pose (:593)
+    if play:
+        assert np.abs(de['obs_quat'][0][15:19] - obs[15:19]).max() < 1e-5              # drawer, door, button, dial restored
+        d_ref = sim.reset_to(np.stack([obs, obs]), mask=np.array([1, 0], np.uint8), restore_env=False)
+        assert np.abs(d_ref['obs_quat'][0][16:19] - [0, 0, 0]).max() < 1e-6           # reference behaviour: defaults

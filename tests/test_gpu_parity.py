@@ -334,3 +334,35 @@ def test_action_decoder_variants(env_id):
         total_bad += res['bad_pose'] + res['bad_vel'] + res['bad_flags'] + res['bad_reward']
     assert total_bad <= 2, total_bad
     env.close()
+
+
+@pytest.mark.parametrize('env_id', ['UR5PlayAbsRPY1Obj-v0', 'pandaPick-v0'])
+def test_reset_from_observation(env_id):
+    """playEnv.reset(o): trajectory replay through the C-ABI (prb_reset_to) against the oracle's reset_to from identical
+    states; masked envs stay untouched; the object comes back exactly where the observation says."""
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle
+    n = 32
+    env = _mk(env_id, n, seed=23)
+    obs = env.reset()
+    a = random_actions(np.random.default_rng(5), n, env_id)
+    for _ in range(5):
+        obs, _, _, _ = env.step(a)
+    o_rows = obs['obs_quat'].copy()
+    st = env.get_state()
+    mask = (np.arange(n) % 4 != 3).astype(np.uint8)
+    new = env.reset(o=o_rows, mask=mask)
+    st2 = env.get_state()
+    assert np.array_equal(st2[mask == 0], st[mask == 0])
+    m = load_model(env_id)
+    o_obj = {13: 7, 19: 8}[m['obs_dim']]
+    worst = 0.0
+    for i in np.nonzero(mask)[0]:
+        o = Oracle(m, seed=23, env_id=int(i))
+        o.state[:] = st[i]
+        d = o.reset_to(o_rows[i])
+        worst = max(worst, float(np.abs(new['obs_quat'][i] - d['obs_quat']).max()), float(np.abs(new['desired_goal'][i] - d['desired_goal']).max()))
+        assert st2[i, -1] == o.state[-1]
+        assert np.abs(new['obs_quat'][i][o_obj:o_obj + 3] - o_rows[i][o_obj:o_obj + 3]).max() < 1e-6
+    assert worst < 5e-5, worst
+    env.close()
