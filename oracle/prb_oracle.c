@@ -1251,7 +1251,7 @@ void orc_step(const prb_model* M, real* state, const real* action, real* out) {
   Out O; memset(&O, 0, sizeof(O));
   /* perform_action :915-934: 0 absolute_rpy, 1 relative_rpy, 2 absolute_quat, 3 relative_quat, 4 absolute_joints,
    * 5 relative_joints; clip to the action space first (:207, bounds :88-112) */
-  const int atype = (int)(M->params[PRB_P_ACTION_TYPE] + 0.5), adim = (atype == 2 || atype == 3) ? 8 : 7;
+  const int atype = (int)(M->params[PRB_P_ACTION_TYPE] + 0.5), adim = (atype == 2 || atype == 3) ? 8 : (atype >= 4 ? M->n_ik + 1 : 7);
   real a[8] = {0};
   for (int k = 0; k < adim - 1; k++) a[k] = clampr(action[k], -M->params[PRB_P_ACTION_HIGH_XYZ], M->params[PRB_P_ACTION_HIGH_XYZ]);
   const real grip = clampr(action[adim - 1], -M->params[PRB_P_ACTION_HIGH_GRIP], M->params[PRB_P_ACTION_HIGH_GRIP]);

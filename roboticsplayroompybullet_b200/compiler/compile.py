@@ -246,39 +246,43 @@ def compile_env(env_id, ref_envs):
              limit_max_impulse=100.0, gear_ratio=-1.0, gear_erp=0.1, gear_max_impulse=50.0 / 300,
              max_coord_vel=100.0, action_high_xyz=6.0, action_high_grip=1.0, obj_reset_dz=0.03,
              arm_lin_damp=0.0, arm_ang_damp=0.0, contact_breaking=0.02, action_type=0.0)
-    if env_id == 'UR5Reach-v0':                             # envList.py:89-91
-        arm_kind = 0
-        d = build_arm(world, ref_envs, arm_kind)
+    # playEnv.__init__ defaults (environments.py:64-67)
+    DEF = dict(env_lo=[-0.18, -0.18, -0.05], env_hi=[0.18, 0.18, 0.15], goal_lo=[-0.18, -0.18, -0.05], goal_hi=[0.18, 0.18, 0.05],
+               obj_lo=[-0.18, -0.18, -0.05], obj_hi=[-0.18, -0.18, -0.05])
+    PLAY = dict(env_hi=[1.0, 1.0, 1.0], goal_lo=[-0.18, 0, 0.05], goal_hi=[0.18, 0.3, 0.1], obj_lo=[-0.18, 0, 0.05], obj_hi=[0.18, 0.3, 0.1])
+    TABLE = {
+        # env id: arm (0 UR5 + Robotiq, 1 Panda), scene, ranges                                           envList.py
+        'UR5Reach-v0': (0, 'default', {}),                                                               # :89-91
+        'pandaReach-v0': (1, 'default', {}),                                                             # :8-10
+        'pandaReach2D-v0': (1, 'default', dict(env_hi=[0.18, 0.18, 0.0], goal_lo=[-0.18, -0.18, -0.06], goal_hi=[0.18, 0.18, -0.05])),   # :24-26
+        'pandaPush-v0': (1, 'push', dict(env_hi=[0.18, 0.18, -0.04], goal_lo=[-0.1, -0.1, -0.06], goal_hi=[0.1, 0.1, -0.05],
+                                         obj_lo=[-0.1, -0.1, -0.06], obj_hi=[0.1, 0.1, -0.05])),          # :12-16
+        'pandaPick-v0': (1, 'push', dict(env_hi=[0.18, 0.18, 0.2], goal_lo=[-0.18, -0.18, 0.0], goal_hi=[0.18, 0.18, 0.1],
+                                         obj_lo=[-0.18, -0.18, 0.0], obj_hi=[0.18, 0.18, 0.1])),          # :18-22
+        'UR5PlayAbsRPY1Obj-v0': (0, 'play', PLAY),                                                       # :93-99
+        'pandaPlayAbsRPY1Obj-v0': (1, 'play', PLAY),                                                     # :73-79
+    }
+    if env_id not in TABLE:
+        raise NotImplementedError(env_id)
+    arm_kind, scene, rng = TABLE[env_id]
+    R = dict(DEF)
+    R.update(rng)
+    d = build_arm(world, ref_envs, arm_kind)
+    ik = dict(ik_calls=4, ik_iters=20) if arm_kind == 0 else dict(ik_calls=1, ik_iters=200)   # inverseKinematics.py:44-50 / environments.py:995-997
+    if scene == 'default':                                  # scenes.py:8-19: ground only, no object
         default_scene(world, -0.07)
-        d.update(env_kind=0, play=0, use_orientation=0, return_velocity=1,
-                 goal_lo=[-0.18, -0.18, -0.05], goal_hi=[0.18, 0.18, 0.05],
-                 obj_lo=[-0.18, -0.18, -0.05], obj_hi=[-0.18, -0.18, -0.05], env_hi=[0.18, 0.18, 0.15],
-                 obs_dim=7, goal_dim=3, fps_dim=4, observation_dim=6,
-                 ik_calls=4, ik_iters=20)
-        p['reset_z_offset'] = 0.2                           # environments.py:580-581
-    elif env_id == 'pandaPick-v0':                          # envList.py:18-22
-        arm_kind = 1
-        d = build_arm(world, ref_envs, arm_kind)
+        d.update(env_kind=0, play=0, use_orientation=0, return_velocity=1, obs_dim=7, goal_dim=3, fps_dim=4, observation_dim=6)
+    elif scene == 'push':                                   # scenes.py:21-43: ground, tray, one cube
         default_scene(world, -0.07)
         tray_box(world)
         add_free_box(world, [0.025] * 3, 0.1, 0.5, [0, -0.06, -0.06])     # scenes.py:33-38
-        d.update(env_kind=1, play=0, use_orientation=0, return_velocity=1,
-                 goal_lo=[-0.18, -0.18, 0.0], goal_hi=[0.18, 0.18, 0.1],
-                 obj_lo=[-0.18, -0.18, 0.0], obj_hi=[0.18, 0.18, 0.1], env_hi=[0.18, 0.18, 0.2],
-                 obs_dim=13, goal_dim=3, fps_dim=7, observation_dim=12,
-                 ik_calls=1, ik_iters=200)
-    elif env_id == 'UR5PlayAbsRPY1Obj-v0':                  # envList.py:93-99
-        arm_kind = 0
-        d = build_arm(world, ref_envs, arm_kind)
+        d.update(env_kind=1, play=0, use_orientation=0, return_velocity=1, obs_dim=13, goal_dim=3, fps_dim=7, observation_dim=12)
+    else:                                                   # scenes.py:46-85: the playroom, one block
         complex_scene(world, ref_envs)
-        d.update(env_kind=2, play=1, use_orientation=1, return_velocity=0,
-                 goal_lo=[-0.18, 0, 0.05], goal_hi=[0.18, 0.3, 0.1],
-                 obj_lo=[-0.18, 0, 0.05], obj_hi=[0.18, 0.3, 0.1], env_hi=[1.0, 1.0, 1.0],
-                 obs_dim=19, goal_dim=11, fps_dim=19, observation_dim=18,
-                 ik_calls=4, ik_iters=20)
-        p['reset_z_offset'] = 0.2
-    else:
-        raise NotImplementedError(env_id)
+        d.update(env_kind=2, play=1, use_orientation=1, return_velocity=0, obs_dim=19, goal_dim=11, fps_dim=19, observation_dim=18)
+    d.update(goal_lo=R['goal_lo'], goal_hi=R['goal_hi'], obj_lo=R['obj_lo'], obj_hi=R['obj_hi'], env_hi=R['env_hi'], **ik)
+    if arm_kind == 0:
+        p['reset_z_offset'] = 0.2                           # environments.py:580-581 (UR5 only)
     d['arm_kind'] = arm_kind
     d['ik_reset_iters'] = 20
     d['n_substeps'] = 12                                    # environments.py:489

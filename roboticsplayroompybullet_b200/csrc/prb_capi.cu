@@ -219,7 +219,7 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
   h->out_floats = tot;
   CK(h, cudaMalloc(&h->out, sizeof(float) * tot));
   CK(h, cudaMemset(h->out, 0, sizeof(float) * tot));
-  CK(h, cudaMalloc(&h->action_stage, sizeof(float) * N * 8));
+  CK(h, cudaMalloc(&h->action_stage, sizeof(float) * N * 8));   // <= 8 entries per action
   CK(h, cudaMalloc(&h->O.overflow, sizeof(unsigned long long)));
   CK(h, cudaMemset(h->O.overflow, 0, sizeof(unsigned long long)));
   CK(h, cudaMalloc(&h->O.dbg, sizeof(int) * 4 * N));
@@ -438,7 +438,7 @@ int prb_step_host(prb_handle* h, const float* action_host, float* out_host, void
   if (!h || !action_host || !out_host) return PRB_ERR_INVALID;
   DevGuard guard(h->device);
   cudaStream_t s = (cudaStream_t)stream;
-  const int adim = action_dim_of((int)(h->hm.params[P_ACTION_TYPE] + 0.5f));
+  const int adim = action_dim_of((int)(h->hm.params[P_ACTION_TYPE] + 0.5f), h->hm.n_ik);
   CK(h, cudaMemcpyAsync(h->action_stage, action_host, sizeof(float) * h->N * adim, cudaMemcpyHostToDevice, s));
   int rc = prb_step(h, h->action_stage, stream);
   if (rc != PRB_OK) return rc;

@@ -265,14 +265,15 @@ PRB_D void ee_world(const DevModel& M, const float* q, v3& pos, float* quat) {
   pos = p + mul(R, ld3(M.site_pos[0]));
   mat_to_quat(mul(R, ldm(M.site_rot[0])), quat);
 }
-PRB_HD int action_dim_of(int action_type) { return (action_type == 2 || action_type == 3) ? 8 : 7; }
+// xyz + quaternion + gripper = 8; joint decoders: one entry per IK joint + gripper (7 UR5, 8 Panda); rpy decoders 7 (environments.py:88-112)
+PRB_HD int action_dim_of(int action_type, int n_ik) { return (action_type == 2 || action_type == 3) ? 8 : (action_type >= 4 ? n_ik + 1 : 7); }
 
 // perform_action (environments.py:915-981) -> goto / goto_joint_poses (:984-1034) -> close_gripper (:1037-1073).
 // action_type: 0 absolute_rpy, 1 relative_rpy, 2 absolute_quat, 3 relative_quat, 4 absolute_joints, 5 relative_joints
 template <int NJ>
 PRB_D void ik_action_env(const DevModel& M, float* st /* this env's state */, const float* act, float* target_out) {
   const int nd = M.nd;
-  const int atype = (int)(M.params[P_ACTION_TYPE] + 0.5f), adim = action_dim_of(atype);
+  const int atype = (int)(M.params[P_ACTION_TYPE] + 0.5f), adim = action_dim_of(atype, NJ);
   float a[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(128) prb_ik_kernel(const DevModel* __restrict_
   if (e >= N) return;
   const DevModel& M = *Mp;
   float* st = state + (size_t)e * M.state_stride;
-  const int adim = action_dim_of((int)(M.params[P_ACTION_TYPE] + 0.5f));
+  const int adim = action_dim_of((int)(M.params[P_ACTION_TYPE] + 0.5f), M.n_ik);
   if (M.n_ik == 6) ik_action_env<6>(M, st, action + (size_t)e * adim, target_poses + (size_t)e * 6);
   else ik_action_env<7>(M, st, action + (size_t)e * adim, target_poses + (size_t)e * 7);
 }

@@ -327,8 +327,48 @@ class UR5PlayRelJoints1Obj(VecPlayEnv):
     env_id = 'UR5PlayRelJoints1Obj-v0'      # relative_joints
 
 
+# the Panda ids (roboticsPlayroomPybullet/__init__.py:3-63, envList.py:8-86); pandaPlay-v0 / pandaPlayJoints-v0 have TWO
+# objects (a second free body and 26-D observations) and are not compiled yet
+class pandaReach(VecPlayEnv):
+    env_id = 'pandaReach-v0'
+
+
+class pandaReach2D(VecPlayEnv):
+    env_id = 'pandaReach2D-v0'
+
+
+class pandaPush(VecPlayEnv):
+    env_id = 'pandaPush-v0'
+
+
+class pandaPlayAbsRPY1Obj(VecPlayEnv):
+    env_id = 'pandaPlayAbsRPY1Obj-v0'
+
+
+class pandaPlay1Obj(VecPlayEnv):
+    env_id = 'pandaPlay1Obj-v0'             # absolute_quat
+
+
+class pandaPlayRel1Obj(VecPlayEnv):
+    env_id = 'pandaPlayRel1Obj-v0'          # relative_quat
+
+
+class pandaPlayRelRPY1Obj(VecPlayEnv):
+    env_id = 'pandaPlayRelRPY1Obj-v0'
+
+
+class pandaPlayAbsJoints1Obj(VecPlayEnv):
+    env_id = 'pandaPlayAbsJoints1Obj-v0'    # 8-D: 7 joints + gripper
+
+
+class pandaPlayRelJoints1Obj(VecPlayEnv):
+    env_id = 'pandaPlayRelJoints1Obj-v0'
+
+
 _REGISTRY = {c.env_id: c for c in (UR5Reach, pandaPick, UR5PlayAbsRPY1Obj, UR5Play1Obj, UR5PlayRel1Obj, UR5PlayRelRPY1Obj,
-                                   UR5PlayAbsJoints1Obj, UR5PlayRelJoints1Obj)}
+                                   UR5PlayAbsJoints1Obj, UR5PlayRelJoints1Obj, pandaReach, pandaReach2D, pandaPush,
+                                   pandaPlayAbsRPY1Obj, pandaPlay1Obj, pandaPlayRel1Obj, pandaPlayRelRPY1Obj,
+                                   pandaPlayAbsJoints1Obj, pandaPlayRelJoints1Obj)}
 
 
 def make(env_id, num_envs=1, **kw):

@@ -16,7 +16,7 @@ import numpy as np
 # (name, kind)   kind: 'i' int32 scalar | 'I' int32 array | 'R' float64 array
 SCHEMA = [
     # ---- scalars
-    ('env_kind', 'i'),          # 0 UR5Reach-v0, 1 pandaPick-v0, 2 UR5PlayAbsRPY1Obj-v0
+    ('env_kind', 'i'),          # 0 reach (no object), 1 push / pick (one object on the tray), 2 playroom
     ('arm_kind', 'i'),          # 0 UR5, 1 Panda
     ('nd', 'i'),                # arm DoF (movable links after folding fixed joints)
     ('n_ik', 'i'),              # leading arm DoF driven by IK / position control (6 or 7)
@@ -79,7 +79,9 @@ PARAM_NAMES = [
 ]
 N_PARAMS = len(PARAM_NAMES)
 
-ENV_KINDS = {'UR5Reach-v0': 0, 'pandaPick-v0': 1, 'UR5PlayAbsRPY1Obj-v0': 2}
+# compiled worlds (one .npz each); the other registered ids are action-decoder variants of these (ACTION_VARIANTS)
+ENV_KINDS = {'UR5Reach-v0': 0, 'pandaPick-v0': 1, 'UR5PlayAbsRPY1Obj-v0': 2,
+             'pandaReach-v0': 0, 'pandaReach2D-v0': 0, 'pandaPush-v0': 1, 'pandaPlayAbsRPY1Obj-v0': 2}
 
 
 class PrbModelStruct(ctypes.Structure):
@@ -159,12 +161,20 @@ ACTION_VARIANTS = {
     'UR5PlayRelRPY1Obj-v0': ('UR5PlayAbsRPY1Obj-v0', 'relative_rpy', 1.0),
     'UR5PlayAbsJoints1Obj-v0': ('UR5PlayAbsRPY1Obj-v0', 'absolute_joints', 6.0),
     'UR5PlayRelJoints1Obj-v0': ('UR5PlayAbsRPY1Obj-v0', 'relative_joints', 1.0),
+    # the Panda in the playroom, one object (envList.py:45-86)
+    'pandaPlay1Obj-v0': ('pandaPlayAbsRPY1Obj-v0', 'absolute_quat', 1.0),
+    'pandaPlayRel1Obj-v0': ('pandaPlayAbsRPY1Obj-v0', 'relative_quat', 1.0),
+    'pandaPlayRelRPY1Obj-v0': ('pandaPlayAbsRPY1Obj-v0', 'relative_rpy', 1.0),
+    'pandaPlayAbsJoints1Obj-v0': ('pandaPlayAbsRPY1Obj-v0', 'absolute_joints', 6.0),
+    'pandaPlayRelJoints1Obj-v0': ('pandaPlayAbsRPY1Obj-v0', 'relative_joints', 1.0),
 }
 
 
 def action_dim(model):
-    """Length of one action: 8 for the quaternion decoders (xyz + quat + gripper), else 7."""
-    return 8 if int(round(model.param('action_type'))) in (2, 3) else 7
+    """Length of one action (environments.py:88-112): 8 for the quaternion decoders (xyz + quat + gripper), one entry per IK
+    joint + gripper for the joint decoders (7 UR5, 8 Panda), else 7 (xyz + rpy + gripper)."""
+    t = int(round(model.param('action_type')))
+    return 8 if t in (2, 3) else (int(model['n_ik']) + 1 if t >= 4 else 7)
 
 
 def load_model(env_id):

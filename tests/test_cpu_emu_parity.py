@@ -16,7 +16,7 @@ def _sync(sim, o, i=0):
     sim.state[i, :o.state_dim] = o.state.astype(np.float32)
 
 
-@pytest.mark.parametrize('env_id', ['UR5Reach-v0', 'pandaPick-v0'])
+@pytest.mark.parametrize('env_id', ['UR5Reach-v0', 'pandaPick-v0', 'pandaReach-v0', 'pandaReach2D-v0', 'pandaPush-v0'])
 def test_emu_step_matches_oracle_arm_envs(env_id):
     m = load_model(env_id)
     sim, o = EmuSim(m, 1, seed=4), Oracle(m, seed=4)
@@ -119,34 +119,41 @@ def test_emu_grasp_sequence_islands_and_arm_solver():
 
 
 @pytest.mark.parametrize('env_id', ['UR5Play1Obj-v0', 'UR5PlayRel1Obj-v0', 'UR5PlayRelRPY1Obj-v0',
-                                    'UR5PlayAbsJoints1Obj-v0', 'UR5PlayRelJoints1Obj-v0'])
+                                    'UR5PlayAbsJoints1Obj-v0', 'UR5PlayRelJoints1Obj-v0',
+                                    'pandaPlayAbsRPY1Obj-v0', 'pandaPlay1Obj-v0', 'pandaPlayRel1Obj-v0', 'pandaPlayRelRPY1Obj-v0',
+                                    'pandaPlayAbsJoints1Obj-v0', 'pandaPlayRelJoints1Obj-v0'])
 def test_emu_action_decoders_match_oracle(env_id):
     """The other UR5 playroom ids differ from UR5PlayAbsRPY1Obj-v0 only by the action decoder
     (environments.py:915-981): kernel vs oracle on the decoded motor targets and the resulting step."""
     from roboticsplayroompybullet_b200.model import action_dim
     m = load_model(env_id)
     A = action_dim(m)
+    nd, nik = m['nd'], m['n_ik']
     sim, o = EmuSim(m, 1, seed=5), Oracle(m, seed=5)
     o.reset()
     rng = np.random.default_rng(7)
-    ee = o.fk_sites(o.state[:12])[0]
+    ee = o.fk_sites(o.state[:nd])[0]
     for _ in range(3):
         if 'Joints' in env_id:
-            a = np.concatenate([rng.uniform(-0.05, 0.05, 6) + (o.state[:6] if 'Abs' in env_id else 0), rng.uniform(-1, 1, 1)])
+            assert A == nik + 1                                                       # 7 (UR5) / 8 (Panda): environments.py:98-107
+            a = np.concatenate([rng.uniform(-0.05, 0.05, nik) + (o.state[:nik] if 'Abs' in env_id else 0), rng.uniform(-1, 1, 1)])
         elif A == 8:
             q = ee[3:7] if 'Rel' not in env_id else np.zeros(4)
             a = np.concatenate([(ee[:3] if 'Rel' not in env_id else 0) + rng.uniform(-0.03, 0.03, 3),
                                 q + rng.uniform(-0.05, 0.05, 4), rng.uniform(-1, 1, 1)])
-        else:
+        elif 'Rel' in env_id:
             a = np.concatenate([rng.uniform(-0.03, 0.03, 3), rng.uniform(-0.1, 0.1, 3), rng.uniform(-1, 1, 1)])
+        else:                                                                         # absolute rpy: around the current pose
+            from oracle.oracle import euler_from_quat
+            a = np.concatenate([ee[:3] + rng.uniform(-0.03, 0.03, 3), euler_from_quat(ee[3:7]) + rng.uniform(-0.1, 0.1, 3), rng.uniform(-1, 1, 1)])
         assert len(a) == A
         _sync(sim, o)
         de, do = sim.step(a[None]), o.step(a)
         assert np.abs(de['target_poses'][0] - do['target_poses']).max() < 5e-6
-        assert np.abs(sim.state[0, :12] - o.state[:12]).max() < 5e-6
+        assert np.abs(sim.state[0, :nd] - o.state[:nd]).max() < 5e-6
         assert np.abs(de['obs_quat'][0][:7] - do['obs_quat'][:7]).max() < 2e-5
         # the command moved the arm the way its decoder says
-        assert np.abs(do['target_poses'] - o.state[:6]).max() < 0.3
+        assert np.abs(do['target_poses'] - o.state[:nik]).max() < 0.3
 
 
 def test_emu_records_read_in_place_when_stage_is_small():

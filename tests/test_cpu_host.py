@@ -52,7 +52,7 @@ def test_create_fails_loudly_without_gpu():
         make('UR5Reach-v0', num_envs=4)
     assert 'no CUDA device' in str(e.value) or 'CUDA' in str(e.value)
     with pytest.raises(NotImplementedError):
-        make('pandaReach-v0', num_envs=1)
+        make('pandaPlay-v0', num_envs=1)            # two-object world: not compiled (envList.py:28-33)
 
 
 def test_product_does_not_import_oracle():

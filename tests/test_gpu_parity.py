@@ -8,6 +8,7 @@ from helpers import compare_step, random_actions, oracle_step_from, POS_TOL, OBS
 pytestmark = pytest.mark.gpu
 
 ENVS = ['UR5Reach-v0', 'UR5PlayAbsRPY1Obj-v0', 'pandaPick-v0']
+PANDA_MORE = ['pandaReach-v0', 'pandaPush-v0', 'pandaPlayAbsRPY1Obj-v0']
 
 
 def _record(name, res):
@@ -24,11 +25,13 @@ def _mk(env_id, n, seed=5):
     return make(env_id, num_envs=n, seed=seed)
 
 
-@pytest.mark.parametrize('env_id', ENVS)
+@pytest.mark.parametrize('env_id', ENVS + PANDA_MORE + ['pandaReach2D-v0'])
 def test_layouts(env_id):
     env = _mk(env_id, 4)
     obs = env.reset()
-    dims = {'UR5Reach-v0': (7, 3, 4, 6), 'pandaPick-v0': (13, 3, 7, 12), 'UR5PlayAbsRPY1Obj-v0': (19, 11, 19, 18)}[env_id]
+    dims = {'UR5Reach-v0': (7, 3, 4, 6), 'pandaPick-v0': (13, 3, 7, 12), 'UR5PlayAbsRPY1Obj-v0': (19, 11, 19, 18),
+            'pandaReach-v0': (7, 3, 4, 6), 'pandaReach2D-v0': (7, 3, 4, 6), 'pandaPush-v0': (13, 3, 7, 12),
+            'pandaPlayAbsRPY1Obj-v0': (19, 11, 19, 18)}[env_id]
     assert obs['obs_quat'].shape == (4, dims[0])
     assert obs['achieved_goal'].shape == (4, dims[1]) and obs['desired_goal'].shape == (4, dims[1])
     assert obs['full_positional_state'].shape == (4, dims[2])
@@ -43,7 +46,7 @@ def test_layouts(env_id):
     env.close()
 
 
-@pytest.mark.parametrize('env_id', ENVS)
+@pytest.mark.parametrize('env_id', ENVS + PANDA_MORE)
 def test_reset_matches_oracle(env_id):
     """Same counter-based RNG stream => same sampled block / arm / goal; settle dynamics agree to
     the pose tolerance."""
@@ -64,7 +67,7 @@ def test_reset_matches_oracle(env_id):
     env.close()
 
 
-@pytest.mark.parametrize('env_id', ENVS)
+@pytest.mark.parametrize('env_id', ENVS + PANDA_MORE)
 def test_step_parity_identical_states(env_id):
     """Every key of the observation dict, reward, success and target poses after one env step from identical states
     (tolerances and the conditioning rule: tests/helpers.py)."""
@@ -251,7 +254,7 @@ def test_parity_at_baseline_size(env_id, N):
     import torch
     from roboticsplayroompybullet_b200.model import load_model
     from oracle.oracle import Oracle
-    play = env_id.startswith('UR5Play')
+    play = 'Play' in env_id
     env = _mk(env_id, N, seed=31)
     obs = env.reset()
     pre = 40 if play else 12
@@ -300,9 +303,11 @@ def test_parity_at_baseline_size(env_id, N):
 
 
 @pytest.mark.parametrize('env_id', ['UR5Play1Obj-v0', 'UR5PlayRel1Obj-v0', 'UR5PlayRelRPY1Obj-v0',
-                                    'UR5PlayAbsJoints1Obj-v0', 'UR5PlayRelJoints1Obj-v0'])
+                                    'UR5PlayAbsJoints1Obj-v0', 'UR5PlayRelJoints1Obj-v0',
+                                    'pandaPlay1Obj-v0', 'pandaPlayRel1Obj-v0', 'pandaPlayRelRPY1Obj-v0',
+                                    'pandaPlayAbsJoints1Obj-v0', 'pandaPlayRelJoints1Obj-v0'])
 def test_action_decoder_variants(env_id):
-    """The other UR5 playroom ids (same world, other action decoder: environments.py:915-981) against the oracle
+    """The other playroom ids of both arms (same world, other action decoder: environments.py:915-981) against the oracle
     from identical states: decoded motor targets and the one-step poses."""
     from roboticsplayroompybullet_b200.model import load_model, action_dim
     from oracle.oracle import Oracle
@@ -318,7 +323,9 @@ def test_action_decoder_variants(env_id):
         st = env.get_state()
         ee = obs['obs_quat'][:, :7]
         if 'Joints' in env_id:
-            a = np.concatenate([rng.uniform(-0.05, 0.05, (n, 6)) + (st[:, :6] if 'Abs' in env_id else 0), rng.uniform(-1, 1, (n, 1))], 1)
+            nik = m['n_ik']
+            assert A == nik + 1
+            a = np.concatenate([rng.uniform(-0.05, 0.05, (n, nik)) + (st[:, :nik] if 'Abs' in env_id else 0), rng.uniform(-1, 1, (n, 1))], 1)
         elif A == 8:
             rel = 'Rel' in env_id
             a = np.concatenate([(0 if rel else ee[:, :3]) + rng.uniform(-0.03, 0.03, (n, 3)),
