@@ -137,7 +137,8 @@ int64_t prb_launch_count(prb_handle* h);
 int64_t prb_overflow_count(prb_handle* h);
 /* Per-env facts of the last substep built, for sizing reports and for tests that must sample every solver path:
  * [N,4] int32 = {arm-island solver class (0: joint-row kernel, 1..4: size class of the arm-island kernel) | q count of
- * the arm island's region << 8, contacts, q count of the env's whole record stream, joint rows}; synchronous. */
+ * the arm island's region << 8, contacts, q count of the env's whole record stream, joint rows | capacity flags << 8
+ * (1: more than 32 overlapping collider pairs, 2: more than 32 contacts, 4: contact between two slide bodies)}; synchronous. */
 int prb_debug_usage(prb_handle* h, int32_t* host_out);
 /* Static facts of the step kernel for reports: dynamic shared memory per block, warps per block. */
 int prb_kernel_info(prb_handle* h, int32_t* smem_bytes_per_block, int32_t* envs_per_block, int32_t* regs_per_thread);

@@ -797,7 +797,7 @@ PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
     unsigned bal = __ballot_sync(FULL, hit);
     if (hit) {
       int slot = n_ovl + __popc(bal & ((1u << lane) - 1u));
-      if (slot < WM::Cfg::MAXOVL) W.ovl[slot] = (unsigned short)k; else W.overflow = 1;
+      if (slot < WM::Cfg::MAXOVL) W.ovl[slot] = (unsigned short)k; else W.overflow |= 1;      // bit 0: overlapping pairs
     }
     n_ovl += __popc(bal);
   }
@@ -862,7 +862,7 @@ PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
   for (int i = 0; i < m; i++) if (off2 + i < WM::Cfg::MAXCONTACT) W.ct[off2 + i] = W.cand[keep[i]];
   if (lane == 0) {
     W.n_contact = total2 < WM::Cfg::MAXCONTACT ? total2 : WM::Cfg::MAXCONTACT;
-    if (total2 > WM::Cfg::MAXCONTACT) W.overflow = 1;
+    if (total2 > WM::Cfg::MAXCONTACT) W.overflow |= 2;                                           // bit 1: contacts
   }
   __syncwarp();
 }

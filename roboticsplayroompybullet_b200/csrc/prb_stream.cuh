@@ -503,7 +503,7 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, int e, int N, c
     if (s0) {
       // sides by kind: arm (P), slide (P or S), free (P, or S under an arm / slide P; both when P and S are free bodies)
       const bool slideP = kP == K_SLIDE, slideS = kS == K_SLIDE, freeP = kP == K_FREE, freeS = kS == K_FREE;
-      if (slideP && slideS) W.overflow = 1;                       // two slide bodies in one contact: not representable
+      if (slideP && slideS) W.overflow |= 4;                       // two slide bodies in one contact: not representable
       const int sld = slideP ? M.col_body[colP] - 1 - M.n_free : (slideS ? M.col_body[colS] - 1 - M.n_free : 0);
       const int fb = freeP ? M.col_body[colP] - 1 : (freeS ? M.col_body[colS] - 1 : 0);
       const float sgnF = freeP ? sP : -sP;
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
       __syncwarp();
       // a dropped contact marks the env; the mark is counted (once per env step) by the launch that observes
       if (lane == 0 && W.overflow) { if (O.ovf_env) O.ovf_env[e] = 1; else if (O.overflow) atomicAdd(O.overflow, 1ull); }
-      if (lane == 0 && O.dbg) { O.dbg[4 * e] = W.dbg_u | (W.dbg_a << 8); O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.n_jrow; }
+      if (lane == 0 && O.dbg) { O.dbg[4 * e] = W.dbg_u | (W.dbg_a << 8); O.dbg[4 * e + 1] = W.dbg_c; O.dbg[4 * e + 2] = W.dbg_p; O.dbg[4 * e + 3] = W.n_jrow | (W.overflow << 8); }
     }
   }
   if (!on) return;
@@ -886,8 +886,20 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel
 }
 
 // ---- slots 1 and 2 (blockIdx.y + 1): islands of free bodies against static geometry / each other.  One thread per
-// env, the bodies' velocity change in registers (IslandV's free-body part), compact records in the stage (records past
-// PGS_STAGE_F are read from the stream in place), warp-uniform loops.
+// env, the bodies' velocity change in registers, compact records in the stage (records past PGS_STAGE_F are read from
+// the stream in place), warp-uniform loops, the next record's loads issued before the current record is solved.
+// Almost every island is ONE body against static geometry: that case runs without any body-index selects (OneBody);
+// a block resting on the drawer makes a two-body island (IslandV's free-body part, register selects).
+struct OneBody {
+  v3 v, w;
+  float I[6], im;
+  PRB_D float jdot(int, float sgn, v3 r, v3 d, bool angular) const { return sgn * (angular ? dot(d, w) : dot(d, v + cross(w, r))); }
+  PRB_D void apply(int, float sgn, v3 r, v3 P, bool angular) {
+    const v3 Ps = P * sgn;
+    if (angular) w = w + symmul(I, Ps);
+    else { v = v + Ps * im; w = w + symmul(I, cross(r, Ps)); }
+  }
+};
 struct FreeRec {
   int iP, iS; float sP; bool two; v3 n, rP, rS;
 };
@@ -899,6 +911,129 @@ PRB_D FreeRec free_rec(int pk, const float4& q1, const float4& q2, const float4*
   f.n = V3(q1.x, q1.y, q1.z); f.rP = V3(q2.x, q2.y, q2.z); f.rS = V3(0, 0, 0);
   if (f.two) { const float4 g = rec[CT_BASE_Q * 32]; f.rS = V3(g.x, g.y, g.z); }
   return f;
+}
+struct FreeQ { float4 q0, q1, q2, q3, q4, q5; };
+template <class BV>
+PRB_D bool free_normal(BV& V, float4* rec, const FreeQ& Q) {
+  const FreeRec f = free_rec(__float_as_int(Q.q0.x), Q.q1, Q.q2, rec);
+  float u = V.jdot(f.iP, f.sP, f.rP, f.n, false);
+  if (f.two) u += V.jdot(f.iS, -f.sP, f.rS, f.n, false);
+  const float l0 = Q.q1.w;
+  const float nl = fmaxf(l0 + (Q.q0.z - l0 * Q.q0.y - u * Q.q0.w), 0.f);
+  const float dl = nl - l0;
+  if (dl != 0.f) {
+    reinterpret_cast<float*>(rec + 32)[3] = nl;
+    V.apply(f.iP, f.sP, f.rP, f.n * dl, false);
+    if (f.two) V.apply(f.iS, -f.sP, f.rS, f.n * dl, false);
+  }
+  return dl != 0.f;
+}
+template <class BV>
+PRB_D bool free_spin(BV& V, float4* rec, const float4& h) {
+  const float4 q0 = rec[0], q1 = rec[32], q2 = rec[64];
+  const float tot = q1.w;
+  if (!(tot > 0.f)) return false;                         // Bullet skips the row while the normal impulse is 0
+  const FreeRec f = free_rec(__float_as_int(q0.x), q1, q2, rec);
+  float u = V.jdot(f.iP, f.sP, f.rP, f.n, true);
+  if (f.two) u += V.jdot(f.iS, -f.sP, f.rS, f.n, true);
+  const float lim = h.y * tot;
+  float* pl = reinterpret_cast<float*>(rec + 96) + 3;
+  const float l0 = *pl;
+  const float nl = clampf(l0 + (h.z - u * h.w), -lim, lim);
+  const float dl = nl - l0;
+  if (dl != 0.f) {
+    *pl = nl;
+    V.apply(f.iP, f.sP, f.rP, f.n * dl, true);
+    if (f.two) V.apply(f.iS, -f.sP, f.rS, f.n * dl, true);
+  }
+  return dl != 0.f;
+}
+// lateral friction: the two rows of a contact are solved together (implicit cone)
+template <class BV>
+PRB_D bool free_friction(BV& V, float4* rec, const FreeQ& Q) {
+  const FreeRec f = free_rec(__float_as_int(Q.q0.x), Q.q1, Q.q2, rec);
+  const v3 t1 = V3(Q.q3.x, Q.q3.y, Q.q3.z), t2 = cross(f.n, t1);
+  float ua = V.jdot(f.iP, f.sP, f.rP, t1, false), ub = V.jdot(f.iP, f.sP, f.rP, t2, false);
+  if (f.two) { ua += V.jdot(f.iS, -f.sP, f.rS, t1, false); ub += V.jdot(f.iS, -f.sP, f.rS, t2, false); }
+  const float lim = Q.q2.w * Q.q1.w;
+  const float la = Q.q5.x, lb = Q.q5.y;
+  const float sumA = la + (Q.q4.x - ua * Q.q4.z);
+  const float sumB = lb + (Q.q4.y - ub * Q.q4.w);
+  float na = sumA, nb = sumB;
+  if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
+    const float ss = sumA * sumA + sumB * sumB;
+    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+    const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
+    na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
+  }
+  const float d1 = na - la, d2 = nb - lb;
+  if (d1 != 0.f || d2 != 0.f) {
+    rec[160] = make_float4(na, nb, 0.f, 0.f);
+    const v3 Pv = t1 * d1 + t2 * d2;
+    V.apply(f.iP, f.sP, f.rP, Pv, false);
+    if (f.two) V.apply(f.iS, -f.sP, f.rS, Pv, false);
+  }
+  return d1 != 0.f || d2 != 0.f;
+}
+// the 50 sweeps of one island; sl: this env's staged column, Gr: its records in the stream
+template <class BV>
+PRB_D void free_sweeps(BV& V, float4* sl, float4* Gr, bool live, int nc, int ns, int ncmax, int nsmax, int t_spin, int iters) {
+#define PGS_PTR(t_) ((t_) < PGS_STAGE_F ? sl + (t_) * 32 : Gr + (t_) * 32)
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    bool changed = false;
+    // ---- contact normals (the next record is loaded while the current one is solved; readable slack after the last)
+    {
+      int t = 0;
+      float4* rec = PGS_PTR(0);
+      FreeQ Q;
+      Q.q0 = rec[0]; Q.q1 = rec[32]; Q.q2 = rec[64];
+#pragma unroll 1
+      for (int c = 0; c < ncmax; c++) {
+        if (live && c < nc) {
+          const int tn = t + ((__float_as_int(Q.q0.x) >> 12) & 255);
+          float4* recn = PGS_PTR(tn);
+          FreeQ N;
+          N.q0 = recn[0]; N.q1 = recn[32]; N.q2 = recn[64];
+          changed |= free_normal(V, rec, Q);
+          t = tn; rec = recn; Q.q0 = N.q0; Q.q1 = N.q1; Q.q2 = N.q2;
+        }
+        __syncwarp();
+      }
+    }
+    // ---- spinning friction
+#pragma unroll 1
+    for (int i = 0; i < nsmax; i++) {
+      if (live && i < ns) {
+        const float4 h = *PGS_PTR(t_spin + i);
+        changed |= free_spin(V, PGS_PTR(__float_as_int(h.x)), h);
+      }
+      __syncwarp();
+    }
+    // ---- lateral friction
+    {
+      int t = 0;
+      float4* rec = PGS_PTR(0);
+      FreeQ Q;
+      Q.q0 = rec[0]; Q.q1 = rec[32]; Q.q2 = rec[64]; Q.q3 = rec[96]; Q.q4 = rec[128]; Q.q5 = rec[160];
+#pragma unroll 1
+      for (int c = 0; c < ncmax; c++) {
+        if (live && c < nc) {
+          const int tn = t + ((__float_as_int(Q.q0.x) >> 12) & 255);
+          float4* recn = PGS_PTR(tn);
+          FreeQ N;
+          N.q0 = recn[0]; N.q1 = recn[32]; N.q2 = recn[64]; N.q3 = recn[96]; N.q4 = recn[128]; N.q5 = recn[160];
+          changed |= free_friction(V, rec, Q);
+          t = tn; rec = recn; Q = N;
+        }
+        __syncwarp();
+      }
+    }
+    // fixed point reached (a sweep changed no impulse): later sweeps are exact repeats, the lane retires
+    live = live && changed;
+    if (!__any_sync(FULL, live)) break;
+  }
+#undef PGS_PTR
 }
 
 __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N,
@@ -916,9 +1051,9 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
     const int info = __float_as_int(h1.x);
     const int cnt = __float_as_int(hs.x);
     const int start = __float_as_int(hs.y), t_spin = __float_as_int(hs.z);
-    bool owner = false;
-    for (int b = 0; b < M.n_free; b++) owner = owner || ((info >> (16 + 2 * b)) & 3) == slot;
-    valid = valid && owner;                                // not owner: merged into another island
+    int n_own = 0, b_own = 0;
+    for (int b = 0; b < M.n_free; b++) if (((info >> (16 + 2 * b)) & 3) == slot) { n_own++; b_own = b; }
+    valid = valid && n_own > 0;                            // no body of this slot: merged into another island
     if (!__any_sync(FULL, valid)) continue;
     const int nc = valid ? (cnt & 0xff) : 0, ns = valid ? ((cnt >> 8) & 0xff) : 0;
     int ncmax = nc, nsmax = ns;
@@ -931,7 +1066,6 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
 #pragma unroll 8
       for (int q = 0; q < tq; q++) sl[q * 32] = Gr[q * 32];
     }
-#define PGS_PTR(t_) ((t_) < PGS_STAGE_F ? sl + (t_) * 32 : Gr + (t_) * 32)
     IslandV V;
     V.clear();
 #pragma unroll
@@ -941,101 +1075,21 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
       V.invm[fb] = i1.z;
     }
     const int iters = M.solver_iters;
-    bool live = valid;
-#pragma unroll 1
-    for (int it = 0; it < iters; it++) {
-      bool changed = false;
-      // ---- contact normals
-      int t = 0;
-#pragma unroll 1
-      for (int c = 0; c < ncmax; c++) {
-        if (live && c < nc) {
-          float4* rec = PGS_PTR(t);
-          const float4 q0 = rec[0], q1 = rec[32], q2 = rec[64];
-          const int pk = __float_as_int(q0.x);
-          const FreeRec f = free_rec(pk, q1, q2, rec);
-          float u = V.jdot(f.iP, f.sP, f.rP, f.n, false);
-          if (f.two) u += V.jdot(f.iS, -f.sP, f.rS, f.n, false);
-          const float l0 = q1.w;
-          const float nl = fmaxf(l0 + (q0.z - l0 * q0.y - u * q0.w), 0.f);
-          const float dl = nl - l0;
-          if (dl != 0.f) {
-            changed = true;
-            reinterpret_cast<float*>(rec + 32)[3] = nl;
-            V.apply(f.iP, f.sP, f.rP, f.n * dl, false);
-            if (f.two) V.apply(f.iS, -f.sP, f.rS, f.n * dl, false);
-          }
-          t += (pk >> 12) & 255;
-        }
-        __syncwarp();
-      }
-      // ---- spinning friction (Bullet skips the row while the normal impulse is 0)
-#pragma unroll 1
-      for (int i = 0; i < nsmax; i++) {
-        if (live && i < ns) {
-          const float4 h = *PGS_PTR(t_spin + i);
-          float4* rec = PGS_PTR(__float_as_int(h.x));
-          const float4 q0 = rec[0], q1 = rec[32], q2 = rec[64];
-          const float tot = q1.w;
-          if (tot > 0.f) {
-            const FreeRec f = free_rec(__float_as_int(q0.x), q1, q2, rec);
-            float u = V.jdot(f.iP, f.sP, f.rP, f.n, true);
-            if (f.two) u += V.jdot(f.iS, -f.sP, f.rS, f.n, true);
-            const float lim = h.y * tot;
-            float* pl = reinterpret_cast<float*>(rec + 96) + 3;
-            const float l0 = *pl;
-            const float nl = clampf(l0 + (h.z - u * h.w), -lim, lim);
-            const float dl = nl - l0;
-            if (dl != 0.f) {
-              changed = true;
-              *pl = nl;
-              V.apply(f.iP, f.sP, f.rP, f.n * dl, true);
-              if (f.two) V.apply(f.iS, -f.sP, f.rS, f.n * dl, true);
-            }
-          }
-        }
-        __syncwarp();
-      }
-      // ---- lateral friction: the two rows of a contact are solved together (implicit cone)
-      t = 0;
-#pragma unroll 1
-      for (int c = 0; c < ncmax; c++) {
-        if (live && c < nc) {
-          float4* rec = PGS_PTR(t);
-          const float4 q0 = rec[0], q1 = rec[32], q2 = rec[64], q3 = rec[96], q4 = rec[128], q5 = rec[160];
-          const int pk = __float_as_int(q0.x);
-          const FreeRec f = free_rec(pk, q1, q2, rec);
-          const v3 t1 = V3(q3.x, q3.y, q3.z), t2 = cross(f.n, t1);
-          float ua = V.jdot(f.iP, f.sP, f.rP, t1, false), ub = V.jdot(f.iP, f.sP, f.rP, t2, false);
-          if (f.two) { ua += V.jdot(f.iS, -f.sP, f.rS, t1, false); ub += V.jdot(f.iS, -f.sP, f.rS, t2, false); }
-          const float lim = q2.w * q1.w;
-          const float la = q5.x, lb = q5.y;
-          const float sumA = la + (q4.x - ua * q4.z);
-          const float sumB = lb + (q4.y - ub * q4.w);
-          float na = sumA, nb = sumB;
-          if (sumA < -lim || sumA > lim || sumB < -lim || sumB > lim) {
-            const float ss = sumA * sumA + sumB * sumB;
-            const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
-            const float ca_ = fabsf(lim * sumA) * inv, cb_ = ss > 0.f ? fabsf(lim * sumB) * inv : fabsf(lim);
-            na = clampf(sumA, -ca_, ca_); nb = clampf(sumB, -cb_, cb_);
-          }
-          const float d1 = na - la, d2 = nb - lb;
-          if (d1 != 0.f || d2 != 0.f) {
-            changed = true;
-            rec[160] = make_float4(na, nb, 0.f, 0.f);
-            const v3 Pv = t1 * d1 + t2 * d2;
-            V.apply(f.iP, f.sP, f.rP, Pv, false);
-            if (f.two) V.apply(f.iS, -f.sP, f.rS, Pv, false);
-          }
-          t += (pk >> 12) & 255;
-        }
-        __syncwarp();
-      }
-      // fixed point reached (a sweep changed no impulse): later sweeps are exact repeats, the lane retires
-      live = live && changed;
-      if (!__any_sync(FULL, live)) break;
+    const bool single = n_own == 1;
+    if (__any_sync(FULL, valid && single)) {               // one body against static geometry: no selects
+      OneBody B;
+      B.v = V3(0, 0, 0); B.w = V3(0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 6; k++) B.I[k] = b_own ? V.I[PRB_MAXFREE - 1][k] : V.I[0][k];
+      B.im = b_own ? V.invm[PRB_MAXFREE - 1] : V.invm[0];
+      const bool on = valid && single;
+      free_sweeps(B, sl, Gr, on, on ? nc : 0, on ? ns : 0, ncmax, nsmax, t_spin, iters);
+      if (on) { if (b_own) { V.fv[PRB_MAXFREE - 1] = B.v; V.fw[PRB_MAXFREE - 1] = B.w; } else { V.fv[0] = B.v; V.fw[0] = B.w; } }
     }
-#undef PGS_PTR
+    if (__any_sync(FULL, valid && !single)) {
+      const bool on = valid && !single;
+      free_sweeps(V, sl, Gr, on, on ? nc : 0, on ? ns : 0, ncmax, nsmax, t_spin, iters);
+    }
     if (valid) {
       float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
 #pragma unroll
