@@ -617,7 +617,8 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const Dev
 //                          ARM_LANES(class) envs / warp, bundle staged by one bulk async copy
 #define PGS_BLOCK 32
 #define PGS_SMEM_J (PGS_STAGE_J * 32 * 16)
-#define PGS_SMEM_F (PGS_STAGE_F * 32 * 16)
+#define PGS_F_SLACKQ 8    // the free-body kernel loads the record after the current one (6 q) ahead of time: readable slack after the stage
+#define PGS_SMEM_F ((PGS_STAGE_F + PGS_F_SLACKQ) * 32 * 16)
 #define PGS_SMEM_ARM(k) (arm_capq(k) * arm_lanes(k) * 16)
 
 #ifdef PRB_EMU
