@@ -28,8 +28,8 @@ sys.path.insert(0, ROOT)
 ENV_ID = 'UR5PlayAbsRPY1Obj-v0'
 RELABEL_EVERY, RELABEL_PHASE = 64, 2       # goal relabelling cadence and its phase in the timed region
 # DRAM bytes (read + write) of the step pipeline per env step at 65536 envs, from the ncu --set full capture in
-# profiles/r1_v27_ncu.md (12 substeps x 1.16 GB + the final setup launch); None for configurations not captured
-MEASURED_TRAFFIC_BYTES = {('UR5PlayAbsRPY1Obj-v0', 65536): 14.0e9}
+# profiles/r2_ncu.md (12 substeps x 0.63 GB + the final setup launch + IK); None for configurations not captured
+MEASURED_TRAFFIC_BYTES = {('UR5PlayAbsRPY1Obj-v0', 65536): 7.7e9}
 BYTES_PER_ENV_STEP = {'UR5Reach-v0': 416, 'pandaPick-v0': 560, 'UR5PlayAbsRPY1Obj-v0': 1044}
 METRIC = 'UR5PlayAbsRPY1Obj-v0 env-steps/s'
 
@@ -349,7 +349,7 @@ def run_gpu(args):
                            'episode_resets': n_reset},
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                              'frac': achieved / peak_gbs, 'traffic': MEASURED_TRAFFIC_BYTES.get((args.env, N)),
-                             'traffic_note': 'bytes per launch set of one env step (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_v27_ncu.md)',
+                             'traffic_note': 'bytes per launch set of one env step (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r2_ncu.md)',
                              'kernel': 'step pipeline per env step: 13 x prb_setup_kernel + 12 x (prb_pgs_joint_kernel, prb_pgs_free_kernel, 5 size classes of prb_pgs_arm_kernel)',
                              'setup_kernels_ms': float(np.mean([t[0] for t in tier_ms])),
                              'pgs_kernels_ms': float(np.mean([t[1] for t in tier_ms])),

@@ -182,23 +182,42 @@ def test_sharding_bit_identical():
 
 
 def test_grasp_and_lift_statistics():
-    """Scripted pick: the block must end up lifted in most envs (contact + friction sanity at scale)."""
+    """Multi-step rollouts are compared STATISTICALLY (contact dynamics are chaotic; north_star): the same scripted pick of
+    52 env steps from the same seeded resets on the GPU and in the oracle.  The block must end up lifted in most envs
+    in both, at the same rate, with the same distribution of final heights; most individual envs still agree closely."""
     from roboticsplayroompybullet_b200.envs import make
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle
     n = 64
     env = make('UR5PlayAbsRPY1Obj-v0', num_envs=n, seed=3)
     obs = env.reset()
     blk = obs['achieved_goal'][:, :3].copy()
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    orc = [Oracle(m, seed=3, env_id=i) for i in range(n)]
+    blk_o = np.array([o.reset()['achieved_goal'][:3] for o in orc])
+    assert np.abs(blk - blk_o).max() < 2e-3                      # same resets
 
-    def act(z, g):
+    def act(b, z, g):
         a = np.zeros((n, 7), np.float32)
-        a[:, 0] = blk[:, 0]; a[:, 1] = blk[:, 1]; a[:, 2] = z; a[:, 6] = g
+        a[:, 0] = b[:, 0]; a[:, 1] = b[:, 1]; a[:, 2] = z; a[:, 6] = g
         return a
-    for k in range(10): env.step(act(0.15, -1))
-    for k in range(15): env.step(act(-0.01, -1))
-    for k in range(12): env.step(act(-0.01, 1))
-    for k in range(15): obs, r, _, _ = env.step(act(0.2, 1))
-    lifted = obs['achieved_goal'][:, 2] > 0.1
-    assert lifted.mean() > 0.7, lifted.mean()
+    plan = [(0.15, -1)] * 10 + [(-0.01, -1)] * 15 + [(-0.01, 1)] * 12 + [(0.2, 1)] * 15
+    for z, g in plan:
+        obs, r, _, _ = env.step(act(blk, z, g))
+    for z, g in plan:
+        a = act(blk_o, z, g)
+        out_o = [o.step(a[i]) for i, o in enumerate(orc)]
+    z_gpu = obs['achieved_goal'][:, 2]
+    z_orc = np.array([d['achieved_goal'][2] for d in out_o])
+    lift_gpu, lift_orc = (z_gpu > 0.1).mean(), (z_orc > 0.1).mean()
+    _record('grasp_and_lift_statistics', {'lift_rate_gpu': float(lift_gpu), 'lift_rate_oracle': float(lift_orc),
+                                          'median_abs_dz': float(np.median(np.abs(z_gpu - z_orc))), 'n': n})
+    assert lift_gpu > 0.7 and lift_orc > 0.7, (lift_gpu, lift_orc)
+    assert abs(lift_gpu - lift_orc) <= 0.08, (lift_gpu, lift_orc)
+    # distribution of final heights: quartiles agree, and the typical env still agrees to a millimetre after 52 steps
+    q = [0.25, 0.5, 0.75]
+    assert np.abs(np.quantile(z_gpu, q) - np.quantile(z_orc, q)).max() < 0.02
+    assert np.median(np.abs(z_gpu - z_orc)) < 1e-3
     env.close()
 
 
