@@ -422,7 +422,7 @@ static void cull_points(int n, const real p[], int m, int i0, int iret[]) {
     real maxdiff = 1e9, diff; *iret = i0;
     for (int i = 0; i < n; i++) if (avail[i]) {
       diff = fabs(A[i] - a); if (diff > PI) diff = 2 * PI - diff;
-      if (diff < maxdiff) { maxdiff = diff; *iret = i; }
+      if (diff < maxdiff - 1e-5) { maxdiff = diff; *iret = i; }   /* ties: the first point wins */
     }
     avail[*iret] = 0; iret++;
   }
@@ -532,7 +532,7 @@ int orc_box_box_impl(v3 p1, const m3* R1, v3 side1h, v3 p2, const m3* R2, v3 sid
   int maxc = 4, idx[8], m = cnum;
   if (cnum > maxc) {
     int i1 = 0; real maxd = dep[0];
-    for (int i = 1; i < cnum; i++) if (dep[i] > maxd) { maxd = dep[i]; i1 = i; }
+    for (int i = 1; i < cnum; i++) if (dep[i] > maxd + 1e-7) { maxd = dep[i]; i1 = i; }   /* ties: the first point wins (same rule as the kernels) */
     cull_points(cnum, ret, maxc, i1, idx); m = maxc;
   } else for (int i = 0; i < cnum; i++) idx[i] = i;
   for (int j = 0; j < m; j++) {
@@ -608,18 +608,22 @@ static int reduce_manifold(const Contact* c, int n, int* keep) {
   for (int i = 0; i < n; i++) if (i != i0) { v3 d = vsub(c[i].pb, c[i0].pb); real v = vdot(d, d); if (v > best * 1.0001 + 1e-12) { best = v; i1 = i; } }
   int i2 = -1; best = -1;
   v3 e01 = vsub(c[i1].pb, c[i0].pb);
-  for (int i = 0; i < n; i++) if (i != i0 && i != i1) { v3 x = vcross(vsub(c[i].pb, c[i0].pb), e01); real v = vdot(x, x); if (v > best * 1.0001 + 1e-16) { best = v; i2 = i; } }
+  for (int i = 0; i < n; i++) if (i != i0 && i != i1) { v3 x = vcross(vsub(c[i].pb, c[i0].pb), e01); real v = vdot(x, x); if (v > best * 1.0001 + 1e-14) { best = v; i2 = i; } }
   int i3 = -1; best = -1;
   for (int i = 0; i < n; i++) if (i != i0 && i != i1 && i != i2) {
     v3 a = vsub(c[i].pb, c[i0].pb), b = vsub(c[i].pb, c[i1].pb), d = vsub(c[i].pb, c[i2].pb);
     real v = vnorm(vcross(a, b)) + vnorm(vcross(b, d)) + vnorm(vcross(d, a));
-    if (v > best * 1.0001 + 1e-10) { best = v; i3 = i; }
+    if (v > best * 1.0001 + 1e-7) { best = v; i3 = i; }
   }
   int sel[4] = {i0, i1, i2, i3}, m = 0;
   for (int i = 0; i < n; i++) if (i == sel[0] || i == sel[1] || i == sel[2] || i == sel[3]) keep[m++] = i;
   return m;
 }
+/* all narrow-phase candidates of the last detect_contacts call, before manifold reduction (tests) */
+static real g_last_cand[4 * MAXCONTACT][10]; static int g_last_ncand = 0;
+int orc_last_candidates(real* out) { for (int i = 0; i < g_last_ncand; i++) for (int k = 0; k < 10; k++) out[10 * i + k] = g_last_cand[i][k]; return g_last_ncand; }
 static int detect_contacts(const prb_model* M, const Poses* P, Contact* C, int maxc) {
+  g_last_ncand = 0;
   static Contact cand[4 * MAXCONTACT];
   int ncand = 0, nc = 0;
   int run_start = 0, run_oa = -1, run_ob = -1;
@@ -643,6 +647,7 @@ static int detect_contacts(const prb_model* M, const Poses* P, Contact* C, int m
     for (int i = 0; i < n && ncand < 4 * MAXCONTACT; i++) {
       cand[ncand].ca = a; cand[ncand].cb = b; cand[ncand].n = cp[i].n; cand[ncand].pb = cp[i].pos; cand[ncand].dist = -cp[i].depth;
       cand[ncand].pa = vadd(cp[i].pos, vscale(cp[i].n, -cp[i].depth));
+      if (g_last_ncand < 4 * MAXCONTACT) { real* o = g_last_cand[g_last_ncand++]; o[0] = a; o[1] = b; o[2] = cp[i].pos.x; o[3] = cp[i].pos.y; o[4] = cp[i].pos.z; o[5] = cp[i].n.x; o[6] = cp[i].n.y; o[7] = cp[i].n.z; o[8] = -cp[i].depth; o[9] = 0; }
       ncand++;
     }
   }

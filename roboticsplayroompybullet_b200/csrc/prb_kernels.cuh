@@ -655,7 +655,7 @@ PRB_DN void cull_points(int n, const float p[], int m, int i0, int iret[]) {
     float maxdiff = 1e9f, diff; *iret = i0;
     for (int i = 0; i < n; i++) if (avail[i]) {
       diff = fabsf(A[i] - a); if (diff > PRB_PI_F) diff = 2 * PRB_PI_F - diff;
-      if (diff < maxdiff) { maxdiff = diff; *iret = i; }
+      if (diff < maxdiff - 1e-5f) { maxdiff = diff; *iret = i; }                               // ties: the first point wins
     }
     avail[*iret] = 0; iret++;
   }
@@ -757,7 +757,7 @@ PRB_DN int box_box(v3 p1, const m3& R1, v3 h1, v3 p2, const m3& R2, v3 h2, CPoin
   int idx[8], m = cnum;
   if (cnum > 4) {
     int i1 = 0; float maxd = dep[0];
-    for (int i = 1; i < cnum; i++) if (dep[i] > maxd) { maxd = dep[i]; i1 = i; }
+    for (int i = 1; i < cnum; i++) if (dep[i] > maxd + 1e-7f) { maxd = dep[i]; i1 = i; }      // ties: the first point wins (as in the oracle)
     cull_points(cnum, ret, 4, i1, idx); m = 4;
   } else for (int i = 0; i < cnum; i++) idx[i] = i;
   for (int j = 0; j < m; j++) {
@@ -846,13 +846,13 @@ PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
       for (int i = 0; i < nn; i++) if (i != i0) { v3 d = V3(c[i].pbx, c[i].pby, c[i].pbz) - p0; float v = dot(d, d); if (v > best * 1.0001f + 1e-12f) { best = v; i1 = i; } }
       v3 p1 = V3(c[i1].pbx, c[i1].pby, c[i1].pbz), e01 = p1 - p0;
       int i2 = -1; best = -1.f;
-      for (int i = 0; i < nn; i++) if (i != i0 && i != i1) { v3 x = cross(V3(c[i].pbx, c[i].pby, c[i].pbz) - p0, e01); float v = dot(x, x); if (v > best * 1.0001f + 1e-16f) { best = v; i2 = i; } }
+      for (int i = 0; i < nn; i++) if (i != i0 && i != i1) { v3 x = cross(V3(c[i].pbx, c[i].pby, c[i].pbz) - p0, e01); float v = dot(x, x); if (v > best * 1.0001f + 1e-14f) { best = v; i2 = i; } }
       v3 p2 = V3(c[i2].pbx, c[i2].pby, c[i2].pbz);
       int i3 = -1; best = -1.f;
       for (int i = 0; i < nn; i++) if (i != i0 && i != i1 && i != i2) {
         v3 pi = V3(c[i].pbx, c[i].pby, c[i].pbz), a = pi - p0, b = pi - p1, d = pi - p2;
         float v = norm(cross(a, b)) + norm(cross(b, d)) + norm(cross(d, a));
-        if (v > best * 1.0001f + 1e-10f) { best = v; i3 = i; }
+        if (v > best * 1.0001f + 1e-7f) { best = v; i3 = i; }
       }
       for (int i = 0; i < nn; i++) if (i == i0 || i == i1 || i == i2 || i == i3) keep[m++] = b0 + i;
     }

@@ -53,7 +53,7 @@
                          // the motor rows fully unrolled with compile-time register indices;
                          // then ceil(njr / 4) q of accumulated impulses (zeroed by the solver), then the contacts
 #define SB_MAXJROW 40    // 2 limit rows + 1 motor per arm DoF, 3 slide motors, gear
-#define SB_MAXCONTACT 32
+#define SB_MAXCONTACT 64 // contacts per env after manifold reduction (two per lane in the row writer)
 // slot 0 contact record, fixed layout (the solver issues every load of a visit at a fixed offset before it has
 // decoded the flags, so nothing depends on a previous load):
 //   +0 H0 {flags, rhs n, invD n, cfm * invD n}     +1 H1 {rhs spin, invD spin, spin coefficient, mu}
@@ -104,7 +104,7 @@
 #define ARM_CAPQ1 220
 #define ARM_CAPQ2 288
 #define ARM_CAPQ3 440
-#define ARM_CAPQ4 ARM_BUFQ_MAX    // the largest islands are staged whole too (4 envs per block); smaller test builds read in place
+#define ARM_CAPQ4 (R0_LIGHT_END + 32 * CR_MAX_Q + CR_MAX_Q + 4)   // 32 arm contacts staged whole (4 envs per block); the rest is read in place
 #endif
 
 PRB_HD int arm_lanes(int k) { return k == 0 ? 32 : (k <= 2 ? 16 : (k == 3 ? 8 : 4)); }
@@ -281,6 +281,23 @@ PRB_D float4 jrow_q(const DevModel& M, int d, int d2, int neg, int sym, float rh
   return make_float4(__int_as_float(pk), rhs, invD, hi);
 }
 
+// the two sides of a contact ordered by kind (P = the higher-ranked side: arm > slide > free > static), their groups
+// (0: arm + slide bodies, 1 + b: free body b, -1: static) and the torsional friction coefficient
+struct ContactSides { int colP, colS, kP, kS, grpP, grpS; bool swapped, has_spin; float spin; };
+PRB_D ContactSides contact_sides(const DevModel& M, const Contact& c) {
+  ContactSides s;
+  const int ca = c.cols & 0xff, cb = (c.cols >> 8) & 0xff;
+  const int kA = body_kind(M, col_dyn_body(M, ca)), kB = body_kind(M, col_dyn_body(M, cb));
+  s.swapped = kind_rank(kB) > kind_rank(kA);
+  s.colP = s.swapped ? cb : ca; s.colS = s.swapped ? ca : cb;
+  s.kP = s.swapped ? kB : kA; s.kS = s.swapped ? kA : kB;
+  s.grpP = s.kP == K_FREE ? M.col_body[s.colP] : 0;
+  s.grpS = s.kS == K_STATIC ? -1 : (s.kS == K_FREE ? M.col_body[s.colS] : 0);
+  s.spin = M.col_spin[ca] * M.col_fric[ca] + M.col_spin[cb] * M.col_fric[cb];
+  s.has_spin = s.spin > 0.f;
+  return s;
+}
+
 // constraint rows of the substep -> record stream / heavy buffers
 template <int ND, class WM>
 PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, int e, int N, const SV& S, float4* __restrict__ hbuf,
@@ -338,76 +355,115 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, int e, int N, c
   const int nL = jtot & 0xff, nMo = (jtot >> 8) & 0xff, nSl = (jtot >> 16) & 0xff, nGe = (jtot >> 24) & 0xff;
   const int njr = nL + nMo + nSl + nGe;            // <= 2 nd + nd + n_slide + 1 <= SB_MAXJROW
   const bool canon = nMo == nd && nSl == M.n_slide;
-  // ---- contacts: lane = contact
+  // ---- contacts: lane = contact, up to TWO per lane (contact h * 32 + lane; the second pass only runs for > 32 contacts)
   const int nc = W.n_contact;
-  int colP = 0, colS = 0, kP = K_STATIC, kS = K_STATIC, grpP = 0, grpS = -1;
-  bool swapped = false, has_spin = false;
-  float spin = 0.f;
-  Contact c;
-  if (lane < nc) {
-    c = W.ct[lane];
-    const int ca = c.cols & 0xff, cb = (c.cols >> 8) & 0xff;
-    const int kA = body_kind(M, col_dyn_body(M, ca)), kB = body_kind(M, col_dyn_body(M, cb));
-    swapped = kind_rank(kB) > kind_rank(kA);
-    colP = swapped ? cb : ca; colS = swapped ? ca : cb;
-    kP = swapped ? kB : kA; kS = swapped ? kA : kB;
-    grpP = kP == K_FREE ? M.col_body[colP] : 0;                 // 0: arm + slide bodies, 1 + b: free body b
-    grpS = kS == K_STATIC ? -1 : (kS == K_FREE ? M.col_body[colS] : 0);
-    spin = M.col_spin[ca] * M.col_fric[ca] + M.col_spin[cb] * M.col_fric[cb];
-    has_spin = spin > 0.f;
-  }
-  // islands over the three groups -> slot of each free body and of each contact
+  const int nh = nc > 32 ? 2 : 1;                        // warp-uniform
+  int slot_[2] = {-1, -1}, size0_[2] = {0, 0}, off0_[2] = {0, 0};
+  int t_[2] = {0, 0}, stride_[2] = {0, 0}, srank_[2] = {0, 0}, region_[2] = {0, 0}, tspin_[2] = {0, 0};
+  // islands over the three groups {arm + slide bodies, free body 0, free body 1} -> slot of each free body and of each contact
   int slotf[PRB_MAXFREE];
   {
-    const bool two = lane < nc && grpS >= 0 && grpS != grpP;
-    const int lo_ = min(grpP, grpS), hi_ = max(grpP, grpS);
-    const bool m01 = __any_sync(FULL, two && lo_ == 0 && hi_ == 1);
-    const bool m02 = __any_sync(FULL, two && lo_ == 0 && hi_ == 2);
-    const bool m12 = __any_sync(FULL, two && lo_ == 1 && hi_ == 2);
+    bool m01 = false, m02 = false, m12 = false;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      if (h < nh) {
+        const int idx = h * 32 + lane;
+        int lo_ = 0, hi_ = 0;
+        bool two = false;
+        if (idx < nc) {
+          const ContactSides cs = contact_sides(M, W.ct[idx]);
+          two = cs.grpS >= 0 && cs.grpS != cs.grpP;
+          lo_ = min(cs.grpP, cs.grpS); hi_ = max(cs.grpP, cs.grpS);
+        }
+        m01 = m01 || __any_sync(FULL, two && lo_ == 0 && hi_ == 1);
+        m02 = m02 || __any_sync(FULL, two && lo_ == 0 && hi_ == 2);
+        m12 = m12 || __any_sync(FULL, two && lo_ == 1 && hi_ == 2);
+      }
+    }
     const bool c01 = m01 || (m12 && m02), c02 = m02 || (m12 && m01), c12 = m12 || (m01 && m02);
     slotf[0] = c01 ? 0 : 1;
     slotf[1] = c02 ? 0 : (c12 ? 1 : 2);
   }
-  const int slot = lane < nc ? (grpP == 0 ? 0 : slotf[grpP - 1]) : -1;
   // ---- placement.  Slot 0: one record per contact, in contact order
-  const bool s0 = slot == 0;
-  const bool armP = s0 && kP == K_ARM;
-  const int size0 = s0 ? CR_BASE_Q + (armP ? (has_spin ? 24 : 18) : 0) : 0;
-  int tot0;
-  const int off0 = warp_excl_scan(size0, lane, &tot0);
+  int tot0 = 0, nc0 = 0;
+  int size12_[2] = {0, 0};
+  bool spin_[2] = {false, false};
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    if (h < nh) {
+      const int idx = h * 32 + lane;
+      if (idx < nc) {
+        const ContactSides cs = contact_sides(M, W.ct[idx]);
+        slot_[h] = cs.grpP == 0 ? 0 : slotf[cs.grpP - 1];
+        spin_[h] = cs.has_spin;
+        if (slot_[h] == 0) size0_[h] = CR_BASE_Q + (cs.kP == K_ARM ? (cs.has_spin ? 24 : 18) : 0);
+        else size12_[h] = CT_BASE_Q + (cs.kS == K_FREE ? 1 : 0);
+      }
+      int tot;
+      off0_[h] = tot0 + warp_excl_scan(size0_[h], lane, &tot);
+      tot0 += tot;
+      nc0 += __popc(__ballot_sync(FULL, slot_[h] == 0));
+    }
+  }
   const int tC0 = R0_JROW + njr + ((njr + 3) >> 2);
   const int tEnd0 = tC0 + tot0;
-  const int nc0 = __popc(__ballot_sync(FULL, s0));
   // slots 1, 2: compact records + spin list per region
-  const int size = (lane < nc && !s0) ? CT_BASE_Q + (kS == K_FREE ? 1 : 0) : 0;
-  int t = 0, stride12 = size, t_spin_mine = 0, spin_rank = 0, region_mine = 0;
   int ncs[3] = {nc0, 0, 0}, nss[3] = {0, 0, 0}, tsp[3] = {0, 0, 0}, start[3] = {0, 0, 0};
   {
     int region = 0;                                   // start of the slot's region relative to Q_S12
 #pragma unroll
     for (int sidx = 1; sidx < 3; sidx++) {
-      const bool mine = slot == sidx;
-      const unsigned mask = __ballot_sync(FULL, mine);
-      const unsigned smask = __ballot_sync(FULL, mine && has_spin);
-      int total;
-      int ts = warp_excl_scan(mine ? size : 0, lane, &total);
-      const bool straddle = mine && ts < PGS_STAGE_F && ts + size > PGS_STAGE_F;
-      const unsigned sm = __ballot_sync(FULL, straddle);
+      unsigned mask[2] = {0u, 0u}, smask[2] = {0u, 0u};
+      int ts[2] = {0, 0}, total = 0;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        if (h < nh) {
+          const bool mine = slot_[h] == sidx;
+          mask[h] = __ballot_sync(FULL, mine);
+          smask[h] = __ballot_sync(FULL, mine && spin_[h]);
+          int tt;
+          ts[h] = total + warp_excl_scan(mine ? size12_[h] : 0, lane, &tt);
+          total += tt;
+        }
+      }
+      // a record never straddles the stage boundary of the free-body solver: the first one that would is moved up to it
       int shift = 0;
-      if (sm) {
-        const int sl_ = __ffs((int)sm) - 1;
-        shift = PGS_STAGE_F - __shfl_sync(FULL, ts, sl_);
-        if (lane >= sl_) ts += shift;
+      {
+        const bool st0 = slot_[0] == sidx && ts[0] < PGS_STAGE_F && ts[0] + size12_[0] > PGS_STAGE_F;
+        const unsigned sm0 = __ballot_sync(FULL, st0);
+        if (sm0) {
+          const int sl_ = __ffs((int)sm0) - 1;
+          shift = PGS_STAGE_F - __shfl_sync(FULL, ts[0], sl_);
+          if (lane >= sl_) ts[0] += shift;
+          ts[1] += shift;
+        } else if (nh > 1) {
+          const bool st1 = slot_[1] == sidx && ts[1] < PGS_STAGE_F && ts[1] + size12_[1] > PGS_STAGE_F;
+          const unsigned sm1 = __ballot_sync(FULL, st1);
+          if (sm1) {
+            const int sl_ = __ffs((int)sm1) - 1;
+            shift = PGS_STAGE_F - __shfl_sync(FULL, ts[1], sl_);
+            if (lane >= sl_) ts[1] += shift;
+          }
+        }
       }
-      const unsigned later = mask & ~((2u << lane) - 1u);          // lanes of this slot after me (lane 31: none)
-      const int nl = later ? __ffs((int)later) - 1 : lane;
-      const int tnext = __shfl_sync(FULL, ts, nl);
       const int tend = total + shift;
-      if (mine) {
-        t = ts; stride12 = later ? tnext - ts : size;
-        t_spin_mine = tend; spin_rank = __popc(smask & ((1u << lane) - 1u)); region_mine = region;
+      const int t_first1 = __shfl_sync(FULL, ts[1], mask[1] ? __ffs((int)mask[1]) - 1 : 0);    // first record of the second pass
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        if (h < nh) {
+          const unsigned later = mask[h] & ~((2u << lane) - 1u);        // lanes of this slot after me in my pass (lane 31: none)
+          const int nl = later ? __ffs((int)later) - 1 : lane;
+          const int tnext = __shfl_sync(FULL, ts[h], nl);
+          if (slot_[h] == sidx) {
+            t_[h] = ts[h];
+            stride_[h] = later ? tnext - ts[h] : ((h == 0 && mask[1]) ? t_first1 - ts[h] : size12_[h]);
+            tspin_[h] = tend; region_[h] = region;
+            srank_[h] = (h ? __popc(smask[0]) : 0) + __popc(smask[h] & ((1u << lane) - 1u));
+          }
+        }
       }
-      ncs[sidx] = __popc(mask); nss[sidx] = __popc(smask); tsp[sidx] = tend; start[sidx] = region;
+      ncs[sidx] = __popc(mask[0]) + __popc(mask[1]); nss[sidx] = __popc(smask[0]) + __popc(smask[1]);
+      tsp[sidx] = tend; start[sidx] = region;
       region += tend + nss[sidx];
     }
     if (lane == 0) { W.dbg_p = Q_S12 + region; W.dbg_a = tEnd0; }
@@ -455,7 +511,20 @@ PRB_D void phase_rows_stream(const DevModel& M, WM& W, int lane, int e, int N, c
   // its unconditional arm-side arithmetic never meets stale NaNs of an env that used this slot before
   if (heavy && lane < CR_MAX_Q - CR_BASE_Q) R.q(tEnd0 + lane) = make_float4(0.f, 0.f, 0.f, 0.f);
   // ---- contact rows
-  if (lane < nc) {
+#pragma unroll 1
+  for (int h = 0; h < nh; h++) {
+    const int idx = h * 32 + lane;
+    if (idx >= nc) continue;
+    const Contact c = W.ct[idx];
+    const ContactSides cs = contact_sides(M, c);
+    const int colP = cs.colP, colS = cs.colS, kP = cs.kP, kS = cs.kS;
+    const bool swapped = cs.swapped, has_spin = cs.has_spin;
+    const float spin = cs.spin;
+    const bool s0 = (h ? slot_[1] : slot_[0]) == 0;
+    const bool armP = s0 && kP == K_ARM;
+    const int size0 = h ? size0_[1] : size0_[0], off0 = h ? off0_[1] : off0_[0];
+    const int t = h ? t_[1] : t_[0], stride12 = h ? stride_[1] : stride_[0], t_spin_mine = h ? tspin_[1] : tspin_[0];
+    const int spin_rank = h ? srank_[1] : srank_[0], region_mine = h ? region_[1] : region_[0];
     const int ca = c.cols & 0xff, cb = (c.cols >> 8) & 0xff;
     v3 n = V3(c.nx, c.ny, c.nz), pb = V3(c.pbx, c.pby, c.pbz), pa = pb + n * c.dist;
     const v3 pP = swapped ? pb : pa, pS = swapped ? pa : pb;

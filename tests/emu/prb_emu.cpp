@@ -94,6 +94,16 @@ float* emu_sbuf() { return g_sbuf.data(); }
 int emu_sbuf_q() { return SB_Q; }
 void emu_class_counts(long long* out, int clear) { for (int k = 0; k < ARM_NCLASS; k++) { out[k] = g_class_count[k]; if (clear) g_class_count[k] = 0; } }
 int emu_arm_nclass() { return ARM_NCLASS; }
+// narrow-phase candidates (before manifold reduction) left in the scratch of warp `w` of the last launched block
+int emu_last_candidates(int w, int n, float* out) {
+  const SetupMemT<SetupCfg>& W = ((const SetupMemT<SetupCfg>*)g_emu_smem2)[w];
+  for (int i = 0; i < n; i++) {
+    const Contact& c = W.cand[i];
+    float* o = out + 9 * i;
+    o[0] = c.pbx; o[1] = c.pby; o[2] = c.pbz; o[3] = c.nx; o[4] = c.ny; o[5] = c.nz; o[6] = c.dist; o[7] = (float)(c.cols & 0xff); o[8] = (float)((c.cols >> 8) & 0xff);
+  }
+  return n;
+}
 // contacts the setup kernel generated for the env of warp `w` of the last launched block: {pb, n, dist, ca, cb} each (tests)
 int emu_last_contacts(int w, float* out) {
   const SetupMemT<SetupCfg>& W = ((const SetupMemT<SetupCfg>*)g_emu_smem2)[w];

@@ -296,3 +296,26 @@ def test_emu_reset_from_observation(env_id):
         assert np.abs(de['obs_quat'][0][15:19] - obs[15:19]).max() < 1e-5              # drawer, door, button, dial restored
         d_ref = sim.reset_to(np.stack([obs, obs]), mask=np.array([1, 0], np.uint8), restore_env=False)
         assert np.abs(d_ref['obs_quat'][0][16:19] - [0, 0, 0]).max() < 1e-6           # reference behaviour: defaults
+
+
+def test_emu_more_than_32_contacts():
+    """13 states with 33-45 contacts after manifold reduction (found by oracle rollouts with 25 % random jumps: the arm rammed
+    into the drawer and the cabinet; tests/golden/many_contacts.npz holds the INPUT states and actions only).  The row writer
+    gives a lane two contacts there and the largest arm islands are read partly in place: no contact may be dropped and
+    the step must match the oracle like any other (one of the states is ill-conditioned and covered by the ulp rule)."""
+    import os
+    from helpers import compare_step, oracle_step_from, OBS_KEYS
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'many_contacts.npz'))
+    m = load_model('UR5PlayAbsRPY1Obj-v0')
+    n = len(g['state'])
+    assert n >= 10 and g['nc'].min() > 32
+    sim = EmuSim(m, n, seed=1)
+    sd = Oracle(m).state_dim
+    sim.state[:, :sd] = g['state']
+    ov0 = sim.L.emu_overflow()
+    de = sim.step(g['action'])
+    assert sim.L.emu_overflow() == ov0                                   # nothing dropped
+    outs = [oracle_step_from(m, g['state'][i], g['action'][i], Oracle)[0] for i in range(n)]
+    res = compare_step(m, {k: de[k] for k in OBS_KEYS}, de['reward'][:, 0], {'is_success': de['is_success'][:, 0]}, outs,
+                       g['state'], g['action'], Oracle)
+    assert res['bad_pose'] == 0 and res['bad_vel'] == 0 and res['bad_reward'] == 0 and res['stiff'] <= 2, res
