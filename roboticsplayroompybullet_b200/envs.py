@@ -81,11 +81,14 @@ class VecPlayEnv:
         self._h_action = torch.empty((N, self.action_dim), dtype=torch.float32).pin_memory()
         self._h_out = torch.empty((self.out_floats,), dtype=torch.float32).pin_memory()
         self._h_views = {}
+        self._h_slices = {}
         off = 0
         for k in OUT_KEYS:
             n = N * self.dims[k]
             self._h_views[k] = self._h_out[off:off + n].view(N, self.dims[k]).numpy()
+            self._h_slices[k] = (off, off + n)
             off += n
+        self._h_out_np = self._h_out.numpy()
         # gym-like metadata (environments.py:84,108-117)
         self._max_episode_steps = None if m['play'] else 250
         high = np.array([m.param('action_high_xyz')] * (self.action_dim - 1) + [m.param('action_high_grip')], np.float32)   # :88-112
@@ -102,8 +105,15 @@ class VecPlayEnv:
     def _obs_dev(self):
         return {k: self.dev[k] for k in OBS_KEYS}
 
-    def _obs_host(self):
-        d = {k: self._h_views[k].copy() for k in OBS_KEYS}
+    def _host_copy(self):
+        """Fresh arrays for the caller (the reference returns copies, environments.py:850-855): ONE copy of the pinned result
+        block, the per-key arrays are views of it."""
+        buf = self._h_out_np.copy()
+        return {k: buf[a:b].reshape(self.num_envs, self.dims[k]) for k, (a, b) in self._h_slices.items()}
+
+    def _obs_host(self, c=None):
+        c = c if c is not None else self._host_copy()
+        d = {k: c[k] for k in OBS_KEYS}
         d['gripper_proprioception'] = d['gripper_proprioception'][:, 0].astype(np.int64)
         d['img'] = None                                  # environments.py:844-845
         return d
@@ -177,11 +187,11 @@ class VecPlayEnv:
         self._h_action.numpy()[...] = a
         _lib.check(self.L, self._h, self.L.prb_step_host(self._h, ctypes.c_void_p(self._h_action.data_ptr()),
                                                         ctypes.c_void_p(self._h_out.data_ptr()), self._stream()))
-        r = self._h_views['reward'][:, 0].copy()
-        info = {'is_success': self._h_views['is_success'][:, 0].astype(np.int64),
-                'target_poses': self._h_views['target_poses'].copy()}
+        c = self._host_copy()
+        r = c['reward'][:, 0]
+        info = {'is_success': c['is_success'][:, 0].astype(np.int64), 'target_poses': c['target_poses']}
         done = np.zeros(self.num_envs, dtype=bool)       # environments.py:212: always False
-        return self._obs_host(), r, done, info
+        return self._obs_host(c), r, done, info
 
     def reset_goal_pos(self, goal):
         t = self.torch
