@@ -600,20 +600,22 @@ typedef struct { int ca, cb; v3 pa, pb, n; real dist; } Contact;
  * (btPersistentManifold, MANIFOLD_CACHE_SIZE 4) and, when a 5th arrives, keeps the deepest and the
  * three that span the largest area (sortCachedPoints).  Restated here as a batch reduction over
  * the candidates of one object pair: deepest, farthest from it, largest triangle, largest gain. */
+#define MTIE 2e-6   /* ties: within 2 um (depth, distance, height over the longest edge) the first candidate wins; same rule as the kernels */
 static int reduce_manifold(const Contact* c, int n, int* keep) {
   if (n <= 4) { for (int i = 0; i < n; i++) keep[i] = i; return n; }
   int i0 = 0;
-  for (int i = 1; i < n; i++) if (c[i].dist < c[i0].dist - 1e-7) i0 = i;   /* ties: the first candidate wins (same rule as the kernels) */
+  for (int i = 1; i < n; i++) if (c[i].dist < c[i0].dist - MTIE) i0 = i;   /* ties: the first candidate wins (same rule as the kernels) */
   int i1 = -1; real best = -1;
-  for (int i = 0; i < n; i++) if (i != i0) { v3 d = vsub(c[i].pb, c[i0].pb); real v = vdot(d, d); if (v > best * 1.0001 + 1e-12) { best = v; i1 = i; } }
+  for (int i = 0; i < n; i++) if (i != i0) { v3 d = vsub(c[i].pb, c[i0].pb); real v = vnorm(d); if (v > best + MTIE) { best = v; i1 = i; } }
   int i2 = -1; best = -1;
   v3 e01 = vsub(c[i1].pb, c[i0].pb);
-  for (int i = 0; i < n; i++) if (i != i0 && i != i1) { v3 x = vcross(vsub(c[i].pb, c[i0].pb), e01); real v = vdot(x, x); if (v > best * 1.0001 + 1e-14) { best = v; i2 = i; } }
+  const real atol = vnorm(e01) * MTIE;
+  for (int i = 0; i < n; i++) if (i != i0 && i != i1) { v3 x = vcross(vsub(c[i].pb, c[i0].pb), e01); real v = vnorm(x); if (v > best + atol) { best = v; i2 = i; } }
   int i3 = -1; best = -1;
   for (int i = 0; i < n; i++) if (i != i0 && i != i1 && i != i2) {
     v3 a = vsub(c[i].pb, c[i0].pb), b = vsub(c[i].pb, c[i1].pb), d = vsub(c[i].pb, c[i2].pb);
     real v = vnorm(vcross(a, b)) + vnorm(vcross(b, d)) + vnorm(vcross(d, a));
-    if (v > best * 1.0001 + 1e-7) { best = v; i3 = i; }
+    if (v > best + 4 * atol) { best = v; i3 = i; }
   }
   int sel[4] = {i0, i1, i2, i3}, m = 0;
   for (int i = 0; i < n; i++) if (i == sel[0] || i == sel[1] || i == sel[2] || i == sel[3]) keep[m++] = i;

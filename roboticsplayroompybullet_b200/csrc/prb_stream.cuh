@@ -151,8 +151,8 @@ PRB_HD size_t sbuf_bytes(int64_t N) { return ((size_t)((N + 31) / 32) * 32 * SB_
 struct SetupCfg {
   static constexpr int MAXJROW = SB_MAXJROW;
   static constexpr int MAXCONTACT = SB_MAXCONTACT;
-  static constexpr int MAXOVL = 32;
-  static constexpr int MAXCAND = 128;
+  static constexpr int MAXOVL = 64;       // overlapping collider pairs into the narrow phase (two per lane beyond 32)
+  static constexpr int MAXCAND = 128;     // narrow-phase candidates before manifold reduction (pairs yield 0-4 points each)
 #ifndef PRB_SETUP_WPB
 #define PRB_SETUP_WPB 8       // measured r2c at 65536 envs: 4 warps 35.6 ms of setup per env step, 8 warps 29.9 ms, 16 warps 31.2 ms
 #endif

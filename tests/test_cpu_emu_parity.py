@@ -299,10 +299,13 @@ def test_emu_reset_from_observation(env_id):
 
 
 def test_emu_more_than_32_contacts():
-    """13 states with 33-45 contacts after manifold reduction (found by oracle rollouts with 25 % random jumps: the arm rammed
-    into the drawer and the cabinet; tests/golden/many_contacts.npz holds the INPUT states and actions only).  The row writer
-    gives a lane two contacts there and the largest arm islands are read partly in place: no contact may be dropped and
-    the step must match the oracle like any other (one of the states is ill-conditioned and covered by the ulp rule)."""
+    """17 states with 33-45 contacts after manifold reduction, four of them with more than 32 overlapping collider pairs in the
+    broad phase (found by oracle rollouts with 25 % random jumps: the arm rammed into the drawer and the cabinet;
+    tests/golden/many_contacts.npz holds the INPUT states and actions only).  The narrow phase and the row writer give a
+    lane two pairs / two contacts there and the largest arm islands are read partly in place: no pair or contact may be
+    dropped and the step must match the oracle like any other (one of the states is ill-conditioned and covered by the
+    ulp rule; another one has a four-way tie in the manifold reduction between coincident candidates of two collider pairs,
+    which only the absolute 2 um tie rule resolves the same way in fp32 and fp64)."""
     import os
     from helpers import compare_step, oracle_step_from, OBS_KEYS
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'many_contacts.npz'))

@@ -19,14 +19,18 @@ from emu_lib import EmuSim  # noqa: E402
 
 m = load_model('UR5PlayAbsRPY1Obj-v0')
 d = np.load(sys.argv[2])
-n = 48
-# spread over the island sizes: sort by the q count of the env's record stream and take every k-th
-order = np.argsort(d['usage'][:, 2])
-sel = order[np.linspace(0, len(order) - 1, n).astype(int)]
+if 'usage' in d.files:
+    n = 48
+    # spread over the island sizes: sort by the q count of the env's record stream and take every k-th
+    order = np.argsort(d['usage'][:, 2])
+    sel = order[np.linspace(0, len(order) - 1, n).astype(int)]
+else:                      # an earlier fixture: keep its input states, regenerate the outputs (after a tie-rule change)
+    n = len(d['state'])
+    sel = np.arange(n)
 sim = EmuSim(m, n, seed=1)
 sd = Oracle(m).state_dim
 sim.state[:, :sd] = d['state'][sel]
 out = sim.step(d['action'][sel])
 np.savez_compressed(sys.argv[3], state=d['state'][sel], action=d['action'][sel], state_after=sim.state[:, :sd].copy(),
                     obs_quat=out['obs_quat'], reward=out['reward'])
-print('wrote', sys.argv[3], 'envs', n, 'stream q range', d['usage'][sel, 2].min(), d['usage'][sel, 2].max())
+print('wrote', sys.argv[3], 'envs', n)
