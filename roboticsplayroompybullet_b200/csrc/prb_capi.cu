@@ -9,6 +9,7 @@
 #include "prb_convert.h"
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "prb_reset.cuh"
 
 struct prb_handle {
@@ -29,6 +30,9 @@ struct prb_handle {
   int* heavy_cnt = nullptr;        // {bundle-list length, -, work counter, -} per class
   // high-priority side streams: the size classes of the arm-island solver overlap each other and the joint / free-body solvers
   cudaStream_t side[ARM_NCLASS] = {};
+  cudaStream_t side_free = nullptr;   // the free-body islands' kernel (independent of the arm's island)
+  cudaEvent_t ev_join_free = nullptr;
+  int free_side = 0;                  // 1: free-body kernel on its own stream, beside the joint-row kernel
   cudaEvent_t ev_fork = nullptr, ev_join[ARM_NCLASS] = {};
   int dims[12] = {};
   int smem = 0, regs = 0;          // setup kernel (reported)
@@ -38,6 +42,7 @@ struct prb_handle {
   unsigned char* pending = nullptr;
   int* reset_ctl = nullptr;
   int* n_pending = nullptr;        // device counter
+  int* elist[2] = {nullptr, nullptr};   // pending envs of the previous / this reset round (compacted, unordered)
   int* n_pending_host = nullptr;   // pinned
   int reset_rounds = 0;            // rounds of the most recent prb_reset
   int timing = 0;
@@ -74,7 +79,8 @@ struct DevGuard {
 // (integrate previous solution + build rows) and the thread-per-env solver launches; a final setup
 // launch integrates the last solution and writes the observation.  No host synchronisation.
 template <int ND>
-static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s, const unsigned char* active = nullptr) {
+static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s, const unsigned char* active = nullptr,
+                       const int* elist = nullptr, int n_list = 0) {
   if (h->fused && active == nullptr) {
     dim3 gl((h->N + CfgL::WPB - 1) / CfgL::WPB), bl(32 * CfgL::WPB);
     prb_step_kernel<ND, CfgL><<<gl, bl, h->smem_fused, s>>>(h->dm, h->state, h->O, nullptr, nullptr, nullptr, nullptr, h->N, nsub, observe);
@@ -84,16 +90,17 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s, con
   }
   h->n_evk = 0;
   const int N = h->N;
-  dim3 gs((N + SetupCfg::WPB - 1) / SetupCfg::WPB), bs(32 * SetupCfg::WPB);
+  const int n = elist != nullptr ? n_list : N;                  // work items: the listed envs (later reset rounds) or all of them
+  dim3 gs((n + SetupCfg::WPB - 1) / SetupCfg::WPB), bs(32 * SetupCfg::WPB);
   // persistent solver blocks: resident blocks per SM (shared-memory limited) x SMs
-  const int ng = (N + PGS_BLOCK - 1) / PGS_BLOCK;
+  const int ng = (n + PGS_BLOCK - 1) / PGS_BLOCK;
   const int pj = 6 * h->sms, pf = 3 * h->sms;
   dim3 gp(ng < pj ? ng : pj), gf(ng < pf ? ng : pf, h->hm.n_free), bp(PGS_BLOCK);
   int gcls[ARM_NCLASS], smcls[ARM_NCLASS];
   for (int k = 0; k < ARM_NCLASS; k++) {
     smcls[k] = PGS_SMEM_ARM(k);
     const int per_sm = (227 * 1024) / (smcls[k] + 1024);
-    const int want = (N + arm_lanes(k) - 1) / arm_lanes(k);       // bundles if every env were in this class
+    const int want = (n + arm_lanes(k) - 1) / arm_lanes(k);       // bundles if every env were in this class
     gcls[k] = (per_sm > 0 ? per_sm : 1) * h->sms;
     if (gcls[k] > want) gcls[k] = want;
   }
@@ -103,7 +110,7 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s, con
     if (flags == 0) break;
     if (timed && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
     if (i < nsub) CK(h, cudaMemsetAsync(h->heavy_cnt, 0, 4 * ARM_NCLASS * sizeof(int), s));
-    prb_setup_kernel<ND><<<gs, bs, h->smem, s>>>(h->dm, h->state, h->sbuf, h->O, N, flags, h->hbuf, h->heavy_cnt, active);
+    prb_setup_kernel<ND><<<gs, bs, h->smem, s>>>(h->dm, h->state, h->sbuf, h->O, N, flags, h->hbuf, h->heavy_cnt, active, elist, n_list);
     h->launches++;
     if (i < nsub) {
       if (timed && h->n_evk < 62) CK(h, cudaEventRecord(h->evk[h->n_evk++], s));
@@ -120,8 +127,17 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s, con
           prb_pgs_arm_kernel<ND, false><<<gcls[k], 32, smcls[k], h->side[k]>>>(h->dm, h->sbuf, hc, h->heavy_cnt + 4 * k, arm_lanes(k), arm_capq(k), arm_bufq(k));
         CK(h, cudaEventRecord(h->ev_join[k], h->side[k]));
       }
-      prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, s>>>(h->dm, h->sbuf, N, active);
-      if (h->hm.n_free > 0) prb_pgs_free_kernel<<<gf, bp, PGS_SMEM_F, s>>>(h->dm, h->sbuf, N, active);
+      prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, s>>>(h->dm, h->sbuf, N, active, elist, n_list);
+      if (h->hm.n_free > 0) {
+        if (h->free_side) {
+          CK(h, cudaStreamWaitEvent(h->side_free, h->ev_fork, 0));
+          prb_pgs_free_kernel<<<gf, bp, PGS_SMEM_F, h->side_free>>>(h->dm, h->sbuf, N, active, elist, n_list);
+          CK(h, cudaEventRecord(h->ev_join_free, h->side_free));
+          CK(h, cudaStreamWaitEvent(s, h->ev_join_free, 0));
+        } else {
+          prb_pgs_free_kernel<<<gf, bp, PGS_SMEM_F, s>>>(h->dm, h->sbuf, N, active, elist, n_list);
+        }
+      }
       for (int k = 0; k < ARM_NCLASS; k++) CK(h, cudaStreamWaitEvent(s, h->ev_join[k], 0));
       h->launches += (h->hm.n_free > 0 ? 2 : 1) + ARM_NCLASS;
     }
@@ -168,19 +184,37 @@ static int reset_rounds(prb_handle* h, const uint8_t* mask_dev, cudaStream_t s) 
   const int max_rounds = RESET_MAX_ATTEMPTS * RESET_MAX_TRIES;
   dim3 gf((N + SetupCfg::WPB - 1) / SetupCfg::WPB), bf(32 * SetupCfg::WPB);
   h->reset_rounds = 0;
+  const bool trace = getenv("PRB_TRACE_RESET") != nullptr;      // per-round wall time and pending count on stderr
   for (int round = 0; round < max_rounds; round++) {
-    prb_reset_place_kernel<<<(N + 127) / 128, 128, 0, s>>>(h->dm, h->state, h->reset_ctl, mask_dev, h->pending, N, h->seed, h->env_offset, round == 0);
+    struct timespec t0, t1;
+    if (trace) clock_gettime(CLOCK_MONOTONIC, &t0);
+    // a masked reset compacts the masked envs into a list first (one more 4-byte read): its rounds cost what those envs cost
+    const bool list0 = round == 0 && mask_dev != nullptr;
+    if (list0) CK(h, cudaMemsetAsync(h->n_pending, 0, sizeof(int), s));
+    prb_reset_place_kernel<<<(N + 127) / 128, 128, 0, s>>>(h->dm, h->state, h->reset_ctl, mask_dev, h->pending, N, h->seed, h->env_offset, round == 0,
+                                                          list0 ? h->elist[1] : nullptr, list0 ? h->n_pending : nullptr);
     h->launches++;
     CK(h, cudaGetLastError());
-    int rc = launch_step<ND>(h, h->hm.settle_steps, 0, s, h->pending);
+    if (list0) {
+      CK(h, cudaMemcpyAsync(h->n_pending_host, h->n_pending, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(h, cudaStreamSynchronize(s));
+      if (*h->n_pending_host == 0) { h->reset_rounds = 0; return PRB_OK; }       // empty mask
+    }
+    // round 0 steps the masked batch; later rounds step the list of pending envs the previous round's finish kernel wrote
+    int rc = (round == 0 && !list0) ? launch_step<ND>(h, h->hm.settle_steps, 0, s, h->pending)
+                                    : launch_step<ND>(h, h->hm.settle_steps, 0, s, nullptr, h->elist[(round - 1) & 1], *h->n_pending_host);
     if (rc != PRB_OK) return rc;
     CK(h, cudaMemsetAsync(h->n_pending, 0, sizeof(int), s));
-    prb_reset_finish_kernel<ND><<<gf, bf, h->smem, s>>>(h->dm, h->state, h->O, h->reset_ctl, h->pending, h->n_pending, N, h->seed, h->env_offset);
+    prb_reset_finish_kernel<ND><<<gf, bf, h->smem, s>>>(h->dm, h->state, h->O, h->reset_ctl, h->pending, h->n_pending, N, h->seed, h->env_offset, h->elist[round & 1]);
     h->launches++;
     CK(h, cudaGetLastError());
     CK(h, cudaMemcpyAsync(h->n_pending_host, h->n_pending, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(h, cudaStreamSynchronize(s));
     h->reset_rounds = round + 1;
+    if (trace) {
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      fprintf(stderr, "[prb_reset] round %d: %.1f ms, %d envs still pending\n", round, 1e3 * (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_nsec - t0.tv_nsec), *h->n_pending_host);
+    }
     if (*h->n_pending_host == 0) break;
   }
   return PRB_OK;
@@ -231,6 +265,7 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
   CK(h, cudaMalloc(&h->reset_ctl, sizeof(int) * 2 * N));
   CK(h, cudaMemset(h->reset_ctl, 0, sizeof(int) * 2 * N));
   CK(h, cudaMalloc(&h->n_pending, sizeof(int)));
+  for (int k = 0; k < 2; k++) CK(h, cudaMalloc(&h->elist[k], sizeof(int) * N));
   CK(h, cudaMallocHost(&h->n_pending_host, sizeof(int)));
   float** slots[12] = {&h->O.obs_quat, &h->O.achieved_goal, &h->O.desired_goal, &h->O.cag, &h->O.fps, &h->O.joints,
                        &h->O.velocity, &h->O.observation, &h->O.proprio, &h->O.reward, &h->O.success, &h->O.target_poses};
@@ -251,6 +286,9 @@ int prb_create(const prb_model* model, const prb_config* cfg, prb_handle** out) 
     int lo_pri = 0, hi_pri = 0;
     CK(h, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
     CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(h, cudaStreamCreateWithFlags(&h->side_free, cudaStreamNonBlocking));
+    CK(h, cudaEventCreateWithFlags(&h->ev_join_free, cudaEventDisableTiming));
+    { const char* v = getenv("PRB_FREE_SIDE"); h->free_side = v ? atoi(v) : 1; }
     for (int k = 0; k < ARM_NCLASS; k++) {
       CK(h, cudaStreamCreateWithPriority(&h->side[k], cudaStreamNonBlocking, hi_pri));
       CK(h, cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
@@ -273,13 +311,15 @@ int prb_destroy(prb_handle* h) {
   DevGuard guard(h->device);
   cudaDeviceSynchronize();
   cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->sbuf);
-  cudaFree(h->O.ovf_env); cudaFree(h->pending); cudaFree(h->reset_ctl); cudaFree(h->n_pending);
+  cudaFree(h->O.ovf_env); cudaFree(h->pending); cudaFree(h->reset_ctl); cudaFree(h->n_pending); cudaFree(h->elist[0]); cudaFree(h->elist[1]);
   if (h->n_pending_host) cudaFreeHost(h->n_pending_host);
   for (int k = 0; k < ARM_NCLASS; k++) {
     if (h->side[k]) cudaStreamDestroy(h->side[k]);
     if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->side_free) cudaStreamDestroy(h->side_free);
+  if (h->ev_join_free) cudaEventDestroy(h->ev_join_free);
   cudaFree(h->hbuf); cudaFree(h->heavy_cnt);
   for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->ev[0]) for (int i = 0; i < 64; i++) cudaEventDestroy(h->evk[i]);

@@ -11,8 +11,10 @@
 //   prb_reset_finish_kernel   warp per env: bounds check -> another try, else arm reset, goal, observation,
 //                             reward -> another attempt while the state is already a success; counts the envs
 //                             that stay pending
-// The host reads that one counter after each round (reset is a synchronous call in the reference too); the
-// typical reset needs one round for ~85 % of the envs and 5-7 shrinking rounds for the rest.
+// The host reads that one counter after each round (reset is a synchronous call in the reference too); a full-batch
+// reset of the play world needs one round for ~69 % of the envs and 8-9 shrinking rounds for the rest.  The finish
+// kernel also writes the list of the envs that stay pending: the next round's step pipeline runs over that list
+// (env_of() in prb_stream.cuh), so a round costs what its envs cost, not what the whole batch costs.
 // Sampling is counter-based: (seed, global env id, attempt, draw), attempt = the env's lifetime reset counter,
 // so results do not depend on sharding or on which envs are reset together.
 #pragma once
@@ -24,7 +26,8 @@
 // ctl[2 e] = attempts made in this call | try index << 8;  ctl[2 e + 1] = RNG attempt id of the current attempt
 __global__ void prb_reset_place_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state, int* __restrict__ ctl,
                                        const unsigned char* __restrict__ mask, unsigned char* __restrict__ pending, int N,
-                                       unsigned long long seed, unsigned env_offset, int first) {
+                                       unsigned long long seed, unsigned env_offset, int first,
+                                       int* __restrict__ list_out = nullptr, int* __restrict__ n_list = nullptr) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
   const DevModel& M = *Mp;
@@ -33,6 +36,7 @@ __global__ void prb_reset_place_kernel(const DevModel* __restrict__ Mp, float* _
     ctl[2 * e] = 0;
   }
   if (!pending[e]) return;
+  if (list_out != nullptr) list_out[atomicAdd(n_list, 1)] = e;      // masked reset: the first round runs over a list too
   float* st = state + (size_t)e * M.state_stride;
   const int nd = M.nd;
   const int o_free = 5 * nd, o_slide = o_free + 13 * M.n_free, o_cnt = o_slide + 2 * M.n_slide + M.goal_dim + 8 + 1;
@@ -63,7 +67,7 @@ template <int ND>
 __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_reset_finish_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state, DevOut O,
                                                                                 int* __restrict__ ctl, unsigned char* __restrict__ pending,
                                                                                 int* __restrict__ n_pending, int N, unsigned long long seed,
-                                                                                unsigned env_offset) {
+                                                                                unsigned env_offset, int* __restrict__ list_out = nullptr) {
   typedef SetupMemT<SetupCfg> WM;
   PRB_SMEM_DECL2;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_reset_finish_kernel(co
   bool oob = false;
   if (M.n_free > 0) for (int k = 0; k < 3; k++) if (W.fpos[0][k] > M.env_hi[k]) oob = true;
   if (oob && t + 1 < RESET_MAX_TRIES) {           // uniform: every lane reads the same shared values
-    if (lane == 0) { ctl[2 * e] = made | ((t + 1) << 8); atomicAdd(n_pending, 1); }
+    if (lane == 0) { ctl[2 * e] = made | ((t + 1) << 8); const int idx = atomicAdd(n_pending, 1); if (list_out) list_out[idx] = e; }
     return;                                       // stays pending: the next round re-seats the objects (draw t + 1)
   }
   float u[4];
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_reset_finish_kernel(co
   __syncwarp();
   store_state(M, W, st, lane);
   if (lane == 0) {
-    if (r > -1.f && made + 1 < RESET_MAX_ATTEMPTS) { ctl[2 * e] = made + 1; atomicAdd(n_pending, 1); }   // already a success: again
+    if (r > -1.f && made + 1 < RESET_MAX_ATTEMPTS) { ctl[2 * e] = made + 1; const int idx = atomicAdd(n_pending, 1); if (list_out) list_out[idx] = e; }   // already a success: again
     else pending[e] = 0;
   }
 }

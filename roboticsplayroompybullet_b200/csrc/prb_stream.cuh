@@ -626,17 +626,29 @@ static char g_emu_smem2[8 * sizeof(SetupMemT<SetupCfg>) + 256];
 #define PRB_SMEM_DECL2 extern __shared__ __align__(16) unsigned char prb_dyn_smem2[]; WM* wm = (WM*)prb_dyn_smem2
 #endif
 
+// Env of work item i.  Normally the identity over [0, N), optionally masked (`active`); the later rounds of a reset
+// pass a compacted list of the envs still pending (`elist`, n_list entries) so that their cost follows the count.
+PRB_D int env_of(int i, int N, const unsigned char* active, const int* elist, int n_list, bool* on) {
+  if (elist != nullptr) { *on = i < n_list; return *on ? elist[i] : 0; }
+  *on = i < N && (active == nullptr || active[i] != 0);
+  return i;
+}
+
+#ifndef PRB_SETUP_MINB
+#define PRB_SETUP_MINB 2       // 2 x 8 warps per SM = 128 registers per thread; measured r2l: 1 block (natural register count) 43.9 ms of setup per env step, 2 x 10 warps at 96 registers (spills) 40.2 ms, this 31.8 ms
+#endif
 template <int ND>
-__global__ void __launch_bounds__(32 * SetupCfg::WPB) prb_setup_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
+__global__ void __launch_bounds__(32 * SetupCfg::WPB, PRB_SETUP_MINB) prb_setup_kernel(const DevModel* __restrict__ Mp, float* __restrict__ state,
                                                                          float* __restrict__ sbuf, DevOut O, int N, int flags,
                                                                          float4* __restrict__ hbuf, int* __restrict__ heavy_cnt,
-                                                                         const unsigned char* __restrict__ active) {
+                                                                         const unsigned char* __restrict__ active,
+                                                                         const int* __restrict__ elist = nullptr, int n_list = 0) {
   typedef SetupMemT<SetupCfg> WM;
   PRB_SMEM_DECL2;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int e = blockIdx.x * SetupCfg::WPB + wib;
-  // masked stepping (reset: only the envs being reset settle); an idle warp still takes part in the block barriers
-  const bool on = e < N && (active == nullptr || active[e] != 0);
+  // masked / listed stepping (reset: only the envs being reset settle); an idle warp still takes part in the block barriers
+  bool on;
+  const int e = env_of(blockIdx.x * SetupCfg::WPB + wib, N, active, elist, n_list, &on);
 #if !PRB_SETUP_SYNC
   if (!on) return;
 #endif
@@ -912,16 +924,17 @@ PRB_D void island_store(const DevModel& M, const IslandV& V, float* sbuf, int e,
 // ---- slot 0 of the light envs: joint rows only
 template <int ND>
 __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_joint_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N,
-                                                                 const unsigned char* __restrict__ active) {
+                                                                 const unsigned char* __restrict__ active,
+                                                                 const int* __restrict__ elist = nullptr, int n_list = 0) {
   PRB_PGS_SMEM_DECL;
   const int lane = threadIdx.x;
   const DevModel& M = *Mp;
   // persistent blocks: a block walks groups of 32 envs (launching one block per group costs more than
   // the solve: each block launch allocates its shared memory); warp-uniform control flow, per-lane predicates
-  const int ngroups = (N + PGS_BLOCK - 1) / PGS_BLOCK;
+  const int ngroups = ((elist != nullptr ? n_list : N) + PGS_BLOCK - 1) / PGS_BLOCK;
   for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-    const int e = g * PGS_BLOCK + lane;
-    bool valid = e < N && (active == nullptr || active[e] != 0);
+    bool valid;
+    const int e = env_of(g * PGS_BLOCK + lane, N, active, elist, n_list, &valid);
     float4* G = stream_col(sbuf, valid ? e : 0);
     const int h0 = valid ? __float_as_int(G[Q_HDR * 32].x) : 0;
     if ((h0 >> 25) & 7) valid = false;                     // heavy: prb_pgs_arm_kernel solves it from its class buffer
@@ -1107,15 +1120,16 @@ PRB_D void free_sweeps(BV& V, float4* sl, float4* Gr, bool live, int nc, int ns,
 }
 
 __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, int N,
-                                                                const unsigned char* __restrict__ active) {
+                                                                const unsigned char* __restrict__ active,
+                                                                const int* __restrict__ elist = nullptr, int n_list = 0) {
   PRB_PGS_SMEM_DECL;
   const int lane = threadIdx.x;
   const int slot = blockIdx.y + 1;
   const DevModel& M = *Mp;
-  const int ngroups = (N + PGS_BLOCK - 1) / PGS_BLOCK;
+  const int ngroups = ((elist != nullptr ? n_list : N) + PGS_BLOCK - 1) / PGS_BLOCK;
   for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {     // persistent blocks, warp-uniform control flow
-    const int e = g * PGS_BLOCK + lane;
-    bool valid = e < N && (active == nullptr || active[e] != 0);
+    bool valid;
+    const int e = env_of(g * PGS_BLOCK + lane, N, active, elist, n_list, &valid);
     float4* G = stream_col(sbuf, valid ? e : 0);
     const float4 h1 = G[(Q_HDR + 1) * 32], hs = G[(Q_HDR + slot) * 32];
     const int info = __float_as_int(h1.x);

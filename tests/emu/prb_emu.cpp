@@ -11,8 +11,9 @@ static std::vector<float4> g_hbuf;
 static long long g_class_count[ARM_NCLASS] = {0};     // envs solved per arm-island class since the last query
 static int g_fused = 0;     // 1: run the fused warp-per-env kernel instead of the split pipeline
 template <int ND>
-static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe, const unsigned char* active = nullptr) {
-  if (g_fused && active == nullptr) {
+static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe, const unsigned char* active = nullptr,
+                        const int* elist = nullptr, int n_list = 0) {
+  if (g_fused && active == nullptr && elist == nullptr) {
     emu_dim3 g, b; b.x = 32 * CfgL::WPB; g.x = (N + CfgL::WPB - 1) / CfgL::WPB;
     emu::launch(g, b, [&]() { prb_step_kernel<ND, CfgL>(&g_M, state, O, nullptr, nullptr, nullptr, nullptr, N, nsub, observe); });
     return;
@@ -21,18 +22,19 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe, co
   g_hbuf.assign(hbuf_bytes(N) / sizeof(float4), make_float4(0.f, 0.f, 0.f, 0.f));
   int heavy_cnt[4 * ARM_NCLASS] = {0};
   emu_dim3 gs, bs, gp, bp;
-  bs.x = 32 * SetupCfg::WPB; gs.x = (N + SetupCfg::WPB - 1) / SetupCfg::WPB;
-  bp.x = PGS_BLOCK; gp.x = (N + PGS_BLOCK - 1) / PGS_BLOCK;
+  const int n = elist != nullptr ? n_list : N;         // work items (prb_capi.cu launch_step)
+  bs.x = 32 * SetupCfg::WPB; gs.x = (n + SetupCfg::WPB - 1) / SetupCfg::WPB;
+  bp.x = PGS_BLOCK; gp.x = (n + PGS_BLOCK - 1) / PGS_BLOCK;
   for (int i = 0; i <= nsub; i++) {
     int flags = (i > 0 ? SETUP_INTEGRATE : 0) | (i < nsub ? SETUP_BUILD : 0) | ((i == nsub && observe) ? SETUP_OBSERVE : 0);
     if (flags == 0) break;
     memset(heavy_cnt, 0, sizeof(heavy_cnt));
-    emu::launch(gs, bs, [&]() { prb_setup_kernel<ND>(&g_M, state, g_sbuf.data(), O, N, flags, g_hbuf.data(), heavy_cnt, active); });
+    emu::launch(gs, bs, [&]() { prb_setup_kernel<ND>(&g_M, state, g_sbuf.data(), O, N, flags, g_hbuf.data(), heavy_cnt, active, elist, n_list); });
     if (i < nsub) {
-      emu::launch(gp, bp, [&]() { prb_pgs_joint_kernel<ND>(&g_M, g_sbuf.data(), N, active); });
+      emu::launch(gp, bp, [&]() { prb_pgs_joint_kernel<ND>(&g_M, g_sbuf.data(), N, active, elist, n_list); });
       for (int y = 0; y < g_M.n_free; y++) {
         emu_dim3 gy = gp;
-        emu::launch_y(gy, bp, y, [&]() { prb_pgs_free_kernel(&g_M, g_sbuf.data(), N, active); });
+        emu::launch_y(gy, bp, y, [&]() { prb_pgs_free_kernel(&g_M, g_sbuf.data(), N, active, elist, n_list); });
       }
       for (int k = 0; k < ARM_NCLASS; k++) {
         g_class_count[k] += heavy_cnt[4 * k];
@@ -56,18 +58,27 @@ static int g_reset_rounds = 0;
 template <int ND>
 static void emu_reset_nd(float* state, DevOut o, const unsigned char* mask, int N, unsigned long long seed, unsigned env_offset) {
   std::vector<unsigned char> pending(N, 0), ovf(N, 0);
-  std::vector<int> ctl(2 * N, 0);
+  std::vector<int> ctl(2 * N, 0), elist[2];
+  elist[0].assign(N, 0); elist[1].assign(N, 0);
+  int n_prev = 0;
   o.ovf_env = ovf.data();
   emu_dim3 gp, bp, gf, bf;
   bp.x = 128; gp.x = (N + 127) / 128;
   bf.x = 32 * SetupCfg::WPB; gf.x = (N + SetupCfg::WPB - 1) / SetupCfg::WPB;
   g_reset_rounds = 0;
   for (int round = 0; round < RESET_MAX_ATTEMPTS * RESET_MAX_TRIES; round++) {
-    emu::launch(gp, bp, [&]() { prb_reset_place_kernel(&g_M, state, ctl.data(), mask, pending.data(), N, seed, env_offset, round == 0); });
-    run_step_nd<ND>(state, o, N, g_M.settle_steps, 0, pending.data());
+    const bool list0 = round == 0 && mask != nullptr;
+    int n0 = 0;
+    emu::launch(gp, bp, [&]() { prb_reset_place_kernel(&g_M, state, ctl.data(), mask, pending.data(), N, seed, env_offset, round == 0,
+                                                       list0 ? elist[1].data() : nullptr, list0 ? &n0 : nullptr); });
+    if (list0) { n_prev = n0; if (n0 == 0) return; }
+    if (round == 0 && !list0) run_step_nd<ND>(state, o, N, g_M.settle_steps, 0, pending.data());
+    else run_step_nd<ND>(state, o, N, g_M.settle_steps, 0, nullptr, elist[(round - 1) & 1].data(), n_prev);
     int n_pending = 0;
-    emu::launch(gf, bf, [&]() { prb_reset_finish_kernel<ND>(&g_M, state, o, ctl.data(), pending.data(), &n_pending, N, seed, env_offset); });
+    int* lout = elist[round & 1].data();
+    emu::launch(gf, bf, [&]() { prb_reset_finish_kernel<ND>(&g_M, state, o, ctl.data(), pending.data(), &n_pending, N, seed, env_offset, lout); });
     g_reset_rounds = round + 1;
+    n_prev = n_pending;
     if (n_pending == 0) break;
   }
 }
