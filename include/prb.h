@@ -117,7 +117,11 @@ int prb_set_state(prb_handle* h, const float* host_in);
 
 /* Same as prb_step, but through HOST buffers: copies action_host [N,A] to the device, steps,
  * copies the whole output block (out_floats floats) back into out_host and synchronises the
- * stream.  This is the call the Python gym mirror makes for numpy in / numpy out stepping. */
+ * stream.  This is the call the Python gym mirror makes for numpy in / numpy out stepping.
+ * out_host may be pinned (one asynchronous copy) or ordinary pageable memory, e.g. the fresh array a
+ * gym step returns: then the block comes back through the handle's pinned staging in chunks that
+ * PRB_HOST_THREADS worker threads (default: 8 on hosts with >= 16 cores) copy out while the next chunk
+ * is still in flight. */
 int prb_step_host(prb_handle* h, const float* action_host, float* out_host, void* stream);
 
 /* Per-kernel device timing for reports: when enabled, prb_step brackets its two kernels with

@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <thread>
+#include <vector>
 #include "prb_reset.cuh"
 
 struct prb_handle {
@@ -21,6 +23,11 @@ struct prb_handle {
   float* state = nullptr;
   float* out = nullptr;
   float* action_stage = nullptr;   // device staging for prb_step_host
+  // prb_step_host into pageable memory: pinned staging block, read back in chunks that worker threads copy out as they land
+  float* out_stage = nullptr;
+  static constexpr int OUT_CHUNKS = 8;
+  cudaEvent_t ev_chunk[OUT_CHUNKS] = {};
+  int host_threads = 4;
   int64_t out_floats = 0;
   DevOut O;
   int64_t launches = 0;
@@ -313,6 +320,7 @@ int prb_destroy(prb_handle* h) {
   cudaFree(h->dm); cudaFree(h->state); cudaFree(h->out); cudaFree(h->action_stage); cudaFree(h->O.overflow); cudaFree(h->O.dbg); cudaFree(h->sbuf);
   cudaFree(h->O.ovf_env); cudaFree(h->pending); cudaFree(h->reset_ctl); cudaFree(h->n_pending); cudaFree(h->elist[0]); cudaFree(h->elist[1]);
   if (h->n_pending_host) cudaFreeHost(h->n_pending_host);
+  if (h->out_stage) { cudaFreeHost(h->out_stage); for (int c = 0; c < prb_handle::OUT_CHUNKS; c++) cudaEventDestroy(h->ev_chunk[c]); }
   for (int k = 0; k < ARM_NCLASS; k++) {
     if (h->side[k]) cudaStreamDestroy(h->side[k]);
     if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
@@ -482,7 +490,51 @@ int prb_step_host(prb_handle* h, const float* action_host, float* out_host, void
   CK(h, cudaMemcpyAsync(h->action_stage, action_host, sizeof(float) * h->N * adim, cudaMemcpyHostToDevice, s));
   int rc = prb_step(h, h->action_stage, stream);
   if (rc != PRB_OK) return rc;
-  CK(h, cudaMemcpyAsync(out_host, h->out, sizeof(float) * h->out_floats, cudaMemcpyDeviceToHost, s));
+  cudaPointerAttributes at;
+  const bool pinned = cudaPointerGetAttributes(&at, out_host) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+  cudaGetLastError();                                  // an unregistered pointer may leave an error behind on older drivers
+  if (pinned) {
+    CK(h, cudaMemcpyAsync(out_host, h->out, sizeof(float) * h->out_floats, cudaMemcpyDeviceToHost, s));
+    CK(h, cudaStreamSynchronize(s));
+    return PRB_OK;
+  }
+  // Pageable destination (a fresh numpy array per step, as the reference returns): read the block back into pinned
+  // staging in chunks; worker threads copy chunk c out while chunk c + 1 is still on the bus.
+  if (!h->out_stage) {
+    CK(h, cudaMallocHost(&h->out_stage, sizeof(float) * h->out_floats));
+    for (int c = 0; c < prb_handle::OUT_CHUNKS; c++) CK(h, cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming));
+    const char* v = getenv("PRB_HOST_THREADS");
+    int hw = (int)std::thread::hardware_concurrency();
+    h->host_threads = v ? atoi(v) : (hw >= 16 ? 8 : (hw >= 8 ? 4 : (hw >= 2 ? 2 : 1)));
+    if (h->host_threads < 1) h->host_threads = 1;
+  }
+  const int NC = prb_handle::OUT_CHUNKS;
+  const int64_t per = ((h->out_floats + NC - 1) / NC + 1023) / 1024 * 1024;       // floats per chunk (4 KB multiples)
+  for (int c = 0; c < NC; c++) {
+    const int64_t a = c * per, b = a + per < h->out_floats ? a + per : h->out_floats;
+    if (a < b) CK(h, cudaMemcpyAsync(h->out_stage + a, h->out + a, sizeof(float) * (b - a), cudaMemcpyDeviceToHost, s));
+    CK(h, cudaEventRecord(h->ev_chunk[c], s));
+  }
+  const int T = h->host_threads < 16 ? h->host_threads : 16;
+  cudaError_t werr[16] = {};
+  auto worker = [&](int t) {
+    if (t > 0) cudaSetDevice(h->device);
+    for (int c = 0; c < NC; c++) {
+      cudaError_t e = cudaEventSynchronize(h->ev_chunk[c]);
+      if (e != cudaSuccess) { werr[t] = e; return; }
+      const int64_t a = c * per, b = a + per < h->out_floats ? a + per : h->out_floats;
+      if (a >= b) continue;
+      const int64_t n = b - a, lo = a + n * t / T, hi = a + n * (t + 1) / T;
+      memcpy(out_host + lo, h->out_stage + lo, sizeof(float) * (hi - lo));
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& x : th) x.join();
+  }
+  for (int t = 0; t < T; t++) CK(h, werr[t]);
   CK(h, cudaStreamSynchronize(s));
   return PRB_OK;
 }

@@ -185,9 +185,12 @@ class VecPlayEnv:
         a = np.asarray(action, np.float32)
         assert a.shape == (self.num_envs, self.action_dim), 'action must be [num_envs, %d]' % self.action_dim
         self._h_action.numpy()[...] = a
+        # the result block lands in a fresh array (the reference returns new arrays every step, environments.py:850-855):
+        # prb_step_host reads it back through pinned staging in chunks and copies them out with worker threads
+        buf = np.empty(self.out_floats, np.float32)
         _lib.check(self.L, self._h, self.L.prb_step_host(self._h, ctypes.c_void_p(self._h_action.data_ptr()),
-                                                        ctypes.c_void_p(self._h_out.data_ptr()), self._stream()))
-        c = self._host_copy()
+                                                        ctypes.c_void_p(buf.ctypes.data), self._stream()))
+        c = {k: buf[i:j].reshape(self.num_envs, self.dims[k]) for k, (i, j) in self._h_slices.items()}
         r = c['reward'][:, 0]
         info = {'is_success': c['is_success'][:, 0].astype(np.int64), 'target_poses': c['target_poses']}
         done = np.zeros(self.num_envs, dtype=bool)       # environments.py:212: always False
