@@ -80,7 +80,7 @@ struct WarpMemT {
     struct {
       float lR[PRB_MAXD][9], lIw[PRB_MAXD][6], lf[PRB_MAXD][3], ln[PRB_MAXD][3];
       float Mm[PRB_MAXD][PRB_MAXD + 1];
-      float aabb[PRB_MAXCOL][6];
+      float2 aabb[PRB_MAXCOL][3];   // per axis (lo, hi): 8-byte loads in the broad phase
       Contact cand[CFG::MAXCAND];
     };
     float A[CFG::ACAP + CFG::APAD];
@@ -497,18 +497,30 @@ PRB_D void phase_crba(const DevModel& M, WM& W, int lane) {
   __syncwarp();
 }
 
-// Cholesky M = L L^T in place (lane = row), then lane c solves for column c of M^-1
+// Cholesky M = L L^T (lane = row: the row lives in registers, the pivot column travels by shuffle; same operations in
+// the same order as the textbook in-place loop), then lane c solves for column c of M^-1
 template <int ND, class WM>
 PRB_D void phase_minv(WM& W, int lane) {
-  for (int k = 0; k < ND; k++) {
-    float d = sqrtf(W.Mm[k][k]);
+  {
+    float Lr[ND];
+    const int row = lane < ND ? lane : ND - 1;        // idle lanes shadow the last row; nothing of theirs is stored
+#pragma unroll
+    for (int c = 0; c < ND; c++) Lr[c] = W.Mm[row][c];
+#pragma unroll
+    for (int k = 0; k < ND; k++) {
+      const float d = sqrtf(__shfl_sync(FULL, Lr[k], k));
+      if (lane == k) Lr[k] = d;
+      else if (lane > k) Lr[k] = Lr[k] / d;
+#pragma unroll
+      for (int c = k + 1; c < ND; c++) {
+        const float lck = __shfl_sync(FULL, Lr[k], c);
+        if (lane > k && c <= lane) Lr[c] -= Lr[k] * lck;
+      }
+    }
     __syncwarp();
-    if (lane == k) W.Mm[k][k] = d;
-    if (lane > k && lane < ND) W.Mm[lane][k] = W.Mm[lane][k] / d;
-    __syncwarp();
-    if (lane > k && lane < ND) {
-      float lrk = W.Mm[lane][k];
-      for (int c = k + 1; c <= lane; c++) W.Mm[lane][c] -= lrk * W.Mm[c][k];
+    if (lane < ND) {
+#pragma unroll
+      for (int c = 0; c < ND; c++) if (c <= lane) W.Mm[lane][c] = Lr[c];
     }
     __syncwarp();
   }
@@ -784,25 +796,35 @@ PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
     v3 e = V3(fabsf(R.m[0]) * h.x + fabsf(R.m[1]) * h.y + fabsf(R.m[2]) * h.z,
               fabsf(R.m[3]) * h.x + fabsf(R.m[4]) * h.y + fabsf(R.m[5]) * h.z,
               fabsf(R.m[6]) * h.x + fabsf(R.m[7]) * h.y + fabsf(R.m[8]) * h.z);
-    st3(&W.aabb[c][0], p - e); st3(&W.aabb[c][3], p + e);
+    W.aabb[c][0] = make_float2(p.x - e.x, p.x + e.x); W.aabb[c][1] = make_float2(p.y - e.y, p.y + e.y); W.aabb[c][2] = make_float2(p.z - e.z, p.z + e.z);
   }
   __syncwarp();
   int n_ovl = 0;
+  // lane = pair, four groups of 32 pairs per trip: the eight index loads of a trip are issued together, ahead of the tests
 #pragma unroll 1
-  for (int base = 0; base < M.n_pair; base += 32) {
-    int k = base + lane;
-    bool hit = false;
-    if (k < M.n_pair) {
-      const float* A = W.aabb[M.pair_a[k]];
-      const float* B = W.aabb[M.pair_b[k]];
-      hit = !(A[0] > B[3] || A[3] < B[0] || A[1] > B[4] || A[4] < B[1] || A[2] > B[5] || A[5] < B[2]);
+  for (int base = 0; base < M.n_pair; base += 128) {
+    int ia[4], ib[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      const int k = base + 32 * g + lane;
+      const bool in = k < M.n_pair;
+      ia[g] = in ? (int)M.pair_a[k] : 0; ib[g] = in ? (int)M.pair_b[k] : 0;
     }
-    unsigned bal = __ballot_sync(FULL, hit);
-    if (hit) {
-      int slot = n_ovl + __popc(bal & ((1u << lane) - 1u));
-      if (slot < WM::Cfg::MAXOVL) W.ovl[slot] = (unsigned short)k; else W.overflow |= 1;      // bit 0: overlapping pairs
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      if (base + 32 * g < M.n_pair) {                  // warp-uniform
+        const int k = base + 32 * g + lane;
+        const float2 ax = W.aabb[ia[g]][0], ay = W.aabb[ia[g]][1], az = W.aabb[ia[g]][2];
+        const float2 bx = W.aabb[ib[g]][0], by = W.aabb[ib[g]][1], bz = W.aabb[ib[g]][2];
+        const bool hit = k < M.n_pair && !(ax.x > bx.y || ax.y < bx.x || ay.x > by.y || ay.y < by.x || az.x > bz.y || az.y < bz.x);
+        const unsigned bal = __ballot_sync(FULL, hit);
+        if (hit) {
+          const int slot = n_ovl + __popc(bal & ((1u << lane) - 1u));
+          if (slot < WM::Cfg::MAXOVL) W.ovl[slot] = (unsigned short)k; else W.overflow |= 1;      // bit 0: overlapping pairs
+        }
+        n_ovl += __popc(bal);
+      }
     }
-    n_ovl += __popc(bal);
   }
   if (n_ovl > WM::Cfg::MAXOVL) n_ovl = WM::Cfg::MAXOVL;
   __syncwarp();

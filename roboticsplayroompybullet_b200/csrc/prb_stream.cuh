@@ -190,7 +190,7 @@ struct SetupMemT {
   Contact ct[CFG::MAXCONTACT];
   float lR[PRB_MAXD][9], lIw[PRB_MAXD][6], lf[PRB_MAXD][3], ln[PRB_MAXD][3];
   float Mm[PRB_MAXD][PRB_MAXD + 1];
-  float aabb[PRB_MAXCOL][6];
+  float2 aabb[PRB_MAXCOL][3];     // per axis (lo, hi)
   Contact cand[CFG::MAXCAND];
 };
 
