@@ -94,8 +94,10 @@
 #endif
 #define PGS_MAXJROW_J ((PGS_STAGE_J - R0_JROW) * 4 / 5)     // njr + ceil(njr / 4) <= PGS_STAGE_J - R0_JROW
 // ---- arm-island ("heavy") size classes: class k gives an env ARM_CAPQ(k) q of shared memory and a thread block
-// ARM_LANES(k) envs, so that every class keeps 3-4 blocks (one warp each) resident per SM; class 4 stages the first
-// ARM_CAPQ(4) q and reads the records beyond that in place.  The heavy buffer of a class is an array of bundles of
+// ARM_LANES(k) envs, so that classes 0-3 keep 3-4 blocks (one warp each) resident per SM; class 4 stages the first
+// ARM_CAPQ(4) q and reads the records beyond that in place.  Class 4 (the largest islands, ~0.2 % of the envs) runs ONE
+// env per warp: its 50-sweep chain is the latency floor of a substep at small batch sizes, and lanes of one warp that
+// take different branches of a visit (free / slide side, spin row, zero impulse change) would serialise into it.  The heavy buffer of a class is an array of bundles of
 // ARM_LANES(k) envs, lane-interleaved like the stage: a block stages its bundle with ONE bulk copy.
 #define ARM_NCLASS 5
 #define ARM_BUFQ_MAX (R0_LIGHT_END + SB_MAXCONTACT * CR_MAX_Q + CR_MAX_Q + 4)
@@ -104,10 +106,16 @@
 #define ARM_CAPQ1 220
 #define ARM_CAPQ2 288
 #define ARM_CAPQ3 440
-#define ARM_CAPQ4 (R0_LIGHT_END + 32 * CR_MAX_Q + CR_MAX_Q + 4)   // 32 arm contacts staged whole (4 envs per block); the rest is read in place
+#define ARM_CAPQ4 (R0_LIGHT_END + 32 * CR_MAX_Q + CR_MAX_Q + 4)   // 32 arm contacts staged whole; the rest is read in place
 #endif
 
-PRB_HD int arm_lanes(int k) { return k == 0 ? 32 : (k <= 2 ? 16 : (k == 3 ? 8 : 4)); }
+#ifndef ARM_LANES3
+#define ARM_LANES3 8
+#endif
+#ifndef ARM_LANES4
+#define ARM_LANES4 1      // measured r2p: 4 / 2 / 1 envs per warp -> 22.4 / 21.0 / 19.6 ms per env step at 8 192 envs (70.6 / 70.2 / 70.6 ms at 65 536)
+#endif
+PRB_HD int arm_lanes(int k) { return k == 0 ? 32 : (k <= 2 ? 16 : (k == 3 ? ARM_LANES3 : ARM_LANES4)); }
 PRB_HD int arm_capq(int k) { return k == 0 ? ARM_CAPQ0 : (k == 1 ? ARM_CAPQ1 : (k == 2 ? ARM_CAPQ2 : (k == 3 ? ARM_CAPQ3 : ARM_CAPQ4))); }
 PRB_HD int arm_bufq(int k) { return k == ARM_NCLASS - 1 ? ARM_BUFQ_MAX : arm_capq(k); }
 // float4 offset of class k's buffer inside the heavy allocation for N envs (every class can take all N)
