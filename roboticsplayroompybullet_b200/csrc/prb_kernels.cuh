@@ -828,93 +828,83 @@ PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
   }
   if (n_ovl > WM::Cfg::MAXOVL) n_ovl = WM::Cfg::MAXOVL;
   __syncwarp();
-  // narrow phase: lane = overlapping pair, in passes of 32 pairs (NP = 2 for the 64-pair configuration; the second
-  // pass only runs when more than 32 pairs overlap).  Candidates are appended in pair order.
-  constexpr int NP = WM::Cfg::MAXOVL / 32;
-  int keyv[NP], offv[NP];
-  int total = 0;
-#pragma unroll
-  for (int h = 0; h < NP; h++) {
-    keyv[h] = -1; offv[h] = 0;
-    if (h * 32 < n_ovl) {                          // warp-uniform
-      const int idx = h * 32 + lane;
-      CPoint cp[4];
-      int n = 0, ca = 0, cb = 0;
-      if (idx < n_ovl) {
-        int k = W.ovl[idx];
-        ca = M.pair_a[k]; cb = M.pair_b[k];
-        m3 Ra, Rb; v3 pa, pb;
-        collider_frame(M, W, ca, Ra, pa);
-        collider_frame(M, W, cb, Rb, pb);
-        n = box_box(pa, Ra, ld3(M.col_half[ca]), pb, Rb, ld3(M.col_half[cb]), cp);
-        keyv[h] = (int)M.col_obj[ca] << 8 | (int)M.col_obj[cb];
-      }
-      int tot;
-      const int off = total + warp_excl_scan(n, lane, &tot);
-      total += tot;
-      offv[h] = off;
-      for (int i = 0; i < n; i++) {
-        if (off + i >= WM::Cfg::MAXCAND) { W.overflow |= 1; break; }     // (only reachable with 64 pairs: 4 x 32 candidates always fit)
-        Contact& c = W.cand[off + i];
-        c.pbx = cp[i].pos.x; c.pby = cp[i].pos.y; c.pbz = cp[i].pos.z;
-        c.nx = cp[i].n.x; c.ny = cp[i].n.y; c.nz = cp[i].n.z; c.dist = -cp[i].depth; c.cols = ca | (cb << 8);
-      }
+  // narrow phase: lane = overlapping pair, in passes of 32 pairs (a second pass only when more than 32 pairs overlap;
+  // ONE loop body: this kernel is instruction-fetch sensitive, unrolled copies of rarely taken passes cost time).
+  // Candidates are appended in pair order.  The same pass marks where the runs of equal object pair begin (the pair
+  // list is sorted by object pair, so runs are contiguous) and writes the run table over the consumed part of W.ovl.
+  int total = 0, n_runs = 0, carry_key = -2;
+#pragma unroll 1
+  for (int h = 0; h * 32 < n_ovl; h++) {
+    const int idx = h * 32 + lane;
+    CPoint cp[4];
+    int n = 0, ca = 0, cb = 0, key = -1;
+    if (idx < n_ovl) {
+      int k = W.ovl[idx];
+      ca = M.pair_a[k]; cb = M.pair_b[k];
+      m3 Ra, Rb; v3 pa, pb;
+      collider_frame(M, W, ca, Ra, pa);
+      collider_frame(M, W, cb, Rb, pb);
+      n = box_box(pa, Ra, ld3(M.col_half[ca]), pb, Rb, ld3(M.col_half[cb]), cp);
+      key = (int)M.col_obj[ca] << 8 | (int)M.col_obj[cb];
     }
+    int tot;
+    const int off = total + warp_excl_scan(n, lane, &tot);
+    total += tot;
+    for (int i = 0; i < n; i++) {
+      if (off + i >= WM::Cfg::MAXCAND) { W.overflow |= 1; break; }     // (only reachable with 64 pairs: 4 x 32 candidates always fit)
+      Contact& c = W.cand[off + i];
+      c.pbx = cp[i].pos.x; c.pby = cp[i].pos.y; c.pbz = cp[i].pos.z;
+      c.nx = cp[i].n.x; c.ny = cp[i].n.y; c.nz = cp[i].n.z; c.dist = -cp[i].depth; c.cols = ca | (cb << 8);
+    }
+    int prev_key = __shfl_up_sync(FULL, key, 1);
+    if (lane == 0) prev_key = carry_key;
+    carry_key = __shfl_sync(FULL, key, 31);
+    const bool run_start = idx < n_ovl && key != prev_key;
+    const unsigned startmask = __ballot_sync(FULL, run_start);
+    __syncwarp();                                  // every lane has read its pair index: entries <= idx of W.ovl are free
+    if (run_start) W.ovl[n_runs + __popc(startmask & ((1u << lane) - 1u))] = (unsigned short)(off < WM::Cfg::MAXCAND ? off : WM::Cfg::MAXCAND);
+    n_runs += __popc(startmask);                   // (run index <= pair index: the table never overtakes the unread pairs)
   }
   const int ncand = total < WM::Cfg::MAXCAND ? total : WM::Cfg::MAXCAND;
-  // ---- manifold reduction: <= 4 points per pair of collision objects (runs of equal object pair;
-  //      the pair list is sorted by object pair, so runs are contiguous).  Lane = overlapping pair
-  //      marks run starts, lane = run reduces it, then an ordered compaction into ct[].
-  unsigned startmask[NP];
-  int n_runs = 0;
-  __syncwarp();                                    // the pair indices in W.ovl are dead from here: it becomes the run table
-#pragma unroll
-  for (int h = 0; h < NP; h++) {
-    int prev_key = __shfl_up_sync(FULL, keyv[h], 1);
-    if (h > 0) { const int last = __shfl_sync(FULL, keyv[h > 0 ? h - 1 : 0], 31); if (lane == 0) prev_key = last; }
-    const int idx = h * 32 + lane;
-    const bool run_start = idx < n_ovl && (idx == 0 || keyv[h] != prev_key);
-    startmask[h] = __ballot_sync(FULL, run_start);
-    if (run_start) W.ovl[n_runs + __popc(startmask[h] & ((1u << lane) - 1u))] = (unsigned short)(offv[h] < ncand ? offv[h] : ncand);   // candidate index where the run begins
-    n_runs += __popc(startmask[h]);
-  }
   __syncwarp();
+  // ---- manifold reduction: <= 4 points per pair of collision objects; lane = run reduces it, then an ordered
+  //      compaction into ct[]
   int total2 = 0;
-#pragma unroll
-  for (int h = 0; h < NP; h++) {
-    if (h * 32 < n_runs) {                         // warp-uniform
-      const int r = h * 32 + lane;
-      int keep[4], m = 0;
-      if (r < n_runs) {
-        int b0 = W.ovl[r], b1 = (r + 1 < n_runs) ? (int)W.ovl[r + 1] : ncand;
-        int nn = b1 - b0;
-        const Contact* c = &W.cand[b0];
-        if (nn <= 4) { m = nn; for (int i = 0; i < nn; i++) keep[i] = b0 + i; }
-        else {
-          int i0 = 0;
-          for (int i = 1; i < nn; i++) if (c[i].dist < c[i0].dist - MTIE) i0 = i;     // ties: the first candidate wins
-          v3 p0 = V3(c[i0].pbx, c[i0].pby, c[i0].pbz);
-          int i1 = -1; float best = -1.f;
-          for (int i = 0; i < nn; i++) if (i != i0) { v3 d = V3(c[i].pbx, c[i].pby, c[i].pbz) - p0; float v = norm(d); if (v > best + MTIE) { best = v; i1 = i; } }
-          v3 p1 = V3(c[i1].pbx, c[i1].pby, c[i1].pbz), e01 = p1 - p0;
-          const float atol = norm(e01) * MTIE;   // an area tolerance: MTIE of height over the longest edge
-          int i2 = -1; best = -1.f;
-          for (int i = 0; i < nn; i++) if (i != i0 && i != i1) { v3 x = cross(V3(c[i].pbx, c[i].pby, c[i].pbz) - p0, e01); float v = norm(x); if (v > best + atol) { best = v; i2 = i; } }
-          v3 p2 = V3(c[i2].pbx, c[i2].pby, c[i2].pbz);
-          int i3 = -1; best = -1.f;
-          for (int i = 0; i < nn; i++) if (i != i0 && i != i1 && i != i2) {
-            v3 pi = V3(c[i].pbx, c[i].pby, c[i].pbz), a = pi - p0, b = pi - p1, d = pi - p2;
-            float v = norm(cross(a, b)) + norm(cross(b, d)) + norm(cross(d, a));
-            if (v > best + 4.f * atol) { best = v; i3 = i; }
-          }
-          for (int i = 0; i < nn; i++) if (i == i0 || i == i1 || i == i2 || i == i3) keep[m++] = b0 + i;
+#pragma unroll 1
+  for (int h = 0; h * 32 < n_runs; h++) {
+    const int r = h * 32 + lane;
+    int keep[4], m = 0;
+    if (r < n_runs) {
+      int b0 = W.ovl[r], b1 = (r + 1 < n_runs) ? (int)W.ovl[r + 1] : ncand;
+      if (b0 > ncand) b0 = ncand;
+      if (b1 > ncand) b1 = ncand;
+      int nn = b1 - b0;
+      const Contact* c = &W.cand[b0];
+      if (nn <= 4) { m = nn; for (int i = 0; i < nn; i++) keep[i] = b0 + i; }
+      else {
+        int i0 = 0;
+        for (int i = 1; i < nn; i++) if (c[i].dist < c[i0].dist - MTIE) i0 = i;     // ties: the first candidate wins
+        v3 p0 = V3(c[i0].pbx, c[i0].pby, c[i0].pbz);
+        int i1 = -1; float best = -1.f;
+        for (int i = 0; i < nn; i++) if (i != i0) { v3 d = V3(c[i].pbx, c[i].pby, c[i].pbz) - p0; float v = norm(d); if (v > best + MTIE) { best = v; i1 = i; } }
+        v3 p1 = V3(c[i1].pbx, c[i1].pby, c[i1].pbz), e01 = p1 - p0;
+        const float atol = norm(e01) * MTIE;   // an area tolerance: MTIE of height over the longest edge
+        int i2 = -1; best = -1.f;
+        for (int i = 0; i < nn; i++) if (i != i0 && i != i1) { v3 x = cross(V3(c[i].pbx, c[i].pby, c[i].pbz) - p0, e01); float v = norm(x); if (v > best + atol) { best = v; i2 = i; } }
+        v3 p2 = V3(c[i2].pbx, c[i2].pby, c[i2].pbz);
+        int i3 = -1; best = -1.f;
+        for (int i = 0; i < nn; i++) if (i != i0 && i != i1 && i != i2) {
+          v3 pi = V3(c[i].pbx, c[i].pby, c[i].pbz), a = pi - p0, b = pi - p1, d = pi - p2;
+          float v = norm(cross(a, b)) + norm(cross(b, d)) + norm(cross(d, a));
+          if (v > best + 4.f * atol) { best = v; i3 = i; }
         }
+        for (int i = 0; i < nn; i++) if (i == i0 || i == i1 || i == i2 || i == i3) keep[m++] = b0 + i;
       }
-      int t2;
-      const int off2 = total2 + warp_excl_scan(m, lane, &t2);
-      total2 += t2;
-      for (int i = 0; i < m; i++) if (off2 + i < WM::Cfg::MAXCONTACT) W.ct[off2 + i] = W.cand[keep[i]];
     }
+    int t2;
+    const int off2 = total2 + warp_excl_scan(m, lane, &t2);
+    total2 += t2;
+    for (int i = 0; i < m; i++) if (off2 + i < WM::Cfg::MAXCONTACT) W.ct[off2 + i] = W.cand[keep[i]];
   }
   if (lane == 0) {
     W.n_contact = total2 < WM::Cfg::MAXCONTACT ? total2 : WM::Cfg::MAXCONTACT;

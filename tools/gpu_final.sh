@@ -3,6 +3,11 @@
 # one steady-state env step and a full-set capture of one substep's kernels.  Usage: gpurun --timeout 2400 -- 'bash tools/gpu_final.sh TAG'
 TAG=${1:-r2}
 mkdir -p gpurun_out
+rm -f gpurun_out/parity_stats.jsonl
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/pytest_$TAG.log; cat gpurun_out/pytest_$TAG.log
+python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke_$TAG.log 2>&1; tail -2 gpurun_out/smoke_$TAG.log
+python tools/exp_reset_trace.py > gpurun_out/reset_trace_$TAG.log 2>&1; grep -a 'full reset\|masked' gpurun_out/reset_trace_$TAG.log
+python tools/exp_usage.py > gpurun_out/usage_$TAG.log 2>&1; tail -12 gpurun_out/usage_$TAG.log
 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_$TAG.json
 python bench.py --impl reference --steps 3 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_ref_$TAG.json
 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --jump-frac 0.05 2>&1 | tail -1 > gpurun_out/bench_jump_$TAG.json

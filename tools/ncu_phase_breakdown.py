@@ -76,18 +76,19 @@ def main():
         if r[0] not in seen:
             seen.add(r[0])
             uniq.append(r)
-    inst, samp, thr = defaultdict(int), defaultdict(int), defaultdict(int)
+    inst, samp, thr, static = defaultdict(int), defaultdict(int), defaultdict(int), defaultdict(int)
     cur = 'prologue'
     for addr, f, ln, ni, ns, nt in uniq:
         if f in spans and ln:
             cur = func_of(f, ln)
         inst[cur] += ni
+        static[cur] += 1
         samp[cur] += ns
         thr[cur] += nt
     ti, ts = sum(inst.values()) or 1, sum(samp.values()) or 1
     print('%d SASS instructions, %.3e warp instructions executed, %d samples' % (len(uniq), ti, ts))
     for p in sorted(inst, key=lambda p: -samp[p]):
-        print('   %-26s inst %6.2f%%   samples %6.2f%%   active lanes %.1f' % (p, 100.0 * inst[p] / ti, 100.0 * samp[p] / ts, thr[p] / max(inst[p], 1)))
+        print('   %-26s inst %6.2f%%   samples %6.2f%%   active lanes %4.1f   SASS %5d' % (p, 100.0 * inst[p] / ti, 100.0 * samp[p] / ts, thr[p] / max(inst[p], 1), static[p]))
 
 
 if __name__ == '__main__':
