@@ -396,3 +396,91 @@ def test_reset_from_observation(env_id):
         assert np.abs(new['obs_quat'][i][o_obj:o_obj + 3] - o_rows[i][o_obj:o_obj + 3]).max() < 1e-6
     assert worst < 5e-5, worst
     env.close()
+
+
+@pytest.mark.parametrize('env_id,tol', [('UR5Reach-v0', 1e-4), ('pandaReach-v0', 1e-2)])
+def test_open_loop_rollout(env_id, tol):
+    """30 env steps OPEN LOOP (360 substeps, no re-synchronisation of the states): the CUDA trajectory and the oracle
+    trajectory of every env stay within the pose tolerance at every step.  The UR5 is held to the one-step tolerance
+    (1e-4 m) over the whole rollout; the 7-DoF Panda reaches a 3-D / 6-D target with a redundant arm, its IK starts from
+    the current joints, its 200-iteration loop stops on a residual threshold (one iteration more or less in fp32) and
+    nothing pulls a null-space difference back, so its bound is looser (measured: 4e-3 worst of 32 envs x 30 steps on the
+    B200, 2.2e-5 for the UR5).  Contact-rich worlds are not rolled out open loop: a contact appearing one substep apart is chaotic."""
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle
+    from helpers import key_errors
+    n = 32
+    env = _mk(env_id, n, seed=9)
+    env.reset()
+    m = load_model(env_id)
+    st = env.get_state()
+    orcs = []
+    for i in range(n):
+        o = Oracle(m)
+        o.state[:] = st[i, :o.state_dim].astype(np.float64)
+        orcs.append(o)
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for t in range(30):
+        if t % 10 == 0:
+            a = random_actions(rng, n, env_id)
+            a[:, :6] = np.clip(a[:, :6], -0.3, 0.3)
+        obs, r, done, info = env.step(a)
+        for i in range(n):
+            d = orcs[i].step(a[i].astype(np.float64))
+            e = key_errors(m, {k: np.asarray(obs[k][i]) for k in OBS_KEYS}, d)
+            worst = max(worst, e['pose'])
+            assert e['pose'] < tol, (t, i, e)
+    _record('open_loop_rollout[%s]' % env_id, {'steps': 30, 'n': n, 'worst_pose': worst})
+    env.close()
+
+
+def test_invariants_at_full_size():
+    """BASELINE.json's full size (65 536 play envs), properties that need no oracle: every env of every key is finite,
+    quaternions are unit, the keys of the observation dict agree with each other (environments.py:849-861), success <=>
+    reward 0, joints inside their limits, nothing fell through the table or left the world, the capacity counter stays 0,
+    and a second handle with the same seed reproduces the whole batch bit for bit (no work-counter / list race)."""
+    import torch
+    from roboticsplayroompybullet_b200.model import load_model
+    sys_path_bench()
+    import bench
+    N = 65536
+    env_id = 'UR5PlayAbsRPY1Obj-v0'
+    m = load_model(env_id)
+    outs = []
+    for rep in range(2):
+        env = _mk(env_id, N, seed=11)
+        o0 = env.reset_device()
+        acts = torch.as_tensor(bench.synth_actions(np.random.default_rng(2), N, 24, env_id, block_xyz=o0['achieved_goal'][:, :3].cpu().numpy(),
+                                                   ee_xyz=o0['obs_quat'][:, :3].cpu().numpy())).cuda()
+        for t in range(24):
+            obs, r, done, info = env.step_device(acts[t])
+        torch.cuda.synchronize()
+        outs.append(({k: obs[k].clone() for k in obs if obs[k] is not None and hasattr(obs[k], 'clone')}, r.clone(), info['is_success'].clone(), env.get_state().copy()))
+        assert env.overflow_count() == 0
+        env.close()
+    (o, r, s, st), (o2, r2, s2, st2) = outs
+    for k in o:
+        assert torch.isfinite(o[k].float()).all(), k
+        assert torch.equal(o[k], o2[k]), k                              # bit-identical replay
+    assert torch.equal(r, r2) and torch.equal(s, s2) and np.array_equal(st, st2)
+    oq = o['obs_quat']
+    assert (oq[:, 3:7].norm(dim=1) - 1).abs().max() < 1e-5 and (oq[:, 11:15].norm(dim=1) - 1).abs().max() < 1e-5
+    assert torch.equal(o['achieved_goal'], oq[:, 8:19])                 # environment state = achieved goal (:849-857)
+    assert torch.equal(o['controllable_achieved_goal'], torch.cat([oq[:, 0:3], oq[:, 7:8]], 1))
+    assert torch.equal(o['full_positional_state'], oq)                  # play layout: no velocities in obs_quat
+    assert torch.equal(o['observation'][:, 0:3], oq[:, 0:3]) and torch.equal(o['observation'][:, 6:], oq[:, 7:])
+    assert torch.equal((r == 0), (s > 0)) and set(torch.unique(r).tolist()) <= {-1.0, 0.0}
+    q = torch.as_tensor(st[:, :6])                                      # the six UR5 joints: URDF limits (soft: ERP rows)
+    lo, hi = torch.as_tensor(np.asarray(m['arm_lo'], np.float32)[:6]), torch.as_tensor(np.asarray(m['arm_hi'], np.float32)[:6])
+    assert ((q >= lo - 2e-2) & (q <= hi + 2e-2)).all()
+    blk = oq[:, 8:11]
+    assert (blk[:, 2] > -0.2).all() and blk.abs().max() < 2.0           # nothing fell out of the world
+    _record('invariants_at_full_size', {'n': N, 'steps': 24, 'success_rate': float(s.float().mean())})
+
+
+def sys_path_bench():
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
