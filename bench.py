@@ -248,6 +248,7 @@ def run_gpu(args):
     for s in range(P + W):
         env.step_device(acts_dev[s])
     torch.cuda.synchronize()
+    state0 = env.get_state()                  # the e2e leg below starts from the same states as the device-timed leg
     acts_host, acts_dev = acts_host[P:], acts_dev[P:]
     sampler = ClockSampler(local)
     sampler.start()
@@ -294,10 +295,12 @@ def run_gpu(args):
     launches = env.launch_count() - l0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     dev_s = sum(step_ms) / 1000.0
-    # ---- end-to-end through the public numpy API: pinned host actions -> H2D -> step -> D2H of the
-    #      whole observation block, every step
+    # ---- end-to-end through the public numpy API: host actions -> H2D -> step -> D2H of the whole observation block
+    #      into a fresh host array, every step; replayed from the state the device-timed leg started from
     for s in range(2):                        # untimed: first-call allocations of the host path (pinned staging, result arrays)
         env.step(acts_host[W + s])
+    env.set_state(state0)                     # same states and actions as the device-timed steps: the same workload, step for step
+    torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     for s in range(K):
