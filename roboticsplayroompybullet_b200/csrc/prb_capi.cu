@@ -128,10 +128,14 @@ static int launch_step(prb_handle* h, int nsub, int observe, cudaStream_t s, con
       for (int k = ARM_NCLASS - 1; k >= 0; k--) {        // largest islands first
         CK(h, cudaStreamWaitEvent(h->side[k], h->ev_fork, 0));
         float4* hc = h->hbuf + arm_class_base(k, N);
-        if (k == ARM_NCLASS - 1)
-          prb_pgs_arm_kernel<ND, true><<<gcls[k], 32, smcls[k], h->side[k]>>>(h->dm, h->sbuf, hc, h->heavy_cnt + 4 * k, arm_lanes(k), arm_capq(k), arm_bufq(k));
-        else
-          prb_pgs_arm_kernel<ND, false><<<gcls[k], 32, smcls[k], h->side[k]>>>(h->dm, h->sbuf, hc, h->heavy_cnt + 4 * k, arm_lanes(k), arm_capq(k), arm_bufq(k));
+        int* wc = h->heavy_cnt + 4 * k;
+        switch (k) {                                      // envs per block = the record stride, a template constant
+          case 0: prb_pgs_arm_kernel<ND, false, arm_lanes(0)><<<gcls[k], 32, smcls[k], h->side[k]>>>(h->dm, h->sbuf, hc, wc, arm_capq(k), arm_bufq(k)); break;
+          case 1: prb_pgs_arm_kernel<ND, false, arm_lanes(1)><<<gcls[k], 32, smcls[k], h->side[k]>>>(h->dm, h->sbuf, hc, wc, arm_capq(k), arm_bufq(k)); break;
+          case 2: prb_pgs_arm_kernel<ND, false, arm_lanes(2)><<<gcls[k], 32, smcls[k], h->side[k]>>>(h->dm, h->sbuf, hc, wc, arm_capq(k), arm_bufq(k)); break;
+          case 3: prb_pgs_arm_kernel<ND, false, arm_lanes(3)><<<gcls[k], 32, smcls[k], h->side[k]>>>(h->dm, h->sbuf, hc, wc, arm_capq(k), arm_bufq(k)); break;
+          default: prb_pgs_arm_kernel<ND, true, arm_lanes(4)><<<gcls[k], 32, smcls[k], h->side[k]>>>(h->dm, h->sbuf, hc, wc, arm_capq(k), arm_bufq(k)); break;
+        }
         CK(h, cudaEventRecord(h->ev_join[k], h->side[k]));
       }
       prb_pgs_joint_kernel<ND><<<gp, bp, PGS_SMEM_J, s>>>(h->dm, h->sbuf, N, active, elist, n_list);
@@ -157,6 +161,13 @@ static int run_step(prb_handle* h, int nsub, int observe, cudaStream_t s, const 
   return h->hm.nd == 12 ? launch_step<12>(h, nsub, observe, s, active) : launch_step<9>(h, nsub, observe, s, active);
 }
 
+template <int ND, bool INPLACE, int LANES>
+static int arm_attrs(prb_handle* h, int smax) {
+  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND, INPLACE, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND, INPLACE, LANES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  return PRB_OK;
+}
+
 template <int ND>
 static int setup_kernels(prb_handle* h) {
   h->smem = SetupCfg::WPB * (int)sizeof(SetupMemT<SetupCfg>);
@@ -170,15 +181,19 @@ static int setup_kernels(prb_handle* h) {
   h->regs = fa.numRegs;
   int smax = 0;
   for (int k = 0; k < ARM_NCLASS; k++) smax = PGS_SMEM_ARM(k) > smax ? PGS_SMEM_ARM(k) : smax;
-  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-  CK(h, cudaFuncSetAttribute(prb_pgs_arm_kernel<ND, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  {
+    int rc = arm_attrs<ND, false, arm_lanes(0)>(h, smax);
+    if (rc == PRB_OK) rc = arm_attrs<ND, false, arm_lanes(1)>(h, smax);
+    if (rc == PRB_OK) rc = arm_attrs<ND, false, arm_lanes(2)>(h, smax);
+    if (rc == PRB_OK) rc = arm_attrs<ND, false, arm_lanes(3)>(h, smax);
+    if (rc == PRB_OK) rc = arm_attrs<ND, true, arm_lanes(4)>(h, smax);
+    if (rc != PRB_OK) return rc;
+  }
   CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_J));
   CK(h, cudaFuncSetAttribute(prb_pgs_joint_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(h, cudaFuncSetAttribute(prb_pgs_free_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PGS_SMEM_F));
   CK(h, cudaFuncSetAttribute(prb_pgs_free_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(h, cudaFuncGetAttributes(&fa, prb_pgs_arm_kernel<ND, false>));
+  CK(h, cudaFuncGetAttributes(&fa, prb_pgs_arm_kernel<ND, false, arm_lanes(2)>));
   h->regs_pgs = fa.numRegs;
   return PRB_OK;
 }

@@ -115,7 +115,7 @@
 #ifndef ARM_LANES4
 #define ARM_LANES4 1      // measured r2p: 4 / 2 / 1 envs per warp -> 22.4 / 21.0 / 19.6 ms per env step at 8 192 envs (70.6 / 70.2 / 70.6 ms at 65 536)
 #endif
-PRB_HD int arm_lanes(int k) { return k == 0 ? 32 : (k <= 2 ? 16 : (k == 3 ? ARM_LANES3 : ARM_LANES4)); }
+PRB_HD constexpr int arm_lanes(int k) { return k == 0 ? 32 : (k <= 2 ? 16 : (k == 3 ? ARM_LANES3 : ARM_LANES4)); }
 PRB_HD int arm_capq(int k) { return k == 0 ? ARM_CAPQ0 : (k == 1 ? ARM_CAPQ1 : (k == 2 ? ARM_CAPQ2 : (k == 3 ? ARM_CAPQ3 : ARM_CAPQ4))); }
 PRB_HD int arm_bufq(int k) { return k == ARM_NCLASS - 1 ? ARM_BUFQ_MAX : arm_capq(k); }
 // float4 offset of class k's buffer inside the heavy allocation for N envs (every class can take all N)
@@ -1203,11 +1203,11 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
 // or the slack after the region), so a visit is: ~12 independent LDS.128 -> 12-FMA dot + free-body terms ->
 // clamp -> 12-FMA update + one STS of the impulse.  No shuffles, no barriers: the env's records and velocities
 // are private to the thread.
-struct ArmRec {              // pointers of one record (shared memory, or the heavy buffer when read in place)
-  float4* p;
-  int stride;
-  PRB_D float4 ld(int k) const { return p[(size_t)k * stride]; }
-  PRB_D float* lam() const { return reinterpret_cast<float*>(p + (size_t)3 * stride); }
+template <int STRIDE>
+struct ArmRec {              // one record: q k at p[k * STRIDE] (shared memory, or the heavy buffer when read in place); the
+  float4* p;                 // stride is the class's envs per block, a compile-time constant: every load is base + immediate
+  PRB_D float4 ld(int k) const { return p[k * STRIDE]; }
+  PRB_D float* lam() const { return reinterpret_cast<float*>(p + 3 * STRIDE); }
 };
 struct FreeGeom { int fb; float sgn; bool two; v3 n, t1, rF, rS; };
 PRB_D FreeGeom free_geom(int flags, const float4& G0, const float4& G1, const float4& G2) {
@@ -1217,7 +1217,8 @@ PRB_D FreeGeom free_geom(int flags, const float4& G0, const float4& G1, const fl
   return g;
 }
 // contact normal: lambda >= 0, soft CFM
-PRB_D bool visit_normal(const ArmRec& r, IslandV& V, const float* sminv, int& size) {
+template <class REC>
+PRB_D bool visit_normal(const REC& r, IslandV& V, const float* sminv, int& size) {
   const float4 H0 = r.ld(0), L = r.ld(3), G0 = r.ld(4), G1 = r.ld(5), G2 = r.ld(6), SL = r.ld(7);
   const float4 J0 = r.ld(8), J1 = r.ld(9), J2 = r.ld(10), B0 = r.ld(11), B1 = r.ld(12), B2 = r.ld(13);
   const int flags = __float_as_int(H0.x);
@@ -1248,7 +1249,8 @@ PRB_D bool visit_normal(const ArmRec& r, IslandV& V, const float* sminv, int& si
   return dl != 0.f;
 }
 // spinning friction: |lambda| <= coefficient * normal impulse (Bullet skips the row while the normal impulse is 0)
-PRB_D bool visit_spin(const ArmRec& r, IslandV& V, const float* sminv, int& size) {
+template <class REC>
+PRB_D bool visit_spin(const REC& r, IslandV& V, const float* sminv, int& size) {
   const float4 H0 = r.ld(0), H1 = r.ld(1), L = r.ld(3), G0 = r.ld(4), G1 = r.ld(5), G2 = r.ld(6), SL = r.ld(7);
   const float4 J0 = r.ld(26), J1 = r.ld(27), J2 = r.ld(28), B0 = r.ld(29), B1 = r.ld(30), B2 = r.ld(31);
   const int flags = __float_as_int(H0.x);
@@ -1280,7 +1282,8 @@ PRB_D bool visit_spin(const ArmRec& r, IslandV& V, const float* sminv, int& size
   return dl != 0.f;
 }
 // lateral friction: the two rows of a contact are solved together (implicit cone)
-PRB_D bool visit_friction(const ArmRec& r, IslandV& V, const float* sminv, int& size) {
+template <class REC>
+PRB_D bool visit_friction(const REC& r, IslandV& V, const float* sminv, int& size) {
   const float4 H0 = r.ld(0), H1 = r.ld(1), H2 = r.ld(2), L = r.ld(3), G0 = r.ld(4), G1 = r.ld(5), G2 = r.ld(6), SL = r.ld(7);
   const float4 Ja0 = r.ld(14), Ja1 = r.ld(15), Ja2 = r.ld(16), Ba0 = r.ld(17), Ba1 = r.ld(18), Ba2 = r.ld(19);
   const float4 Jb0 = r.ld(20), Jb1 = r.ld(21), Jb2 = r.ld(22), Bb0 = r.ld(23), Bb1 = r.ld(24), Bb2 = r.ld(25);
@@ -1351,11 +1354,13 @@ PRB_D void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsign
 PRB_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
-// lanes: envs per block (<= 32, the other threads of the warp idle); capq: staged q per env; bufq: q reserved per env in the
-// class buffer (> capq only for the last class, whose islands may be read in place beyond the stage)
-template <int ND, bool INPLACE>
+// LANES: envs per block (<= 32, the other threads of the warp idle; compile time: it is the stride of every record load);
+// capq: staged q per env; bufq: q reserved per env in the class buffer (> capq only for the last class, whose islands may
+// be read in place beyond the stage)
+template <int ND, bool INPLACE, int LANES>
 __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restrict__ Mp, float* __restrict__ sbuf, float4* __restrict__ hcls,
-                                                                int* __restrict__ heavy_cnt, int lanes, int capq, int bufq) {
+                                                                int* __restrict__ heavy_cnt, int capq, int bufq) {
+  constexpr int lanes = LANES;
   PRB_PGS_SMEM_DECL;
   const int lane = threadIdx.x;
   const DevModel& M = *Mp;
@@ -1417,7 +1422,7 @@ __global__ void __launch_bounds__(32) prb_pgs_arm_kernel(const DevModel* __restr
     const int tC0 = R.t_jlam + ((R.njr + 3) >> 2);
     const int iters = M.solver_iters;
     bool live = valid;
-#define ARM_REC(t_) ArmRec{(INPLACE && (t_) + CR_MAX_Q > capq) ? gcol + (size_t)(t_) * lanes : col + (size_t)(t_) * lanes, lanes}
+#define ARM_REC(t_) ArmRec<LANES>{(INPLACE && (t_) + CR_MAX_Q > capq) ? gcol + (t_) * lanes : col + (t_) * lanes}
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
       bool changed = false;

@@ -40,10 +40,15 @@ static void run_step_nd(float* state, DevOut O, int N, int nsub, int observe, co
         g_class_count[k] += heavy_cnt[4 * k];
         emu_dim3 gh, bq; gh.x = 2; bq.x = 32;             // two persistent blocks share the class's work counter
         float4* hc = g_hbuf.data() + arm_class_base(k, N);
-        if (k == ARM_NCLASS - 1)
-          emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND, true>(&g_M, g_sbuf.data(), hc, heavy_cnt + 4 * k, arm_lanes(k), arm_capq(k), arm_bufq(k)); });
-        else
-          emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND, false>(&g_M, g_sbuf.data(), hc, heavy_cnt + 4 * k, arm_lanes(k), arm_capq(k), arm_bufq(k)); });
+        int* wc = heavy_cnt + 4 * k;
+        const int cq = arm_capq(k), bq_ = arm_bufq(k);
+        switch (k) {
+          case 0: emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND, false, arm_lanes(0)>(&g_M, g_sbuf.data(), hc, wc, cq, bq_); }); break;
+          case 1: emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND, false, arm_lanes(1)>(&g_M, g_sbuf.data(), hc, wc, cq, bq_); }); break;
+          case 2: emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND, false, arm_lanes(2)>(&g_M, g_sbuf.data(), hc, wc, cq, bq_); }); break;
+          case 3: emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND, false, arm_lanes(3)>(&g_M, g_sbuf.data(), hc, wc, cq, bq_); }); break;
+          default: emu::launch(gh, bq, [&]() { prb_pgs_arm_kernel<ND, true, arm_lanes(4)>(&g_M, g_sbuf.data(), hc, wc, cq, bq_); }); break;
+        }
       }
     }
   }
