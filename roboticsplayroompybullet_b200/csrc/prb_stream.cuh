@@ -1067,9 +1067,11 @@ PRB_D bool free_friction(BV& V, float4* rec, const FreeQ& Q) {
   return d1 != 0.f || d2 != 0.f;
 }
 // the 50 sweeps of one island; sl: this env's staged column, Gr: its records in the stream
-template <class BV>
+// STAGED: every island of the warp fits the stage -> every record pointer is a shared-memory pointer (LDS / STS); otherwise
+// a pointer may be either, and all accesses of the sweep become generic loads.
+template <class BV, bool STAGED>
 PRB_D void free_sweeps(BV& V, float4* sl, float4* Gr, bool live, int nc, int ns, int ncmax, int nsmax, int t_spin, int iters) {
-#define PGS_PTR(t_) ((t_) < PGS_STAGE_F ? sl + (t_) * 32 : Gr + (t_) * 32)
+#define PGS_PTR(t_) ((STAGED || (t_) < PGS_STAGE_F) ? sl + (t_) * 32 : Gr + (t_) * 32)
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
     bool changed = false;
@@ -1175,12 +1177,14 @@ __global__ void __launch_bounds__(PGS_BLOCK) prb_pgs_free_kernel(const DevModel*
       for (int k = 0; k < 6; k++) B.I[k] = b_own ? V.I[PRB_MAXFREE - 1][k] : V.I[0][k];
       B.im = b_own ? V.invm[PRB_MAXFREE - 1] : V.invm[0];
       const bool on = valid && single;
-      free_sweeps(B, sl, Gr, on, on ? nc : 0, on ? ns : 0, ncmax, nsmax, t_spin, iters);
+      // (the solver reads one record ahead: PGS_F_SLACKQ q of slack follow the stage)
+      if (__all_sync(FULL, !on || t_spin + ns <= PGS_STAGE_F)) free_sweeps<OneBody, true>(B, sl, Gr, on, on ? nc : 0, on ? ns : 0, ncmax, nsmax, t_spin, iters);
+      else free_sweeps<OneBody, false>(B, sl, Gr, on, on ? nc : 0, on ? ns : 0, ncmax, nsmax, t_spin, iters);
       if (on) { if (b_own) { V.fv[PRB_MAXFREE - 1] = B.v; V.fw[PRB_MAXFREE - 1] = B.w; } else { V.fv[0] = B.v; V.fw[0] = B.w; } }
     }
     if (__any_sync(FULL, valid && !single)) {
       const bool on = valid && !single;
-      free_sweeps(V, sl, Gr, on, on ? nc : 0, on ? ns : 0, ncmax, nsmax, t_spin, iters);
+      free_sweeps<IslandV, false>(V, sl, Gr, on, on ? nc : 0, on ? ns : 0, ncmax, nsmax, t_spin, iters);
     }
     if (valid) {
       float* gd = reinterpret_cast<float*>(G + Q_DV * 32);
