@@ -22,7 +22,7 @@ for s in range(T):
 u = np.concatenate(agg)
 ovf = u[:, 3] >> 8
 u[:, 3] &= 0xff
-print('capacity flags per env-substep: pairs>32 %.5f  contacts>32 %.5f  slide-slide %.5f' % tuple(((ovf >> b) & 1).mean() for b in range(3)))
+print('capacity flags per env-substep: pairs>64 %.5f  contacts>64 %.5f  slide-slide %.5f' % tuple(((ovf >> b) & 1).mean() for b in range(3)))
 for i, name in [(1, 'contacts'), (2, 'stream q'), (3, 'joint rows')]:
     x = u[:, i]
     print(name, 'mean %.1f' % x.mean(), 'pct50/90/99/99.9/max', [int(np.percentile(x, p)) for p in (50, 90, 99, 99.9, 100)])
