@@ -29,7 +29,7 @@ ENV_ID = 'UR5PlayAbsRPY1Obj-v0'
 RELABEL_EVERY, RELABEL_PHASE = 64, 2       # goal relabelling cadence and its phase in the timed region
 # DRAM bytes (read + write) of the step pipeline per env step at 65536 envs, from the ncu --set full capture in
 # profiles/r2_ncu.md (12 substeps x 0.63 GB + the final setup launch + IK); None for configurations not captured
-MEASURED_TRAFFIC_BYTES = {('UR5PlayAbsRPY1Obj-v0', 65536): 7.3e9}
+MEASURED_TRAFFIC_BYTES = {('UR5PlayAbsRPY1Obj-v0', 65536): 7.5e9}
 BYTES_PER_ENV_STEP = {'UR5Reach-v0': 416, 'pandaPick-v0': 560, 'UR5PlayAbsRPY1Obj-v0': 1044}
 METRIC = 'UR5PlayAbsRPY1Obj-v0 env-steps/s'
 
