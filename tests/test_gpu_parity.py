@@ -484,3 +484,26 @@ def sys_path_bench():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     if root not in sys.path:
         sys.path.insert(0, root)
+
+
+def test_step_host_pinned_and_pageable_agree():
+    """prb_step_host (include/prb.h) with a pinned destination (one asynchronous copy) and with a pageable one (chunks
+    through the handle's pinned staging, copied out by worker threads): the same bytes; odd sizes exercise the chunk
+    boundaries (the block is split into 8 chunks of a multiple of 1024 floats)."""
+    import ctypes
+    from roboticsplayroompybullet_b200 import lib as _lib
+    for n in (1, 37, 1000):
+        envs = [_mk('UR5PlayAbsRPY1Obj-v0', n, seed=13) for _ in range(2)]
+        for e in envs:
+            e.reset()
+        a = random_actions(np.random.default_rng(n), n, 'UR5PlayAbsRPY1Obj-v0')
+        e0, e1 = envs
+        e0._h_action.numpy()[...] = a
+        e1._h_action.numpy()[...] = a
+        pageable = np.full(e0.out_floats, np.nan, np.float32)
+        _lib.check(e0.L, e0._h, e0.L.prb_step_host(e0._h, ctypes.c_void_p(e0._h_action.data_ptr()), ctypes.c_void_p(pageable.ctypes.data), e0._stream()))
+        _lib.check(e1.L, e1._h, e1.L.prb_step_host(e1._h, ctypes.c_void_p(e1._h_action.data_ptr()), ctypes.c_void_p(e1._h_out.data_ptr()), e1._stream()))
+        pinned = e1._h_out.numpy()
+        assert np.isfinite(pageable).all() and np.array_equal(pageable, pinned), n
+        for e in envs:
+            e.close()
