@@ -115,7 +115,10 @@
 #ifndef ARM_LANES4
 #define ARM_LANES4 1      // measured r2p: 4 / 2 / 1 envs per warp -> 22.4 / 21.0 / 19.6 ms per env step at 8 192 envs (70.6 / 70.2 / 70.6 ms at 65 536)
 #endif
-PRB_HD constexpr int arm_lanes(int k) { return k == 0 ? 32 : (k <= 2 ? 16 : (k == 3 ? ARM_LANES3 : ARM_LANES4)); }
+#ifndef ARM_LANES12
+#define ARM_LANES12 8      // measured r2u at 65 536 envs: 16 / 12 / 8 / 6 / 4 envs per warp in classes 1-2 -> 69.5 / 68.8 / 68.6 / 72.1 / 75.9 ms per env step
+#endif
+PRB_HD constexpr int arm_lanes(int k) { return k == 0 ? 32 : (k <= 2 ? ARM_LANES12 : (k == 3 ? ARM_LANES3 : ARM_LANES4)); }
 PRB_HD int arm_capq(int k) { return k == 0 ? ARM_CAPQ0 : (k == 1 ? ARM_CAPQ1 : (k == 2 ? ARM_CAPQ2 : (k == 3 ? ARM_CAPQ3 : ARM_CAPQ4))); }
 PRB_HD int arm_bufq(int k) { return k == ARM_NCLASS - 1 ? ARM_BUFQ_MAX : arm_capq(k); }
 // float4 offset of class k's buffer inside the heavy allocation for N envs (every class can take all N)
