@@ -94,7 +94,7 @@
 #endif
 #define PGS_MAXJROW_J ((PGS_STAGE_J - R0_JROW) * 4 / 5)     // njr + ceil(njr / 4) <= PGS_STAGE_J - R0_JROW
 // ---- arm-island ("heavy") size classes: class k gives an env ARM_CAPQ(k) q of shared memory and a thread block
-// ARM_LANES(k) envs, so that classes 0-3 keep 3-4 blocks (one warp each) resident per SM; class 4 stages the first
+// ARM_LANES(k) envs, so that classes 0-3 keep 3-7 blocks (one warp each; 48-56 envs) resident per SM; class 4 stages the first
 // ARM_CAPQ(4) q and reads the records beyond that in place.  Class 4 (the largest islands, ~0.2 % of the envs) runs ONE
 // env per warp: its 50-sweep chain is the latency floor of a substep at small batch sizes, and lanes of one warp that
 // take different branches of a visit (free / slide side, spin row, zero impulse change) would serialise into it.  The heavy buffer of a class is an array of bundles of

@@ -61,7 +61,7 @@ def main():
         'the largest arm islands, does not shrink with the batch).', '', ''])
     table = subprocess.check_output([sys.executable, os.path.join(ROOT, 'tools', 'ncu_summary.py'), raw_csv]).decode()
     lines = table.split('\n')
-    lines[0] = ('| metric | `prb_setup_kernel<12>` | `prb_pgs_arm_kernel` class 4 (1 env/warp) | class 3 (8 envs/warp) | class 2 (16) | class 1 (16) | '
+    lines[0] = ('| metric | `prb_setup_kernel<12>` | `prb_pgs_arm_kernel` class 4 (1 env/warp) | class 3 (8 envs/warp) | class 2 (8) | class 1 (8) | '
                 'class 0 (32) | `prb_pgs_joint_kernel<12>` | `prb_pgs_free_kernel` |')
     table = '\n'.join(lines)
     phase = subprocess.check_output([sys.executable, os.path.join(ROOT, 'tools', 'ncu_phase_breakdown.py'), src_csv]).decode()
