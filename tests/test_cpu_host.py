@@ -121,3 +121,22 @@ def test_synthetic_actions_shape_and_rate():
     j = bench.synth_actions(np.random.default_rng(0), 64, 200, 'UR5PlayAbsRPY1Obj-v0', jump_frac=0.05)
     outside = np.abs(j[..., :3]).max(-1) > 0.6
     assert 0.01 < outside.mean() < 0.12        # ~5% jumps into the +-6 clip box
+
+
+def test_bench_reference_arm_cli():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys, the
+    oracle port on all host cores for a bounded sample; under torchrun only rank 0 works, the other ranks exit 0 silently."""
+    import json
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '1'],
+                         env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ''
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--env', 'UR5Reach-v0', '--preroll', '4',
+                          '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'env-steps/s' and line['higher_is_better'] is True
+    assert line['value'] > 0 and line['gpu_launches'] == 0 and line['dtype'] == 'f64'
+    cb = line['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] == (os.cpu_count() or 1) and cb['value'] == line['value'] and 'procs x' in cb['sample']
+    assert line['e2e'] == {'value': line['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
