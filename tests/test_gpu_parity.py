@@ -507,3 +507,45 @@ def test_step_host_pinned_and_pageable_agree():
         assert np.isfinite(pageable).all() and np.array_equal(pageable, pinned), n
         for e in envs:
             e.close()
+
+
+@pytest.mark.parametrize('n', [1, 33])
+def test_ragged_batch_sizes(n):
+    """Batch sizes that fill neither a warp of envs (32 per solver warp), nor a setup block (8), nor a class bundle: one
+    env and 33 envs, every action from the corners of the +-6 clip box (environments.py:207), against the oracle."""
+    from roboticsplayroompybullet_b200.model import load_model
+    from oracle.oracle import Oracle
+    env_id = 'UR5PlayAbsRPY1Obj-v0'
+    env = _mk(env_id, n, seed=21)
+    env.reset()
+    m = load_model(env_id)
+    rng = np.random.default_rng(n)
+    bad = 0
+    for step in range(3):
+        st = env.get_state()
+        a = random_actions(rng, n, env_id)
+        if step == 2:
+            a[:, :6] = rng.choice([-7.0, 7.0], (n, 6))                 # beyond the clip box: clipped to +-6
+        obs, r, done, info = env.step(a)
+        assert np.isfinite(obs['obs_quat']).all() and np.isfinite(info['target_poses']).all()
+        outs = [oracle_step_from(m, st[i], np.clip(a[i], -6, 6) if step == 2 else a[i], Oracle)[0] for i in range(n)]
+        res = compare_step(m, obs, r, info, outs, st, np.clip(a, -6, 6) if step == 2 else a, Oracle)
+        bad += res['bad_pose'] + res['bad_flags'] + res['bad_reward']
+    assert bad <= 1, bad
+    env.close()
+
+
+def test_empty_mask_reset_is_a_no_op():
+    env = _mk('UR5PlayAbsRPY1Obj-v0', 40, seed=22)
+    env.reset()
+    env.step(random_actions(np.random.default_rng(0), 40, 'UR5PlayAbsRPY1Obj-v0'))
+    before = env.get_state()
+    env.reset(mask=np.zeros(40, np.uint8))
+    assert env.reset_rounds() == 0 and np.array_equal(env.get_state(), before)
+    one = np.zeros(40, np.uint8)
+    one[17] = 1
+    env.reset(mask=one)
+    after = env.get_state()
+    keep = np.arange(40) != 17
+    assert env.reset_rounds() >= 1 and np.array_equal(after[keep], before[keep]) and not np.array_equal(after[17], before[17])
+    env.close()
