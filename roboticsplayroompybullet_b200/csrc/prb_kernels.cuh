@@ -787,7 +787,7 @@ PRB_DN int box_box(v3 p1, const m3& R1, v3 h1, v3 p2, const m3& R2, v3 h2, CPoin
 // equal and the first one (pair order) wins (tie rules: the parity checker applies the same rule in fp64).
 constexpr float MTIE = 2e-6f;
 template <class WM>
-PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
+PRB_D void phase_collide_broad(const DevModel& M, WM& W, int lane) {
 #pragma unroll 1
   for (int c = lane; c < M.n_col; c += 32) {
     m3 R; v3 p;
@@ -827,7 +827,14 @@ PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
     }
   }
   if (n_ovl > WM::Cfg::MAXOVL) n_ovl = WM::Cfg::MAXOVL;
+  if (lane == 0) W.n_ovl = n_ovl;
   __syncwarp();
+}
+
+// second half of the collision phase (its own function: the setup kernel re-aligns the warps of a block between the halves)
+template <class WM>
+PRB_D void phase_collide_narrow(const DevModel& M, WM& W, int lane) {
+  const int n_ovl = W.n_ovl;
   // narrow phase: lane = overlapping pair, in passes of 32 pairs (a second pass only when more than 32 pairs overlap;
   // ONE loop body: this kernel is instruction-fetch sensitive, unrolled copies of rarely taken passes cost time).
   // Candidates are appended in pair order.  The same pass marks where the runs of equal object pair begin (the pair
@@ -911,6 +918,12 @@ PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
     if (total2 > WM::Cfg::MAXCONTACT) W.overflow |= 2;                                           // bit 1: contacts
   }
   __syncwarp();
+}
+
+template <class WM>
+PRB_D void phase_collide(const DevModel& M, WM& W, int lane) {
+  phase_collide_broad(M, W, lane);
+  phase_collide_narrow(M, W, lane);
 }
 
 // ============================================================================ constraint rows

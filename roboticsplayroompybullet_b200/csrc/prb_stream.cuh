@@ -171,15 +171,22 @@ struct SetupCfg {
 };
 // PRB_SETUP_SYNC: the warps of a block are re-aligned with a block barrier between the phases of the setup kernel.  Its
 // code (~15k SASS instructions, executed once per warp) is far larger than the instruction caches; warps drifting apart
-// each stream it on their own (r2b: 3.4 stall cycles per issue waiting for instructions).  Measured r2c: no gain over
-// simply running 8 warps per block (29.7 vs 29.9 ms), so off by default.
+// each stream it on their own (r2b: 3.4 stall cycles per issue waiting for instructions).  Measured r2c (15k instructions):
+// no gain over simply running 8 warps per block (29.7 vs 29.9 ms).  Measured r2v (16.8k instructions after the 64-pair /
+// 64-contact capacity, instruction-cache hit rate 66 %): 30.7 -> 27.8 ms of setup per env step, so ON by default.
+// Level 2 adds barriers inside the dynamics phase (CRBA | M^-1 | v*).
 #ifndef PRB_SETUP_SYNC
-#define PRB_SETUP_SYNC 0
+#define PRB_SETUP_SYNC 1
 #endif
 #if PRB_SETUP_SYNC && !defined(PRB_EMU)
 #define SETUP_ALIGN() __syncthreads()
 #else
 #define SETUP_ALIGN() ((void)0)
+#endif
+#if PRB_SETUP_SYNC >= 2 && !defined(PRB_EMU)
+#define SETUP_ALIGN2() __syncthreads()
+#else
+#define SETUP_ALIGN2() ((void)0)
 #endif
 
 // shared memory of one env in the setup kernel: state + the substep's kinematics / collision scratch
@@ -681,9 +688,15 @@ __global__ void __launch_bounds__(32 * SetupCfg::WPB, PRB_SETUP_MINB) prb_setup_
     SETUP_ALIGN();
     if (on) phase_fk(M, W, lane, true);
     SETUP_ALIGN();
-    if (on) phase_collide(M, W, lane);
+    if (on) phase_collide_broad(M, W, lane);
     SETUP_ALIGN();
-    if (on) { phase_crba(M, W, lane); phase_minv<ND>(W, lane); phase_vstar(M, W, lane); }
+    if (on) phase_collide_narrow(M, W, lane);
+    SETUP_ALIGN();
+    if (on) phase_crba(M, W, lane);
+    SETUP_ALIGN2();
+    if (on) phase_minv<ND>(W, lane);
+    SETUP_ALIGN2();
+    if (on) phase_vstar(M, W, lane);
     SETUP_ALIGN();
     if (on) {
       phase_rows_stream<ND>(M, W, lane, e, N, S, hbuf, heavy_cnt);
